@@ -1,0 +1,130 @@
+/*
+ * tfnas_b200 — C ABI of the B200-native TF-NAS supernet search hot path.
+ *
+ * The reference (AberHu/TF-NAS) has no FFI/plugin seam: its hot path is the Python
+ * class API of models/model_search.py, and all arithmetic is delegated to PyTorch.
+ * This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md): plain pointers and sizes, no torch types.  Every entry point
+ *   - returns 0 on success, a negative TFNAS_E_* code otherwise (message via
+ *     tfnas_last_error()), never throws across the ABI;
+ *   - never allocates or frees caller memory, never synchronises the device;
+ *   - launches only on the cudaStream_t it is given (passed as void*).
+ * All tensors are fp32, contiguous NCHW, device memory, 16-byte aligned.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   tfnas_mixedop_fwd / _bwd      MixedOP.forward        models/model_search.py:58-91
+ *                                 MBInvertedResBlock.forward  models/layers.py:539-561
+ *                                 F.gumbel_softmax call  models/model_search.py:87
+ *                                 get_lookup_latency dot models/model_search.py:88,90
+ *                                 (+ the autograd mirror of all of the above)
+ *   tfnas_stage_sink_fwd / _bwd   MixedStage.forward sink sum  models/model_search.py:202-204
+ */
+#ifndef TFNAS_B200_H
+#define TFNAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFNAS_MAX_OPS 8
+#define TFNAS_ABI_VERSION 1
+
+enum {
+  TFNAS_OK = 0,
+  TFNAS_E_INVALID = -1,     /* bad descriptor / argument */
+  TFNAS_E_UNSUPPORTED = -2, /* shape outside what the kernels tile */
+  TFNAS_E_WORKSPACE = -3,   /* workspace / saved buffer too small */
+  TFNAS_E_CUDA = -4         /* a CUDA runtime call failed */
+};
+
+enum { TFNAS_ACT_RELU = 0, TFNAS_ACT_SWISH = 1 };
+
+/* Shape of one MixedOP (reference ctor models/model_search.py:33-47). */
+typedef struct TfnasMixedOpDesc {
+  int32_t N, ic, oc, H, W;
+  int32_t stride;             /* 1 or 2 */
+  int32_t act;                /* TFNAS_ACT_* */
+  int32_t num_ops;            /* <= TFNAS_MAX_OPS */
+  int32_t mc[TFNAS_MAX_OPS];  /* mid (expanded) width per candidate: arbitrary >= 1 */
+  int32_t k[TFNAS_MAX_OPS];   /* depthwise kernel: 3 or 5 */
+  int32_t se[TFNAS_MAX_OPS];  /* squeeze-excite hidden width, 0 = no SE */
+} TfnasMixedOpDesc;
+
+/* Device pointers of one candidate's parameters (reference state_dict names in comments). */
+typedef struct TfnasCandPtrs {
+  float* w1;    /* inverted_bottleneck.conv.weight        [mc, ic]   */
+  float* dw;    /* depth_conv.conv.weight                 [mc, k*k]  */
+  float* w3;    /* point_linear.conv.weight               [oc, mc]   */
+  float* se_rw; /* squeeze_excite.conv_reduce.weight      [se, mc]   (NULL if se==0) */
+  float* se_rb; /* squeeze_excite.conv_reduce.bias        [se]       */
+  float* se_ew; /* squeeze_excite.conv_expand.weight      [mc, se]   */
+  float* se_eb; /* squeeze_excite.conv_expand.bias        [mc]       */
+} TfnasCandPtrs;
+
+int tfnas_version(void);
+const char* tfnas_last_error(void);
+
+/* Bytes of the buffer kept from forward to backward ("saved": D, Z, statistics, SE state). */
+size_t tfnas_mixedop_saved_bytes(const TfnasMixedOpDesc* d, uint32_t cand_mask);
+/* Bytes of scratch for one forward or backward call (max of both). */
+size_t tfnas_mixedop_workspace_bytes(const TfnasMixedOpDesc* d, uint32_t cand_mask, int want_wgrad);
+
+/*
+ * Forward.  cand_mask = 0xFF: alpha mode (MixedOP.forward(sampling=False)):
+ *   w = softmax((log_alphas + gumbel)/T), out = sum_i w_i * op_i(x), out_lat = sum_i w_i*lat8[i].
+ * cand_mask one-hot: sampled mode (sampling=True): out = op_idx(x); log_alphas/gumbel/lat8/out_lat
+ *   may be NULL.
+ * weights: host array of num_ops TfnasCandPtrs (entries of inactive candidates are ignored).
+ * log_alphas, gumbel, lat8: device arrays of num_ops floats.  out_lat: device scalar.
+ */
+int tfnas_mixedop_fwd(const TfnasMixedOpDesc* d, uint32_t cand_mask,
+                      const float* x, const TfnasCandPtrs* weights,
+                      const float* log_alphas, const float* gumbel, const float* lat8, float T,
+                      float* out, float* out_lat,
+                      void* saved, size_t saved_bytes,
+                      void* workspace, size_t ws_bytes, void* stream);
+
+/*
+ * Backward.  dout: dL/dout; dlat: device scalar dL/dout_lat (NULL = 0).
+ * dx: dL/dx (written); NULL = input needs no gradient (then only dlog_alphas is produced).
+ * dlog_alphas: device [num_ops] (written; alpha mode only, else may be NULL).
+ * dweights: host array of num_ops TfnasCandPtrs receiving dL/dW of the ACTIVE candidates
+ *   (written, not accumulated), or NULL when weight gradients are not wanted (alpha step).
+ */
+int tfnas_mixedop_bwd(const TfnasMixedOpDesc* d, uint32_t cand_mask,
+                      const float* x, const TfnasCandPtrs* weights,
+                      const float* dout, const float* dlat, float T,
+                      const void* saved, size_t saved_bytes,
+                      float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights,
+                      void* workspace, size_t ws_bytes, void* stream);
+
+/*
+ * MixedStage sink (models/model_search.py:202-204): out = sum_j softmax(betas)_j * res[j],
+ * out_lat = sum_j softmax(betas)_j * cumlat[j].  res: host array of K device pointers, each
+ * numel floats.  cumlat: device [K] or NULL (then out_lat untouched).
+ */
+int tfnas_stage_sink_fwd(int K, size_t numel, const float* const* res, const float* betas,
+                         const float* cumlat, float* out, float* out_lat, void* stream);
+/*
+ * Backward of the sink: dres[j] = beta_j * dout (written), dbetas[k] (written),
+ * dcumlat[j] = beta_j * dlat (written if non-NULL).  workspace: >= 32 bytes.
+ */
+int tfnas_stage_sink_bwd(int K, size_t numel, const float* const* res, const float* betas,
+                         const float* cumlat, const float* dout, const float* dlat,
+                         float* const* dres, float* dbetas, float* dcumlat,
+                         void* workspace, size_t ws_bytes, void* stream);
+
+/* Test helper: byte offsets of the regions of the saved buffer, in the order
+ * {xmom, bn1, bn2, bn3, mixw, lat, se_p, se_t, se_g, UH, D, Z, total} (13 entries). */
+int tfnas_debug_saved_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, size_t* out13);
+
+/* Number of kernel launches issued through this library since load (bench "gpu_launches"). */
+uint64_t tfnas_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFNAS_B200_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of libtfnas_b200.so (the C ABI declared in include/tfnas_b200.h).
+
+There is NO fallback: if the shared library is missing or fails to load, importing the ops
+raises.  Build it with ``python -m tfnas_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+MAX_OPS = 8
+ACT_RELU, ACT_SWISH = 0, 1
+ACT_CODE = {'relu': ACT_RELU, 'swish': ACT_SWISH}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libtfnas_b200.so')
+
+
+class MixedOpDesc(ctypes.Structure):
+    _fields_ = [('N', ctypes.c_int32), ('ic', ctypes.c_int32), ('oc', ctypes.c_int32),
+                ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('stride', ctypes.c_int32),
+                ('act', ctypes.c_int32), ('num_ops', ctypes.c_int32),
+                ('mc', ctypes.c_int32 * MAX_OPS), ('k', ctypes.c_int32 * MAX_OPS),
+                ('se', ctypes.c_int32 * MAX_OPS)]
+
+
+class CandPtrs(ctypes.Structure):
+    _fields_ = [('w1', ctypes.c_void_p), ('dw', ctypes.c_void_p), ('w3', ctypes.c_void_p),
+                ('se_rw', ctypes.c_void_p), ('se_rb', ctypes.c_void_p),
+                ('se_ew', ctypes.c_void_p), ('se_eb', ctypes.c_void_p)]
+
+
+CandArray = CandPtrs * MAX_OPS
+EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
+           'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
+           'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
+           'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout']
+
+_lib = None
+
+
+class TfnasError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library once; raise loudly when it is absent (no CPU / torch fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TfnasError('%s not built: run `python -m tfnas_b200.build` (needs nvcc); '
+                         'tfnas_b200 has no fallback path' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, u32, f32, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_float, ctypes.c_int
+    dp = ctypes.POINTER(MixedOpDesc)
+    cp = ctypes.POINTER(CandPtrs)
+    lib.tfnas_version.restype = i32
+    lib.tfnas_last_error.restype = ctypes.c_char_p
+    lib.tfnas_launch_count.restype = ctypes.c_uint64
+    lib.tfnas_mixedop_saved_bytes.restype = sz
+    lib.tfnas_mixedop_saved_bytes.argtypes = [dp, u32]
+    lib.tfnas_mixedop_workspace_bytes.restype = sz
+    lib.tfnas_mixedop_workspace_bytes.argtypes = [dp, u32, i32]
+    lib.tfnas_mixedop_fwd.restype = i32
+    lib.tfnas_mixedop_fwd.argtypes = [dp, u32, vp, cp, vp, vp, vp, f32, vp, vp, vp, sz, vp, sz, vp]
+    lib.tfnas_mixedop_bwd.restype = i32
+    lib.tfnas_mixedop_bwd.argtypes = [dp, u32, vp, cp, vp, vp, f32, vp, sz, vp, vp, cp, vp, sz, vp]
+    lib.tfnas_stage_sink_fwd.restype = i32
+    lib.tfnas_stage_sink_fwd.argtypes = [i32, sz, ctypes.POINTER(vp), vp, vp, vp, vp, vp]
+    lib.tfnas_stage_sink_bwd.restype = i32
+    lib.tfnas_stage_sink_bwd.argtypes = [i32, sz, ctypes.POINTER(vp), vp, vp, vp, vp, ctypes.POINTER(vp), vp, vp,
+                                         vp, sz, vp]
+    lib.tfnas_debug_saved_layout.restype = i32
+    lib.tfnas_debug_saved_layout.argtypes = [dp, u32, ctypes.POINTER(sz)]
+    if lib.tfnas_version() != 1:
+        raise TfnasError('ABI version mismatch: %d' % lib.tfnas_version())
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise TfnasError('tfnas_b200 error %d: %s' % (rc, load().tfnas_last_error().decode()))
+
+
+def launch_count():
+    return int(load().tfnas_launch_count())

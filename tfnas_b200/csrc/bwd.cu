@@ -1,0 +1,877 @@
+// Backward phases B1..B4 of one MixedOP call (see DESIGN.md "Kernels"; math: SURVEY.md appendix C,
+// validated on CPU in oracle/fused_math.py).
+//
+//  B1  k_b1, k_b2prep        BN3-backward sums  sG[c] = sum G, sGY_i[c] = sum G*yhat_i ; dL/dw_i
+//  B2  k_dc<TC,ACT>          dz on load from (G, Z); dc = W3^T dz (K = oc); non-SE: dd-hat = dc*act'(d-hat),
+//                            BN2-backward sums; SE: dg[n,c] = sum_hw dc*b
+//      k_se_bwd<ACT>         SE FCs backward -> dp ;  k_b2b<ACT>: SE candidates' dd-hat + BN2-backward sums
+//  B3a k_dw_bwd<KS,S,ACT,WG> dd on load from (DC, D); transposed depthwise -> DA (+ depthwise weight grad)
+//  B3b k_dx<TK,ACT>          du-hat = DA*act'(UH) on load, BN1-backward sums, dx_main = sum_i W1_i^T (r1 du-hat)
+//  B4  k_b4prep, k_dxfin<TK> BN1 backward folded into an ic x ic correction: dx = dx_main - cvec - Mm (x - mu_x) (+G)
+//      k_alpha_grad          softmax/Gumbel Jacobian -> dL/dlog_alpha
+//  weight-grad mode (sampled w-step): k_wgrad<MODE>, k_w1fin, k_se_wgrad
+#include "kernels.h"
+#include "pw.cuh"
+#include <stdio.h>
+#include <string.h>
+
+// ----------------------------------------------------------------------------------------------
+// B1
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_b1(Plan P, const float* __restrict__ G, const float* __restrict__ Zb,
+                                            const float* __restrict__ bn3, double* __restrict__ sG,
+                                            double* __restrict__ sGY) {
+  const int c = blockIdx.x, oc = P.oc, na = P.na, HWo = P.HWo;
+  const int nsplit = gridDim.y;
+  const int i0 = (int)((long long)P.Q * blockIdx.y / nsplit), i1 = (int)((long long)P.Q * (blockIdx.y + 1) / nsplit);
+  float mu[TFNAS_MAX_OPS], r[TFNAS_MAX_OPS], acc[TFNAS_MAX_OPS], sg = 0.f;
+#pragma unroll
+  for (int s = 0; s < TFNAS_MAX_OPS; ++s) {
+    acc[s] = 0.f;
+    mu[s] = s < na ? bn3[s * oc + c] : 0.f;
+    r[s] = s < na ? bn3[na * oc + s * oc + c] : 0.f;
+  }
+  for (int i = i0 + threadIdx.x; i < i1; i += NT) {
+    int n = i / HWo, hw = i - n * HWo;
+    float g = G[((size_t)n * oc + c) * HWo + hw];
+    sg += g;
+#pragma unroll
+    for (int s = 0; s < TFNAS_MAX_OPS; ++s)
+      if (s < na) acc[s] += g * (Zb[((size_t)(n * na + s) * oc + c) * HWo + hw] - mu[s]) * r[s];
+  }
+  __shared__ double red[NT / 32][TFNAS_MAX_OPS + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v = warp_sum_d((double)sg);
+  if (lane == 0) red[warp][TFNAS_MAX_OPS] = v;
+#pragma unroll
+  for (int s = 0; s < TFNAS_MAX_OPS; ++s) {
+    double t = warp_sum_d((double)acc[s]);
+    if (lane == 0) red[warp][s] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x <= TFNAS_MAX_OPS) {
+    double t = 0;
+    for (int w = 0; w < NT / 32; ++w) t += red[w][threadIdx.x];
+    if (threadIdx.x == TFNAS_MAX_OPS) atomicAdd(&sG[c], t);
+    else if ((int)threadIdx.x < na) atomicAdd(&sGY[threadIdx.x * oc + c], t);
+  }
+}
+
+// dzc[slot*oc + o] = {A = w_i*r3, B = sG/Q, C = sGY/Q, 0}; dmix[id] = sum_c sGY
+__global__ void k_b2prep(Plan P, const float* __restrict__ mixw, const float* __restrict__ bn3,
+                         const double* __restrict__ sG, const double* __restrict__ sGY, float4* __restrict__ dzc,
+                         float* __restrict__ dmix) {
+  const int oc = P.oc, na = P.na;
+  const double invQ = 1.0 / (double)P.Q;
+  for (int i = threadIdx.x; i < na * oc; i += blockDim.x) {
+    int s = i / oc, o = i - s * oc;
+    float w = mixw[P.c[s].id];
+    dzc[i] = make_float4(w * bn3[na * oc + i], (float)(sG[o] * invQ), (float)(sGY[i] * invQ), 0.f);
+  }
+  if (threadIdx.x < TFNAS_MAX_OPS) dmix[threadIdx.x] = 0.f;
+  __syncthreads();
+  if ((int)threadIdx.x < na) {
+    double t = 0;
+    for (int o = 0; o < oc; ++o) t += sGY[threadIdx.x * oc + o];
+    dmix[P.c[threadIdx.x].id] = (float)t;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// B2: dc = W3^T dz
+// ----------------------------------------------------------------------------------------------
+template <int TC, int ACT>
+__global__ void __launch_bounds__(NT) k_dc(Plan P, const float* __restrict__ G, const float* __restrict__ Zb,
+                                            const float* __restrict__ bn3, const float4* __restrict__ dzc,
+                                            const float* __restrict__ D, const float* __restrict__ bn2,
+                                            float* __restrict__ DC, float* __restrict__ dg, double* __restrict__ sD) {
+  __shared__ __align__(16) float ins[PW_KC * PW_LDP];
+  __shared__ __align__(16) float ws[PW_KC * (8 * TC + 4)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = blockIdx.z;
+  const Cand& cd = P.c[slot];
+  const int mc = cd.mc, oc = P.oc, na = P.na;
+  const int c0 = blockIdx.y * 8 * TC;
+  if (c0 >= mc) return;
+  const int no = min(8 * TC, mc - c0);
+  Px4 px;
+  px_decomp(px, blockIdx.x * PW_TPX + lane * 4, P.Q, P.HWo);
+  float acc[TC][4];
+#pragma unroll
+  for (int j = 0; j < TC; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  for (int k0 = 0; k0 < oc; k0 += PW_KC) {
+    const int nk = min(PW_KC, oc - k0);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PW_KC / 8; ++i) {
+      const int kk = warp + i * 8, o = k0 + kk;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kk < nk) {
+        const float4 cf = dzc[slot * oc + o];
+        const float mu3 = bn3[slot * oc + o], r3 = bn3[na * oc + slot * oc + o];
+        float g[4], z[4];
+        load4(g, G, px, oc, o, P.HWo);
+        load4(z, Zb, px, na * oc, slot * oc + o, P.HWo);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? cf.x * (g[e] - cf.y - (z[e] - mu3) * r3 * cf.z) : 0.f;
+      }
+      *(float4*)(ins + kk * PW_LDP + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    stage_w_n<TC>(ws, cd.w3, mc, c0, no, k0, nk);
+    __syncthreads();
+    if (warp * TC < no) pw_mma<TC>(acc, ins, ws, lane, warp);
+  }
+  if (warp * TC >= no) return;
+  const bool gated = cd.se > 0;
+  // are all lanes of this warp inside one image? (then the SE partial sum is one atomic per warp)
+  const int n_first = __shfl_sync(0xffffffffu, px.n[0], 0);
+  const bool one_img = __all_sync(0xffffffffu, (!px.v[0]) || (px.n[0] == n_first && px.n[3] == n_first && px.v[3]));
+#pragma unroll
+  for (int j = 0; j < TC; ++j) {
+    const int c = c0 + warp * TC + j;   // warp-uniform
+    if (c >= mc) continue;
+    const int cst = cd.coff + c;
+    const float mu = bn2[cst], r = bn2[P.MC + cst];
+    float d[4];
+    load4(d, D, px, P.MC, cst, P.HWo);
+    if (gated) {
+      store4(DC, acc[j], px, P.MC, cst, P.HWo);
+      float part[4], tot = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        part[e] = px.v[e] ? acc[j][e] * act_f<ACT>((d[e] - mu) * r) : 0.f;
+        tot += part[e];
+      }
+      if (one_img) {
+        tot = warp_sum(tot);
+        if (lane == 0) atomicAdd(&dg[(size_t)n_first * P.MCse + cd.soff + c], tot);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (px.v[e]) atomicAdd(&dg[(size_t)px.n[e] * P.MCse + cd.soff + c], part[e]);
+      }
+    } else {
+      float o[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float dh = (d[e] - mu) * r;
+        o[e] = px.v[e] ? acc[j][e] * act_df<ACT>(dh) : 0.f;
+        s1 += o[e];
+        s2 += o[e] * dh;
+      }
+      store4(DC, o, px, P.MC, cst, P.HWo);
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        atomicAdd(&sD[2 * cst], (double)s1);
+        atomicAdd(&sD[2 * cst + 1], (double)s2);
+      }
+    }
+  }
+}
+
+// SE backward through sigmoid / expand FC / act / reduce FC.  grid (N, na).  dg -> dp in place.
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_se_bwd(Plan P, const float* __restrict__ seg, const float* __restrict__ set,
+                                                float* __restrict__ dg, float* __restrict__ sede,
+                                                float* __restrict__ sedt) {
+  extern __shared__ float sm[];
+  const Cand& cd = P.c[blockIdx.y];
+  if (cd.se == 0) return;
+  const int n = blockIdx.x, mc = cd.mc, se = cd.se, tid = threadIdx.x;
+  float* des = sm;        // [mc]
+  float* dts = sm + mc;   // [se]
+  for (int c = tid; c < mc; c += NT) {
+    size_t i = (size_t)n * P.MCse + cd.soff + c;
+    float g = seg[i];
+    float de = dg[i] * g * (1.f - g);
+    des[c] = de;
+    if (sede) sede[i] = de;
+  }
+  __syncthreads();
+  for (int j = tid; j < se; j += NT) {
+    float a = 0.f;
+    for (int c = 0; c < mc; ++c) a += cd.ew[(size_t)c * se + j] * des[c];
+    size_t i = (size_t)n * P.SEH + cd.hoff + j;
+    float dt = a * act_df<ACT>(set[i]);
+    dts[j] = dt;
+    if (sedt) sedt[i] = dt;
+  }
+  __syncthreads();
+  for (int c = tid; c < mc; c += NT) {
+    float a = 0.f;
+    for (int j = 0; j < se; ++j) a += cd.rw[(size_t)j * mc + c] * dts[j];
+    dg[(size_t)n * P.MCse + cd.soff + c] = a;
+  }
+}
+
+// SE candidates: db = dc*g + dp/HWo ; dd-hat = db*act'(d-hat) in place ; BN2-backward sums.  warp per plane.
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_b2b(Plan P, const float* __restrict__ D, const float* __restrict__ bn2,
+                                             const float* __restrict__ seg, const float* __restrict__ dp,
+                                             float* __restrict__ DC, double* __restrict__ sD) {
+  const int widx = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y;
+  if (widx >= P.MCse) return;
+  int s = -1;
+  for (int i = 0; i < P.na; ++i)
+    if (P.c[i].se > 0 && widx >= P.c[i].soff && widx < P.c[i].soff + P.c[i].mc) s = i;
+  const int cst = P.c[s].coff + (widx - P.c[s].soff);
+  const float mu = bn2[cst], r = bn2[P.MC + cst];
+  const float g = seg[(size_t)n * P.MCse + widx];
+  const float dpn = dp[(size_t)n * P.MCse + widx] / (float)P.HWo;
+  const size_t base = ((size_t)n * P.MC + cst) * P.HWo;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < P.HWo; i += 32) {
+    float dh = (D[base + i] - mu) * r;
+    float v = (DC[base + i] * g + dpn) * act_df<ACT>(dh);
+    DC[base + i] = v;
+    s1 += v;
+    s2 += v * dh;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    atomicAdd(&sD[2 * cst], (double)s1);
+    atomicAdd(&sD[2 * cst + 1], (double)s2);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// B3a: transposed depthwise
+// ----------------------------------------------------------------------------------------------
+
+static DwCfg dwb_config(const Plan& P, int KS) {
+  DwCfg c;
+  const int S = P.stride, pad = KS / 2;
+  int CPB = 1;
+  while (CPB < 32 && CPB * P.HW < 2048) CPB <<= 1;
+  c.CPB = CPB;
+  c.WP = P.Wo + 2 * pad;
+  for (int tiles = 1;; ++tiles) {
+    int R = cdiv(P.H, tiles);
+    int IR = (R + KS - 2) / S + 2;
+    size_t smem = (size_t)CPB * IR * c.WP * 4;
+    if (smem <= 40 * 1024 || R == 1) {
+      c.R = R; c.IR = IR; c.tiles = cdiv(P.H, R); c.smem = smem;
+      break;
+    }
+  }
+  return c;
+}
+
+template <int KS, int S, int ACT, bool WG>
+__global__ void __launch_bounds__(NT) k_dw_bwd(Plan P, DwWork Wk, DwCfg cfg, const float* __restrict__ DC,
+                                                const float* __restrict__ D, const float* __restrict__ bn2,
+                                                const double* __restrict__ sD, const float* __restrict__ UH,
+                                                float* __restrict__ DA, DwGrads gw) {
+  extern __shared__ float dds[];   // [CPB][IR][WP]
+  constexpr int pad = KS / 2;
+  const int tid = threadIdx.x, n = blockIdx.z;
+  int e = 0;
+  while (e + 1 < Wk.n && (int)blockIdx.y >= Wk.gstart[e + 1]) ++e;
+  const Cand& cd = P.c[Wk.slot[e]];
+  const int CPB = cfg.CPB, IR = cfg.IR, WP = cfg.WP;
+  const int cbase = ((int)blockIdx.y - Wk.gstart[e]) * CPB;
+  const int nc = min(CPB, cd.mc - cbase);
+  const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo;
+  const int r0 = blockIdx.x * cfg.R, r1 = min(H, r0 + cfg.R);
+  // output rows touching input rows [r0, r1): oy*S - pad + ky = r
+  int t0 = r0 + pad - KS + 1;
+  const int oy_lo = max(0, t0 > 0 ? (t0 + S - 1) / S : 0);
+  const int oy_hi = min(Ho - 1, (r1 - 1 + pad) / S);
+  const double invQ = 1.0 / (double)P.Q;
+  for (int i = tid; i < CPB * IR * WP; i += NT) {
+    int c = i / (IR * WP), rem = i - c * IR * WP;
+    int lr = rem / WP, lc = rem - lr * WP;
+    int oy = oy_lo + lr, ox = lc - pad;
+    float v = 0.f;
+    if (c < nc && oy <= oy_hi && ox >= 0 && ox < Wo) {
+      const int cst = cd.coff + cbase + c;
+      const float mu = bn2[cst], r = bn2[P.MC + cst];
+      const float m1 = (float)(sD[2 * cst] * invQ), m2 = (float)(sD[2 * cst + 1] * invQ);
+      const size_t a = (((size_t)n * P.MC + cst) * Ho + oy) * Wo + ox;
+      const float dh = (D[a] - mu) * r;
+      v = r * (DC[a] - m1 - dh * m2);
+    }
+    dds[i] = v;
+  }
+  __syncthreads();
+  const int TPC = NT / CPB;
+  const int cl = tid / TPC, jl = tid - cl * TPC;
+  float gacc[WG ? KS * KS : 1];
+#pragma unroll
+  for (int i = 0; i < (WG ? KS * KS : 1); ++i) gacc[i] = 0.f;
+  if (cl < nc) {
+    const int cst = cd.coff + cbase + cl;
+    float wr[KS * KS];
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) wr[i] = cd.dw[(size_t)(cbase + cl) * KS * KS + i];
+    const float* db = dds + (size_t)cl * IR * WP;
+    const size_t pbase = (((size_t)n * P.MC + cst) * H + r0) * W;
+    const int npx = (r1 - r0) * W;
+    for (int p = jl; p < npx; p += TPC) {
+      int rl = p / W, col = p - rl * W;
+      int r = r0 + rl;
+      float a = 0.f;
+      if (WG) a = act_f<ACT>(UH[pbase + p]);
+      float v = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+        int ty = r + pad - ky;
+        if (ty < 0 || (S == 2 && (ty & 1))) continue;
+        int oy = ty / S;
+        if (oy < oy_lo || oy > oy_hi) continue;
+        const float* drow = db + (size_t)(oy - oy_lo) * WP + pad;
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          int tx = col + pad - kx;
+          if (S == 2 && (tx & 1)) continue;
+          // tx may be negative (>= -pad): arithmetic shift keeps ox = floor(tx/2) for even tx
+          int ox = S == 2 ? (tx >> 1) : tx;
+          float dd = drow[ox];
+          v += wr[ky * KS + kx] * dd;
+          if (WG) gacc[ky * KS + kx] += dd * a;
+        }
+      }
+      DA[pbase + p] = v;
+    }
+  }
+  if (WG) {
+    float* gp = gw.p[e];
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) {
+      float t = group_sum(gacc[i], TPC);
+      if (jl == 0 && cl < nc) atomicAdd(&gp[(size_t)(cbase + cl) * KS * KS + i], t);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// B3b: dx_main = sum_i W1_i^T (r1 * du-hat), K = stacked MC
+// ----------------------------------------------------------------------------------------------
+template <int TK, int ACT>
+__global__ void __launch_bounds__(NT) k_dx(Plan P, OcTile T, int ksplit, const float* __restrict__ DA,
+                                            const float* __restrict__ UH, const float* __restrict__ bn1,
+                                            float* __restrict__ dx, double* __restrict__ sU) {
+  __shared__ __align__(16) float ins[PW_KC * PW_LDP];
+  __shared__ __align__(16) float ws[PW_KC * (8 * TK + 4)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ic = P.ic;
+  Px4 px;
+  px_decomp(px, blockIdx.x * PW_TPX + lane * 4, P.P, P.HW);
+  float acc[TK][4];
+#pragma unroll
+  for (int j = 0; j < TK; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  // this CTA's share of the stacked K chunks
+  int total_chunks = 0;
+  for (int s = 0; s < P.na; ++s) total_chunks += (P.c[s].mc + PW_KC - 1) / PW_KC;
+  const int ch0 = (int)((long long)total_chunks * blockIdx.y / ksplit);
+  const int ch1 = (int)((long long)total_chunks * (blockIdx.y + 1) / ksplit);
+  int chunk = 0;
+  for (int s = 0; s < P.na; ++s) {
+    const Cand& cd = P.c[s];
+    for (int k0 = 0; k0 < cd.mc; k0 += PW_KC, ++chunk) {
+      if (chunk < ch0 || chunk >= ch1) continue;
+      const int nk = min(PW_KC, cd.mc - k0);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < PW_KC / 8; ++i) {
+        const int kk = warp + i * 8;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (kk < nk) {   // warp-uniform
+          const int cst = cd.coff + k0 + kk;
+          const float r1 = bn1[P.MC + cst];
+          float da[4], uh[4];
+          load4(da, DA, px, P.MC, cst, P.HW);
+          load4(uh, UH, px, P.MC, cst, P.HW);
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float du = px.v[e] ? da[e] * act_df<ACT>(uh[e]) : 0.f;
+            s1 += du;
+            s2 += du * uh[e];
+            v[e] = du * r1;
+          }
+          s1 = warp_sum(s1);
+          s2 = warp_sum(s2);
+          if (lane == 0) {
+            atomicAdd(&sU[2 * cst], (double)s1);
+            atomicAdd(&sU[2 * cst + 1], (double)s2);
+          }
+        }
+        *(float4*)(ins + kk * PW_LDP + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      stage_w_n<TK>(ws, cd.w1, ic, 0, ic, k0, nk);
+      __syncthreads();
+      if (warp < T.ng) pw_mma<TK>(acc, ins, ws, lane, warp);
+    }
+  }
+  if (warp < T.ng) {
+#pragma unroll
+    for (int j = 0; j < TK; ++j) {
+      const int k = warp * TK + j;
+      if (k < ic) {
+        if (ksplit == 1) store4(dx, acc[j], px, ic, k, P.HW);
+        else atomic_add4(dx, acc[j], px, ic, k, P.HW);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// B4: fold the BN1 backward into an ic x ic correction
+// ----------------------------------------------------------------------------------------------
+// grid (ic): row k of Mm[k][k'] = sum_c W1[c][k] r1_c^2 m2_c W1[c][k'] ; cvec2[k] = sum_c W1[c][k] r1_c m1_c - sum_k' Mm[k][k'] mu_x[k']
+__global__ void __launch_bounds__(NT) k_b4prep(Plan P, const float* __restrict__ bn1, const double* __restrict__ sU,
+                                                const double* __restrict__ xmom, float* __restrict__ Mm,
+                                                float* __restrict__ cvec2) {
+  const int k = blockIdx.x, ic = P.ic, tid = threadIdx.x;
+  const double invP = 1.0 / (double)P.P;
+  __shared__ double red[NT];
+  double cv = 0.0, corr = 0.0;
+  for (int kp = tid; kp < ((ic + NT - 1) / NT) * NT; kp += NT) {
+    double m = 0.0;
+    if (kp < ic) {
+      for (int s = 0; s < P.na; ++s) {
+        const Cand& cd = P.c[s];
+        for (int c = 0; c < cd.mc; ++c) {
+          const int cst = cd.coff + c;
+          const double r1 = (double)bn1[P.MC + cst];
+          const double wk = (double)cd.w1[(size_t)c * ic + k];
+          m += wk * r1 * r1 * (sU[2 * cst + 1] * invP) * (double)cd.w1[(size_t)c * ic + kp];
+        }
+      }
+      Mm[k * ic + kp] = (float)m;
+      corr += m * xmom[kp];
+    }
+  }
+  // cvec: split the stacked channels over the threads
+  for (int cst = tid; cst < P.MC; cst += NT) {
+    int s = 0;
+    while (s + 1 < P.na && cst >= P.c[s + 1].coff) ++s;
+    const Cand& cd = P.c[s];
+    cv += (double)cd.w1[(size_t)(cst - cd.coff) * ic + k] * (double)bn1[P.MC + cst] * (sU[2 * cst] * invP);
+  }
+  red[tid] = cv - corr;
+  __syncthreads();
+  for (int o = NT / 2; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) cvec2[k] = (float)red[0];
+}
+
+// dx = dx_main - Mm x - cvec2 (+ G)
+template <int TK>
+__global__ void __launch_bounds__(NT) k_dxfin(Plan P, OcTile T, const float* __restrict__ x,
+                                               const float* __restrict__ Mm, const float* __restrict__ cvec2,
+                                               const float* __restrict__ G, float* __restrict__ dx) {
+  __shared__ __align__(16) float ins[PW_KC * PW_LDP];
+  __shared__ __align__(16) float ws[PW_KC * (8 * TK + 4)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ic = P.ic;
+  Px4 px;
+  px_decomp(px, blockIdx.x * PW_TPX + lane * 4, P.P, P.HW);
+  float acc[TK][4];
+#pragma unroll
+  for (int j = 0; j < TK; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  for (int k0 = 0; k0 < ic; k0 += PW_KC) {
+    const int nk = min(PW_KC, ic - k0);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PW_KC / 8; ++i) {
+      const int kk = warp + i * 8;
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kk < nk) load4(d, x, px, ic, k0 + kk, P.HW);
+      *(float4*)(ins + kk * PW_LDP + lane * 4) = make_float4(d[0], d[1], d[2], d[3]);
+    }
+    stage_w_t<TK>(ws, Mm, ic, 0, ic, k0, nk);
+    __syncthreads();
+    if (warp < T.ng) pw_mma<TK>(acc, ins, ws, lane, warp);
+  }
+  if (warp < T.ng) {
+#pragma unroll
+    for (int j = 0; j < TK; ++j) {
+      const int k = warp * TK + j;
+      if (k < ic) {
+        float m[4], o[4], g[4] = {0.f, 0.f, 0.f, 0.f};
+        load4(m, dx, px, ic, k, P.HW);
+        if (P.residual) load4(g, G, px, ic, k, P.HW);   // residual => oc == ic, HWo == HW
+        const float cv = cvec2[k];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = m[e] - acc[j][e] - cv + g[e];
+        store4(dx, o, px, ic, k, P.HW);
+      }
+    }
+  }
+}
+
+__global__ void k_alpha_grad(int num_ops, const float* __restrict__ mixw, const float* __restrict__ lat,
+                             const float* __restrict__ dmix, const float* __restrict__ dlat, float T,
+                             float* __restrict__ dalpha) {
+  if (threadIdx.x != 0) return;
+  float dl = dlat ? *dlat : 0.f;
+  float dw[TFNAS_MAX_OPS], dot = 0.f;
+  for (int i = 0; i < num_ops; ++i) {
+    dw[i] = dmix[i] + dl * lat[i];
+    dot += dw[i] * mixw[i];
+  }
+  for (int i = 0; i < num_ops; ++i) dalpha[i] = mixw[i] * (dw[i] - dot) / T;
+}
+
+// ----------------------------------------------------------------------------------------------
+// weight gradients (sampled w-step: one active candidate)
+// ----------------------------------------------------------------------------------------------
+// Out[a][b] += sum_p U[a][p] * V[b][p].  MODE 0 (W3): a = oc (U = dz), b = mc (V = c), pixels Q.
+//                                         MODE 1 (W1): a = mc (U = du-hat), b = ic (V = x), pixels P -> Smat.
+#define WG_T 64
+#define WG_KP 32
+#define WG_LD (WG_T + 4)
+template <int MODE, int ACT>
+__global__ void __launch_bounds__(NT) k_wgrad(Plan P, int slot, const float* __restrict__ A0,
+                                               const float* __restrict__ A1, const float* __restrict__ B0,
+                                               const float* __restrict__ bnA, const float4* __restrict__ dzc,
+                                               const float* __restrict__ bnB, const float* __restrict__ seg,
+                                               float* __restrict__ Out) {
+  __shared__ __align__(16) float Us[WG_KP * WG_LD];
+  __shared__ __align__(16) float Vs[WG_KP * WG_LD];
+  const Cand& cd = P.c[slot];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int na_ = MODE == 0 ? P.oc : cd.mc;    // rows of Out
+  const int nb_ = MODE == 0 ? cd.mc : P.ic;    // cols of Out
+  const int HWp = MODE == 0 ? P.HWo : P.HW;
+  const int total = MODE == 0 ? P.Q : P.P;
+  const int a0 = blockIdx.x * WG_T, b0 = blockIdx.y * WG_T;
+  const int nsplit = gridDim.z;
+  int p_lo = (int)((long long)total * blockIdx.z / nsplit), p_hi = (int)((long long)total * (blockIdx.z + 1) / nsplit);
+  p_lo = p_lo / WG_KP * WG_KP;
+  if ((int)blockIdx.z + 1 < nsplit) p_hi = p_hi / WG_KP * WG_KP;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int pp = tid & 31, rr = tid >> 5;   // staging: 32 pixels x 8 rows per pass
+  for (int p0 = p_lo; p0 < p_hi; p0 += WG_KP) {
+    const int p = p0 + pp;
+    const bool pv = p < p_hi;
+    const int n = pv ? p / HWp : 0, hw = pv ? p - n * HWp : 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < WG_T / 8; ++i) {
+      const int row = rr + i * 8;
+      float u = 0.f, v = 0.f;
+      const int a = a0 + row, b = b0 + row;
+      if (MODE == 0) {
+        if (pv && a < na_) {   // dz[o][p]
+          const float4 cf = dzc[slot * P.oc + a];
+          const float mu3 = bnA[slot * P.oc + a], r3 = bnA[P.na * P.oc + slot * P.oc + a];
+          float g = A0[((size_t)n * P.oc + a) * HWp + hw];
+          float z = A1[((size_t)(n * P.na + slot) * P.oc + a) * HWp + hw];
+          u = cf.x * (g - cf.y - (z - mu3) * r3 * cf.z);
+        }
+        if (pv && b < nb_) {   // c[c][p] = act(BN2(d)) * gate
+          const int cst = cd.coff + b;
+          float d = B0[((size_t)n * P.MC + cst) * HWp + hw];
+          v = act_f<ACT>((d - bnB[cst]) * bnB[P.MC + cst]);
+          if (cd.se > 0) v *= seg[(size_t)n * P.MCse + cd.soff + b];
+        }
+      } else {
+        if (pv && a < na_) {   // du-hat[c][p] = DA * act'(UH)
+          const int cst = cd.coff + a;
+          const size_t idx = ((size_t)n * P.MC + cst) * HWp + hw;
+          u = A0[idx] * act_df<ACT>(A1[idx]);
+        }
+        if (pv && b < nb_) v = B0[((size_t)n * P.ic + b) * HWp + hw];
+      }
+      Us[pp * WG_LD + row] = u;
+      Vs[pp * WG_LD + row] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int q = 0; q < WG_KP; ++q) {
+      float4 ua = *(const float4*)(Us + q * WG_LD + ty * 4);
+      float4 vb = *(const float4*)(Vs + q * WG_LD + tx * 4);
+      const float uu[4] = {ua.x, ua.y, ua.z, ua.w}, vv[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += uu[i] * vv[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int a = a0 + ty * 4 + i, b = b0 + tx * 4 + j;
+      if (a < na_ && b < nb_) atomicAdd(&Out[(size_t)a * nb_ + b], acc[i][j]);
+    }
+}
+
+// dW1[c][k] = r1 ( S[c][k] - m1 P mu_x[k] - m2 r1 P (W1 cov)[c][k] ).  one warp per channel c
+__global__ void __launch_bounds__(NT) k_w1fin(Plan P, int slot, const float* __restrict__ Smat,
+                                               const float* __restrict__ bn1, const double* __restrict__ sU,
+                                               const double* __restrict__ xmom, float* __restrict__ gw1) {
+  const Cand& cd = P.c[slot];
+  const int c = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= cd.mc) return;
+  const int ic = P.ic, cst = cd.coff + c;
+  const double r1 = (double)bn1[P.MC + cst];
+  const double s1 = sU[2 * cst], s2 = sU[2 * cst + 1];   // = m1*P, m2*P
+  const double* mean = xmom;
+  const double* cov = xmom + ic;
+  const float* w = cd.w1 + (size_t)c * ic;
+  for (int k = lane; k < ic; k += 32) {
+    double wc = 0.0;
+    for (int kp = 0; kp < ic; ++kp) wc += (double)w[kp] * cov[kp * ic + k];
+    gw1[(size_t)c * ic + k] = (float)(r1 * ((double)Smat[(size_t)c * ic + k] - s1 * mean[k] - s2 * r1 * wc));
+  }
+}
+
+// SE weight grads: sums over the batch
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_se_wgrad(Plan P, int slot, const float* __restrict__ sede,
+                                                  const float* __restrict__ sedt, const float* __restrict__ sep,
+                                                  const float* __restrict__ set, TfnasCandPtrs gw) {
+  const Cand& cd = P.c[slot];
+  const int mc = cd.mc, se = cd.se, N = P.N;
+  const int i = blockIdx.x * NT + threadIdx.x;
+  if (i < mc * se) {
+    {   // conv_expand.weight [mc][se]
+      int c = i / se, j = i - c * se;
+      float a = 0.f;
+      for (int n = 0; n < N; ++n)
+        a += sede[(size_t)n * P.MCse + cd.soff + c] * act_f<ACT>(set[(size_t)n * P.SEH + cd.hoff + j]);
+      gw.se_ew[i] = a;
+    }
+    {   // conv_reduce.weight [se][mc]
+      int j = i / mc, c = i - j * mc;
+      float a = 0.f;
+      for (int n = 0; n < N; ++n)
+        a += sedt[(size_t)n * P.SEH + cd.hoff + j] * sep[(size_t)n * P.MCse + cd.soff + c];
+      gw.se_rw[i] = a;
+    }
+  }
+  if (i < mc) {
+    float a = 0.f;
+    for (int n = 0; n < N; ++n) a += sede[(size_t)n * P.MCse + cd.soff + i];
+    gw.se_eb[i] = a;
+  }
+  if (i < se) {
+    float a = 0.f;
+    for (int n = 0; n < N; ++n) a += sedt[(size_t)n * P.SEH + cd.hoff + i];
+    gw.se_rb[i] = a;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+template <int TC>
+static void launch_dc(const Plan& P, int maxmc, const float* G, const float* Zb, const float* bn3, const float4* dzc,
+                      const float* D, const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st) {
+  dim3 grid(cdiv(P.Q, PW_TPX), cdiv(maxmc, 8 * TC), P.na);
+  if (P.act == TFNAS_ACT_RELU)
+    k_dc<TC, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
+  else
+    k_dc<TC, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
+  count_launch(1);
+}
+
+template <int KS, int S>
+static void launch_dw_bwd(const Plan& P, const float* DC, const float* D, const float* bn2, const double* sD,
+                          const float* UH, float* DA, const TfnasCandPtrs* dweights, cudaStream_t st) {
+  DwCfg cfg = dwb_config(P, KS);
+  DwWork w;
+  w.n = 0;
+  w.gstart[0] = 0;
+  DwGrads gw;
+  memset(&gw, 0, sizeof(gw));
+  for (int s = 0; s < P.na; ++s) {
+    if (P.c[s].k != KS) continue;
+    w.slot[w.n] = s;
+    w.gstart[w.n + 1] = w.gstart[w.n] + cdiv(P.c[s].mc, cfg.CPB);
+    if (dweights && w.n < 4) gw.p[w.n] = dweights[P.c[s].id].dw;
+    ++w.n;
+  }
+  if (!w.n) return;
+  dim3 grid(cfg.tiles, w.gstart[w.n], P.N);
+  const bool relu = P.act == TFNAS_ACT_RELU;
+  if (dweights) {
+    auto kern = relu ? k_dw_bwd<KS, S, TFNAS_ACT_RELU, true> : k_dw_bwd<KS, S, TFNAS_ACT_SWISH, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    kern<<<grid, NT, cfg.smem, st>>>(P, w, cfg, DC, D, bn2, sD, UH, DA, gw);
+  } else {
+    auto kern = relu ? k_dw_bwd<KS, S, TFNAS_ACT_RELU, false> : k_dw_bwd<KS, S, TFNAS_ACT_SWISH, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    kern<<<grid, NT, cfg.smem, st>>>(P, w, cfg, DC, D, bn2, sD, UH, DA, gw);
+  }
+  count_launch(1);
+}
+
+template <int TK>
+static void launch_dx(const Plan& P, OcTile T, int ksplit, const float* DA, const float* UH, const float* bn1,
+                      float* dx, double* sU, cudaStream_t st) {
+  dim3 grid(cdiv(P.P, PW_TPX), ksplit);
+  if (P.act == TFNAS_ACT_RELU)
+    k_dx<TK, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, T, ksplit, DA, UH, bn1, dx, sU);
+  else
+    k_dx<TK, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, T, ksplit, DA, UH, bn1, dx, sU);
+  count_launch(1);
+}
+
+template <int TK>
+static void launch_dxfin(const Plan& P, OcTile T, const float* x, const float* Mm, const float* cvec2, const float* G,
+                         float* dx, cudaStream_t st) {
+  k_dxfin<TK><<<cdiv(P.P, PW_TPX), NT, 0, st>>>(P, T, x, Mm, cvec2, G, dx);
+  count_launch(1);
+}
+
+void launch_backward(const Plan& P, const float* x, const float* dout, const float* dlat, float T,
+                     int alpha_mode, const char* saved, const SavedLayout& L, const BwdScratch& S,
+                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st) {
+  const double* xmom = (const double*)(saved + L.xmom);
+  const float* bn1 = (const float*)(saved + L.bn1);
+  const float* bn2 = (const float*)(saved + L.bn2);
+  const float* bn3 = (const float*)(saved + L.bn3);
+  const float* mixw = (const float*)(saved + L.mixw);
+  const float* latsave = (const float*)(saved + L.lat);
+  const float* sep = (const float*)(saved + L.sep);
+  const float* set = (const float*)(saved + L.set);
+  const float* seg = (const float*)(saved + L.seg);
+  const float* UH = (const float*)(saved + L.UH);
+  const float* D = (const float*)(saved + L.D);
+  const float* Zb = (const float*)(saved + L.Z);
+  const bool relu = P.act == TFNAS_ACT_RELU;
+  const int ic = P.ic, oc = P.oc;
+  // zero the accumulators: [sG | sGY | sD | sU] doubles are contiguous, then dg floats
+  cudaMemsetAsync(S.sG, 0, (size_t)(oc + P.na * oc + 4 * P.MC) * sizeof(double), st);
+  if (P.MCse > 0) cudaMemsetAsync(S.dg, 0, (size_t)P.N * P.MCse * sizeof(float), st);
+  // B1
+  {
+    int nsplit = max(1, min(cdiv(P.Q, 1024), cdiv(4 * sm_count(), oc)));
+    k_b1<<<dim3(oc, nsplit), NT, 0, st>>>(P, dout, Zb, bn3, S.sG, S.sGY);
+    k_b2prep<<<1, 256, 0, st>>>(P, mixw, bn3, S.sG, S.sGY, S.dzc, S.dmix);
+    count_launch(2);
+  }
+  const float4* dzc = S.dzc;
+  if (!dx) {   // input needs no gradient (first MixedOP of the alpha step): only dL/dlog_alpha
+    if (alpha_mode && dlog_alphas) {
+      k_alpha_grad<<<1, 32, 0, st>>>(P.num_ops, mixw, latsave, S.dmix, dlat, T, dlog_alphas);
+      count_launch(1);
+    }
+    return;
+  }
+  // B2
+  {
+    int maxmc = 0;
+    for (int s = 0; s < P.na; ++s) maxmc = max(maxmc, P.c[s].mc);
+    if (maxmc > 64) launch_dc<16>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
+    else launch_dc<8>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
+  }
+  if (dweights) {   // dW3 (needs DC untouched? no: uses dz and c only)
+    for (int s = 0; s < P.na; ++s) {
+      const Cand& cd = P.c[s];
+      float* gw3 = dweights[cd.id].w3;
+      cudaMemsetAsync(gw3, 0, (size_t)oc * cd.mc * sizeof(float), st);
+      int nsplit = max(1, min(cdiv(P.Q, 2048), cdiv(6 * sm_count(), cdiv(oc, WG_T) * cdiv(cd.mc, WG_T))));
+      dim3 grid(cdiv(oc, WG_T), cdiv(cd.mc, WG_T), nsplit);
+      if (relu) k_wgrad<0, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, dout, Zb, D, bn3, dzc, bn2, seg, gw3);
+      else k_wgrad<0, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, dout, Zb, D, bn3, dzc, bn2, seg, gw3);
+      count_launch(1);
+    }
+  }
+  // SE backward + B2b
+  if (P.MCse > 0) {
+    int maxmc = 0, maxse = 0;
+    for (int s = 0; s < P.na; ++s)
+      if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); }
+    size_t smem = (size_t)(maxmc + maxse) * 4;
+    float* sede = dweights ? S.sede : nullptr;
+    float* sedt = dweights ? S.sedt : nullptr;
+    dim3 gpl(cdiv(P.MCse * 32, NT), P.N);
+    if (relu) {
+      k_se_bwd<TFNAS_ACT_RELU><<<dim3(P.N, P.na), NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
+      k_b2b<TFNAS_ACT_RELU><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
+    } else {
+      k_se_bwd<TFNAS_ACT_SWISH><<<dim3(P.N, P.na), NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
+      k_b2b<TFNAS_ACT_SWISH><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
+    }
+    count_launch(2);
+    if (dweights) {
+      for (int s = 0; s < P.na; ++s) {
+        const Cand& cd = P.c[s];
+        if (!cd.se) continue;
+        int tot = max(cd.mc * cd.se, max(cd.mc, cd.se));
+        if (relu) k_se_wgrad<TFNAS_ACT_RELU><<<cdiv(tot, NT), NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
+        else k_se_wgrad<TFNAS_ACT_SWISH><<<cdiv(tot, NT), NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
+        count_launch(1);
+      }
+    }
+  }
+  // B3a
+  if (dweights)
+    for (int s = 0; s < P.na; ++s)
+      cudaMemsetAsync(dweights[P.c[s].id].dw, 0, (size_t)P.c[s].mc * P.c[s].k * P.c[s].k * sizeof(float), st);
+  if (P.stride == 1) {
+    launch_dw_bwd<3, 1>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
+    launch_dw_bwd<5, 1>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
+  } else {
+    launch_dw_bwd<3, 2>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
+    launch_dw_bwd<5, 2>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
+  }
+  // B3b
+  OcTile Tx = oc_tile(ic, 24);
+  {
+    int tiles = cdiv(P.P, PW_TPX);
+    int total_chunks = 0;
+    for (int s = 0; s < P.na; ++s) total_chunks += cdiv(P.c[s].mc, PW_KC);
+    int ksplit = max(1, min(total_chunks, cdiv(2 * sm_count(), tiles)));
+    if (ksplit > 1) cudaMemsetAsync(dx, 0, (size_t)P.P * ic * sizeof(float), st);
+    switch (Tx.TC) {
+      case 4: launch_dx<4>(P, Tx, ksplit, S.DA, UH, bn1, dx, S.sU, st); break;
+      case 8: launch_dx<8>(P, Tx, ksplit, S.DA, UH, bn1, dx, S.sU, st); break;
+      case 12: launch_dx<12>(P, Tx, ksplit, S.DA, UH, bn1, dx, S.sU, st); break;
+      case 16: launch_dx<16>(P, Tx, ksplit, S.DA, UH, bn1, dx, S.sU, st); break;
+      default: launch_dx<24>(P, Tx, ksplit, S.DA, UH, bn1, dx, S.sU, st); break;
+    }
+  }
+  if (dweights) {   // dW1 via Smat
+    for (int s = 0; s < P.na; ++s) {
+      const Cand& cd = P.c[s];
+      float* Sm = S.Smat + (size_t)cd.coff * ic;
+      cudaMemsetAsync(Sm, 0, (size_t)cd.mc * ic * sizeof(float), st);
+      int nsplit = max(1, min(cdiv(P.P, 2048), cdiv(6 * sm_count(), cdiv(cd.mc, WG_T) * cdiv(ic, WG_T))));
+      dim3 grid(cdiv(cd.mc, WG_T), cdiv(ic, WG_T), nsplit);
+      if (relu) k_wgrad<1, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
+      else k_wgrad<1, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
+      k_w1fin<<<cdiv(cd.mc * 32, NT), NT, 0, st>>>(P, s, Sm, bn1, S.sU, xmom, dweights[cd.id].w1);
+      count_launch(2);
+    }
+  }
+  // B4
+  {
+    float* cvec2 = S.cvec2;
+    float* Mm = S.Mm;
+    k_b4prep<<<ic, NT, 0, st>>>(P, bn1, S.sU, xmom, Mm, cvec2);
+    count_launch(1);
+    switch (Tx.TC) {
+      case 4: launch_dxfin<4>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
+      case 8: launch_dxfin<8>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
+      case 12: launch_dxfin<12>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
+      case 16: launch_dxfin<16>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
+      default: launch_dxfin<24>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
+    }
+  }
+  if (alpha_mode && dlog_alphas) {
+    k_alpha_grad<<<1, 32, 0, st>>>(P.num_ops, mixw, latsave, S.dmix, dlat, T, dlog_alphas);
+    count_launch(1);
+  }
+}

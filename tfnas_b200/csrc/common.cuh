@@ -1,0 +1,74 @@
+// Shared device/host definitions for the tfnas_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tfnas_b200.h"
+
+#define BN_EPS 1e-5f
+#define NT 256  // threads per CTA of every tile kernel
+
+// One ACTIVE candidate in "slot" order (slot s = s-th set bit of cand_mask).
+struct Cand {
+  int id;     // original candidate index 0..7
+  int mc;     // mid width
+  int k;      // 3 / 5
+  int se;     // SE hidden width (0 = none)
+  int coff;   // offset in the stacked mid-channel space [0, MC)
+  int soff;   // offset in the stacked SE-gated mid-channel space [0, MCse)  (valid if se>0)
+  int hoff;   // offset in the stacked SE-hidden space [0, SEH)
+  int pad_;
+  const float *w1, *dw, *w3, *rw, *rb, *ew, *eb;
+};
+
+// Per-MixedOP-call plan, passed BY VALUE to kernels.
+struct Plan {
+  int N, ic, oc, H, W, Ho, Wo, stride, act, na;
+  int MC, MCse, SEH;   // stacked widths over active candidates
+  int HW, HWo;         // H*W, Ho*Wo
+  int P, Q;            // N*H*W, N*Ho*Wo (assumed < 2^31)
+  int residual;
+  int num_ops;         // candidates of the MixedOP (softmax width in alpha mode)
+  Cand c[TFNAS_MAX_OPS];
+};
+
+// Depthwise kernels: channel groups (CPB channels each) of the candidates sharing one kernel size.
+struct DwWork {
+  int n;                  // entries
+  int slot[TFNAS_MAX_OPS];
+  int gstart[TFNAS_MAX_OPS + 1];
+};
+struct DwCfg { int CPB, R, IR, WP, tiles; size_t smem; };
+struct DwGrads { float* p[4]; };   // depthwise weight-grad pointers per DwWork entry
+
+template <int ACT>
+__device__ __forceinline__ float act_f(float x) {
+  if (ACT == TFNAS_ACT_RELU) return fmaxf(x, 0.f);
+  return x / (1.f + __expf(-x));
+}
+// derivative of the activation at pre-activation x
+template <int ACT>
+__device__ __forceinline__ float act_df(float x) {
+  if (ACT == TFNAS_ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over aligned groups of `width` lanes (width power of two <= 32)
+__device__ __forceinline__ float group_sum(float v, int width) {
+  for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

@@ -1,0 +1,671 @@
+// Forward phases F0..F4 of one MixedOP call (see DESIGN.md "Kernels").
+//
+//  F0  k_xsum, k_xcov, k_xfin   input moments mean_x[ic], cov_x[ic,ic]           (x read twice)
+//      k_bn1                    analytic BN1 statistics  mu1 = W1 mu_x, v1 = diag(W1 cov W1^T)
+//  F1a k_expand<TC>             expand 1x1 (K=ic) + BN1 normalisation -> UH
+//  F1b k_dw_fwd<KS,S,ACT>       depthwise KSxKS/S over act(UH) -> D, BN2 sums
+//  F2  k_se_pool, k_se_fc       SE squeeze (mean of act(BN2(d))) and the two FCs -> gate g
+//  F3  k_project<TC,ACT>           c = act(BN2(d))*g ; z = W3 c -> Z, BN3 sums
+//  F4  k_f4prep, k_f4           Gumbel-softmax mixing weights, latency dot, out = sum_i w_i BN3(z_i) (+x)
+//
+// Reference arithmetic: models/layers.py:539-561, models/model_search.py:86-91.
+#include "kernels.h"
+#include "pw.cuh"
+#include <stdio.h>
+
+// ----------------------------------------------------------------------------------------------
+// F0: input moments
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_xsum(Plan P, const float* __restrict__ x, double* __restrict__ xsum) {
+  const int k = blockIdx.x;
+  const int nsplit = gridDim.y, sp = blockIdx.y;
+  const int n0 = (int)((long long)P.N * sp / nsplit), n1 = (int)((long long)P.N * (sp + 1) / nsplit);
+  double acc = 0.0;
+  for (int n = n0; n < n1; ++n) {
+    const float* p = x + ((size_t)n * P.ic + k) * P.HW;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < P.HW; i += NT) s += p[i];
+    acc += (double)s;
+  }
+  __shared__ double red[NT / 32];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < NT / 32; ++i) t += red[i];
+    atomicAdd(&xsum[k], t);
+  }
+}
+
+// centred second moment; grid (chunks per image, N).  smem: xs[icp][XC_LD] + red
+#define XC_TPX 128
+#define XC_LD (XC_TPX + 4)
+__global__ void __launch_bounds__(NT) k_xcov(Plan P, const float* __restrict__ x,
+                                              const double* __restrict__ xsum, double* __restrict__ xcov) {
+  extern __shared__ float sm[];
+  const int ic = P.ic, nb = (ic + 3) >> 2, icp = nb * 4, nblk = nb * nb;
+  float* xs = sm;                      // [icp][XC_LD]
+  float* mean = xs + icp * XC_LD;      // [icp]
+  float* red = mean + icp;             // [nblk_local*16] when nsplit > 1
+  const int n = blockIdx.y;
+  const int chunks = gridDim.x;
+  const int px0 = (int)((long long)P.HW * blockIdx.x / chunks), px1 = (int)((long long)P.HW * (blockIdx.x + 1) / chunks);
+  const int tid = threadIdx.x;
+  for (int k = tid; k < icp; k += NT) mean[k] = k < ic ? (float)(xsum[k] / (double)P.P) : 0.f;
+  const int nsplit = nblk >= NT ? 1 : NT / nblk;
+  const int myblk = nsplit == 1 ? tid : tid % nblk;
+  const int mysp = nsplit == 1 ? 0 : tid / nblk;
+  const bool active = nsplit == 1 ? true : (tid < nblk * nsplit);
+  // per-thread accumulators for up to MAXB blocks when nsplit==1 would blow registers: loop blocks outermost
+  // and keep the pixel loop inside, re-reading xs (smem) — x stays resident per chunk step.
+  const int nloops = nsplit == 1 ? (nblk + NT - 1) / NT : 1;
+  // accumulate across the pixel steps of this CTA in registers for ONE block at a time requires the
+  // pixel tile to stay resident; so for nloops>1 we flush per pixel step to smem-less global atomics.
+  // To keep it simple and exact: accumulate per (block) in a local array of nloops<=9 x 16 floats.
+  float acc[9][16];
+#pragma unroll
+  for (int l = 0; l < 9; ++l)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[l][e] = 0.f;
+  for (int p0 = px0; p0 < px1; p0 += XC_TPX) {
+    const int np = min(XC_TPX, px1 - p0);
+    __syncthreads();
+    for (int i = tid; i < icp * XC_TPX; i += NT) {
+      int k = i / XC_TPX, p = i - k * XC_TPX;
+      float v = 0.f;
+      if (k < ic && p < np) v = x[((size_t)n * ic + k) * P.HW + p0 + p] - mean[k];
+      xs[k * XC_LD + p] = v;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int l = 0; l < 9; ++l) {
+        if (l < nloops) {
+          int blk = myblk + l * NT;
+          if (blk < nblk) {
+            int bi = blk / nb, bj = blk - bi * nb;
+            if (bj >= bi) {
+              const float* xi = xs + (bi * 4) * XC_LD;
+              const float* xj = xs + (bj * 4) * XC_LD;
+              for (int q = mysp; q < XC_TPX / 4; q += nsplit) {
+                float4 a[4], b[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  a[r] = *(const float4*)(xi + r * XC_LD + q * 4);
+                  b[r] = *(const float4*)(xj + r * XC_LD + q * 4);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    acc[l][r * 4 + c] += a[r].x * b[c].x + a[r].y * b[c].y + a[r].z * b[c].z + a[r].w * b[c].w;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // reduce across splits (if any) through shared memory, then one double atomic per entry per CTA
+  __syncthreads();
+  if (nsplit > 1) {
+    for (int i = tid; i < nblk * 16; i += NT) red[i] = 0.f;
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) atomicAdd(&red[myblk * 16 + e], acc[0][e]);
+    }
+    __syncthreads();
+    for (int i = tid; i < nblk * 16; i += NT) {
+      int blk = i >> 4, e = i & 15;
+      int bi = blk / nb, bj = blk - bi * nb;
+      if (bj < bi) continue;
+      int r = bi * 4 + (e >> 2), c = bj * 4 + (e & 3);
+      if (r < ic && c < ic) {
+        double v = (double)red[i];
+        atomicAdd(&xcov[r * ic + c], v);
+        if (bj > bi) atomicAdd(&xcov[c * ic + r], v);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int l = 0; l < 9; ++l) {
+      if (l < nloops) {
+        int blk = myblk + l * NT;
+        if (blk < nblk) {
+          int bi = blk / nb, bj = blk - bi * nb;
+          if (bj >= bi) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              int r = bi * 4 + (e >> 2), c = bj * 4 + (e & 3);
+              if (r < ic && c < ic) {
+                double v = (double)acc[l][e];
+                atomicAdd(&xcov[r * ic + c], v);
+                if (bj > bi) atomicAdd(&xcov[c * ic + r], v);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// normalise the accumulators into mean / biased covariance (double, kept in `saved`)
+__global__ void k_xfin(int ic, int Pn, const double* __restrict__ xsum, const double* __restrict__ xcov,
+                       double* __restrict__ xmom) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double inv = 1.0 / (double)Pn;
+  if (i < ic) xmom[i] = xsum[i] * inv;
+  if (i < ic * ic) xmom[ic + i] = xcov[i] * inv;
+}
+
+// analytic BN1 statistics, one warp per stacked mid channel
+__global__ void __launch_bounds__(NT) k_bn1(Plan P, const double* __restrict__ xmom, float* __restrict__ bn1) {
+  const int warp = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P.MC) return;
+  int s = 0;
+  while (s + 1 < P.na && warp >= P.c[s + 1].coff) ++s;
+  const int ic = P.ic;
+  const float* w = P.c[s].w1 + (size_t)(warp - P.c[s].coff) * ic;
+  const double* mean = xmom;
+  const double* cov = xmom + ic;
+  double mu = 0.0, v = 0.0;
+  for (int j = lane; j < ic; j += 32) {
+    double t = 0.0;
+    for (int k = 0; k < ic; ++k) t += (double)w[k] * cov[k * ic + j];
+    double wj = (double)w[j];
+    v += t * wj;
+    mu += wj * mean[j];
+  }
+  mu = warp_sum_d(mu);
+  v = warp_sum_d(v);
+  if (lane == 0) {
+    bn1[warp] = (float)mu;
+    bn1[P.MC + warp] = (float)(1.0 / sqrt(fmax(v, 0.0) + (double)BN_EPS));
+  }
+}
+
+// sums -> (mean, rstd)
+__global__ void k_bnfin(int C, double invM, const double* __restrict__ st, float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = st[2 * c] * invM;
+  double v = st[2 * c + 1] * invM - m * m;
+  out[c] = (float)m;
+  out[C + c] = (float)(1.0 / sqrt(fmax(v, 0.0) + (double)BN_EPS));
+}
+
+// ----------------------------------------------------------------------------------------------
+// F1a: expand 1x1 (K = ic) + BN1 normalisation -> UH (pre-activation, normalised)
+// ----------------------------------------------------------------------------------------------
+template <int TC>
+__global__ void __launch_bounds__(NT) k_expand(Plan P, const float* __restrict__ x, const float* __restrict__ bn1,
+                                                float* __restrict__ UH) {
+  __shared__ __align__(16) float ins[PW_KC * PW_LDP];
+  __shared__ __align__(16) float ws[PW_KC * (8 * TC + 4)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Cand& cd = P.c[blockIdx.z];
+  const int o0 = blockIdx.y * 8 * TC;
+  if (o0 >= cd.mc) return;
+  const int no = min(8 * TC, cd.mc - o0);
+  Px4 px;
+  px_decomp(px, blockIdx.x * PW_TPX + lane * 4, P.P, P.HW);
+  float acc[TC][4];
+#pragma unroll
+  for (int j = 0; j < TC; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  for (int k0 = 0; k0 < P.ic; k0 += PW_KC) {
+    const int nk = min(PW_KC, P.ic - k0);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PW_KC / 8; ++i) {
+      const int kk = warp + i * 8;
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kk < nk) load4(d, x, px, P.ic, k0 + kk, P.HW);
+      *(float4*)(ins + kk * PW_LDP + lane * 4) = make_float4(d[0], d[1], d[2], d[3]);
+    }
+    stage_w_t<TC>(ws, cd.w1, P.ic, o0, no, k0, nk);
+    __syncthreads();
+    if (warp * TC < no) pw_mma<TC>(acc, ins, ws, lane, warp);
+  }
+#pragma unroll
+  for (int j = 0; j < TC; ++j) {
+    const int c = o0 + warp * TC + j;
+    if (c < cd.mc) {
+      const float mu = bn1[cd.coff + c], r = bn1[P.MC + cd.coff + c];
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (acc[j][e] - mu) * r;
+      store4(UH, o, px, P.MC, cd.coff + c, P.HW);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// F1b: depthwise KSxKS stride S over act(UH) -> D, BN2 sums
+// ----------------------------------------------------------------------------------------------
+
+static DwCfg dw_config(const Plan& P, int KS, int rows_total, int cols_out, bool bwd) {
+  // fwd: tile over OUTPUT rows (rows_total = Ho); bwd: tile over INPUT rows (rows_total = H)
+  DwCfg c;
+  const int S = P.stride, pad = KS / 2;
+  int per_plane = bwd ? P.HW : P.HWo;
+  int CPB = 1;
+  while (CPB < 32 && CPB * per_plane < 2048) CPB <<= 1;
+  c.CPB = CPB;
+  c.WP = (bwd ? P.Wo : P.W) + 2 * pad;
+  for (int tiles = 1;; ++tiles) {
+    int R = cdiv(rows_total, tiles);
+    int IR = bwd ? (R + KS - 1 + S - 1) / S + 1 : (R - 1) * S + KS;
+    size_t smem = (size_t)CPB * IR * c.WP * 4;
+    if (smem <= 40 * 1024 || R == 1) {
+      c.R = R; c.IR = IR; c.tiles = cdiv(rows_total, R); c.smem = smem;
+      break;
+    }
+  }
+  (void)cols_out;
+  return c;
+}
+
+static void dw_work(const Plan& P, int KS, int CPB, DwWork& w) {
+  w.n = 0;
+  w.gstart[0] = 0;
+  for (int s = 0; s < P.na; ++s) {
+    if (P.c[s].k != KS) continue;
+    w.slot[w.n] = s;
+    w.gstart[w.n + 1] = w.gstart[w.n] + cdiv(P.c[s].mc, CPB);
+    ++w.n;
+  }
+}
+
+template <int KS, int S, int ACT>
+__global__ void __launch_bounds__(NT) k_dw_fwd(Plan P, DwWork Wk, DwCfg cfg, const float* __restrict__ UH,
+                                                float* __restrict__ D, double* __restrict__ st2) {
+  extern __shared__ float as[];   // [CPB][IR][WP]
+  constexpr int pad = KS / 2;
+  const int tid = threadIdx.x, n = blockIdx.z;
+  int e = 0;
+  while (e + 1 < Wk.n && (int)blockIdx.y >= Wk.gstart[e + 1]) ++e;
+  const Cand& cd = P.c[Wk.slot[e]];
+  const int CPB = cfg.CPB, IR = cfg.IR, WP = cfg.WP;
+  const int cbase = ((int)blockIdx.y - Wk.gstart[e]) * CPB;      // first local channel of this group
+  const int nc = min(CPB, cd.mc - cbase);
+  const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo;
+  const int oy0 = blockIdx.x * cfg.R, oy1 = min(Ho, oy0 + cfg.R);
+  const int r_lo = oy0 * S - pad;
+  // stage act(UH) with zero halo
+  for (int i = tid; i < CPB * IR * WP; i += NT) {
+    int c = i / (IR * WP), rem = i - c * IR * WP;
+    int lr = rem / WP, lc = rem - lr * WP;
+    int r = r_lo + lr, col = lc - pad;
+    float v = 0.f;
+    if (c < nc && r >= 0 && r < H && col >= 0 && col < W)
+      v = act_f<ACT>(UH[(((size_t)n * P.MC + cd.coff + cbase + c) * H + r) * W + col]);
+    as[i] = v;
+  }
+  __syncthreads();
+  const int TPC = NT / CPB;
+  const int cl = tid / TPC, jl = tid - cl * TPC;
+  float s1 = 0.f, s2 = 0.f;
+  if (cl < nc) {
+    float wr[KS * KS];
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) wr[i] = cd.dw[(size_t)(cbase + cl) * KS * KS + i];
+    const float* ab = as + (size_t)cl * IR * WP;
+    float* dp = D + (((size_t)n * P.MC + cd.coff + cbase + cl) * Ho + oy0) * Wo;
+    const int nout = (oy1 - oy0) * Wo;
+    for (int o = jl; o < nout; o += TPC) {
+      int oyl = o / Wo, ox = o - oyl * Wo;
+      const float* ap = ab + (size_t)(oyl * S) * WP + ox * S;
+      float v = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) v += wr[ky * KS + kx] * ap[ky * WP + kx];
+      dp[o] = v;
+      s1 += v;
+      s2 += v * v;
+    }
+  }
+  s1 = group_sum(s1, TPC);
+  s2 = group_sum(s2, TPC);
+  if (jl == 0 && cl < nc) {
+    atomicAdd(&st2[2 * (cd.coff + cbase + cl)], (double)s1);
+    atomicAdd(&st2[2 * (cd.coff + cbase + cl) + 1], (double)s2);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// F2: squeeze-excite
+// ----------------------------------------------------------------------------------------------
+// one warp per (n, SE-gated stacked channel)
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_se_pool(Plan P, const float* __restrict__ D, const float* __restrict__ bn2,
+                                                 float* __restrict__ sep) {
+  const int widx = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y;
+  if (widx >= P.MCse) return;
+  int s = -1;
+  for (int i = 0; i < P.na; ++i)
+    if (P.c[i].se > 0 && widx >= P.c[i].soff && widx < P.c[i].soff + P.c[i].mc) s = i;
+  const int c = P.c[s].coff + (widx - P.c[s].soff);
+  const float mu = bn2[c], r = bn2[P.MC + c];
+  const float* d = D + ((size_t)n * P.MC + c) * P.HWo;
+  float acc = 0.f;
+  for (int i = lane; i < P.HWo; i += 32) acc += act_f<ACT>((d[i] - mu) * r);
+  acc = warp_sum(acc);
+  if (lane == 0) sep[(size_t)n * P.MCse + widx] = acc / (float)P.HWo;
+}
+
+// grid (N, na): t = Wr p + br ; h = act(t) ; g = sigmoid(We h + be)
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_se_fc(Plan P, const float* __restrict__ sep, float* __restrict__ set,
+                                               float* __restrict__ seg) {
+  extern __shared__ float sm[];
+  const Cand& cd = P.c[blockIdx.y];
+  if (cd.se == 0) return;
+  const int n = blockIdx.x, mc = cd.mc, se = cd.se;
+  float* ps = sm;        // [mc]
+  float* hs = sm + mc;   // [se]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < mc; i += NT) ps[i] = sep[(size_t)n * P.MCse + cd.soff + i];
+  __syncthreads();
+  for (int j = warp; j < se; j += NT / 32) {
+    const float* w = cd.rw + (size_t)j * mc;
+    float a = 0.f;
+    for (int i = lane; i < mc; i += 32) a += w[i] * ps[i];
+    a = warp_sum(a);
+    if (lane == 0) {
+      float t = a + cd.rb[j];
+      set[(size_t)n * P.SEH + cd.hoff + j] = t;
+      hs[j] = act_f<ACT>(t);
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < mc; c += NT / 32) {
+    const float* w = cd.ew + (size_t)c * se;
+    float a = 0.f;
+    for (int j = lane; j < se; j += 32) a += w[j] * hs[j];
+    a = warp_sum(a);
+    if (lane == 0) seg[(size_t)n * P.MCse + cd.soff + c] = sigmoid_f(a + cd.eb[c]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// F3: project 1x1 (K = mc) with the BN2/act/SE-gate prologue fused -> Z, BN3 sums
+// ----------------------------------------------------------------------------------------------
+template <int TC, int ACT>
+__global__ void __launch_bounds__(NT) k_project(Plan P, OcTile T, const float* __restrict__ D,
+                                                 const float* __restrict__ bn2, const float* __restrict__ seg,
+                                                 float* __restrict__ Zb, double* __restrict__ st3) {
+  __shared__ __align__(16) float ins[PW_KC * PW_LDP];
+  __shared__ __align__(16) float ws[PW_KC * (8 * TC + 4)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = blockIdx.z;
+  const Cand& cd = P.c[slot];
+  const int mc = cd.mc, oc = P.oc;
+  const int o0 = blockIdx.y * T.occ, no = min(T.occ, oc - o0);
+  Px4 px;
+  px_decomp(px, blockIdx.x * PW_TPX + lane * 4, P.Q, P.HWo);
+  float acc[TC][4];
+#pragma unroll
+  for (int j = 0; j < TC; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const bool gated = cd.se > 0;
+  for (int k0 = 0; k0 < mc; k0 += PW_KC) {
+    const int nk = min(PW_KC, mc - k0);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PW_KC / 8; ++i) {
+      const int kk = warp + i * 8, k = k0 + kk;
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if (kk < nk) {
+        const int cst = cd.coff + k;
+        const float mu = bn2[cst], r = bn2[P.MC + cst];
+        float d[4];
+        load4(d, D, px, P.MC, cst, P.HWo);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float b = act_f<ACT>((d[e] - mu) * r);
+          if (gated) b *= seg[(size_t)px.n[e] * P.MCse + cd.soff + k];
+          o[e] = px.v[e] ? b : 0.f;
+        }
+      }
+      *(float4*)(ins + kk * PW_LDP + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    stage_w_t<TC>(ws, cd.w3, mc, o0, no, k0, nk);
+    __syncthreads();
+    if (warp < T.ng) pw_mma<TC>(acc, ins, ws, lane, warp);
+  }
+  if (warp < T.ng) {
+#pragma unroll
+    for (int j = 0; j < TC; ++j) {
+      const int o = warp * TC + j;   // warp-uniform
+      float s1 = 0.f, s2 = 0.f;
+      if (o < no) {
+        store4(Zb, acc[j], px, P.na * oc, slot * oc + o0 + o, P.HWo);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (px.v[e]) { s1 += acc[j][e]; s2 += acc[j][e] * acc[j][e]; }
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0 && o < no) {
+        atomicAdd(&st3[2 * (slot * oc + o0 + o)], (double)s1);
+        atomicAdd(&st3[2 * (slot * oc + o0 + o) + 1], (double)s2);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// F4: mixing weights, latency, combine
+// ----------------------------------------------------------------------------------------------
+// one CTA: w = softmax((log_alpha + g)/T) over ALL num_ops (alpha mode) or 1.0 (sampled mode);
+// coef[slot][c] = w * r3 ; bias[c] = -sum w r3 mu3 ; out_lat = sum w lat
+__global__ void k_f4prep(Plan P, int alpha_mode, const float* __restrict__ log_alphas,
+                         const float* __restrict__ gumbel, const float* __restrict__ lat8, float T,
+                         const float* __restrict__ bn3, float* __restrict__ mixw, float* __restrict__ latsave,
+                         float* __restrict__ coef, float* __restrict__ out_lat) {
+  __shared__ float w[TFNAS_MAX_OPS];
+  const int num_ops = P.num_ops;
+  if (threadIdx.x == 0) {
+    if (alpha_mode) {
+      float l[TFNAS_MAX_OPS], m = -INFINITY;
+      for (int i = 0; i < num_ops; ++i) { l[i] = (log_alphas[i] + gumbel[i]) / T; m = fmaxf(m, l[i]); }
+      float s = 0.f;
+      for (int i = 0; i < num_ops; ++i) { l[i] = expf(l[i] - m); s += l[i]; }
+      float lat = 0.f;
+      for (int i = 0; i < num_ops; ++i) {
+        w[i] = l[i] / s;
+        mixw[i] = w[i];
+        latsave[i] = lat8[i];
+        lat += w[i] * lat8[i];
+      }
+      *out_lat = lat;
+    } else {
+      for (int i = 0; i < TFNAS_MAX_OPS; ++i) { w[i] = 1.f; mixw[i] = 1.f; latsave[i] = 0.f; }
+    }
+  }
+  __syncthreads();
+  const int oc = P.oc, C3 = P.na * oc;
+  for (int c = threadIdx.x; c < oc; c += blockDim.x) {
+    float b = 0.f;
+    for (int s = 0; s < P.na; ++s) {
+      float wi = w[P.c[s].id];
+      float r3 = bn3[C3 + s * oc + c], mu3 = bn3[s * oc + c];
+      coef[s * oc + c] = wi * r3;
+      b -= wi * r3 * mu3;
+    }
+    coef[C3 + c] = b;
+  }
+}
+
+// out[n,c,:] = sum_s coef[s,c] * Z[n,s,c,:] + bias[c] (+ x[n,c,:])
+__global__ void __launch_bounds__(NT) k_f4(Plan P, const float* __restrict__ Zb, const float* __restrict__ coef,
+                                            const float* __restrict__ x, float* __restrict__ out) {
+  const int HWo = P.HWo, oc = P.oc, na = P.na;
+  const size_t total = (size_t)P.N * oc * HWo;
+  if ((HWo & 3) == 0) {
+    const size_t nv = total >> 2;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < nv; i += (size_t)gridDim.x * NT) {
+      size_t e = i << 2;
+      int plane = (int)(e / HWo);
+      int hw = (int)(e - (size_t)plane * HWo);
+      int n = plane / oc, c = plane - n * oc;
+      float b = coef[na * oc + c];
+      float4 o = make_float4(b, b, b, b);
+      for (int s = 0; s < na; ++s) {
+        float cf = coef[s * oc + c];
+        float4 z = *(const float4*)(Zb + ((size_t)(n * na + s) * oc + c) * HWo + hw);
+        o.x += cf * z.x; o.y += cf * z.y; o.z += cf * z.z; o.w += cf * z.w;
+      }
+      if (P.residual) {
+        float4 r = *(const float4*)(x + e);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      *(float4*)(out + e) = o;
+    }
+  } else {
+    for (size_t e = (size_t)blockIdx.x * NT + threadIdx.x; e < total; e += (size_t)gridDim.x * NT) {
+      int plane = (int)(e / HWo);
+      int hw = (int)(e - (size_t)plane * HWo);
+      int n = plane / oc, c = plane - n * oc;
+      float o = coef[na * oc + c];
+      for (int s = 0; s < na; ++s) o += coef[s * oc + c] * Zb[((size_t)(n * na + s) * oc + c) * HWo + hw];
+      if (P.residual) o += x[e];
+      out[e] = o;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+template <int KS, int S>
+static void launch_dw_fwd(const Plan& P, const float* UH, float* D, double* st2, cudaStream_t st) {
+  DwCfg cfg = dw_config(P, KS, P.Ho, P.Wo, false);
+  DwWork w;
+  dw_work(P, KS, cfg.CPB, w);
+  if (!w.n) return;
+  dim3 grid(cfg.tiles, w.gstart[w.n], P.N);
+  auto kern = P.act == TFNAS_ACT_RELU ? k_dw_fwd<KS, S, TFNAS_ACT_RELU> : k_dw_fwd<KS, S, TFNAS_ACT_SWISH>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+  kern<<<grid, NT, cfg.smem, st>>>(P, w, cfg, UH, D, st2);
+  count_launch(1);
+}
+
+template <int TC>
+static void launch_project(const Plan& P, OcTile T, const float* D, const float* bn2, const float* seg, float* Zb,
+                           double* st3, cudaStream_t st) {
+  dim3 grid(cdiv(P.Q, PW_TPX), T.nchunk, P.na);
+  if (P.act == TFNAS_ACT_RELU)
+    k_project<TC, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, T, D, bn2, seg, Zb, st3);
+  else
+    k_project<TC, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, T, D, bn2, seg, Zb, st3);
+  count_launch(1);
+}
+
+void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
+                    const float* lat8, float T, int alpha_mode, float* out, float* out_lat,
+                    char* saved, const SavedLayout& L, const FwdScratch& S, cudaStream_t st) {
+  double* xmom = (double*)(saved + L.xmom);
+  float* bn1 = (float*)(saved + L.bn1);
+  float* bn2 = (float*)(saved + L.bn2);
+  float* bn3 = (float*)(saved + L.bn3);
+  float* mixw = (float*)(saved + L.mixw);
+  float* latsave = (float*)(saved + L.lat);
+  float* sep = (float*)(saved + L.sep);
+  float* set = (float*)(saved + L.set);
+  float* seg = (float*)(saved + L.seg);
+  float* UH = (float*)(saved + L.UH);
+  float* D = (float*)(saved + L.D);
+  float* Zb = (float*)(saved + L.Z);
+  const int ic = P.ic;
+  // zero the accumulators (xsum, xcov, st2, st3 are contiguous in the workspace)
+  size_t zbytes = (size_t)(ic + ic * ic + 2 * P.MC + 2 * P.na * P.oc) * sizeof(double);
+  cudaMemsetAsync(S.xsum, 0, zbytes, st);
+  // F0
+  {
+    int split = max(1, min(P.N, 4 * sm_count() / max(ic, 1)));
+    k_xsum<<<dim3(ic, split), NT, 0, st>>>(P, x, S.xsum);
+    int nb = (ic + 3) / 4, icp = nb * 4, nblk = nb * nb;
+    int chunks = max(1, min(cdiv(P.HW, XC_TPX), cdiv(4 * sm_count(), P.N)));
+    size_t smem = (size_t)(icp * XC_LD + icp + (nblk < NT ? nblk * 16 : 0)) * 4;
+    cudaFuncSetAttribute(k_xcov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_xcov<<<dim3(chunks, P.N), NT, smem, st>>>(P, x, S.xsum, S.xcov);
+    k_xfin<<<cdiv(ic * ic, 256), 256, 0, st>>>(ic, P.P, S.xsum, S.xcov, xmom);
+    k_bn1<<<cdiv(P.MC * 32, NT), NT, 0, st>>>(P, xmom, bn1);
+    count_launch(4);
+  }
+  // F1a
+  {
+    int maxmc = 0;
+    for (int s = 0; s < P.na; ++s) maxmc = max(maxmc, P.c[s].mc);
+    if (maxmc > 64) {
+      dim3 grid(cdiv(P.P, PW_TPX), cdiv(maxmc, 128), P.na);
+      k_expand<16><<<grid, NT, 0, st>>>(P, x, bn1, UH);
+    } else {
+      dim3 grid(cdiv(P.P, PW_TPX), cdiv(maxmc, 64), P.na);
+      k_expand<8><<<grid, NT, 0, st>>>(P, x, bn1, UH);
+    }
+    count_launch(1);
+  }
+  // F1b
+  if (P.stride == 1) {
+    launch_dw_fwd<3, 1>(P, UH, D, S.st2, st);
+    launch_dw_fwd<5, 1>(P, UH, D, S.st2, st);
+  } else {
+    launch_dw_fwd<3, 2>(P, UH, D, S.st2, st);
+    launch_dw_fwd<5, 2>(P, UH, D, S.st2, st);
+  }
+  k_bnfin<<<cdiv(P.MC, 256), 256, 0, st>>>(P.MC, 1.0 / (double)P.Q, S.st2, bn2);
+  count_launch(1);
+  // F2
+  if (P.MCse > 0) {
+    int maxmc = 0, maxse = 0;
+    for (int s = 0; s < P.na; ++s)
+      if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); }
+    size_t smem = (size_t)(maxmc + maxse) * 4;
+    if (P.act == TFNAS_ACT_RELU) {
+      k_se_pool<TFNAS_ACT_RELU><<<dim3(cdiv(P.MCse * 32, NT), P.N), NT, 0, st>>>(P, D, bn2, sep);
+      k_se_fc<TFNAS_ACT_RELU><<<dim3(P.N, P.na), NT, smem, st>>>(P, sep, set, seg);
+    } else {
+      k_se_pool<TFNAS_ACT_SWISH><<<dim3(cdiv(P.MCse * 32, NT), P.N), NT, 0, st>>>(P, D, bn2, sep);
+      k_se_fc<TFNAS_ACT_SWISH><<<dim3(P.N, P.na), NT, smem, st>>>(P, sep, set, seg);
+    }
+    count_launch(2);
+  }
+  // F3
+  {
+    OcTile T3 = oc_tile(P.oc, 16);
+    switch (T3.TC) {
+      case 4: launch_project<4>(P, T3, D, bn2, seg, Zb, S.st3, st); break;
+      case 8: launch_project<8>(P, T3, D, bn2, seg, Zb, S.st3, st); break;
+      case 12: launch_project<12>(P, T3, D, bn2, seg, Zb, S.st3, st); break;
+      default: launch_project<16>(P, T3, D, bn2, seg, Zb, S.st3, st); break;
+    }
+  }
+  k_bnfin<<<cdiv(P.na * P.oc, 256), 256, 0, st>>>(P.na * P.oc, 1.0 / (double)P.Q, S.st3, bn3);
+  // F4
+  k_f4prep<<<1, 256, 0, st>>>(P, alpha_mode, log_alphas, gumbel, lat8, T, bn3, mixw, latsave, S.coef, out_lat);
+  size_t total = (size_t)P.N * P.oc * P.HWo;
+  int blocks = (int)min((size_t)(8 * sm_count()), (total / 4 + NT - 1) / NT);
+  k_f4<<<max(blocks, 1), NT, 0, st>>>(P, Zb, S.coef, x, out);
+  count_launch(3);
+}

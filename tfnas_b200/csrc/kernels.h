@@ -1,0 +1,63 @@
+// Host-side launch wrappers (implemented in fwd.cu / bwd.cu / stage.cu), called from api.cu.
+#pragma once
+#include "common.cuh"
+
+// Layout of the buffer kept from forward to backward.  All offsets in BYTES from the base.
+struct SavedLayout {
+  size_t xmom;   // double [ic + ic*ic] : mean_x, cov_x (biased)
+  size_t bn1;    // float  [2*MC]       : mu1, r1
+  size_t bn2;    // float  [2*MC]       : mu2, r2
+  size_t bn3;    // float  [2*na*oc]    : mu3, r3
+  size_t mixw;   // float  [8]          : mixing weights by ORIGINAL candidate id (1.0 in sampled mode)
+  size_t lat;    // float  [8]          : LUT latencies by original id
+  size_t sep;    // float  [N*MCse]     : SE pooled input p
+  size_t set;    // float  [N*SEH]      : SE hidden pre-activation t
+  size_t seg;    // float  [N*MCse]     : SE gate g
+  size_t UH;     // float  [N*MC*HW]    : BN1-normalised expand output (pre-activation)
+  size_t D;      // float  [N*MC*HWo]   : depthwise output (pre-BN2)
+  size_t Z;      // float  [N*na*oc*HWo]: project output (pre-BN3)
+  size_t total;
+};
+
+struct FwdScratch {   // all device pointers into the workspace
+  double* xsum;   // [ic]
+  double* xcov;   // [ic*ic]
+  double* st2;    // [2*MC]
+  double* st3;    // [2*na*oc]
+  float* coef;    // [na*oc + oc]
+};
+
+struct BwdScratch {
+  float* DC;      // [N*MC*HWo]  dL/dc, then dL/dd-hat in place
+  float* DA;      // [N*MC*HW]   dL/da (output of the transposed depthwise)
+  double* sG;     // [oc]
+  double* sGY;    // [na*oc]
+  float* dg;      // [N*MCse]    SE: sum_hw dc*b, then dp in place
+  double* sD;     // [2*MC]
+  double* sU;     // [2*MC]
+  float4* dzc;    // [na*oc]  per (slot, out channel) BN3-backward coefficients
+  float* cvec2;   // [ic]
+  float* Mm;      // [ic*ic]
+  float* dmix;    // [8]  dL/dw_i (data term)
+  float* sede;    // [N*MCse]  SE: dL/de (pre-sigmoid)     (weight-grad mode)
+  float* sedt;    // [N*SEH]   SE: dL/dt (pre-act hidden)  (weight-grad mode)
+  float* Smat;    // [MC*ic]   sum_p du-hat x^T            (weight-grad mode)
+};
+
+int sm_count();
+
+void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
+                    const float* lat8, float T, int alpha_mode, float* out, float* out_lat,
+                    char* saved, const SavedLayout& L, const FwdScratch& S, cudaStream_t st);
+
+void launch_backward(const Plan& P, const float* x, const float* dout, const float* dlat, float T,
+                     int alpha_mode, const char* saved, const SavedLayout& L, const BwdScratch& S,
+                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st);
+
+void launch_sink_fwd(int K, size_t numel, const float* const* res, const float* betas,
+                     const float* cumlat, float* out, float* out_lat, cudaStream_t st);
+void launch_sink_bwd(int K, size_t numel, const float* const* res, const float* betas,
+                     const float* cumlat, const float* dout, const float* dlat, float* const* dres,
+                     float* dbetas, float* dcumlat, double* ws, cudaStream_t st);
+
+void count_launch(int n);

@@ -1,0 +1,168 @@
+"""torch.autograd bridges onto the C ABI: one Function per MixedOP call, one per stage sink.
+
+PyTorch is plumbing here (device memory from its caching allocator, the current CUDA stream,
+autograd bookkeeping between MixedOPs); every FLOP of the MixedOP / sink runs in
+libtfnas_b200.so.  Nothing in this file falls back to torch math.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CandArray, CandPtrs, MixedOpDesc, check
+
+_SLOTS = ('w1', 'dw', 'w3', 'se_rw', 'se_rb', 'se_ew', 'se_eb')
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda_f32(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise _lib.TfnasError('%s must be a CUDA float32 tensor (tfnas_b200 has no CPU path)' % name)
+
+
+class MixedOpCall(object):
+    """Static description of one MixedOP evaluation (shape, candidate set, noise, LUT row)."""
+
+    __slots__ = ('desc', 'mask', 'alpha_mode', 'T', 'gumbel', 'lat8', 'active', 'n_per')
+
+    def __init__(self, N, ic, oc, H, W, stride, act, mcs, ks, ses, mask, T=1.0, gumbel=None, lat8=None):
+        d = MixedOpDesc()
+        d.N, d.ic, d.oc, d.H, d.W, d.stride = N, ic, oc, H, W, stride
+        d.act = _lib.ACT_CODE[act]
+        d.num_ops = len(mcs)
+        for i in range(len(mcs)):
+            d.mc[i], d.k[i], d.se[i] = mcs[i], ks[i], ses[i]
+        self.desc = d
+        self.mask = mask
+        full = (1 << len(mcs)) - 1
+        self.alpha_mode = (mask & full) == full and len(mcs) > 1
+        self.T = float(T)
+        self.gumbel = gumbel
+        self.lat8 = lat8
+        self.active = [i for i in range(len(mcs)) if mask >> i & 1]
+        self.n_per = [7 if ses[i] > 0 else 3 for i in self.active]
+
+    def out_shape(self):
+        d = self.desc
+        return (d.N, d.oc, (d.H - 1) // d.stride + 1, (d.W - 1) // d.stride + 1)
+
+
+def _cand_array(call, tensors):
+    """tensors: flat list over active candidates (3 or 7 each) -> CandArray indexed by candidate id."""
+    arr = CandArray()
+    pos = 0
+    for i, n in zip(call.active, call.n_per):
+        for name, t in zip(_SLOTS[:n], tensors[pos:pos + n]):
+            setattr(arr[i], name, t.data_ptr())
+        pos += n
+    return arr
+
+
+class MixedOpFn(torch.autograd.Function):
+    """forward(x, log_alphas_or_None, call, *weights) -> (out, out_lat)."""
+
+    @staticmethod
+    def forward(ctx, x, log_alphas, call, *weights):
+        lib = _lib.load()
+        _require_cuda_f32(x, 'x')
+        x = x.contiguous()
+        weights = tuple(w.contiguous() for w in weights)
+        for w in weights:
+            _require_cuda_f32(w, 'weight')
+        d = call.desc
+        if tuple(x.shape) != (d.N, d.ic, d.H, d.W):
+            raise _lib.TfnasError('x shape %s does not match descriptor' % (tuple(x.shape),))
+        nsaved = lib.tfnas_mixedop_saved_bytes(ctypes.byref(d), call.mask)
+        nws = lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), call.mask, 0)
+        if nsaved == 0:
+            check(-1)
+        saved = torch.empty(nsaved, dtype=torch.uint8, device=x.device)
+        ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+        out = torch.empty(call.out_shape(), dtype=torch.float32, device=x.device)
+        out_lat = torch.zeros((), dtype=torch.float32, device=x.device)
+        arr = _cand_array(call, weights)
+        la = log_alphas.contiguous() if call.alpha_mode else None
+        check(lib.tfnas_mixedop_fwd(ctypes.byref(d), call.mask, _ptr(x), arr, _ptr(la),
+                                    _ptr(call.gumbel) if call.alpha_mode else None,
+                                    _ptr(call.lat8) if call.alpha_mode else None, call.T,
+                                    _ptr(out), _ptr(out_lat), _ptr(saved), nsaved, _ptr(ws), nws, _stream()))
+        ctx.call = call
+        ctx.saved_buf = saved
+        ctx.save_for_backward(x, *weights)
+        return out, out_lat
+
+    @staticmethod
+    def backward(ctx, gout, glat):
+        lib = _lib.load()
+        call = ctx.call
+        d = call.desc
+        x = ctx.saved_tensors[0]
+        weights = ctx.saved_tensors[1:]
+        need_dx = ctx.needs_input_grad[0]
+        need_da = call.alpha_mode and ctx.needs_input_grad[1]
+        need_dw = any(ctx.needs_input_grad[3:])
+        gout = gout.contiguous()
+        dx = torch.empty_like(x) if (need_dx or need_dw) else None
+        dalpha = torch.zeros(d.num_ops, dtype=torch.float32, device=x.device) if need_da else None
+        arr = _cand_array(call, weights)
+        grads = None
+        garr = None
+        if need_dw:
+            grads = [torch.empty_like(w) for w in weights]
+            garr = _cand_array(call, grads)
+        nws = lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), call.mask, 1 if need_dw else 0)
+        ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+        gl = glat.contiguous() if (glat is not None and call.alpha_mode) else None
+        check(lib.tfnas_mixedop_bwd(ctypes.byref(d), call.mask, _ptr(x), arr, _ptr(gout), _ptr(gl), call.T,
+                                    _ptr(ctx.saved_buf), ctx.saved_buf.numel(), _ptr(dx), _ptr(dalpha), garr,
+                                    _ptr(ws), nws, _stream()))
+        ctx.saved_buf = None
+        return (dx if need_dx else None, dalpha, None) + (tuple(grads) if grads else (None,) * len(weights))
+
+
+class StageSinkFn(torch.autograd.Function):
+    """forward(betas, cumlat_or_None, *res) -> (out, out_lat): models/model_search.py:202-204."""
+
+    @staticmethod
+    def forward(ctx, betas, cumlat, *res):
+        lib = _lib.load()
+        K = len(res)
+        res = tuple(r.contiguous() for r in res)
+        for r in res:
+            _require_cuda_f32(r, 'res')
+        out = torch.empty_like(res[0])
+        out_lat = torch.zeros((), dtype=torch.float32, device=out.device)
+        ptrs = (ctypes.c_void_p * K)(*[r.data_ptr() for r in res])
+        cl = cumlat.contiguous() if cumlat is not None else None
+        check(lib.tfnas_stage_sink_fwd(K, out.numel(), ptrs, _ptr(betas), _ptr(cl), _ptr(out),
+                                       _ptr(out_lat) if cl is not None else None, _stream()))
+        ctx.has_lat = cl is not None
+        ctx.save_for_backward(betas, cl if cl is not None else betas, *res)
+        return out, out_lat
+
+    @staticmethod
+    def backward(ctx, gout, glat):
+        lib = _lib.load()
+        betas, cl = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        res = ctx.saved_tensors[2:]
+        K = len(res)
+        if not ctx.has_lat:
+            cl = None
+        gout = gout.contiguous()
+        dres = [torch.empty_like(r) for r in res]
+        dbetas = torch.empty_like(betas)
+        dcum = torch.empty(K, dtype=torch.float32, device=gout.device) if cl is not None else None
+        ws = torch.empty(64, dtype=torch.uint8, device=gout.device)
+        ptrs = (ctypes.c_void_p * K)(*[r.data_ptr() for r in res])
+        dptrs = (ctypes.c_void_p * K)(*[r.data_ptr() for r in dres])
+        gl = glat.contiguous() if (glat is not None and cl is not None) else None
+        check(lib.tfnas_stage_sink_bwd(K, gout.numel(), ptrs, _ptr(betas), _ptr(cl), _ptr(gout), _ptr(gl), dptrs,
+                                       _ptr(dbetas), _ptr(dcum), _ptr(ws), 64, _stream()))
+        return (dbetas, dcum) + tuple(dres)
