@@ -121,6 +121,21 @@ int tfnas_stage_sink_bwd(int K, size_t numel, const float* const* res, const flo
  * {xmom, bn1, bn2, bn3, mixw, lat, se_p, se_t, se_g, UH, D, Z, total} (13 entries). */
 int tfnas_debug_saved_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, size_t* out13);
 
+/*
+ * Per-kernel timing for bench.py's roofline: when enabled, every kernel launch is bracketed by
+ * CUDA events on its stream.  tfnas_prof_collect synchronises those events and aggregates by
+ * kernel name: total milliseconds, algorithmic bytes and flops (as modelled in DESIGN.md) and
+ * launch count.  Returns the number of entries written (<= max_entries) or a negative error.
+ * Enabling (or disabling) clears previously recorded launches.
+ */
+typedef struct TfnasProfEntry {
+  char name[32];
+  double ms, bytes, flops;
+  int64_t launches;
+} TfnasProfEntry;
+int tfnas_prof_enable(int on);
+int tfnas_prof_collect(TfnasProfEntry* out, int max_entries);
+
 /* Number of kernel launches issued through this library since load (bench "gpu_launches"). */
 uint64_t tfnas_launch_count(void);
 

@@ -153,7 +153,7 @@ def oracle_alpha(P, x, gum, lats, ic, oc, stride, act, T=5.0, G=None, dlat=0.0, 
     Pd = {k: v.to(dtype).clone().requires_grad_(True) for k, v in P.items()}
     xd = x.to(dtype).clone().requires_grad_(True)
     out, lat = port.mixedop_alpha(xd, Pd, 'b.', ic, oc, stride, act, T, gum.to(dtype), [float(v) for v in lats])
-    r = dict(out=out.detach(), out_lat=float(lat))
+    r = dict(out=out.detach(), out_lat=float(lat.detach()))
     if G is not None:
         ((out * G.to(dtype)).sum() + lat * dlat).backward()
         r['dx'] = xd.grad

@@ -1,0 +1,64 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/tfnas_b200.h declares, and
+rejects bad descriptors with error codes (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tfnas_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'tfnas_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(tfnas_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_exports_match_header():
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.EXPORTS) == names
+    assert lib.tfnas_version() == 1
+
+
+def _desc(**kw):
+    d = _lib.MixedOpDesc()
+    d.N, d.ic, d.oc, d.H, d.W, d.stride, d.act, d.num_ops = 2, 16, 24, 8, 8, 2, 0, 8
+    for i in range(8):
+        d.mc[i], d.k[i], d.se[i] = 48, (3, 3, 5, 5)[i % 4], (16 if i >= 4 else 0)
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
+
+
+def test_sizes_and_validation_without_gpu():
+    lib = _lib.load()
+    d = _desc()
+    full = lib.tfnas_mixedop_saved_bytes(ctypes.byref(d), 0xFF)
+    one = lib.tfnas_mixedop_saved_bytes(ctypes.byref(d), 0x02)
+    assert full > one > 0
+    # D + UH + Z dominate: N*MC*(HW + HWo)*4 + N*8*oc*HWo*4
+    assert full >= 2 * 384 * (64 + 16) * 4 + 2 * 8 * 24 * 16 * 4
+    assert lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), 0xFF, 0) > 0
+    assert lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), 0x02, 1) > lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), 0x02, 0)
+    bad = _desc(stride=3)
+    assert lib.tfnas_mixedop_saved_bytes(ctypes.byref(bad), 0xFF) == 0
+    assert b'stride' in lib.tfnas_last_error()
+    bad = _desc(ic=400)
+    assert lib.tfnas_mixedop_saved_bytes(ctypes.byref(bad), 0xFF) == 0
+    arr = _lib.CandArray()
+    rc = lib.tfnas_mixedop_fwd(ctypes.byref(_desc(num_ops=9)), 0xFF, None, arr, None, None, None, 1.0, None, None,
+                               None, 0, None, 0, None)
+    assert rc == -1
+    rc = lib.tfnas_mixedop_fwd(ctypes.byref(d), 0xFF, None, arr, None, None, None, 1.0, None, None, None, 0, None, 0, None)
+    assert rc == -1 and b'null' in lib.tfnas_last_error()
+    rc = lib.tfnas_stage_sink_fwd(7, 16, None, None, None, None, None, None)
+    assert rc == -1
+    with pytest.raises(_lib.TfnasError):
+        _lib.check(rc)

@@ -1,0 +1,80 @@
+"""Host-side behaviour of the drop-in classes (no GPU): constructor surface, state_dict names,
+switch / sampling logic, error behaviour, and the 'no CPU fallback' rule."""
+import random
+
+import pytest
+import torch
+
+from tests import golden_inputs as gi
+from tfnas_b200 import _lib, config
+from tfnas_b200.model_search import MixedOP, MixedStage, Network, NoisePlan, OPS, PRIMITIVES, injected
+
+
+def _net():
+    mcs = config.get_mc_num_dddict(config.mc_mask_dddict)
+    torch.manual_seed(2)
+    return Network(100, mcs, gi.load_lut())
+
+
+def test_surface_and_state_dict():
+    net = _net()
+    assert len(PRIMITIVES) == 8 and set(OPS) == set(PRIMITIVES)
+    sd = net.state_dict()
+    assert len(sd) == 754 and len(list(net.buffers())) == 0
+    assert len(net.weight_parameters()) == 730 and len(net.arch_parameters()) == 24
+    assert len(net.log_alphas_parameters()) == 18 and len(net.betas_parameters()) == 6
+    keys = list(sd)
+    assert keys.index('stage1.betas') < keys.index('stage1.block1.log_alphas')
+    op = net.stage2.block1.m_ops[5]
+    assert tuple(op.inverted_bottleneck.conv.weight.shape) == (144, 24, 1, 1)
+    assert tuple(op.depth_conv.conv.weight.shape) == (144, 1, 3, 3)
+    assert tuple(op.squeeze_excite.conv_reduce.weight.shape) == (48, 144, 1, 1)
+    assert (op.name, op.in_channels, op.se_channels, op.out_channels, op.kernel_size, op.stride, op.act_func,
+            op.mid_channels) == ('MBInvertedResBlock', 24, 48, 40, 3, 2, 'swish', 144)
+    assert torch.allclose(net.stage1.block1.log_alphas.exp().sum(), torch.tensor(1.0))
+    # exec()-style surgery used by train_search.py:172-193
+    exec('net.stage1.block1.m_ops[0].inverted_bottleneck.conv.weight.data = torch.zeros(40, 16, 1, 1)')
+    assert net.stage1.block1.m_ops[0].inverted_bottleneck.conv.weight.shape[0] == 40
+
+
+def test_lookup_latency_and_errors():
+    net = _net()
+    lats = net.stage1.block1.get_lookup_latency(112)
+    lut = gi.load_lut()
+    assert lats[0] == lut['MBInvertedResBlock_112_16_0_24_k3_s2_relu'][48]
+    assert lats[7] == lut['MBInvertedResBlock_112_16_32_24_k5_s2_relu'][96]
+    with pytest.raises(KeyError):
+        net.stage2.block1.get_lookup_latency(32)
+    with pytest.raises(ValueError):
+        MixedStage([16], [24], [2], [False], ['relu'], {}, {}, 7)
+    op = net.stage1.block1
+    with pytest.raises(ValueError):
+        op._sample_index('max')
+    with pytest.raises(AttributeError):
+        MixedOP(16, 24, 2, False, 'relu', 8, {i: 48 for i in range(8)}, {}).T   # T is not set by the ctor
+
+
+def test_sampling_indices_follow_reference_semantics():
+    net = _net()
+    op = net.stage3.block2
+    noise = -torch.empty(8).exponential_().log()
+    with injected(NoisePlan(noise=[noise, noise])):
+        ig = op._sample_index('gumbel')
+        assert ig == int(torch.argmax(op.log_alphas.detach() + noise))
+        assert op.switches[ig] is False and sum(op.switches) == 7
+        random.seed(3)
+        ir = op._sample_index('random')
+    assert ir != ig and all(op.switches)
+    random.seed(3)
+    rest = [j for j in range(8) if j != ig]
+    assert ir == rest[random.choice(range(7))]
+    with injected(NoisePlan(indices=[4])):
+        assert op._sample_index('random') == 4
+
+
+def test_no_cpu_fallback():
+    net = _net()
+    net.set_temperature(5.0)
+    x = torch.randn(1, 3, 32, 32)
+    with pytest.raises(_lib.TfnasError):
+        net(x, sampling=True, mode='gumbel')

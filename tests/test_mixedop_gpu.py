@@ -1,0 +1,151 @@
+"""GPU parity: the CUDA MixedOP (through the drop-in classes / autograd bridge, i.e. through the
+C ABI) against the CPU oracle on the same seeded inputs.  North-star tolerance: 1e-3 relative on
+outputs and alpha-grads; observed ~1e-6, asserted at 1e-4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port, ref_shim
+from tests import golden_inputs as gi
+from tests import helpers as H
+from tfnas_b200 import config
+from tfnas_b200.config import CAND_SPEC, lut_key
+from tfnas_b200.model_search import MixedOP, NoisePlan, injected
+from tfnas_b200.ops import StageSinkFn
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4          # asserted
+NORTH_STAR = 1e-3   # the contract (BASELINE.json)
+
+
+def _fake_lut(ic, oc, s, act, size, mcs, lats):
+    lut = {}
+    for i, (k, _e, sm) in enumerate(CAND_SPEC):
+        lut.setdefault(lut_key(size, ic, sm * ic, oc, k, s, act), {})[mcs[i]] = float(lats[i])
+    return lut
+
+
+def _build(P, ic, oc, s, act, mcs, lut):
+    op = MixedOP(ic, oc, s, False, act, 8, {i: mcs[i] for i in range(8)}, lut)
+    op.load_state_dict({k[2:]: v for k, v in P.items()})
+    op.set_temperature(5.0)
+    return op.cuda()
+
+
+CASES = [
+    # ic, oc, s, act, H, N, ragged, W
+    (16, 24, 2, 'relu', 16, 2, False, None),
+    (24, 24, 1, 'relu', 12, 3, True, None),
+    (24, 40, 2, 'swish', 14, 2, False, None),
+    (40, 40, 1, 'swish', 7, 4, True, None),
+    (80, 112, 1, 'swish', 6, 2, False, 9),
+    (112, 192, 2, 'swish', 7, 3, True, None),
+    (192, 320, 1, 'swish', 7, 2, False, None),
+    (8, 8, 1, 'relu', 5, 1, True, 3),       # N=1, tiny odd plane
+]
+
+
+@pytest.mark.parametrize('ic,oc,s,act,size,N,ragged,W', CASES)
+def test_alpha_mode_matches_oracle(ic, oc, s, act, size, N, ragged, W):
+    mcs = H.default_mcs(ic, ragged)
+    P, x, gum, lats = H.make_problem(ic, oc, s, size, N, mcs, seed=ic + size, W=W)
+    # LUT rows that share a key (e3/e6 non-SE) must carry both widths
+    lut = _fake_lut(ic, oc, s, act, x.shape[-1], mcs, lats)
+    lat_list = [lut[lut_key(x.shape[-1], ic, sm * ic, oc, k, s, act)][mcs[i]] for i, (k, _e, sm) in enumerate(CAND_SPEC)]
+    op = _build(P, ic, oc, s, act, mcs, lut)
+    xg = x.cuda().requires_grad_(True)
+    with injected(NoisePlan(noise=[gum])):
+        out, lat = op(xg, False, 'max')
+    g = torch.Generator().manual_seed(5)
+    G = torch.randn(out.shape, generator=g)
+    (out * G.cuda()).sum().add(lat * 0.37).backward()
+    ref = H.oracle_alpha(P, x, gum, torch.tensor(lat_list), ic, oc, s, act, 5.0, G, 0.37)
+    assert H.rel_l2(out, ref['out']) < TOL and H.rel_max(out, ref['out']) < TOL
+    assert abs(float(lat) - ref['out_lat']) < 1e-5 * max(1.0, abs(ref['out_lat']))
+    assert H.rel_l2(xg.grad, ref['dx']) < TOL
+    assert H.rel_l2(op.log_alphas.grad, ref['dalpha']) < NORTH_STAR / 2
+    assert abs(float(op.log_alphas.grad.sum())) < 1e-4 * float(op.log_alphas.grad.abs().max()) + 1e-7
+
+
+@pytest.mark.parametrize('ic,oc,s,act,size,N,ragged,W', CASES[:6])
+@pytest.mark.parametrize('idx', [0, 3, 5, 6])
+def test_sampled_mode_and_weight_grads(ic, oc, s, act, size, N, ragged, W, idx):
+    mcs = H.default_mcs(ic, ragged)
+    P, x, gum, lats = H.make_problem(ic, oc, s, size, N, mcs, seed=3 * ic + size, W=W)
+    op = _build(P, ic, oc, s, act, mcs, {})
+    xg = x.cuda().requires_grad_(True)
+    with injected(NoisePlan(indices=[idx])):
+        out, lat = op(xg, True, 'random')
+    assert lat == 0
+    g = torch.Generator().manual_seed(6)
+    G = torch.randn(out.shape, generator=g)
+    (out * G.cuda()).sum().backward()
+    ref = H.oracle_single(P, x, ic, oc, s, act, idx, G)
+    assert H.rel_l2(out, ref['out']) < TOL
+    assert H.rel_l2(xg.grad, ref['dx']) < TOL
+    sd = dict(op.named_parameters())
+    for (i, sname), gref in ref['wgrads'].items():
+        got = sd['m_ops.%d.%s' % (i, H.NAMES[sname])].grad
+        assert got is not None and H.rel_l2(got, gref) < 5 * TOL, sname
+    for n, p in op.named_parameters():   # un-sampled candidates keep grad None (quirk Q5)
+        if n.startswith('m_ops.') and not n.startswith('m_ops.%d.' % idx):
+            assert p.grad is None
+
+
+def test_cfg1_golden_fixture():
+    """BASELINE configs[0]: stage2.block1 MixedOP, bs=2, 32x32, vs the real reference's output."""
+    z = np.load(os.path.join(gi.GOLDEN_DIR, 'mixedop_cfg1.npz'))
+    c = gi.CFG1
+    lut = gi.patched_lut_cfg1(gi.load_lut())
+    P, x, Gt, nseed = gi.cfg1_inputs()
+    mcd = config.get_mc_num_dddict(config.mc_mask_dddict)['stage2']['block1']
+    op = MixedOP(c['ic'], c['oc'], c['stride'], False, c['act'], 8, mcd, lut)
+    op.load_state_dict({k[2:]: v for k, v in P.items()})
+    op.set_temperature(5.0)
+    op.cuda()
+    xg = x.cuda().requires_grad_(True)
+    with injected(NoisePlan(noise=ref_shim.draw_plan_noise(nseed, 1))):
+        out, lat = op(xg, False, 'max')
+    (out * Gt.cuda()).sum().add(lat * 0.37).backward()
+    assert H.rel_l2(out, torch.from_numpy(z['out'])) < TOL
+    assert abs(float(lat) - float(z['lat'])) < 1e-5
+    assert H.rel_l2(xg.grad, torch.from_numpy(z['dx'])) < TOL
+    assert H.rel_l2(op.log_alphas.grad, torch.from_numpy(z['dalpha'])) < NORTH_STAR / 2
+
+
+def test_lut_miss_raises_keyerror():
+    mcd = config.get_mc_num_dddict(config.mc_mask_dddict)['stage2']['block1']
+    op = MixedOP(24, 40, 2, False, 'swish', 8, mcd, gi.load_lut()).cuda()
+    op.set_temperature(5.0)
+    with pytest.raises(KeyError):
+        op(torch.randn(2, 24, 32, 32, device='cuda'), False, 'max')
+
+
+@pytest.mark.parametrize('K,shape,with_lat', [(1, (2, 5, 3, 3), True), (2, (3, 8, 4, 4), True), (4, (2, 6, 7, 7), True),
+                                              (3, (2, 4, 5, 5), False)])
+def test_stage_sink(K, shape, with_lat):
+    g = torch.Generator().manual_seed(K)
+    res = [torch.randn(shape, generator=g).cuda().requires_grad_(True) for _ in range(K)]
+    betas = torch.randn(K, generator=g).cuda().requires_grad_(True)
+    cum = torch.rand(K, generator=g).cuda().requires_grad_(True) if with_lat else None
+    out, lat = StageSinkFn.apply(betas, cum, *res)
+    G = torch.randn(shape, generator=g).cuda()
+    loss = (out * G).sum() + (lat * 0.7 if with_lat else 0)
+    loss.backward()
+    r2 = [r.detach().double().cpu().requires_grad_(True) for r in res]
+    b2 = betas.detach().double().cpu().requires_grad_(True)
+    c2 = cum.detach().double().cpu().requires_grad_(True) if with_lat else None
+    w = torch.softmax(b2, -1)
+    o2 = sum(w[j] * r2[j] for j in range(K))
+    l2 = (o2 * G.double().cpu()).sum()
+    if with_lat:
+        l2 = l2 + 0.7 * sum(w[j] * c2[j] for j in range(K))
+    l2.backward()
+    assert H.rel_l2(out, o2.detach()) < 1e-6
+    assert H.rel_l2(betas.grad, b2.grad) < 1e-5 or float(b2.grad.abs().max()) < 1e-12
+    for a, b in zip(res, r2):
+        assert H.rel_l2(a.grad, b.grad) < 1e-6
+    if with_lat:
+        assert H.rel_l2(cum.grad, c2.grad) < 1e-6

@@ -1,0 +1,77 @@
+"""GPU parity of the full supernet (drop-in Network) against the golden vectors produced by the
+real reference: alpha-step logits / latency / alpha- and beta-grads, and the bi-sampled w-step."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_shim
+from tests import golden_inputs as gi
+from tests import helpers as H
+from tfnas_b200 import config
+from tfnas_b200.model_search import Network, NoisePlan, injected
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3   # north-star tolerance on logits and alpha-grads (norm-relative)
+
+
+def _net():
+    mcs = config.get_mc_num_dddict(config.mc_mask_dddict)
+    P, x, tgt = gi.network_inputs()
+    net = Network(100, mcs, gi.load_lut())
+    net.load_state_dict(P)
+    net.set_temperature(5.0)
+    return net.cuda().train(), x.cuda(), tgt.cuda()
+
+
+def test_alpha_step_matches_reference_golden():
+    z = np.load(os.path.join(gi.GOLDEN_DIR, 'network_alpha.npz'))
+    net, x, tgt = _net()
+    for p in net.weight_parameters():
+        p.requires_grad_(False)
+    with injected(NoisePlan(noise=ref_shim.draw_plan_noise(gi.NET['noise_seed']))):
+        logits, lat = net(x, sampling=False)
+    loss = F.cross_entropy(logits, tgt) + torch.abs(lat / gi.NET['target_lat'] - 1.) * gi.NET['lambda_lat']
+    loss.backward()
+    npar = dict(net.named_parameters())
+    da = torch.stack([npar[str(n)].grad for n in z['alpha_names']])
+    db = torch.cat([npar[str(n)].grad for n in z['beta_names']])
+    e = dict(logits=H.rel_l2(logits, torch.from_numpy(z['logits'])), lat=abs(float(lat) - float(z['lat'])),
+             loss=abs(float(loss) - float(z['loss'])), dalpha=H.rel_l2(da, torch.from_numpy(z['dalpha'])),
+             dalpha_max=H.rel_max(da, torch.from_numpy(z['dalpha'])), dbeta=H.rel_l2(db, torch.from_numpy(z['dbeta'])))
+    print('alpha-step errors', e)
+    assert e['logits'] < TOL and e['lat'] < 1e-4 and e['loss'] < 1e-4
+    assert e['dalpha'] < TOL and e['dalpha_max'] < TOL and e['dbeta'] < TOL
+
+
+def test_bisampled_wstep_matches_reference_golden():
+    z = np.load(os.path.join(gi.GOLDEN_DIR, 'network_wstep.npz'))
+    net, x, tgt = _net()
+    for p in net.arch_parameters():
+        p.requires_grad_(False)
+    random.seed(gi.NET['py_seed'])
+    noise = ref_shim.draw_plan_noise(gi.NET['wstep_noise_seed'])
+    with injected(NoisePlan(noise=noise)):
+        lg, zero = net(x, sampling=True, mode='gumbel')
+    idx_g = [m.switches.index(False) for m in net.modules() if hasattr(m, 'switches')]
+    lr, _ = net(x, sampling=True, mode='random')
+    assert zero == 0.0 and idx_g == [int(v) for v in z['idx_g']]
+    (F.cross_entropy(lg, tgt) + F.cross_entropy(lr, tgt)).backward()
+    assert H.rel_l2(lg, torch.from_numpy(z['logits_g'])) < TOL
+    assert H.rel_l2(lr, torch.from_numpy(z['logits_r'])) < TOL
+    npar = dict(net.named_parameters())
+    worst = 0.0
+    for n, gn in zip(z['wnames'], z['gnorm']):
+        g = npar[str(n)].grad
+        if gn < 0:
+            assert g is None
+        else:
+            worst = max(worst, abs(float(g.norm()) - gn) / (gn + 1e-12))
+    print('w-step worst grad-norm rel err', worst)
+    assert worst < 5e-3
+    assert H.rel_l2(npar['first_stem.conv.weight'].grad, torch.from_numpy(z['g_first_stem'])) < 5e-3
+    assert H.rel_l2(npar['classifier.linear.weight'].grad, torch.from_numpy(z['g_classifier'])) < TOL
+    assert all(all(m.switches) for m in net.modules() if hasattr(m, 'switches'))

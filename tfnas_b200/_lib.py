@@ -28,11 +28,17 @@ class CandPtrs(ctypes.Structure):
                 ('se_ew', ctypes.c_void_p), ('se_eb', ctypes.c_void_p)]
 
 
+class ProfEntry(ctypes.Structure):
+    _fields_ = [('name', ctypes.c_char * 32), ('ms', ctypes.c_double), ('bytes', ctypes.c_double),
+                ('flops', ctypes.c_double), ('launches', ctypes.c_int64)]
+
+
 CandArray = CandPtrs * MAX_OPS
 EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
-           'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout']
+           'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout',
+           'tfnas_prof_enable', 'tfnas_prof_collect']
 
 _lib = None
 
@@ -71,6 +77,10 @@ def load():
                                          vp, sz, vp]
     lib.tfnas_debug_saved_layout.restype = i32
     lib.tfnas_debug_saved_layout.argtypes = [dp, u32, ctypes.POINTER(sz)]
+    lib.tfnas_prof_enable.restype = i32
+    lib.tfnas_prof_enable.argtypes = [i32]
+    lib.tfnas_prof_collect.restype = i32
+    lib.tfnas_prof_collect.argtypes = [ctypes.POINTER(ProfEntry), i32]
     if lib.tfnas_version() != 1:
         raise TfnasError('ABI version mismatch: %d' % lib.tfnas_version())
     _lib = lib
@@ -84,3 +94,17 @@ def check(rc):
 
 def launch_count():
     return int(load().tfnas_launch_count())
+
+
+def prof_enable(on=True):
+    check(load().tfnas_prof_enable(1 if on else 0))
+
+
+def prof_collect(max_entries=64):
+    """-> list of dicts {name, ms, bytes, flops, launches}, aggregated per kernel name."""
+    buf = (ProfEntry * max_entries)()
+    n = load().tfnas_prof_collect(buf, max_entries)
+    if n < 0:
+        check(n)
+    return [dict(name=buf[i].name.decode(), ms=buf[i].ms, bytes=buf[i].bytes, flops=buf[i].flops,
+                 launches=int(buf[i].launches)) for i in range(n)]

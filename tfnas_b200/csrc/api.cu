@@ -1,5 +1,9 @@
 // C-ABI entry points (include/tfnas_b200.h): descriptor validation, buffer layout, launch sequencing.
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -9,6 +13,37 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- optional per-launch profiling (CUDA events on the launching stream) -----------------------
+struct ProfRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_pool;
+static std::mutex g_prof_mu;
+
+static cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(const char* name, double bytes, double flops, cudaStream_t st) : rec_(nullptr), st_(st) {
+  count_launch(1);
+  if (!g_prof) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec* r = new ProfRec{name, bytes, flops, get_event(), get_event()};
+  cudaEventRecord(r->e0, st);
+  rec_ = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec_) return;
+  ProfRec* r = (ProfRec*)rec_;
+  cudaEventRecord(r->e1, st_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_recs.push_back(*r);
+  delete r;
+}
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -222,6 +257,43 @@ int tfnas_mixedop_bwd(const TfnasMixedOpDesc* d, uint32_t cand_mask, const float
   launch_backward(P, x, dout, dlat, T, alpha_mode, (const char*)saved, L, S, dx, dlog_alphas, dweights,
                   (cudaStream_t)stream);
   return check_cuda("tfnas_mixedop_bwd");
+}
+
+int tfnas_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_recs) { g_pool.push_back(r.e0); g_pool.push_back(r.e1); }
+  g_recs.clear();
+  g_prof = on != 0;
+  return TFNAS_OK;
+}
+
+int tfnas_prof_collect(TfnasProfEntry* out, int max_entries) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, TfnasProfEntry> agg;
+  std::vector<std::string> order;
+  for (auto& r : g_recs) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return fail(TFNAS_E_CUDA, "prof: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto it = agg.find(r.name);
+    if (it == agg.end()) {
+      TfnasProfEntry e;
+      memset(&e, 0, sizeof(e));
+      strncpy(e.name, r.name, sizeof(e.name) - 1);
+      it = agg.insert({r.name, e}).first;
+      order.push_back(r.name);
+    }
+    it->second.ms += ms;
+    it->second.bytes += r.bytes;
+    it->second.flops += r.flops;
+    it->second.launches += 1;
+  }
+  int n = 0;
+  for (auto& k : order) {
+    if (n >= max_entries) break;
+    out[n++] = agg[k];
+  }
+  return n;
 }
 
 /* debug/test helper: byte offsets of the saved-buffer regions, in SavedLayout order (12 entries + total) */

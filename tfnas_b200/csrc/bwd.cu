@@ -678,11 +678,12 @@ template <int TC>
 static void launch_dc(const Plan& P, int maxmc, const float* G, const float* Zb, const float* bn3, const float4* dzc,
                       const float* D, const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st) {
   dim3 grid(cdiv(P.Q, PW_TPX), cdiv(maxmc, 8 * TC), P.na);
+  ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
+               2.0 * P.Q * (double)P.MC * P.oc, st);
   if (P.act == TFNAS_ACT_RELU)
     k_dc<TC, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
   else
     k_dc<TC, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
-  count_launch(1);
 }
 
 template <int KS, int S>
@@ -694,16 +695,20 @@ static void launch_dw_bwd(const Plan& P, const float* DC, const float* D, const 
   w.gstart[0] = 0;
   DwGrads gw;
   memset(&gw, 0, sizeof(gw));
+  double mck = 0;
   for (int s = 0; s < P.na; ++s) {
     if (P.c[s].k != KS) continue;
     w.slot[w.n] = s;
     w.gstart[w.n + 1] = w.gstart[w.n] + cdiv(P.c[s].mc, cfg.CPB);
     if (dweights && w.n < 4) gw.p[w.n] = dweights[P.c[s].id].dw;
+    mck += P.c[s].mc;
     ++w.n;
   }
   if (!w.n) return;
   dim3 grid(cfg.tiles, w.gstart[w.n], P.N);
   const bool relu = P.act == TFNAS_ACT_RELU;
+  ProfScope ps(KS == 3 ? "dw_bwd_k3" : "dw_bwd_k5", 4.0 * mck * (2.0 * P.Q + (dweights ? 2.0 : 1.0) * P.P),
+               2.0 * KS * KS * mck * P.Q * (dweights ? 2 : 1), st);
   if (dweights) {
     auto kern = relu ? k_dw_bwd<KS, S, TFNAS_ACT_RELU, true> : k_dw_bwd<KS, S, TFNAS_ACT_SWISH, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
@@ -713,25 +718,24 @@ static void launch_dw_bwd(const Plan& P, const float* DC, const float* D, const 
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     kern<<<grid, NT, cfg.smem, st>>>(P, w, cfg, DC, D, bn2, sD, UH, DA, gw);
   }
-  count_launch(1);
 }
 
 template <int TK>
 static void launch_dx(const Plan& P, OcTile T, int ksplit, const float* DA, const float* UH, const float* bn1,
                       float* dx, double* sU, cudaStream_t st) {
   dim3 grid(cdiv(P.P, PW_TPX), ksplit);
+  ProfScope ps("dx", 4.0 * P.P * (2.0 * P.MC + P.ic) + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   if (P.act == TFNAS_ACT_RELU)
     k_dx<TK, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, T, ksplit, DA, UH, bn1, dx, sU);
   else
     k_dx<TK, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, T, ksplit, DA, UH, bn1, dx, sU);
-  count_launch(1);
 }
 
 template <int TK>
 static void launch_dxfin(const Plan& P, OcTile T, const float* x, const float* Mm, const float* cvec2, const float* G,
                          float* dx, cudaStream_t st) {
+  ProfScope ps("dxfin", 4.0 * P.P * P.ic * (3.0 + (P.residual ? 1 : 0)), 2.0 * P.P * (double)P.ic * P.ic, st);
   k_dxfin<TK><<<cdiv(P.P, PW_TPX), NT, 0, st>>>(P, T, x, Mm, cvec2, G, dx);
-  count_launch(1);
 }
 
 void launch_backward(const Plan& P, const float* x, const float* dout, const float* dlat, float T,
@@ -757,15 +761,16 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   // B1
   {
     int nsplit = max(1, min(cdiv(P.Q, 1024), cdiv(4 * sm_count(), oc)));
-    k_b1<<<dim3(oc, nsplit), NT, 0, st>>>(P, dout, Zb, bn3, S.sG, S.sGY);
-    k_b2prep<<<1, 256, 0, st>>>(P, mixw, bn3, S.sG, S.sGY, S.dzc, S.dmix);
-    count_launch(2);
+    { ProfScope ps("b1", 4.0 * P.Q * oc * (1 + P.na), 3.0 * P.Q * oc * P.na, st);
+      k_b1<<<dim3(oc, nsplit), NT, 0, st>>>(P, dout, Zb, bn3, S.sG, S.sGY); }
+    { ProfScope ps("b2prep", 32.0 * P.na * oc, 0, st);
+      k_b2prep<<<1, 256, 0, st>>>(P, mixw, bn3, S.sG, S.sGY, S.dzc, S.dmix); }
   }
   const float4* dzc = S.dzc;
   if (!dx) {   // input needs no gradient (first MixedOP of the alpha step): only dL/dlog_alpha
     if (alpha_mode && dlog_alphas) {
+      ProfScope ps("alpha_grad", 128, 0, st);
       k_alpha_grad<<<1, 32, 0, st>>>(P.num_ops, mixw, latsave, S.dmix, dlat, T, dlog_alphas);
-      count_launch(1);
     }
     return;
   }
@@ -776,43 +781,42 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     if (maxmc > 64) launch_dc<16>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
     else launch_dc<8>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
   }
-  if (dweights) {   // dW3 (needs DC untouched? no: uses dz and c only)
+  if (dweights) {   // dW3 = sum_p dz c^T
     for (int s = 0; s < P.na; ++s) {
       const Cand& cd = P.c[s];
       float* gw3 = dweights[cd.id].w3;
       cudaMemsetAsync(gw3, 0, (size_t)oc * cd.mc * sizeof(float), st);
       int nsplit = max(1, min(cdiv(P.Q, 2048), cdiv(6 * sm_count(), cdiv(oc, WG_T) * cdiv(cd.mc, WG_T))));
       dim3 grid(cdiv(oc, WG_T), cdiv(cd.mc, WG_T), nsplit);
+      ProfScope ps("wgrad_w3", 4.0 * P.Q * (2.0 * oc + cd.mc), 2.0 * P.Q * (double)oc * cd.mc, st);
       if (relu) k_wgrad<0, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, dout, Zb, D, bn3, dzc, bn2, seg, gw3);
       else k_wgrad<0, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, dout, Zb, D, bn3, dzc, bn2, seg, gw3);
-      count_launch(1);
     }
   }
   // SE backward + B2b
   if (P.MCse > 0) {
     int maxmc = 0, maxse = 0;
+    double fcw = 0;
     for (int s = 0; s < P.na; ++s)
-      if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); }
+      if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); fcw += 2.0 * P.c[s].mc * P.c[s].se; }
     size_t smem = (size_t)(maxmc + maxse) * 4;
     float* sede = dweights ? S.sede : nullptr;
     float* sedt = dweights ? S.sedt : nullptr;
     dim3 gpl(cdiv(P.MCse * 32, NT), P.N);
-    if (relu) {
-      k_se_bwd<TFNAS_ACT_RELU><<<dim3(P.N, P.na), NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
-      k_b2b<TFNAS_ACT_RELU><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
-    } else {
-      k_se_bwd<TFNAS_ACT_SWISH><<<dim3(P.N, P.na), NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
-      k_b2b<TFNAS_ACT_SWISH><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
-    }
-    count_launch(2);
+    { ProfScope ps("se_bwd", 4.0 * fcw + 12.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
+      if (relu) k_se_bwd<TFNAS_ACT_RELU><<<dim3(P.N, P.na), NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
+      else k_se_bwd<TFNAS_ACT_SWISH><<<dim3(P.N, P.na), NT, smem, st>>>(P, seg, set, S.dg, sede, sedt); }
+    { ProfScope ps("b2b", 12.0 * P.Q * P.MCse, 8.0 * P.Q * P.MCse, st);
+      if (relu) k_b2b<TFNAS_ACT_RELU><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
+      else k_b2b<TFNAS_ACT_SWISH><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD); }
     if (dweights) {
       for (int s = 0; s < P.na; ++s) {
         const Cand& cd = P.c[s];
         if (!cd.se) continue;
         int tot = max(cd.mc * cd.se, max(cd.mc, cd.se));
+        ProfScope ps("se_wgrad", 8.0 * cd.mc * cd.se, 4.0 * P.N * cd.mc * cd.se, st);
         if (relu) k_se_wgrad<TFNAS_ACT_RELU><<<cdiv(tot, NT), NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
         else k_se_wgrad<TFNAS_ACT_SWISH><<<cdiv(tot, NT), NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
-        count_launch(1);
       }
     }
   }
@@ -850,28 +854,27 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       cudaMemsetAsync(Sm, 0, (size_t)cd.mc * ic * sizeof(float), st);
       int nsplit = max(1, min(cdiv(P.P, 2048), cdiv(6 * sm_count(), cdiv(cd.mc, WG_T) * cdiv(ic, WG_T))));
       dim3 grid(cdiv(cd.mc, WG_T), cdiv(ic, WG_T), nsplit);
-      if (relu) k_wgrad<1, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
-      else k_wgrad<1, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
-      k_w1fin<<<cdiv(cd.mc * 32, NT), NT, 0, st>>>(P, s, Sm, bn1, S.sU, xmom, dweights[cd.id].w1);
-      count_launch(2);
+      { ProfScope ps("wgrad_w1", 4.0 * P.P * (2.0 * cd.mc + ic), 2.0 * P.P * (double)ic * cd.mc, st);
+        if (relu) k_wgrad<1, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
+        else k_wgrad<1, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm); }
+      { ProfScope ps("w1fin", 12.0 * cd.mc * ic, 2.0 * cd.mc * ic * ic, st);
+        k_w1fin<<<cdiv(cd.mc * 32, NT), NT, 0, st>>>(P, s, Sm, bn1, S.sU, xmom, dweights[cd.id].w1); }
     }
   }
   // B4
   {
-    float* cvec2 = S.cvec2;
-    float* Mm = S.Mm;
-    k_b4prep<<<ic, NT, 0, st>>>(P, bn1, S.sU, xmom, Mm, cvec2);
-    count_launch(1);
+    { ProfScope ps("b4prep", 4.0 * P.MC * ic, 2.0 * P.MC * ic * ic, st);
+      k_b4prep<<<ic, NT, 0, st>>>(P, bn1, S.sU, xmom, S.Mm, S.cvec2); }
     switch (Tx.TC) {
-      case 4: launch_dxfin<4>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
-      case 8: launch_dxfin<8>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
-      case 12: launch_dxfin<12>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
-      case 16: launch_dxfin<16>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
-      default: launch_dxfin<24>(P, Tx, x, Mm, cvec2, dout, dx, st); break;
+      case 4: launch_dxfin<4>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
+      case 8: launch_dxfin<8>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
+      case 12: launch_dxfin<12>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
+      case 16: launch_dxfin<16>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
+      default: launch_dxfin<24>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
     }
   }
   if (alpha_mode && dlog_alphas) {
+    ProfScope ps("alpha_grad", 128, 0, st);
     k_alpha_grad<<<1, 32, 0, st>>>(P.num_ops, mixw, latsave, S.dmix, dlat, T, dlog_alphas);
-    count_launch(1);
   }
 }

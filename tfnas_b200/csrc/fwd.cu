@@ -563,22 +563,25 @@ static void launch_dw_fwd(const Plan& P, const float* UH, float* D, double* st2,
   DwWork w;
   dw_work(P, KS, cfg.CPB, w);
   if (!w.n) return;
+  double mck = 0;
+  for (int i = 0; i < w.n; ++i) mck += P.c[w.slot[i]].mc;
   dim3 grid(cfg.tiles, w.gstart[w.n], P.N);
   auto kern = P.act == TFNAS_ACT_RELU ? k_dw_fwd<KS, S, TFNAS_ACT_RELU> : k_dw_fwd<KS, S, TFNAS_ACT_SWISH>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+  ProfScope ps(KS == 3 ? "dw_fwd_k3" : "dw_fwd_k5", 4.0 * mck * ((double)P.P + P.Q), 2.0 * KS * KS * mck * P.Q, st);
   kern<<<grid, NT, cfg.smem, st>>>(P, w, cfg, UH, D, st2);
-  count_launch(1);
 }
 
 template <int TC>
 static void launch_project(const Plan& P, OcTile T, const float* D, const float* bn2, const float* seg, float* Zb,
                            double* st3, cudaStream_t st) {
   dim3 grid(cdiv(P.Q, PW_TPX), T.nchunk, P.na);
+  ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
+               2.0 * P.Q * (double)P.MC * P.oc, st);
   if (P.act == TFNAS_ACT_RELU)
     k_project<TC, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, T, D, bn2, seg, Zb, st3);
   else
     k_project<TC, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, T, D, bn2, seg, Zb, st3);
-  count_launch(1);
 }
 
 void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
@@ -597,26 +600,31 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
   float* D = (float*)(saved + L.D);
   float* Zb = (float*)(saved + L.Z);
   const int ic = P.ic;
+  const double xbytes = 4.0 * P.P * ic;
   // zero the accumulators (xsum, xcov, st2, st3 are contiguous in the workspace)
   size_t zbytes = (size_t)(ic + ic * ic + 2 * P.MC + 2 * P.na * P.oc) * sizeof(double);
   cudaMemsetAsync(S.xsum, 0, zbytes, st);
   // F0
   {
     int split = max(1, min(P.N, 4 * sm_count() / max(ic, 1)));
-    k_xsum<<<dim3(ic, split), NT, 0, st>>>(P, x, S.xsum);
+    { ProfScope ps("xsum", xbytes, 1.0 * P.P * ic, st);
+      k_xsum<<<dim3(ic, split), NT, 0, st>>>(P, x, S.xsum); }
     int nb = (ic + 3) / 4, icp = nb * 4, nblk = nb * nb;
     int chunks = max(1, min(cdiv(P.HW, XC_TPX), cdiv(4 * sm_count(), P.N)));
     size_t smem = (size_t)(icp * XC_LD + icp + (nblk < NT ? nblk * 16 : 0)) * 4;
     cudaFuncSetAttribute(k_xcov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_xcov<<<dim3(chunks, P.N), NT, smem, st>>>(P, x, S.xsum, S.xcov);
-    k_xfin<<<cdiv(ic * ic, 256), 256, 0, st>>>(ic, P.P, S.xsum, S.xcov, xmom);
-    k_bn1<<<cdiv(P.MC * 32, NT), NT, 0, st>>>(P, xmom, bn1);
-    count_launch(4);
+    { ProfScope ps("xcov", xbytes, 1.0 * P.P * ic * ic, st);
+      k_xcov<<<dim3(chunks, P.N), NT, smem, st>>>(P, x, S.xsum, S.xcov); }
+    { ProfScope ps("xfin", 16.0 * ic * ic, 0, st);
+      k_xfin<<<cdiv(ic * ic, 256), 256, 0, st>>>(ic, P.P, S.xsum, S.xcov, xmom); }
+    { ProfScope ps("bn1", 4.0 * P.MC * ic + 8.0 * ic * ic, 2.0 * P.MC * ic * ic, st);
+      k_bn1<<<cdiv(P.MC * 32, NT), NT, 0, st>>>(P, xmom, bn1); }
   }
   // F1a
   {
     int maxmc = 0;
     for (int s = 0; s < P.na; ++s) maxmc = max(maxmc, P.c[s].mc);
+    ProfScope ps("expand", xbytes + 4.0 * P.P * P.MC + 4.0 * P.MC * ic, 2.0 * P.P * (double)P.MC * ic, st);
     if (maxmc > 64) {
       dim3 grid(cdiv(P.P, PW_TPX), cdiv(maxmc, 128), P.na);
       k_expand<16><<<grid, NT, 0, st>>>(P, x, bn1, UH);
@@ -624,7 +632,6 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
       dim3 grid(cdiv(P.P, PW_TPX), cdiv(maxmc, 64), P.na);
       k_expand<8><<<grid, NT, 0, st>>>(P, x, bn1, UH);
     }
-    count_launch(1);
   }
   // F1b
   if (P.stride == 1) {
@@ -634,22 +641,23 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
     launch_dw_fwd<3, 2>(P, UH, D, S.st2, st);
     launch_dw_fwd<5, 2>(P, UH, D, S.st2, st);
   }
-  k_bnfin<<<cdiv(P.MC, 256), 256, 0, st>>>(P.MC, 1.0 / (double)P.Q, S.st2, bn2);
-  count_launch(1);
+  { ProfScope ps("bnfin", 24.0 * P.MC, 0, st);
+    k_bnfin<<<cdiv(P.MC, 256), 256, 0, st>>>(P.MC, 1.0 / (double)P.Q, S.st2, bn2); }
   // F2
   if (P.MCse > 0) {
     int maxmc = 0, maxse = 0;
+    double fcw = 0;
     for (int s = 0; s < P.na; ++s)
-      if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); }
+      if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); fcw += 2.0 * P.c[s].mc * P.c[s].se; }
     size_t smem = (size_t)(maxmc + maxse) * 4;
-    if (P.act == TFNAS_ACT_RELU) {
-      k_se_pool<TFNAS_ACT_RELU><<<dim3(cdiv(P.MCse * 32, NT), P.N), NT, 0, st>>>(P, D, bn2, sep);
-      k_se_fc<TFNAS_ACT_RELU><<<dim3(P.N, P.na), NT, smem, st>>>(P, sep, set, seg);
-    } else {
-      k_se_pool<TFNAS_ACT_SWISH><<<dim3(cdiv(P.MCse * 32, NT), P.N), NT, 0, st>>>(P, D, bn2, sep);
-      k_se_fc<TFNAS_ACT_SWISH><<<dim3(P.N, P.na), NT, smem, st>>>(P, sep, set, seg);
-    }
-    count_launch(2);
+    const bool relu = P.act == TFNAS_ACT_RELU;
+    { ProfScope ps("se_pool", 4.0 * P.Q * P.MCse, 4.0 * P.Q * P.MCse, st);
+      dim3 g(cdiv(P.MCse * 32, NT), P.N);
+      if (relu) k_se_pool<TFNAS_ACT_RELU><<<g, NT, 0, st>>>(P, D, bn2, sep);
+      else k_se_pool<TFNAS_ACT_SWISH><<<g, NT, 0, st>>>(P, D, bn2, sep); }
+    { ProfScope ps("se_fc", 4.0 * fcw + 8.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
+      if (relu) k_se_fc<TFNAS_ACT_RELU><<<dim3(P.N, P.na), NT, smem, st>>>(P, sep, set, seg);
+      else k_se_fc<TFNAS_ACT_SWISH><<<dim3(P.N, P.na), NT, smem, st>>>(P, sep, set, seg); }
   }
   // F3
   {
@@ -661,11 +669,13 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
       default: launch_project<16>(P, T3, D, bn2, seg, Zb, S.st3, st); break;
     }
   }
-  k_bnfin<<<cdiv(P.na * P.oc, 256), 256, 0, st>>>(P.na * P.oc, 1.0 / (double)P.Q, S.st3, bn3);
+  { ProfScope ps("bnfin", 24.0 * P.na * P.oc, 0, st);
+    k_bnfin<<<cdiv(P.na * P.oc, 256), 256, 0, st>>>(P.na * P.oc, 1.0 / (double)P.Q, S.st3, bn3); }
   // F4
-  k_f4prep<<<1, 256, 0, st>>>(P, alpha_mode, log_alphas, gumbel, lat8, T, bn3, mixw, latsave, S.coef, out_lat);
+  { ProfScope ps("f4prep", 12.0 * P.na * P.oc, 0, st);
+    k_f4prep<<<1, 256, 0, st>>>(P, alpha_mode, log_alphas, gumbel, lat8, T, bn3, mixw, latsave, S.coef, out_lat); }
   size_t total = (size_t)P.N * P.oc * P.HWo;
   int blocks = (int)min((size_t)(8 * sm_count()), (total / 4 + NT - 1) / NT);
-  k_f4<<<max(blocks, 1), NT, 0, st>>>(P, Zb, S.coef, x, out);
-  count_launch(3);
+  { ProfScope ps("combine", 4.0 * total * (P.na + 1 + (P.residual ? 1 : 0)), 2.0 * total * P.na, st);
+    k_f4<<<max(blocks, 1), NT, 0, st>>>(P, Zb, S.coef, x, out); }
 }

@@ -61,3 +61,12 @@ void launch_sink_bwd(int K, size_t numel, const float* const* res, const float* 
                      float* dbetas, float* dcumlat, double* ws, cudaStream_t st);
 
 void count_launch(int n);
+
+// RAII launch marker: counts the launch and, when profiling is enabled (tfnas_prof_enable), brackets
+// it with CUDA events on the launching stream and records its algorithmic bytes / flops.
+struct ProfScope {
+  ProfScope(const char* name, double bytes, double flops, cudaStream_t st);
+  ~ProfScope();
+  void* rec_;
+  cudaStream_t st_;
+};

@@ -94,8 +94,8 @@ void launch_sink_fwd(int K, size_t numel, const float* const* res, const float* 
   SinkPtrs p;
   for (int j = 0; j < 4; ++j) { p.res[j] = j < K ? res[j] : nullptr; p.dres[j] = nullptr; }
   int blocks = (int)min((size_t)(8 * sm_count()), (numel / 4 + NT - 1) / NT);
+  ProfScope ps("sink_fwd", 4.0 * numel * (K + 1), 2.0 * numel * K, st);
   k_sink_fwd<<<max(blocks, 1), NT, 0, st>>>(K, numel, p, betas, cumlat, out, out_lat);
-  count_launch(1);
 }
 
 void launch_sink_bwd(int K, size_t numel, const float* const* res, const float* betas, const float* cumlat,
@@ -105,7 +105,8 @@ void launch_sink_bwd(int K, size_t numel, const float* const* res, const float* 
   for (int j = 0; j < 4; ++j) { p.res[j] = j < K ? res[j] : nullptr; p.dres[j] = j < K ? dres[j] : nullptr; }
   cudaMemsetAsync(ws, 0, 4 * sizeof(double), st);
   int blocks = (int)min((size_t)(4 * sm_count()), (numel + NT - 1) / NT);
-  k_sink_bwd<<<max(blocks, 1), NT, 0, st>>>(K, numel, p, betas, dout, ws);
-  k_sink_fin<<<1, 32, 0, st>>>(K, betas, cumlat, dlat, ws, dbetas, dcumlat);
-  count_launch(2);
+  { ProfScope ps("sink_bwd", 4.0 * numel * (2 * K + 1), 3.0 * numel * K, st);
+    k_sink_bwd<<<max(blocks, 1), NT, 0, st>>>(K, numel, p, betas, dout, ws); }
+  { ProfScope ps("sink_fin", 64, 0, st);
+    k_sink_fin<<<1, 32, 0, st>>>(K, betas, cumlat, dlat, ws, dbetas, dcumlat); }
 }
