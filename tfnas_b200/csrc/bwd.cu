@@ -341,10 +341,11 @@ __global__ void __launch_bounds__(NT) k_dw_bwd(Plan P, DwWork Wk, DwCfg cfg, con
   }
   if (WG) {
     float* gp = gw.p[e];
+    const int GW = TPC < 32 ? TPC : 32;
 #pragma unroll
     for (int i = 0; i < KS * KS; ++i) {
-      float t = group_sum(gacc[i], TPC);
-      if (jl == 0 && cl < nc) atomicAdd(&gp[(size_t)(cbase + cl) * KS * KS + i], t);
+      float t = group_sum(gacc[i], GW);
+      if ((jl & (GW - 1)) == 0 && cl < nc) atomicAdd(&gp[(size_t)(cbase + cl) * KS * KS + i], t);
     }
   }
 }

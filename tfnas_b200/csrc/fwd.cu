@@ -330,9 +330,11 @@ __global__ void __launch_bounds__(NT) k_dw_fwd(Plan P, DwWork Wk, DwCfg cfg, con
       s2 += v * v;
     }
   }
-  s1 = group_sum(s1, TPC);
-  s2 = group_sum(s2, TPC);
-  if (jl == 0 && cl < nc) {
+  // TPC threads share a channel; reduce within the warp (or sub-warp group), one atomic per group
+  const int GW = TPC < 32 ? TPC : 32;
+  s1 = group_sum(s1, GW);
+  s2 = group_sum(s2, GW);
+  if ((jl & (GW - 1)) == 0 && cl < nc) {
     atomicAdd(&st2[2 * (cd.coff + cbase + cl)], (double)s1);
     atomicAdd(&st2[2 * (cd.coff + cbase + cl) + 1], (double)s2);
   }

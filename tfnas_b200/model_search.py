@@ -25,7 +25,7 @@ from .config import CAND_SPEC, PRIMITIVES, lut_key
 from .ops import MixedOpCall, MixedOpFn, StageSinkFn
 
 __all__ = ['PRIMITIVES', 'OPS', 'MixedOP', 'MixedStage', 'Network', 'MBInvertedResBlock', 'ConvLayer',
-           'LinearLayer']
+           'LinearLayer', 'NoisePlan', 'injected', 'seed_noise', 'draw_gumbel']
 
 
 class _Holder(nn.Sequential):
@@ -126,8 +126,23 @@ class injected(object):
         _ACTIVE_PLAN[0] = self.prev
 
 
+_NOISE = dict(gen=None, rnd=random)
+
+
+def seed_noise(seed):
+    """Give the search its own CPU streams for Gumbel noise and the 'random' mode (needed under
+    data parallelism so every rank samples the same sub-network).  ``None`` restores the reference
+    behaviour: global torch CPU generator + global python ``random``."""
+    if seed is None:
+        _NOISE['gen'], _NOISE['rnd'] = None, random
+    else:
+        _NOISE['gen'] = torch.Generator().manual_seed(int(seed))
+        _NOISE['rnd'] = random.Random(int(seed))
+
+
 def draw_gumbel(n, generator=None):
     """Same draw as F.gumbel_softmax's noise, from the CPU generator (reference :62,:87)."""
+    generator = generator if generator is not None else _NOISE['gen']
     return -torch.empty(n).exponential_(generator=generator).log()
 
 
@@ -206,7 +221,7 @@ class MixedOP(nn.Module):
                 forced = self.fink_ori_idx(int(torch.argmax(self._alphas_on_host()[live]).item()))
         elif mode == 'random':
             if forced is None:
-                forced = self.fink_ori_idx(random.choice(range(len(live))))
+                forced = self.fink_ori_idx(_NOISE['rnd'].choice(range(len(live))))
         else:
             raise ValueError('invalid sampling mode...')
         self.reset_switches()

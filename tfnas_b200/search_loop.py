@@ -1,0 +1,166 @@
+"""The search inner loops: ``train_wo_arch`` / ``train_w_arch`` / ``validate`` with the reference's
+names, argument meaning and update rules (train_search.py:318-462), over the B200 MixedOP kernels.
+
+Deliberate differences: meters are accumulated on the device and read back only at
+``print_freq`` (the reference calls ``.item()`` three times per step); gradients are averaged over
+ranks by ``parallel.GradSync`` when torch.distributed is initialised.
+"""
+import logging
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .parallel import GradSync
+
+
+class DeviceMeter(object):
+    """AverageMeter (tools/utils.py:37-58) whose sum lives on the device."""
+
+    def __init__(self):
+        self.sum = None
+        self.cnt = 0
+
+    def update(self, val, n=1):
+        v = val.detach().float() * n
+        self.sum = v if self.sum is None else self.sum + v
+        self.cnt += n
+
+    @property
+    def avg(self):
+        return float(self.sum) / max(self.cnt, 1) if self.sum is not None else 0.0
+
+
+def accuracy(output, target, topk=(1,)):
+    """tools/utils.py:61-74, returning device tensors (no host sync)."""
+    maxk = max(topk)
+    _, pred = output.topk(maxk, 1, True, True)
+    correct = pred.t().eq(target.view(1, -1).expand_as(pred.t()))
+    return [correct[:k].reshape(-1).float().sum(0).mul_(100.0 / target.size(0)) for k in topk]
+
+
+def _set_requires_grad(net, weights, arch):
+    for p in net.weight_parameters():
+        p.requires_grad = weights
+    for p in net.arch_parameters():
+        p.requires_grad = arch
+
+
+def w_step(model, x_w, target_w, criterion, optimizer_w, grad_clip, sync=None, bisample=True):
+    """One weight step (train_search.py:370-385): loss = CE(gumbel path) [+ CE(random other path)]."""
+    net = model.module
+    _set_requires_grad(net, True, False)
+    logits_g, _ = model(x_w, sampling=True, mode='gumbel')
+    loss = criterion(logits_g, target_w)
+    if bisample:
+        logits_r, _ = model(x_w, sampling=True, mode='random')
+        loss = loss + criterion(logits_r, target_w)
+    else:
+        net.reset_switches()
+    optimizer_w.zero_grad()
+    loss.backward()
+    if sync is not None:
+        sync(net.weight_parameters())
+    if grad_clip > 0:
+        nn.utils.clip_grad_norm_(net.weight_parameters(), grad_clip)
+    optimizer_w.step()
+    return loss, logits_g
+
+
+def alpha_step(model, x_a, target_a, criterion, optimizer_a, target_lat, lambda_lat, grad_clip, sync=None):
+    """One architecture step (train_search.py:404-422) incl. the log_softmax renormalisation."""
+    net = model.module
+    _set_requires_grad(net, False, True)
+    logits_a, lat = model(x_a, sampling=False)
+    loss_a = criterion(logits_a, target_a)
+    loss_l = torch.abs(lat / target_lat - 1.) * lambda_lat
+    loss = loss_a + loss_l
+    optimizer_a.zero_grad()
+    loss.backward()
+    if sync is not None:
+        sync(net.arch_parameters())
+    if grad_clip > 0:
+        nn.utils.clip_grad_norm_(net.arch_parameters(), grad_clip)
+    optimizer_a.step()
+    for p in net.arch_parameters():      # applies to betas too (quirk Q4)
+        p.data = F.log_softmax(p.detach().data, dim=-1)
+    return loss_a, loss_l
+
+
+def train_wo_arch(train_queue, model, criterion, optimizer_w, args, sync=None):
+    objs_w, top1, top5 = DeviceMeter(), DeviceMeter(), DeviceMeter()
+    model.train()
+    sync = sync if sync is not None else GradSync()
+    for step, (x_w, target_w) in enumerate(train_queue):
+        x_w = x_w.cuda(non_blocking=True)
+        target_w = target_w.cuda(non_blocking=True)
+        loss, logits = w_step(model, x_w, target_w, criterion, optimizer_w, args.grad_clip, sync, bisample=False)
+        prec1, prec5 = accuracy(logits, target_w, topk=(1, 5))
+        n = x_w.size(0)
+        objs_w.update(loss, n)
+        top1.update(prec1, n)
+        top5.update(prec5, n)
+        if step % args.print_freq == 0:
+            logging.info('TRAIN wo_Arch Step: %04d Objs: %f R1: %f R5: %f', step, objs_w.avg, top1.avg, top5.avg)
+    return top1.avg
+
+
+def train_w_arch(train_queue, val_queue, model, criterion, optimizer_w, optimizer_a, args, sync=None):
+    objs_a, objs_l, objs_w = DeviceMeter(), DeviceMeter(), DeviceMeter()
+    top1, top5 = DeviceMeter(), DeviceMeter()
+    model.train()
+    sync = sync if sync is not None else GradSync()
+    val_queue_iter = None
+    for step, (x_w, target_w) in enumerate(train_queue):
+        x_w = x_w.cuda(non_blocking=True)
+        target_w = target_w.cuda(non_blocking=True)
+        loss_w, logits = w_step(model, x_w, target_w, criterion, optimizer_w, args.grad_clip, sync, bisample=True)
+        prec1, prec5 = accuracy(logits, target_w, topk=(1, 5))
+        n = x_w.size(0)
+        objs_w.update(loss_w, n)
+        top1.update(prec1, n)
+        top5.update(prec5, n)
+        if step % 2 == 0:
+            try:
+                x_a, target_a = next(val_queue_iter)
+            except (StopIteration, TypeError):
+                val_queue_iter = iter(val_queue)
+                x_a, target_a = next(val_queue_iter)
+            x_a = x_a.cuda(non_blocking=True)
+            target_a = target_a.cuda(non_blocking=True)
+            loss_a, loss_l = alpha_step(model, x_a, target_a, criterion, optimizer_a, args.target_lat,
+                                        args.lambda_lat, args.grad_clip, sync)
+            n = x_a.size(0)
+            objs_a.update(loss_a, n)
+            objs_l.update(loss_l, n)
+        if step % args.print_freq == 0:
+            logging.info('TRAIN w_Arch Step: %04d Objs_W: %f R1: %f R5: %f Objs_A: %f Objs_L: %f',
+                         step, objs_w.avg, top1.avg, top5.avg, objs_a.avg, objs_l.avg)
+    return top1.avg
+
+
+def validate(val_queue, model, criterion, args):
+    objs, top1, top5 = DeviceMeter(), DeviceMeter(), DeviceMeter()
+    model.train()    # batch statistics on purpose: no running stats exist (quirk Q7)
+    for step, (x, target) in enumerate(val_queue):
+        x = x.cuda(non_blocking=True)
+        target = target.cuda(non_blocking=True)
+        with torch.no_grad():
+            logits, _ = model(x, sampling=True, mode='gumbel')
+            loss = criterion(logits, target)
+        model.module.reset_switches()
+        prec1, prec5 = accuracy(logits, target, topk=(1, 5))
+        n = x.size(0)
+        objs.update(loss, n)
+        top1.update(prec1, n)
+        top5.update(prec5, n)
+        if step % args.print_freq == 0:
+            logging.info('VALIDATE Step: %04d Objs: %f R1: %f R5: %f', step, objs.avg, top1.avg, top5.avg)
+    return top1.avg
+
+
+def make_optimizers(net, w_lr=0.025, w_mom=0.9, w_wd=1e-5, a_lr=0.01, a_beta1=0.5, a_beta2=0.999, a_wd=5e-4):
+    """train_search.py:196-206."""
+    optimizer_w = torch.optim.SGD(net.weight_parameters(), lr=w_lr, momentum=w_mom, weight_decay=w_wd)
+    optimizer_a = torch.optim.Adam(net.arch_parameters(), lr=a_lr, betas=(a_beta1, a_beta2), weight_decay=a_wd)
+    return optimizer_w, optimizer_a
