@@ -136,6 +136,14 @@ typedef struct TfnasProfEntry {
 int tfnas_prof_enable(int on);
 int tfnas_prof_collect(TfnasProfEntry* out, int max_entries);
 
+/*
+ * Test helper for the tcgen05 building blocks: C[n][p] = sum_k B[n][k] * A[k][p] (A: [K][M], B: [N][K],
+ * C: [N][M], all device fp32) computed with the 3-term tf32 split on the tensor cores.  N <= 256.
+ * wp_scratch: >= ceil(K/32) * 2 * roundup(N,16) * 128 bytes.
+ */
+int tfnas_umma_selftest(int M, int N, int K, const float* A, const float* B, float* C, float* wp_scratch,
+                        size_t wp_bytes, int variant, void* stream);
+
 /* Number of kernel launches issued through this library since load (bench "gpu_launches"). */
 uint64_t tfnas_launch_count(void);
 

@@ -96,6 +96,27 @@ def test_sampled_mode_and_weight_grads(ic, oc, s, act, size, N, ragged, W, idx):
             assert p.grad is None
 
 
+def test_alpha_mode_with_weight_grads():
+    """Not used by train_search (weights are frozen in the alpha step) but legal through the class API:
+    all 8 candidates' weight grads in one call."""
+    ic, oc, s, act, size, N = 16, 16, 1, 'swish', 10, 2
+    mcs = H.default_mcs(ic, True)
+    P, x, gum, lats = H.make_problem(ic, oc, s, size, N, mcs, seed=77)
+    lut = _fake_lut(ic, oc, s, act, size, mcs, lats)
+    op = _build(P, ic, oc, s, act, mcs, lut)
+    xg = x.cuda().requires_grad_(True)
+    with injected(NoisePlan(noise=[gum])):
+        out, lat = op(xg, False, 'max')
+    G = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out * G.cuda()).sum().backward()
+    from oracle import port as _port
+    Pd = {k: v.double().clone().requires_grad_(True) for k, v in P.items()}
+    o, _l = _port.mixedop_alpha(x.double(), Pd, 'b.', ic, oc, s, act, 5.0, gum.double(), [0.0] * 8)
+    (o * G.double()).sum().backward()
+    for n, p in op.named_parameters():
+        assert p.grad is not None and H.rel_l2(p.grad, Pd['b.' + n].grad) < 5 * TOL, n
+
+
 def test_cfg1_golden_fixture():
     """BASELINE configs[0]: stage2.block1 MixedOP, bs=2, 32x32, vs the real reference's output."""
     z = np.load(os.path.join(gi.GOLDEN_DIR, 'mixedop_cfg1.npz'))

@@ -38,7 +38,7 @@ EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
            'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout',
-           'tfnas_prof_enable', 'tfnas_prof_collect']
+           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest']
 
 _lib = None
 
@@ -81,6 +81,8 @@ def load():
     lib.tfnas_prof_enable.argtypes = [i32]
     lib.tfnas_prof_collect.restype = i32
     lib.tfnas_prof_collect.argtypes = [ctypes.POINTER(ProfEntry), i32]
+    lib.tfnas_umma_selftest.restype = i32
+    lib.tfnas_umma_selftest.argtypes = [i32, i32, i32, vp, vp, vp, vp, sz, i32, vp]
     if lib.tfnas_version() != 1:
         raise TfnasError('ABI version mismatch: %d' % lib.tfnas_version())
     _lib = lib

@@ -142,6 +142,7 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
   size_t dzc = take((size_t)P.na * P.oc * sizeof(float4));
   size_t cvec2 = take((size_t)P.ic * 4);
   size_t Mm = take((size_t)P.ic * P.ic * 4);
+  size_t a12 = take((size_t)2 * P.MC * 4);
   size_t dmix = take(TFNAS_MAX_OPS * 4);
   size_t dg = take((size_t)P.N * P.MCse * 4);
   size_t sede = want_wgrad ? take((size_t)P.N * P.MCse * 4) : 0;
@@ -157,6 +158,7 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
     S.dzc = (float4*)(base + dzc);
     S.cvec2 = (float*)(base + cvec2);
     S.Mm = (float*)(base + Mm);
+    S.a12 = (float*)(base + a12);
     S.dmix = (float*)(base + dmix);
     S.dg = (float*)(base + dg);
     S.sede = want_wgrad ? (float*)(base + sede) : nullptr;

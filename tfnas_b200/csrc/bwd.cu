@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(NT) k_dc(Plan P, const float* __restrict__ G, 
   }
 }
 
-// SE backward through sigmoid / expand FC / act / reduce FC.  grid (N, na).  dg -> dp in place.
+// SE backward through sigmoid / expand FC / act / reduce FC.  grid (ceil(N/SE_NB), na).  dg -> dp in place.
 template <int ACT>
 __global__ void __launch_bounds__(NT) k_se_bwd(Plan P, const float* __restrict__ seg, const float* __restrict__ set,
                                                 float* __restrict__ dg, float* __restrict__ sede,
@@ -180,30 +180,54 @@ __global__ void __launch_bounds__(NT) k_se_bwd(Plan P, const float* __restrict__
   extern __shared__ float sm[];
   const Cand& cd = P.c[blockIdx.y];
   if (cd.se == 0) return;
-  const int n = blockIdx.x, mc = cd.mc, se = cd.se, tid = threadIdx.x;
-  float* des = sm;        // [mc]
-  float* dts = sm + mc;   // [se]
-  for (int c = tid; c < mc; c += NT) {
-    size_t i = (size_t)n * P.MCse + cd.soff + c;
-    float g = seg[i];
-    float de = dg[i] * g * (1.f - g);
-    des[c] = de;
-    if (sede) sede[i] = de;
+  const int n0 = blockIdx.x * SE_NB, nb = min(SE_NB, P.N - n0), mc = cd.mc, se = cd.se, tid = threadIdx.x;
+  float* des = sm;                 // [SE_NB][mc]
+  float* dts = sm + SE_NB * mc;    // [SE_NB][se]
+  for (int i = tid; i < SE_NB * mc; i += NT) {
+    int b = i / mc, c = i - b * mc;
+    float de = 0.f;
+    if (b < nb) {
+      size_t gi = (size_t)(n0 + b) * P.MCse + cd.soff + c;
+      float g = seg[gi];
+      de = dg[gi] * g * (1.f - g);
+      if (sede) sede[gi] = de;
+    }
+    des[i] = de;
   }
   __syncthreads();
   for (int j = tid; j < se; j += NT) {
-    float a = 0.f;
-    for (int c = 0; c < mc; ++c) a += cd.ew[(size_t)c * se + j] * des[c];
-    size_t i = (size_t)n * P.SEH + cd.hoff + j;
-    float dt = a * act_df<ACT>(set[i]);
-    dts[j] = dt;
-    if (sedt) sedt[i] = dt;
+    float a[SE_NB];
+#pragma unroll
+    for (int b = 0; b < SE_NB; ++b) a[b] = 0.f;
+    for (int c = 0; c < mc; ++c) {
+      const float wv = cd.ew[(size_t)c * se + j];
+#pragma unroll
+      for (int b = 0; b < SE_NB; ++b) a[b] += wv * des[b * mc + c];
+    }
+#pragma unroll
+    for (int b = 0; b < SE_NB; ++b) {
+      float dt = 0.f;
+      if (b < nb) {
+        size_t ti = (size_t)(n0 + b) * P.SEH + cd.hoff + j;
+        dt = a[b] * act_df<ACT>(set[ti]);
+        if (sedt) sedt[ti] = dt;
+      }
+      dts[b * se + j] = dt;
+    }
   }
   __syncthreads();
   for (int c = tid; c < mc; c += NT) {
-    float a = 0.f;
-    for (int j = 0; j < se; ++j) a += cd.rw[(size_t)j * mc + c] * dts[j];
-    dg[(size_t)n * P.MCse + cd.soff + c] = a;
+    float a[SE_NB];
+#pragma unroll
+    for (int b = 0; b < SE_NB; ++b) a[b] = 0.f;
+    for (int j = 0; j < se; ++j) {
+      const float wv = cd.rw[(size_t)j * mc + c];
+#pragma unroll
+      for (int b = 0; b < SE_NB; ++b) a[b] += wv * dts[b * se + j];
+    }
+#pragma unroll
+    for (int b = 0; b < SE_NB; ++b)
+      if (b < nb) dg[(size_t)(n0 + b) * P.MCse + cd.soff + c] = a[b];
   }
 }
 
@@ -244,16 +268,17 @@ __global__ void __launch_bounds__(NT) k_b2b(Plan P, const float* __restrict__ D,
 // ----------------------------------------------------------------------------------------------
 
 static DwCfg dwb_config(const Plan& P, int KS) {
+  // tile over INPUT rows; the dd tile holds the output rows those input rows touch, zero-haloed
   DwCfg c;
   const int S = P.stride, pad = KS / 2;
   int CPB = 1;
   while (CPB < 32 && CPB * P.HW < 2048) CPB <<= 1;
   c.CPB = CPB;
-  c.WP = P.Wo + 2 * pad;
+  c.WP = dw_wp(P.Wo, pad);
   for (int tiles = 1;; ++tiles) {
     int R = cdiv(P.H, tiles);
-    int IR = (R + KS - 2) / S + 2;
-    size_t smem = (size_t)CPB * IR * c.WP * 4;
+    int IR = S == 1 ? R + KS - 1 : (R + KS - 2) / S + 2;
+    size_t smem = ((size_t)CPB * IR * c.WP + 16) * 4;
     if (smem <= 40 * 1024 || R == 1) {
       c.R = R; c.IR = IR; c.tiles = cdiv(P.H, R); c.smem = smem;
       break;
@@ -267,9 +292,9 @@ __global__ void __launch_bounds__(NT) k_dw_bwd(Plan P, DwWork Wk, DwCfg cfg, con
                                                 const float* __restrict__ D, const float* __restrict__ bn2,
                                                 const double* __restrict__ sD, const float* __restrict__ UH,
                                                 float* __restrict__ DA, DwGrads gw) {
-  extern __shared__ float dds[];   // [CPB][IR][WP]
+  extern __shared__ __align__(16) float dds[];   // [CPB][IR][WP] (+16 slack)
   constexpr int pad = KS / 2;
-  const int tid = threadIdx.x, n = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.z;
   int e = 0;
   while (e + 1 < Wk.n && (int)blockIdx.y >= Wk.gstart[e + 1]) ++e;
   const Cand& cd = P.c[Wk.slot[e]];
@@ -279,24 +304,27 @@ __global__ void __launch_bounds__(NT) k_dw_bwd(Plan P, DwWork Wk, DwCfg cfg, con
   const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo;
   const int r0 = blockIdx.x * cfg.R, r1 = min(H, r0 + cfg.R);
   // output rows touching input rows [r0, r1): oy*S - pad + ky = r
-  int t0 = r0 + pad - KS + 1;
+  const int t0 = r0 + pad - KS + 1;
   const int oy_lo = max(0, t0 > 0 ? (t0 + S - 1) / S : 0);
   const int oy_hi = min(Ho - 1, (r1 - 1 + pad) / S);
+  const int row0 = S == 1 ? r0 - pad : oy_lo;       // dd row held by tile row 0
   const double invQ = 1.0 / (double)P.Q;
-  for (int i = tid; i < CPB * IR * WP; i += NT) {
-    int c = i / (IR * WP), rem = i - c * IR * WP;
-    int lr = rem / WP, lc = rem - lr * WP;
-    int oy = oy_lo + lr, ox = lc - pad;
-    float v = 0.f;
-    if (c < nc && oy <= oy_hi && ox >= 0 && ox < Wo) {
-      const int cst = cd.coff + cbase + c;
-      const float mu = bn2[cst], r = bn2[P.MC + cst];
-      const float m1 = (float)(sD[2 * cst] * invQ), m2 = (float)(sD[2 * cst + 1] * invQ);
-      const size_t a = (((size_t)n * P.MC + cst) * Ho + oy) * Wo + ox;
-      const float dh = (D[a] - mu) * r;
-      v = r * (DC[a] - m1 - dh * m2);
+  for (int i = tid; i < (CPB * IR * WP + 16) / 4; i += NT) ((float4*)dds)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  // stage dd = r2 (dd-hat - m1 - d-hat m2): one warp per (channel, output row)
+  for (int rho = warp; rho < nc * IR; rho += NT / 32) {
+    const int c = rho / IR, lr = rho - c * IR;
+    const int oy = row0 + lr;
+    if (oy < 0 || oy >= Ho) continue;
+    const int cst = cd.coff + cbase + c;
+    const float mu = bn2[cst], r = bn2[P.MC + cst];
+    const float m1 = (float)(sD[2 * cst] * invQ), m2 = (float)(sD[2 * cst + 1] * invQ);
+    const size_t a = (((size_t)n * P.MC + cst) * Ho + oy) * Wo;
+    float* dst = dds + ((size_t)c * IR + lr) * WP + pad;
+    for (int ox = lane; ox < Wo; ox += 32) {
+      const float dh = (D[a + ox] - mu) * r;
+      dst[ox] = r * (DC[a + ox] - m1 - dh * m2);
     }
-    dds[i] = v;
   }
   __syncthreads();
   const int TPC = NT / CPB;
@@ -311,32 +339,68 @@ __global__ void __launch_bounds__(NT) k_dw_bwd(Plan P, DwWork Wk, DwCfg cfg, con
     for (int i = 0; i < KS * KS; ++i) wr[i] = cd.dw[(size_t)(cbase + cl) * KS * KS + i];
     const float* db = dds + (size_t)cl * IR * WP;
     const size_t pbase = (((size_t)n * P.MC + cst) * H + r0) * W;
-    const int npx = (r1 - r0) * W;
-    for (int p = jl; p < npx; p += TPC) {
-      int rl = p / W, col = p - rl * W;
-      int r = r0 + rl;
-      float a = 0.f;
-      if (WG) a = act_f<ACT>(UH[pbase + p]);
-      float v = 0.f;
+    const int gpr = (W + 3) >> 2;
+    const int ngroups = (r1 - r0) * gpr;
+    for (int g = jl; g < ngroups; g += TPC) {
+      const int rl = g / gpr, col0 = (g - rl * gpr) * 4;
+      const int r = r0 + rl;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      if (WG) {
 #pragma unroll
-      for (int ky = 0; ky < KS; ++ky) {
-        int ty = r + pad - ky;
-        if (ty < 0 || (S == 2 && (ty & 1))) continue;
-        int oy = ty / S;
-        if (oy < oy_lo || oy > oy_hi) continue;
-        const float* drow = db + (size_t)(oy - oy_lo) * WP + pad;
+        for (int j = 0; j < 4; ++j)
+          if (col0 + j < W) a[j] = act_f<ACT>(UH[pbase + (size_t)rl * W + col0 + j]);
+      }
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if (S == 1) {
+        // da[r][col] = sum_{ky',kx'} w[KS-1-ky'][KS-1-kx'] dd[r-pad+ky'][col-pad+kx'] : a correlation with the
+        // flipped filter over the zero-haloed dd tile (tile row 0 <-> dd row r0-pad, tile col pad <-> dd col 0)
 #pragma unroll
-        for (int kx = 0; kx < KS; ++kx) {
-          int tx = col + pad - kx;
-          if (S == 2 && (tx & 1)) continue;
-          // tx may be negative (>= -pad): arithmetic shift keeps ox = floor(tx/2) for even tx
-          int ox = S == 2 ? (tx >> 1) : tx;
-          float dd = drow[ox];
-          v += wr[ky * KS + kx] * dd;
-          if (WG) gacc[ky * KS + kx] += dd * a;
+        for (int kyp = 0; kyp < KS; ++kyp) {
+          const float* rp = db + (size_t)(rl + kyp) * WP + col0;
+          float4 t0v = *(const float4*)rp, t1v = *(const float4*)(rp + 4);
+          const float v[8] = {t0v.x, t0v.y, t0v.z, t0v.w, t1v.x, t1v.y, t1v.z, t1v.w};
+#pragma unroll
+          for (int kxp = 0; kxp < KS; ++kxp) {
+            const int tap = (KS - 1 - kyp) * KS + (KS - 1 - kxp);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              o[j] += wr[tap] * v[j + kxp];
+              if (WG) gacc[tap] += v[j + kxp] * a[j];
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+          const int ty = r + pad - ky;
+          if (ty < 0 || (ty & 1)) continue;
+          const int oy = ty >> 1;
+          if (oy < oy_lo || oy > oy_hi) continue;
+          const float* drow = db + (size_t)(oy - oy_lo) * WP + pad + (col0 >> 1);
+          const float v[4] = {drow[-1], drow[0], drow[1], drow[2]};
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              constexpr int dummy = 0;
+              (void)dummy;
+              const int t = j + pad - kx;          // compile-time after unrolling
+              if ((t & 1) == 0) {
+                const float dd = v[(t >> 1) + 1];
+                o[j] += wr[ky * KS + kx] * dd;
+                if (WG) gacc[ky * KS + kx] += dd * a[j];
+              }
+            }
         }
       }
-      DA[pbase + p] = v;
+      float* q = DA + pbase + (size_t)rl * W + col0;
+      if ((W & 3) == 0) {
+        *(float4*)q = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col0 + j < W) q[j] = o[j];
+      }
     }
   }
   if (WG) {
@@ -427,44 +491,62 @@ __global__ void __launch_bounds__(NT) k_dx(Plan P, OcTile T, int ksplit, const f
 // ----------------------------------------------------------------------------------------------
 // B4: fold the BN1 backward into an ic x ic correction
 // ----------------------------------------------------------------------------------------------
-// grid (ic): row k of Mm[k][k'] = sum_c W1[c][k] r1_c^2 m2_c W1[c][k'] ; cvec2[k] = sum_c W1[c][k] r1_c m1_c - sum_k' Mm[k][k'] mu_x[k']
-__global__ void __launch_bounds__(NT) k_b4prep(Plan P, const float* __restrict__ bn1, const double* __restrict__ sU,
-                                                const double* __restrict__ xmom, float* __restrict__ Mm,
-                                                float* __restrict__ cvec2) {
+// per stacked channel: a1 = r1*m1, a2 = r1^2*m2  (m = BN1-backward means)
+__global__ void k_b4coef(int MC, double invP, const float* __restrict__ bn1, const double* __restrict__ sU,
+                         float* __restrict__ a12) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= MC) return;
+  double r1 = (double)bn1[MC + c];
+  a12[c] = (float)(r1 * sU[2 * c] * invP);
+  a12[MC + c] = (float)(r1 * r1 * sU[2 * c + 1] * invP);
+}
+
+// grid (ic, nsplit): partial row k of Mm[k][k'] = sum_c W1[c][k] a2_c W1[c][k'] and cvec[k] = sum_c W1[c][k] a1_c over
+// this block's share of the stacked channels; float atomics into the zeroed Mm / cvec.
+__global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ a12, float* __restrict__ Mm,
+                                              float* __restrict__ cvec) {
   const int k = blockIdx.x, ic = P.ic, tid = threadIdx.x;
-  const double invP = 1.0 / (double)P.P;
-  __shared__ double red[NT];
-  double cv = 0.0, corr = 0.0;
-  for (int kp = tid; kp < ((ic + NT - 1) / NT) * NT; kp += NT) {
-    double m = 0.0;
-    if (kp < ic) {
-      for (int s = 0; s < P.na; ++s) {
-        const Cand& cd = P.c[s];
-        for (int c = 0; c < cd.mc; ++c) {
-          const int cst = cd.coff + c;
-          const double r1 = (double)bn1[P.MC + cst];
-          const double wk = (double)cd.w1[(size_t)c * ic + k];
-          m += wk * r1 * r1 * (sU[2 * cst + 1] * invP) * (double)cd.w1[(size_t)c * ic + kp];
-        }
+  const int KP = ((ic + 31) / 32) * 32;       // threads along k'
+  const int parts = NT / KP;                  // thread groups striding over channels (ic <= 192 -> parts >= 1)
+  const int kp = tid % KP, part = tid / KP;
+  const int c_lo = (int)((long long)P.MC * blockIdx.y / gridDim.y), c_hi = (int)((long long)P.MC * (blockIdx.y + 1) / gridDim.y);
+  float m = 0.f, cv = 0.f;
+  if (part < parts) {
+    for (int s = 0; s < P.na; ++s) {
+      const Cand& cd = P.c[s];
+      const int lo = max(c_lo, cd.coff), hi = min(c_hi, cd.coff + cd.mc);
+      for (int cst = lo + part; cst < hi; cst += parts) {
+        const float* w = cd.w1 + (size_t)(cst - cd.coff) * ic;
+        const float wk = w[k];
+        if (kp < ic) m += wk * a12[P.MC + cst] * w[kp];
+        if (kp == 0) cv += wk * a12[cst];
       }
-      Mm[k * ic + kp] = (float)m;
-      corr += m * xmom[kp];
     }
   }
-  // cvec: split the stacked channels over the threads
-  for (int cst = tid; cst < P.MC; cst += NT) {
-    int s = 0;
-    while (s + 1 < P.na && cst >= P.c[s + 1].coff) ++s;
-    const Cand& cd = P.c[s];
-    cv += (double)cd.w1[(size_t)(cst - cd.coff) * ic + k] * (double)bn1[P.MC + cst] * (sU[2 * cst] * invP);
-  }
-  red[tid] = cv - corr;
+  __shared__ float red[NT];
+  red[tid] = m;
   __syncthreads();
-  for (int o = NT / 2; o > 0; o >>= 1) {
-    if (tid < o) red[tid] += red[tid + o];
-    __syncthreads();
+  if (part == 0 && kp < ic) {
+    for (int q = 1; q < parts; ++q) m += red[q * KP + kp];
+    atomicAdd(&Mm[k * ic + kp], m);
   }
-  if (tid == 0) cvec2[k] = (float)red[0];
+  __syncthreads();
+  red[tid] = (kp == 0 && part < parts) ? cv : 0.f;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += red[q * KP];
+    atomicAdd(&cvec[k], t);
+  }
+}
+
+// cvec2[k] = cvec[k] - sum_k' Mm[k][k'] mu_x[k']
+__global__ void k_b4fin(int ic, const float* __restrict__ Mm, const double* __restrict__ xmom, float* __restrict__ cvec) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ic) return;
+  double t = 0.0;
+  for (int kp = 0; kp < ic; ++kp) t += (double)Mm[k * ic + kp] * xmom[kp];
+  cvec[k] = (float)((double)cvec[k] - t);
 }
 
 // dx = dx_main - Mm x - cvec2 (+ G)
@@ -800,13 +882,19 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     double fcw = 0;
     for (int s = 0; s < P.na; ++s)
       if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); fcw += 2.0 * P.c[s].mc * P.c[s].se; }
-    size_t smem = (size_t)(maxmc + maxse) * 4;
+    size_t smem = (size_t)SE_NB * (maxmc + maxse) * 4;
     float* sede = dweights ? S.sede : nullptr;
     float* sedt = dweights ? S.sedt : nullptr;
     dim3 gpl(cdiv(P.MCse * 32, NT), P.N);
     { ProfScope ps("se_bwd", 4.0 * fcw + 12.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
-      if (relu) k_se_bwd<TFNAS_ACT_RELU><<<dim3(P.N, P.na), NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
-      else k_se_bwd<TFNAS_ACT_SWISH><<<dim3(P.N, P.na), NT, smem, st>>>(P, seg, set, S.dg, sede, sedt); }
+      dim3 g(cdiv(P.N, SE_NB), P.na);
+      if (relu) {
+        cudaFuncSetAttribute(k_se_bwd<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_se_bwd<TFNAS_ACT_RELU><<<g, NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
+      } else {
+        cudaFuncSetAttribute(k_se_bwd<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_se_bwd<TFNAS_ACT_SWISH><<<g, NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
+      } }
     { ProfScope ps("b2b", 12.0 * P.Q * P.MCse, 8.0 * P.Q * P.MCse, st);
       if (relu) k_b2b<TFNAS_ACT_RELU><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
       else k_b2b<TFNAS_ACT_SWISH><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD); }
@@ -864,8 +952,15 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   }
   // B4
   {
-    { ProfScope ps("b4prep", 4.0 * P.MC * ic, 2.0 * P.MC * ic * ic, st);
-      k_b4prep<<<ic, NT, 0, st>>>(P, bn1, S.sU, xmom, S.Mm, S.cvec2); }
+    // cvec2 and Mm are adjacent in the workspace: one memset
+    cudaMemsetAsync(S.cvec2, 0, (size_t)((char*)(S.Mm + ic * ic) - (char*)S.cvec2), st);
+    { ProfScope ps("b4coef", 24.0 * P.MC, 0, st);
+      k_b4coef<<<cdiv(P.MC, 256), 256, 0, st>>>(P.MC, 1.0 / (double)P.P, bn1, S.sU, S.a12); }
+    { ProfScope ps("b4mm", 4.0 * P.MC * ic, 2.0 * P.MC * ic * ic, st);
+      int nsplit = max(1, min(cdiv(P.MC, 64), cdiv(4 * sm_count(), ic)));
+      k_b4mm<<<dim3(ic, nsplit), NT, 0, st>>>(P, S.a12, S.Mm, S.cvec2); }
+    { ProfScope ps("b4fin", 4.0 * ic * ic, 2.0 * ic * ic, st);
+      k_b4fin<<<cdiv(ic, 64), 64, 0, st>>>(ic, S.Mm, xmom, S.cvec2); }
     switch (Tx.TC) {
       case 4: launch_dxfin<4>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
       case 8: launch_dxfin<8>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;

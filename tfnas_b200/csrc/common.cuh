@@ -6,6 +6,7 @@
 
 #define BN_EPS 1e-5f
 #define NT 256  // threads per CTA of every tile kernel
+#define SE_NB 8 // images per CTA in the squeeze-excite FC kernels
 
 // One ACTIVE candidate in "slot" order (slot s = s-th set bit of cand_mask).
 struct Cand {
@@ -68,6 +69,32 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 __device__ __forceinline__ float group_sum(float v, int width) {
   for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// padded row width of a depthwise smem tile: interior [pad, pad+W), zero halo, multiple of 4
+static inline int dw_wp(int W, int pad) { return (W + 2 * pad + 3) / 4 * 4; }
+
+// Four consecutive outputs (ox0 % 4 == 0) of a KSxKS stride-S correlation from a zero-haloed smem tile.
+// `ap` points at tile(row = oy*S, col = ox0*S) (16B aligned: WP % 4 == 0), wr = weights [KS*KS].
+template <int KS, int S>
+__device__ __forceinline__ void dw_row4(float (&o)[4], const float* ap, int WP, const float (&wr)[KS * KS]) {
+  constexpr int NV = 3 * S + KS;            // input columns touched by 4 outputs
+  constexpr int NV4 = (NV + 3) / 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < KS; ++ky) {
+    float v[NV4 * 4];
+#pragma unroll
+    for (int q = 0; q < NV4; ++q) {
+      float4 t = *(const float4*)(ap + ky * WP + q * 4);
+      v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+    }
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] += wr[ky * KS + kx] * v[j * S + kx];
+  }
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -248,25 +248,23 @@ __global__ void __launch_bounds__(NT) k_expand(Plan P, const float* __restrict__
 // F1b: depthwise KSxKS stride S over act(UH) -> D, BN2 sums
 // ----------------------------------------------------------------------------------------------
 
-static DwCfg dw_config(const Plan& P, int KS, int rows_total, int cols_out, bool bwd) {
-  // fwd: tile over OUTPUT rows (rows_total = Ho); bwd: tile over INPUT rows (rows_total = H)
+static DwCfg dw_config(const Plan& P, int KS) {
+  // tile over OUTPUT rows; CPB channels per CTA; the `a` tile is [CPB][IR][WP] floats (+ slack for over-reads)
   DwCfg c;
   const int S = P.stride, pad = KS / 2;
-  int per_plane = bwd ? P.HW : P.HWo;
   int CPB = 1;
-  while (CPB < 32 && CPB * per_plane < 2048) CPB <<= 1;
+  while (CPB < 32 && CPB * P.HWo < 2048) CPB <<= 1;
   c.CPB = CPB;
-  c.WP = (bwd ? P.Wo : P.W) + 2 * pad;
+  c.WP = dw_wp(P.W, pad);
   for (int tiles = 1;; ++tiles) {
-    int R = cdiv(rows_total, tiles);
-    int IR = bwd ? (R + KS - 1 + S - 1) / S + 1 : (R - 1) * S + KS;
-    size_t smem = (size_t)CPB * IR * c.WP * 4;
+    int R = cdiv(P.Ho, tiles);
+    int IR = (R - 1) * S + KS;
+    size_t smem = ((size_t)CPB * IR * c.WP + 16) * 4;
     if (smem <= 40 * 1024 || R == 1) {
-      c.R = R; c.IR = IR; c.tiles = cdiv(rows_total, R); c.smem = smem;
+      c.R = R; c.IR = IR; c.tiles = cdiv(P.Ho, R); c.smem = smem;
       break;
     }
   }
-  (void)cols_out;
   return c;
 }
 
@@ -284,9 +282,9 @@ static void dw_work(const Plan& P, int KS, int CPB, DwWork& w) {
 template <int KS, int S, int ACT>
 __global__ void __launch_bounds__(NT) k_dw_fwd(Plan P, DwWork Wk, DwCfg cfg, const float* __restrict__ UH,
                                                 float* __restrict__ D, double* __restrict__ st2) {
-  extern __shared__ float as[];   // [CPB][IR][WP]
+  extern __shared__ __align__(16) float as[];   // [CPB][IR][WP] (+16 slack)
   constexpr int pad = KS / 2;
-  const int tid = threadIdx.x, n = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.z;
   int e = 0;
   while (e + 1 < Wk.n && (int)blockIdx.y >= Wk.gstart[e + 1]) ++e;
   const Cand& cd = P.c[Wk.slot[e]];
@@ -296,15 +294,24 @@ __global__ void __launch_bounds__(NT) k_dw_fwd(Plan P, DwWork Wk, DwCfg cfg, con
   const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo;
   const int oy0 = blockIdx.x * cfg.R, oy1 = min(Ho, oy0 + cfg.R);
   const int r_lo = oy0 * S - pad;
-  // stage act(UH) with zero halo
-  for (int i = tid; i < CPB * IR * WP; i += NT) {
-    int c = i / (IR * WP), rem = i - c * IR * WP;
-    int lr = rem / WP, lc = rem - lr * WP;
-    int r = r_lo + lr, col = lc - pad;
-    float v = 0.f;
-    if (c < nc && r >= 0 && r < H && col >= 0 && col < W)
-      v = act_f<ACT>(UH[(((size_t)n * P.MC + cd.coff + cbase + c) * H + r) * W + col]);
-    as[i] = v;
+  // zero the tile (halo + slack), then stage act(UH) rows: one warp per (channel, row)
+  for (int i = tid; i < (CPB * IR * WP + 16) / 4; i += NT) ((float4*)as)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int rho = warp; rho < nc * IR; rho += NT / 32) {
+    const int c = rho / IR, lr = rho - c * IR;
+    const int r = r_lo + lr;
+    if (r < 0 || r >= H) continue;
+    const float* src = UH + (((size_t)n * P.MC + cd.coff + cbase + c) * H + r) * W;
+    float* dst = as + ((size_t)c * IR + lr) * WP + pad;
+    if ((W & 3) == 0) {
+      for (int v = lane; v < (W >> 2); v += 32) {
+        float4 t = *(const float4*)(src + v * 4);
+        dst[v * 4] = act_f<ACT>(t.x); dst[v * 4 + 1] = act_f<ACT>(t.y);
+        dst[v * 4 + 2] = act_f<ACT>(t.z); dst[v * 4 + 3] = act_f<ACT>(t.w);
+      }
+    } else {
+      for (int col = lane; col < W; col += 32) dst[col] = act_f<ACT>(src[col]);
+    }
   }
   __syncthreads();
   const int TPC = NT / CPB;
@@ -316,18 +323,22 @@ __global__ void __launch_bounds__(NT) k_dw_fwd(Plan P, DwWork Wk, DwCfg cfg, con
     for (int i = 0; i < KS * KS; ++i) wr[i] = cd.dw[(size_t)(cbase + cl) * KS * KS + i];
     const float* ab = as + (size_t)cl * IR * WP;
     float* dp = D + (((size_t)n * P.MC + cd.coff + cbase + cl) * Ho + oy0) * Wo;
-    const int nout = (oy1 - oy0) * Wo;
-    for (int o = jl; o < nout; o += TPC) {
-      int oyl = o / Wo, ox = o - oyl * Wo;
-      const float* ap = ab + (size_t)(oyl * S) * WP + ox * S;
-      float v = 0.f;
+    const int gpr = (Wo + 3) >> 2;                 // groups of 4 outputs per row
+    const int ngroups = (oy1 - oy0) * gpr;
+    for (int g = jl; g < ngroups; g += TPC) {
+      const int oyl = g / gpr, ox0 = (g - oyl * gpr) * 4;
+      float o[4];
+      dw_row4<KS, S>(o, ab + (size_t)(oyl * S) * WP + ox0 * S, WP, wr);
+      float* q = dp + oyl * Wo + ox0;
+      if ((Wo & 3) == 0) {
+        *(float4*)q = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
-      for (int ky = 0; ky < KS; ++ky)
+        for (int j = 0; j < 4; ++j) { s1 += o[j]; s2 += o[j] * o[j]; }
+      } else {
 #pragma unroll
-        for (int kx = 0; kx < KS; ++kx) v += wr[ky * KS + kx] * ap[ky * WP + kx];
-      dp[o] = v;
-      s1 += v;
-      s2 += v * v;
+        for (int j = 0; j < 4; ++j)
+          if (ox0 + j < Wo) { q[j] = o[j]; s1 += o[j]; s2 += o[j] * o[j]; }
+      }
     }
   }
   // TPC threads share a channel; reduce within the warp (or sub-warp group), one atomic per group
@@ -362,37 +373,60 @@ __global__ void __launch_bounds__(NT) k_se_pool(Plan P, const float* __restrict_
   if (lane == 0) sep[(size_t)n * P.MCse + widx] = acc / (float)P.HWo;
 }
 
-// grid (N, na): t = Wr p + br ; h = act(t) ; g = sigmoid(We h + be)
+// grid (ceil(N/SE_NB), na): t = Wr p + br ; h = act(t) ; g = sigmoid(We h + be), SE_NB images per CTA so
+// that each weight row is read once per SE_NB images.
 template <int ACT>
 __global__ void __launch_bounds__(NT) k_se_fc(Plan P, const float* __restrict__ sep, float* __restrict__ set,
                                                float* __restrict__ seg) {
   extern __shared__ float sm[];
   const Cand& cd = P.c[blockIdx.y];
   if (cd.se == 0) return;
-  const int n = blockIdx.x, mc = cd.mc, se = cd.se;
-  float* ps = sm;        // [mc]
-  float* hs = sm + mc;   // [se]
+  const int n0 = blockIdx.x * SE_NB, nb = min(SE_NB, P.N - n0), mc = cd.mc, se = cd.se;
+  float* ps = sm;               // [SE_NB][mc]
+  float* hs = sm + SE_NB * mc;  // [SE_NB][se]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < mc; i += NT) ps[i] = sep[(size_t)n * P.MCse + cd.soff + i];
+  for (int i = tid; i < SE_NB * mc; i += NT) {
+    int b = i / mc, c = i - b * mc;
+    ps[i] = b < nb ? sep[(size_t)(n0 + b) * P.MCse + cd.soff + c] : 0.f;
+  }
   __syncthreads();
   for (int j = warp; j < se; j += NT / 32) {
     const float* w = cd.rw + (size_t)j * mc;
-    float a = 0.f;
-    for (int i = lane; i < mc; i += 32) a += w[i] * ps[i];
-    a = warp_sum(a);
-    if (lane == 0) {
-      float t = a + cd.rb[j];
-      set[(size_t)n * P.SEH + cd.hoff + j] = t;
-      hs[j] = act_f<ACT>(t);
+    float a[SE_NB];
+#pragma unroll
+    for (int b = 0; b < SE_NB; ++b) a[b] = 0.f;
+    for (int i = lane; i < mc; i += 32) {
+      const float wv = w[i];
+#pragma unroll
+      for (int b = 0; b < SE_NB; ++b) a[b] += wv * ps[b * mc + i];
+    }
+    const float bias = cd.rb[j];
+#pragma unroll
+    for (int b = 0; b < SE_NB; ++b) {
+      float t = warp_sum(a[b]) + bias;
+      if (lane == 0 && b < nb) {
+        set[(size_t)(n0 + b) * P.SEH + cd.hoff + j] = t;
+        hs[b * se + j] = act_f<ACT>(t);
+      }
     }
   }
   __syncthreads();
   for (int c = warp; c < mc; c += NT / 32) {
     const float* w = cd.ew + (size_t)c * se;
-    float a = 0.f;
-    for (int j = lane; j < se; j += 32) a += w[j] * hs[j];
-    a = warp_sum(a);
-    if (lane == 0) seg[(size_t)n * P.MCse + cd.soff + c] = sigmoid_f(a + cd.eb[c]);
+    float a[SE_NB];
+#pragma unroll
+    for (int b = 0; b < SE_NB; ++b) a[b] = 0.f;
+    for (int j = lane; j < se; j += 32) {
+      const float wv = w[j];
+#pragma unroll
+      for (int b = 0; b < SE_NB; ++b) a[b] += wv * hs[b * se + j];
+    }
+    const float bias = cd.eb[c];
+#pragma unroll
+    for (int b = 0; b < SE_NB; ++b) {
+      float t = warp_sum(a[b]);
+      if (lane == 0 && b < nb) seg[(size_t)(n0 + b) * P.MCse + cd.soff + c] = sigmoid_f(t + bias);
+    }
   }
 }
 
@@ -561,7 +595,7 @@ int sm_count() {
 
 template <int KS, int S>
 static void launch_dw_fwd(const Plan& P, const float* UH, float* D, double* st2, cudaStream_t st) {
-  DwCfg cfg = dw_config(P, KS, P.Ho, P.Wo, false);
+  DwCfg cfg = dw_config(P, KS);
   DwWork w;
   dw_work(P, KS, cfg.CPB, w);
   if (!w.n) return;
@@ -651,15 +685,21 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
     double fcw = 0;
     for (int s = 0; s < P.na; ++s)
       if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); fcw += 2.0 * P.c[s].mc * P.c[s].se; }
-    size_t smem = (size_t)(maxmc + maxse) * 4;
+    size_t smem = (size_t)SE_NB * (maxmc + maxse) * 4;
     const bool relu = P.act == TFNAS_ACT_RELU;
     { ProfScope ps("se_pool", 4.0 * P.Q * P.MCse, 4.0 * P.Q * P.MCse, st);
       dim3 g(cdiv(P.MCse * 32, NT), P.N);
       if (relu) k_se_pool<TFNAS_ACT_RELU><<<g, NT, 0, st>>>(P, D, bn2, sep);
       else k_se_pool<TFNAS_ACT_SWISH><<<g, NT, 0, st>>>(P, D, bn2, sep); }
     { ProfScope ps("se_fc", 4.0 * fcw + 8.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
-      if (relu) k_se_fc<TFNAS_ACT_RELU><<<dim3(P.N, P.na), NT, smem, st>>>(P, sep, set, seg);
-      else k_se_fc<TFNAS_ACT_SWISH><<<dim3(P.N, P.na), NT, smem, st>>>(P, sep, set, seg); }
+      dim3 g(cdiv(P.N, SE_NB), P.na);
+      if (relu) {
+        cudaFuncSetAttribute(k_se_fc<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_se_fc<TFNAS_ACT_RELU><<<g, NT, smem, st>>>(P, sep, set, seg);
+      } else {
+        cudaFuncSetAttribute(k_se_fc<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_se_fc<TFNAS_ACT_SWISH><<<g, NT, smem, st>>>(P, sep, set, seg);
+      } }
   }
   // F3
   {

@@ -36,8 +36,9 @@ struct BwdScratch {
   double* sD;     // [2*MC]
   double* sU;     // [2*MC]
   float4* dzc;    // [na*oc]  per (slot, out channel) BN3-backward coefficients
-  float* cvec2;   // [ic]
+  float* cvec2;   // [ic]        (cvec2 and Mm adjacent: zeroed by one memset)
   float* Mm;      // [ic*ic]
+  float* a12;     // [2*MC]  BN1-backward per-channel coefficients
   float* dmix;    // [8]  dL/dw_i (data term)
   float* sede;    // [N*MCse]  SE: dL/de (pre-sigmoid)     (weight-grad mode)
   float* sedt;    // [N*SEH]   SE: dL/dt (pre-act hidden)  (weight-grad mode)
