@@ -121,6 +121,10 @@ int tfnas_stage_sink_bwd(int K, size_t numel, const float* const* res, const flo
  * {xmom, bn1, bn2, bn3, mixw, lat, se_p, se_t, se_g, UH, D, Z, total} (13 entries). */
 int tfnas_debug_saved_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, size_t* out13);
 
+/* Test helper: byte offsets of the backward workspace regions
+ * {sG, sGY, sD, sU, cvec2, Mm, dg, DC, DA, total} (10 entries). */
+int tfnas_debug_bwd_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, int want_wgrad, size_t* out10);
+
 /*
  * Per-kernel timing for bench.py's roofline: when enabled, every kernel launch is bracketed by
  * CUDA events on its stream.  tfnas_prof_collect synchronises those events and aggregates by

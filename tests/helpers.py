@@ -55,6 +55,34 @@ def make_problem(ic, oc, stride, H, N, mcs, seed=0, dtype=torch.float32, wscale=
     return P, x, gum, lats
 
 
+def relu_margin(P, x, ic, stride, act, active):
+    """Smallest |pre-activation| feeding a ReLU (fp64).  Two correct fp32 implementations may disagree on the
+    gate of an element that sits within rounding of 0, which perturbs BN-backward sums visibly on tiny
+    problems; parity tests pick seeds whose margin is comfortably above fp32 rounding."""
+    if act != 'relu':
+        return 1.0
+    from oracle import fused_math as fm
+    Pd = {k: v.double() for k, v in P.items()}
+    cands = [fm.cand_weights(Pd, 'b.', i) for i in range(8)]
+    _o, S = fm.forward(x.double(), cands, list(active), stride, act, torch.full((8,), 0.125, dtype=torch.float64))
+    m = 1.0
+    for i in active:
+        c = S['c'][i]
+        u = torch.einsum('ck,nkhw->nchw', cands[i]['w1'], x.double())
+        uh = (u - c['mu1'][None, :, None, None]) * c['r1'][None, :, None, None]
+        dh = (c['d'] - c['mu2'][None, :, None, None]) * c['r2'][None, :, None, None]
+        m = min(m, float(uh.abs().min()), float(dh.abs().min()))
+    return m
+
+
+def make_conditioned_problem(ic, oc, stride, H, N, mcs, seed, act, active=range(8), W=None, margin=5e-6):
+    for t in range(50):
+        P, x, gum, lats = make_problem(ic, oc, stride, H, N, mcs, seed + 1000 * t, W=W)
+        if relu_margin(P, x, ic, stride, act, active) > margin:
+            return P, x, gum, lats
+    raise RuntimeError('no well-conditioned seed found')
+
+
 def default_mcs(ic, ragged=False):
     m = [3 * ic, 6 * ic, 3 * ic, 6 * ic, 3 * ic, 6 * ic, 3 * ic, 6 * ic]
     if ragged:
@@ -141,6 +169,16 @@ def raw_call(P, x, gum, lats, ic, oc, stride, act, mcs, mask, T=5.0, G=None, dla
         _lib.check(lib.tfnas_mixedop_bwd(ctypes.byref(d), mask, vp(xd), arr, vp(Gd), vp(dl), T, vp(saved), nsaved,
                                          vp(dx), vp(dal), garr if want_wgrad else None, vp(ws), nws, st))
         torch.cuda.synchronize()
+        boffs = (ctypes.c_size_t * 10)()
+        _lib.check(lib.tfnas_debug_bwd_layout(ctypes.byref(d), mask, 1 if want_wgrad else 0, boffs))
+
+        def wreg(idx, n, dt=torch.float32):
+            nb = n * (8 if dt == torch.float64 else 4)
+            return ws[boffs[idx]:boffs[idx] + nb].view(dt).cpu()
+        r['sD'] = wreg(2, 2 * MC, torch.float64).view(MC, 2)
+        r['sU'] = wreg(3, 2 * MC, torch.float64).view(MC, 2)
+        r['DC'] = wreg(7, N * MC * Ho * Wo).view(N, MC, Ho, Wo)
+        r['DA'] = wreg(8, N * MC * H * W).view(N, MC, H, W)
         r['dx'] = dx.cpu() if need_dx else None
         r['dalpha'] = dal.cpu()
         r['wgrads'] = {k: v.cpu() for k, v in gd.items()}

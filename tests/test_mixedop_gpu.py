@@ -52,7 +52,7 @@ CASES = [
 @pytest.mark.parametrize('ic,oc,s,act,size,N,ragged,W', CASES)
 def test_alpha_mode_matches_oracle(ic, oc, s, act, size, N, ragged, W):
     mcs = H.default_mcs(ic, ragged)
-    P, x, gum, lats = H.make_problem(ic, oc, s, size, N, mcs, seed=ic + size, W=W)
+    P, x, gum, lats = H.make_conditioned_problem(ic, oc, s, size, N, mcs, ic + size, act, W=W)
     # LUT rows that share a key (e3/e6 non-SE) must carry both widths
     lut = _fake_lut(ic, oc, s, act, x.shape[-1], mcs, lats)
     lat_list = [lut[lut_key(x.shape[-1], ic, sm * ic, oc, k, s, act)][mcs[i]] for i, (k, _e, sm) in enumerate(CAND_SPEC)]
@@ -75,7 +75,7 @@ def test_alpha_mode_matches_oracle(ic, oc, s, act, size, N, ragged, W):
 @pytest.mark.parametrize('idx', [0, 3, 5, 6])
 def test_sampled_mode_and_weight_grads(ic, oc, s, act, size, N, ragged, W, idx):
     mcs = H.default_mcs(ic, ragged)
-    P, x, gum, lats = H.make_problem(ic, oc, s, size, N, mcs, seed=3 * ic + size, W=W)
+    P, x, gum, lats = H.make_conditioned_problem(ic, oc, s, size, N, mcs, 3 * ic + size, act, active=[idx], W=W)
     op = _build(P, ic, oc, s, act, mcs, {})
     xg = x.cuda().requires_grad_(True)
     with injected(NoisePlan(indices=[idx])):

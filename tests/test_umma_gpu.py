@@ -32,7 +32,8 @@ def run_selftest(M, N, K, variant=0, seed=0):
 @pytest.mark.parametrize('M,N,K', [(128, 128, 32), (128, 16, 8), (256, 96, 64), (1000, 112, 200), (130, 256, 576), (49, 24, 1152)])
 def test_split_tf32_gemm_is_fp32_accurate(M, N, K):
     C, ref = run_selftest(M, N, K)
-    assert H.rel_l2(C, ref) < 2e-6
+    # fp32 accumulation over K terms: ~sqrt(K) * 2^-24, plus the dropped lo*lo term (2^-22)
+    assert H.rel_l2(C, ref) < 1e-6 + 2e-7 * K ** 0.5
 
 
 def test_single_tf32_is_not_enough():

@@ -37,7 +37,7 @@ CandArray = CandPtrs * MAX_OPS
 EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
-           'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout',
+           'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout', 'tfnas_debug_bwd_layout',
            'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest']
 
 _lib = None
@@ -77,6 +77,8 @@ def load():
                                          vp, sz, vp]
     lib.tfnas_debug_saved_layout.restype = i32
     lib.tfnas_debug_saved_layout.argtypes = [dp, u32, ctypes.POINTER(sz)]
+    lib.tfnas_debug_bwd_layout.restype = i32
+    lib.tfnas_debug_bwd_layout.argtypes = [dp, u32, i32, ctypes.POINTER(sz)]
     lib.tfnas_prof_enable.restype = i32
     lib.tfnas_prof_enable.argtypes = [i32]
     lib.tfnas_prof_collect.restype = i32

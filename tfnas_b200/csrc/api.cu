@@ -123,7 +123,9 @@ static size_t fwd_scratch(const Plan& P, char* base, FwdScratch& S) {
   size_t nd = (size_t)P.ic + (size_t)P.ic * P.ic + 2 * (size_t)P.MC + 2 * (size_t)P.na * P.oc;
   size_t acc = take(nd * sizeof(double));
   size_t coef = take((size_t)(P.na * P.oc + P.oc) * 4);
+  size_t umprep = take(umma_fwd_prep_bytes(P));
   if (base) {
+    S.umprep = (float*)(base + umprep);
     S.xsum = (double*)(base + acc);
     S.xcov = S.xsum + P.ic;
     S.st2 = S.xcov + (size_t)P.ic * P.ic;
@@ -150,7 +152,9 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
   size_t Smat = want_wgrad ? take((size_t)P.MC * P.ic * 4) : 0;
   size_t DC = take((size_t)P.N * P.MC * P.HWo * 4);
   size_t DA = take((size_t)P.N * P.MC * P.HW * 4);
+  size_t umprep = take(umma_bwd_prep_bytes(P));
   if (base) {
+    S.umprep = (float*)(base + umprep);
     S.sG = (double*)(base + acc);
     S.sGY = S.sG + P.oc;
     S.sD = S.sGY + (size_t)P.na * P.oc;
@@ -307,6 +311,21 @@ int tfnas_debug_saved_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, size
   saved_layout(P, L);
   const size_t v[13] = {L.xmom, L.bn1, L.bn2, L.bn3, L.mixw, L.lat, L.sep, L.set, L.seg, L.UH, L.D, L.Z, L.total};
   for (int i = 0; i < 13; ++i) out13[i] = v[i];
+  return TFNAS_OK;
+}
+
+/* debug/test helper: byte offsets of backward-workspace regions {sG, sGY, sD, sU, cvec2, Mm, dg, DC, DA, total} */
+int tfnas_debug_bwd_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, int want_wgrad, size_t* out10) {
+  Plan P;
+  int rc = build_plan(d, cand_mask, nullptr, P);
+  if (rc != TFNAS_OK) return rc;
+  BwdScratch S;
+  char* base = (char*)4096;
+  size_t total = bwd_scratch(P, want_wgrad, base, S);
+  const char* v[9] = {(char*)S.sG, (char*)S.sGY, (char*)S.sD, (char*)S.sU, (char*)S.cvec2, (char*)S.Mm, (char*)S.dg,
+                      (char*)S.DC, (char*)S.DA};
+  for (int i = 0; i < 9; ++i) out10[i] = (size_t)(v[i] - base);
+  out10[9] = total;
   return TFNAS_OK;
 }
 

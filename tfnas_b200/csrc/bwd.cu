@@ -858,7 +858,9 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     return;
   }
   // B2
-  {
+  if (umma_enabled()) {
+    umma_dc(P, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, S.umprep, st);
+  } else {
     int maxmc = 0;
     for (int s = 0; s < P.na; ++s) maxmc = max(maxmc, P.c[s].mc);
     if (maxmc > 64) launch_dc<16>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
@@ -922,7 +924,14 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   }
   // B3b
   OcTile Tx = oc_tile(ic, 24);
-  {
+  if (umma_enabled()) {
+    size_t off = 0;     // the dx weights follow the dc weights in the prep buffer
+    for (int s = 0; s < P.na; ++s) {
+      int nN = cdiv(P.c[s].mc, 256), Nc = cdiv(cdiv(P.c[s].mc, nN), 16) * 16;
+      off += (size_t)nN * cdiv(oc, 32) * 2 * Nc * 32;
+    }
+    umma_dx(P, S.DA, UH, bn1, dx, S.sU, S.umprep + off, st);
+  } else {
     int tiles = cdiv(P.P, PW_TPX);
     int total_chunks = 0;
     for (int s = 0; s < P.na; ++s) total_chunks += cdiv(P.c[s].mc, PW_KC);

@@ -657,7 +657,9 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
       k_bn1<<<cdiv(P.MC * 32, NT), NT, 0, st>>>(P, xmom, bn1); }
   }
   // F1a
-  {
+  if (umma_enabled()) {
+    umma_expand(P, x, bn1, UH, S.umprep, st);
+  } else {
     int maxmc = 0;
     for (int s = 0; s < P.na; ++s) maxmc = max(maxmc, P.c[s].mc);
     ProfScope ps("expand", xbytes + 4.0 * P.P * P.MC + 4.0 * P.MC * ic, 2.0 * P.P * (double)P.MC * ic, st);
@@ -702,7 +704,15 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
       } }
   }
   // F3
-  {
+  if (umma_enabled()) {
+    // the project weights follow the expand weights in the prep buffer
+    size_t off = 0;
+    for (int s = 0; s < P.na; ++s) {
+      int nN = cdiv(P.c[s].mc, 256), Nc = cdiv(cdiv(P.c[s].mc, nN), 16) * 16;
+      off += (size_t)nN * cdiv(P.ic, 32) * 2 * Nc * 32;
+    }
+    umma_project(P, D, bn2, seg, Zb, S.st3, S.umprep + off, st);
+  } else {
     OcTile T3 = oc_tile(P.oc, 16);
     switch (T3.TC) {
       case 4: launch_project<4>(P, T3, D, bn2, seg, Zb, S.st3, st); break;

@@ -25,6 +25,7 @@ struct FwdScratch {   // all device pointers into the workspace
   double* st2;    // [2*MC]
   double* st3;    // [2*na*oc]
   float* coef;    // [na*oc + oc]
+  float* umprep;  // pre-split / pre-swizzled weights for the tcgen05 GEMMs (expand, project)
 };
 
 struct BwdScratch {
@@ -43,9 +44,22 @@ struct BwdScratch {
   float* sede;    // [N*MCse]  SE: dL/de (pre-sigmoid)     (weight-grad mode)
   float* sedt;    // [N*SEH]   SE: dL/dt (pre-act hidden)  (weight-grad mode)
   float* Smat;    // [MC*ic]   sum_p du-hat x^T            (weight-grad mode)
+  float* umprep;  // pre-split / pre-swizzled weights for the tcgen05 GEMMs (dc, dx)
 };
 
 int sm_count();
+
+// tcgen05 GEMM path (umma_pw.cu); TFNAS_GEMM=simt selects the CUDA-core kernels instead (A/B debugging only)
+int umma_enabled();
+size_t umma_fwd_prep_bytes(const Plan& P);
+size_t umma_bwd_prep_bytes(const Plan& P);
+void umma_expand(const Plan& P, const float* x, const float* bn1, float* UH, float* prep_buf, cudaStream_t st);
+void umma_project(const Plan& P, const float* D, const float* bn2, const float* seg, float* Zb, double* st3,
+                  float* prep_buf, cudaStream_t st);
+void umma_dc(const Plan& P, const float* G, const float* Zb, const float* bn3, const float4* dzc, const float* D,
+             const float* bn2, float* DC, float* dg, double* sD, float* prep_buf, cudaStream_t st);
+void umma_dx(const Plan& P, const float* DA, const float* UH, const float* bn1, float* dx, double* sU, float* prep_buf,
+             cudaStream_t st);
 
 void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
                     const float* lat8, float T, int alpha_mode, float* out, float* out_lat,

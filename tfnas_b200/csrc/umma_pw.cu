@@ -1,0 +1,664 @@
+// tcgen05 versions of the four flattened-pixel 1x1-conv GEMMs (expand, project, dc, dx).
+//
+//   Out[o][p] = sum_k W[o][k] * In[k][p],   p = flattened (n,h,w) pixel, 128 pixels per CTA (MMA M = 128)
+//
+// * In rows are produced by each kernel's PROLOGUE (BN / activation / SE gate / BN-backward applied on
+//   load), split into tf32 hi/lo and written by the CTA's 256 threads into the MN-major shared-memory
+//   operand (128B swizzle, 32B base).  Global loads of chunk c+1 are issued before chunk c is emitted.
+// * W is pre-split and pre-swizzled once per call by k_umma_prep_w into K-major 128B-swizzle blocks, and
+//   brought in per K chunk with ONE bulk (TMA) copy by one thread.
+// * Three kind::tf32 MMAs per K=8 step (hi*hi + lo*hi + hi*lo) accumulate in TMEM (fp32); two smem stages
+//   so the tensor core works on chunk c while the threads stage chunk c+1.
+// * EPILOGUE: each warp reads its TMEM lane quarter (thread = pixel, 16 channels per tcgen05.ld) and
+//   applies the kernel's epilogue (BN statistics, SE partial sums, coalesced per-channel stores).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "kernels.h"
+#include "pw.cuh"
+#include "umma.cuh"
+
+using namespace umma;
+
+#define UM_KC 32                 // K rows per chunk (one 128 B swizzle row of the weights)
+#define UM_STAGES 2
+
+// One GEMM's weight-side geometry for one candidate slot
+struct UmW {
+  const float* wp;   // prepped weights: [nN][nK][2][Nc*128 B]
+  int Nout;          // true output channels
+  int Nc;            // channels per N chunk (multiple of 16, <= 256)
+  int nN;            // number of N chunks
+  int nK;            // number of K chunks (of 32)
+};
+struct UmWAll { UmW s[TFNAS_MAX_OPS]; };
+
+static inline void um_tile(int Nout, int& Nc, int& nN) {
+  nN = cdiv(Nout, 256);
+  Nc = cdiv(cdiv(Nout, nN), 16) * 16;
+}
+
+// element (r, k) of the logical weight = src[r*ld_r + k*ld_k]; rows >= nrows / k >= K are zero
+__global__ void __launch_bounds__(256) k_umma_prep_w(const float* __restrict__ src, int ld_r, int ld_k, int nrows, int K,
+                                                      int Nc, int nN, int nK, float* __restrict__ dst) {
+  const int kc = blockIdx.x, nc = blockIdx.y;
+  char* base = (char*)dst + ((size_t)nc * nK + kc) * 2 * Nc * 128;
+  for (int i = threadIdx.x; i < Nc * UM_KC; i += blockDim.x) {
+    int r, kk;
+    if (ld_k == 1) { r = i / UM_KC; kk = i - r * UM_KC; }      // coalesce along k
+    else { kk = i / Nc; r = i - kk * Nc; }                      // coalesce along rows
+    const int gr = nc * Nc + r, k = kc * UM_KC + kk;
+    float x = (gr < nrows && k < K) ? src[(size_t)gr * ld_r + (size_t)k * ld_k] : 0.f;
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    *(float*)(base + k_elem_off(r, kk)) = hi;
+    *(float*)(base + (size_t)Nc * 128 + k_elem_off(r, kk)) = lo;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// shared skeleton
+// -------------------------------------------------------------------------------------------------
+struct UmSmem {
+  unsigned char* a_hi[UM_STAGES];
+  unsigned char* a_lo[UM_STAGES];
+  unsigned char* b[UM_STAGES];      // hi block followed by lo block
+  uint64_t* bar_b;                  // [UM_STAGES]
+  uint64_t* bar_mma;                // [UM_STAGES]
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ void um_carve(unsigned char* raw, int Nc, UmSmem& S) {
+  unsigned char* sm = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  const size_t stage = 32768 + (size_t)2 * Nc * 128;     // multiple of 1024 because Nc % 16 == 0 -> 2*Nc*128 % 4096 == 0
+#pragma unroll
+  for (int s = 0; s < UM_STAGES; ++s) {
+    S.a_hi[s] = sm + s * stage;
+    S.a_lo[s] = S.a_hi[s] + 16384;
+    S.b[s] = S.a_hi[s] + 32768;
+  }
+  S.bar_b = (uint64_t*)(sm + UM_STAGES * stage);
+  S.bar_mma = S.bar_b + UM_STAGES;
+  S.tmem_slot = (uint32_t*)(S.bar_mma + UM_STAGES);
+}
+static inline size_t um_smem_bytes(int Nc) { return 1024 + UM_STAGES * (32768 + (size_t)2 * Nc * 128) + 64; }
+
+// write 4 pixels (one 16 B chunk) of row kk, split into hi / lo
+__device__ __forceinline__ void um_put(unsigned char* a_hi, unsigned char* a_lo, int lane, int kk, const float (&v)[4]) {
+  float h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
+  const uint32_t off = mn_chunk_off(lane * 4, kk, UM_KC * 128);
+  *(float4*)(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+  *(float4*)(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+// issue the 12 MMAs of one K chunk (one thread)
+__device__ __forceinline__ void um_issue(const UmSmem& S, int s, int Nc, uint32_t tmem, uint32_t idesc, bool first) {
+  const uint32_t ah = smem_u32(S.a_hi[s]), al = smem_u32(S.a_lo[s]);
+  const uint32_t bh = smem_u32(S.b[s]), bl = bh + Nc * 128;
+#pragma unroll
+  for (int q = 0; q < UM_KC / 8; ++q) {
+    const uint64_t dah = smem_desc(ah + q * 1024, UM_KC * 128, 512, SWIZZLE_128B_BASE32B);
+    const uint64_t dal = smem_desc(al + q * 1024, UM_KC * 128, 512, SWIZZLE_128B_BASE32B);
+    const uint64_t dbh = smem_desc(bh + q * 32, 16, 1024, SWIZZLE_128B);
+    const uint64_t dbl = smem_desc(bl + q * 32, 16, 1024, SWIZZLE_128B);
+    mma_tf32(tmem, dah, dbh, idesc, (first && q == 0) ? 0u : 1u);
+    mma_tf32(tmem, dal, dbh, idesc, 1u);
+    mma_tf32(tmem, dah, dbl, idesc, 1u);
+  }
+}
+
+// Generic main loop.  F supplies:
+//   int   nchunks()                                   K chunks this CTA walks
+//   void  load(int c, float4 (&ra)[4], float4 (&rb)[4])     global loads of chunk c (rows warp+8i, 4 px / lane)
+//   void  emit(int c, ra, rb, a_hi, a_lo)                   prologue math + hi/lo split + st.shared
+//   const void* wsrc(int c)                                 prepped weight block of chunk c (2*Nc*128 bytes)
+template <class F>
+__device__ __forceinline__ void um_mainloop(F& f, const UmSmem& S, int Nc, uint32_t tmem, uint32_t idesc) {
+  const int tid = threadIdx.x;
+  const int n = f.nchunks();
+  float4 ra[4], rb[4];
+  if (n > 0) f.load(0, ra, rb);
+  uint32_t ph_b[UM_STAGES] = {0, 0}, ph_m[UM_STAGES] = {0, 0};
+  for (int c = 0; c < n; ++c) {
+    const int s = c & (UM_STAGES - 1);
+    if (c >= UM_STAGES) {           // the MMAs that read this stage two chunks ago must have retired
+      mbar_wait(&S.bar_mma[s], ph_m[s]);
+      ph_m[s] ^= 1;
+      tc_fence_after();
+    }
+    if (tid == 0) {
+      mbar_expect_tx(&S.bar_b[s], 2 * Nc * 128);
+      bulk_g2s(S.b[s], f.wsrc(c), 2 * Nc * 128, &S.bar_b[s]);
+    }
+    f.emit(c, ra, rb, S.a_hi[s], S.a_lo[s]);
+    if (c + 1 < n) f.load(c + 1, ra, rb);      // in flight while the tensor core works on chunk c
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(&S.bar_b[s], ph_b[s]);
+      tc_fence_after();
+      um_issue(S, s, Nc, tmem, idesc, c == 0);
+      mma_commit(&S.bar_mma[s]);
+    }
+    ph_b[s] ^= 1;
+  }
+  // drain: wait for the last (up to two) commits
+  for (int c = max(0, n - UM_STAGES); c < n; ++c) {
+    const int s = c & (UM_STAGES - 1);
+    mbar_wait(&S.bar_mma[s], ph_m[s]);
+    ph_m[s] ^= 1;
+  }
+  tc_fence_after();
+}
+
+__device__ __forceinline__ uint32_t um_setup(const UmSmem& S, int Nc) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < UM_STAGES; ++s) { mbar_init(&S.bar_b[s], 1); mbar_init(&S.bar_mma[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(S.tmem_slot, tmem_cols(Nc));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *S.tmem_slot;
+}
+__device__ __forceinline__ void um_teardown(uint32_t tmem, int Nc) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem, tmem_cols(Nc));
+}
+
+// per-thread pixel of the epilogue: warp w -> lane quarter (w & 3), thread = lane
+struct EpiPx { int p, n, hw; bool v; };
+__device__ __forceinline__ EpiPx epi_px(int tile0, int total, int HW) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  EpiPx e;
+  e.p = tile0 + (warp & 3) * 32 + lane;
+  e.v = e.p < total;
+  e.n = e.v ? e.p / HW : 0;
+  e.hw = e.v ? e.p - e.n * HW : 0;
+  return e;
+}
+// column range of this warp: warps w and w+4 split the Nc columns in halves (multiples of 16)
+__device__ __forceinline__ void epi_cols(int Nc, int& c_lo, int& c_hi) {
+  const int half = (threadIdx.x >> 5) >> 2;
+  const int h = (Nc / 2 + 15) / 16 * 16;
+  c_lo = half * h;
+  c_hi = min(Nc, (half + 1) * h);
+}
+__device__ __forceinline__ uint32_t epi_taddr(uint32_t tmem, int col) {
+  return tmem + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16) + (uint32_t)col;
+}
+
+// load 4 consecutive pixels of plane `ch` as float4 (vector when aligned, else masked scalars)
+__device__ __forceinline__ float4 ld4(const float* __restrict__ T, const Px4& px, int C, int ch, int HW) {
+  float d[4];
+  load4(d, T, px, C, ch, HW);
+  return make_float4(d[0], d[1], d[2], d[3]);
+}
+
+// -------------------------------------------------------------------------------------------------
+// F1a: expand
+// -------------------------------------------------------------------------------------------------
+struct ExpandF {
+  const Plan& P; const UmW& W; const float* x; Px4 px; int nc; int lane, warp;
+  __device__ int nchunks() const { return W.nK; }
+  __device__ void load(int c, float4 (&ra)[4], float4 (&rb)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = c * UM_KC + warp + i * 8;
+      ra[i] = k < P.ic ? ld4(x, px, P.ic, k, P.HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ void emit(int c, const float4 (&ra)[4], const float4 (&rb)[4], unsigned char* ah, unsigned char* al) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float v[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+      um_put(ah, al, lane, warp + i * 8, v);
+    }
+  }
+  __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
+};
+
+__global__ void __launch_bounds__(NT) k_um_expand(Plan P, UmWAll WA, const float* __restrict__ x,
+                                                   const float* __restrict__ bn1, float* __restrict__ UH) {
+  extern __shared__ __align__(1024) unsigned char um_raw[];
+  const int slot = blockIdx.z, nc = blockIdx.y;
+  const UmW& W = WA.s[slot];
+  if (nc >= W.nN) return;
+  const Cand& cd = P.c[slot];
+  UmSmem S;
+  um_carve(um_raw, W.Nc, S);
+  const uint32_t tmem = um_setup(S, W.Nc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ExpandF f{P, W, x, Px4(), nc, lane, warp};
+  px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.P, P.HW);
+  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
+  const EpiPx e = epi_px(blockIdx.x * 128, P.P, P.HW);
+  int c_lo, c_hi;
+  epi_cols(W.Nc, c_lo, c_hi);
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    float v[16];
+    tmem_ld16(epi_taddr(tmem, c0), v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = nc * W.Nc + c0 + j;
+      if (c < cd.mc && e.v) {
+        const int cst = cd.coff + c;
+        UH[((size_t)e.n * P.MC + cst) * P.HW + e.hw] = (v[j] - bn1[cst]) * bn1[P.MC + cst];
+      }
+    }
+  }
+  um_teardown(tmem, W.Nc);
+}
+
+// -------------------------------------------------------------------------------------------------
+// F3: project
+// -------------------------------------------------------------------------------------------------
+template <int ACT>
+struct ProjectF {
+  const Plan& P; const UmW& W; const Cand& cd; const float* D; const float* bn2; const float* seg; Px4 px; int nc; int lane, warp;
+  __device__ int nchunks() const { return W.nK; }
+  __device__ void load(int c, float4 (&ra)[4], float4 (&rb)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = c * UM_KC + warp + i * 8;
+      ra[i] = k < cd.mc ? ld4(D, px, P.MC, cd.coff + k, P.HWo) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ void emit(int c, const float4 (&ra)[4], const float4 (&rb)[4], unsigned char* ah, unsigned char* al) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = warp + i * 8, k = c * UM_KC + kk;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k < cd.mc) {
+        const int cst = cd.coff + k;
+        const float mu = bn2[cst], r = bn2[P.MC + cst];
+        const float d[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float b = act_f<ACT>((d[e] - mu) * r);
+          if (cd.se > 0) b *= seg[(size_t)px.n[e] * P.MCse + cd.soff + k];
+          v[e] = px.v[e] ? b : 0.f;
+        }
+      }
+      um_put(ah, al, lane, kk, v);
+    }
+  }
+  __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_um_project(Plan P, UmWAll WA, const float* __restrict__ D,
+                                                    const float* __restrict__ bn2, const float* __restrict__ seg,
+                                                    float* __restrict__ Zb, double* __restrict__ st3) {
+  extern __shared__ __align__(1024) unsigned char um_raw[];
+  const int slot = blockIdx.z, nc = blockIdx.y;
+  const UmW& W = WA.s[slot];
+  if (nc >= W.nN) return;
+  const Cand& cd = P.c[slot];
+  UmSmem S;
+  um_carve(um_raw, W.Nc, S);
+  const uint32_t tmem = um_setup(S, W.Nc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ProjectF<ACT> f{P, W, cd, D, bn2, seg, Px4(), nc, lane, warp};
+  px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.Q, P.HWo);
+  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
+  const EpiPx e = epi_px(blockIdx.x * 128, P.Q, P.HWo);
+  const int oc = P.oc;
+  int c_lo, c_hi;
+  epi_cols(W.Nc, c_lo, c_hi);
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    float v[16];
+    tmem_ld16(epi_taddr(tmem, c0), v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int o = nc * W.Nc + c0 + j;          // warp-uniform
+      if (o < oc) {
+        const float z = e.v ? v[j] : 0.f;
+        if (e.v) Zb[((size_t)e.n * P.na * oc + slot * oc + o) * P.HWo + e.hw] = z;
+        const float s1 = warp_sum(z), s2 = warp_sum(z * z);
+        if (lane == 0) {
+          atomicAdd(&st3[2 * (slot * oc + o)], (double)s1);
+          atomicAdd(&st3[2 * (slot * oc + o) + 1], (double)s2);
+        }
+      }
+    }
+  }
+  um_teardown(tmem, W.Nc);
+}
+
+// -------------------------------------------------------------------------------------------------
+// B2: dc = W3^T dz
+// -------------------------------------------------------------------------------------------------
+struct DcF {
+  const Plan& P; const UmW& W; const float* G; const float* Zb; const float* bn3; const float4* dzc; Px4 px; int nc, slot; int lane, warp;
+  __device__ int nchunks() const { return W.nK; }
+  __device__ void load(int c, float4 (&ra)[4], float4 (&rb)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = c * UM_KC + warp + i * 8;
+      if (o < P.oc) {
+        ra[i] = ld4(G, px, P.oc, o, P.HWo);
+        rb[i] = ld4(Zb, px, P.na * P.oc, slot * P.oc + o, P.HWo);
+      } else {
+        ra[i] = rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  __device__ void emit(int c, const float4 (&ra)[4], const float4 (&rb)[4], unsigned char* ah, unsigned char* al) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = warp + i * 8, o = c * UM_KC + kk;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (o < P.oc) {
+        const float4 cf = dzc[slot * P.oc + o];
+        const float mu3 = bn3[slot * P.oc + o], r3 = bn3[P.na * P.oc + slot * P.oc + o];
+        const float g[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, z[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? cf.x * (g[e] - cf.y - (z[e] - mu3) * r3 * cf.z) : 0.f;
+      }
+      um_put(ah, al, lane, kk, v);
+    }
+  }
+  __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_um_dc(Plan P, UmWAll WA, const float* __restrict__ G, const float* __restrict__ Zb,
+                                               const float* __restrict__ bn3, const float4* __restrict__ dzc,
+                                               const float* __restrict__ D, const float* __restrict__ bn2,
+                                               float* __restrict__ DC, float* __restrict__ dg, double* __restrict__ sD) {
+  extern __shared__ __align__(1024) unsigned char um_raw[];
+  const int slot = blockIdx.z, nc = blockIdx.y;
+  const UmW& W = WA.s[slot];
+  if (nc >= W.nN) return;
+  const Cand& cd = P.c[slot];
+  UmSmem S;
+  um_carve(um_raw, W.Nc, S);
+  const uint32_t tmem = um_setup(S, W.Nc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  DcF f{P, W, G, Zb, bn3, dzc, Px4(), nc, slot, lane, warp};
+  px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.Q, P.HWo);
+  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
+  const EpiPx e = epi_px(blockIdx.x * 128, P.Q, P.HWo);
+  const bool gated = cd.se > 0;
+  const int n_first = __shfl_sync(0xffffffffu, e.n, 0);
+  const bool one_img = __all_sync(0xffffffffu, (!e.v) || e.n == n_first);
+  int c_lo, c_hi;
+  epi_cols(W.Nc, c_lo, c_hi);
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    float v[16];
+    tmem_ld16(epi_taddr(tmem, c0), v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = nc * W.Nc + c0 + j;      // warp-uniform
+      if (c < cd.mc) {
+        const int cst = cd.coff + c;
+        const size_t a = ((size_t)e.n * P.MC + cst) * P.HWo + e.hw;
+        const float d = e.v ? D[a] : 0.f;
+        const float dh = (d - bn2[cst]) * bn2[P.MC + cst];
+        if (gated) {
+          if (e.v) DC[a] = v[j];
+          float part = e.v ? v[j] * act_f<ACT>(dh) : 0.f;
+          if (one_img) {
+            part = warp_sum(part);
+            if (lane == 0) atomicAdd(&dg[(size_t)n_first * P.MCse + cd.soff + c], part);
+          } else if (e.v) {
+            atomicAdd(&dg[(size_t)e.n * P.MCse + cd.soff + c], part);
+          }
+        } else {
+          const float o = e.v ? v[j] * act_df<ACT>(dh) : 0.f;
+          if (e.v) DC[a] = o;
+          const float s1 = warp_sum(o), s2 = warp_sum(o * dh);
+          if (lane == 0) {
+            atomicAdd(&sD[2 * cst], (double)s1);
+            atomicAdd(&sD[2 * cst + 1], (double)s2);
+          }
+        }
+      }
+    }
+  }
+  um_teardown(tmem, W.Nc);
+}
+
+// -------------------------------------------------------------------------------------------------
+// B3b: dx_main = sum_i W1_i^T (r1 * du-hat), K = stacked mid channels (per-candidate chunks of 32)
+// -------------------------------------------------------------------------------------------------
+struct DxChunks {            // chunk c of the stacked K axis -> (slot, first local channel)
+  int total;
+  int first[TFNAS_MAX_OPS + 1];   // first chunk index of each slot
+};
+
+template <int ACT>
+struct DxF {
+  const Plan& P; const UmW& W; const DxChunks& CH; const float* DA; const float* UH; const float* bn1; double* sU; Px4 px;
+  int ch0, ch1; int lane, warp;
+  __device__ int nchunks() const { return ch1 - ch0; }
+  __device__ void locate(int c, int& slot, int& k0) const {
+    const int g = ch0 + c;
+    slot = 0;
+    while (slot + 1 < P.na && g >= CH.first[slot + 1]) ++slot;
+    k0 = (g - CH.first[slot]) * UM_KC;
+  }
+  __device__ void load(int c, float4 (&ra)[4], float4 (&rb)[4]) const {
+    int slot, k0;
+    locate(c, slot, k0);
+    const Cand& cd = P.c[slot];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + warp + i * 8;
+      if (k < cd.mc) {
+        ra[i] = ld4(DA, px, P.MC, cd.coff + k, P.HW);
+        rb[i] = ld4(UH, px, P.MC, cd.coff + k, P.HW);
+      } else {
+        ra[i] = rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  __device__ void emit(int c, const float4 (&ra)[4], const float4 (&rb)[4], unsigned char* ah, unsigned char* al) const {
+    int slot, k0;
+    locate(c, slot, k0);
+    const Cand& cd = P.c[slot];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = warp + i * 8, k = k0 + kk;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k < cd.mc) {     // warp-uniform
+        const int cst = cd.coff + k;
+        const float r1 = bn1[P.MC + cst];
+        const float da[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, uh[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float du = px.v[e] ? da[e] * act_df<ACT>(uh[e]) : 0.f;
+          s1 += du;
+          s2 += du * uh[e];
+          v[e] = du * r1;
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+          atomicAdd(&sU[2 * cst], (double)s1);
+          atomicAdd(&sU[2 * cst + 1], (double)s2);
+        }
+      }
+      um_put(ah, al, lane, kk, v);
+    }
+  }
+  __device__ const void* wsrc(int c) const { return (const char*)W.wp + (size_t)(ch0 + c) * 2 * W.Nc * 128; }
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_um_dx(Plan P, UmW W, DxChunks CH, int ksplit, const float* __restrict__ DA,
+                                               const float* __restrict__ UH, const float* __restrict__ bn1,
+                                               float* __restrict__ dx, double* __restrict__ sU) {
+  extern __shared__ __align__(1024) unsigned char um_raw[];
+  UmSmem S;
+  um_carve(um_raw, W.Nc, S);
+  const uint32_t tmem = um_setup(S, W.Nc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ch0 = (int)((long long)CH.total * blockIdx.y / ksplit), ch1 = (int)((long long)CH.total * (blockIdx.y + 1) / ksplit);
+  DxF<ACT> f{P, W, CH, DA, UH, bn1, sU, Px4(), ch0, ch1, lane, warp};
+  px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.P, P.HW);
+  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
+  const EpiPx e = epi_px(blockIdx.x * 128, P.P, P.HW);
+  int c_lo, c_hi;
+  epi_cols(W.Nc, c_lo, c_hi);
+  if (ch1 > ch0) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+      float v[16];
+      tmem_ld16(epi_taddr(tmem, c0), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = c0 + j;
+        if (k < P.ic && e.v) {
+          float* q = dx + ((size_t)e.n * P.ic + k) * P.HW + e.hw;
+          if (ksplit == 1) *q = v[j];
+          else atomicAdd(q, v[j]);
+        }
+      }
+    }
+  }
+  um_teardown(tmem, W.Nc);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+static int g_use_umma = -1;
+int umma_enabled() {
+  if (g_use_umma < 0) {
+    const char* e = getenv("TFNAS_GEMM");
+    g_use_umma = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return g_use_umma;
+}
+
+// bytes of prepped weights for a [Nout x K] GEMM
+static size_t um_prep_bytes(int Nout, int K) {
+  int Nc, nN;
+  um_tile(Nout, Nc, nN);
+  return (size_t)nN * cdiv(K, UM_KC) * 2 * Nc * 128;
+}
+size_t umma_fwd_prep_bytes(const Plan& P) {
+  size_t b = 0;
+  for (int s = 0; s < P.na; ++s) b += um_prep_bytes(P.c[s].mc, P.ic) + um_prep_bytes(P.oc, P.c[s].mc);
+  return b + 1024;
+}
+size_t umma_bwd_prep_bytes(const Plan& P) {
+  size_t b = 0;
+  int chunks = 0;
+  for (int s = 0; s < P.na; ++s) { b += um_prep_bytes(P.c[s].mc, P.oc); chunks += cdiv(P.c[s].mc, UM_KC); }
+  int Nc, nN;
+  um_tile(P.ic, Nc, nN);
+  return b + (size_t)chunks * 2 * Nc * 128 + 1024;
+}
+
+static void prep(const float* src, int ld_r, int ld_k, int nrows, int K, UmW& W, float*& cursor, cudaStream_t st) {
+  um_tile(nrows, W.Nc, W.nN);
+  W.nK = cdiv(K, UM_KC);
+  W.Nout = nrows;
+  W.wp = cursor;
+  { ProfScope ps("um_prep_w", 4.0 * nrows * K * 3, 0, st);
+    k_umma_prep_w<<<dim3(W.nK, W.nN), 256, 0, st>>>(src, ld_r, ld_k, nrows, K, W.Nc, W.nN, W.nK, cursor); }
+  cursor += (size_t)W.nN * W.nK * 2 * W.Nc * 32;
+}
+
+void umma_expand(const Plan& P, const float* x, const float* bn1, float* UH, float* prep_buf, cudaStream_t st) {
+  UmWAll WA;
+  float* cur = prep_buf;
+  int maxN = 0, maxNc = 0;
+  for (int s = 0; s < P.na; ++s) {
+    prep(P.c[s].w1, P.ic, 1, P.c[s].mc, P.ic, WA.s[s], cur, st);
+    maxN = max(maxN, WA.s[s].nN);
+    maxNc = max(maxNc, WA.s[s].Nc);
+  }
+  size_t smem = um_smem_bytes(maxNc);
+  cudaFuncSetAttribute(k_um_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
+  k_um_expand<<<dim3(cdiv(P.P, 128), maxN, P.na), NT, smem, st>>>(P, WA, x, bn1, UH);
+}
+
+void umma_project(const Plan& P, const float* D, const float* bn2, const float* seg, float* Zb, double* st3,
+                  float* prep_buf, cudaStream_t st) {
+  UmWAll WA;
+  float* cur = prep_buf;
+  int maxN = 0, maxNc = 0;
+  for (int s = 0; s < P.na; ++s) {
+    prep(P.c[s].w3, P.c[s].mc, 1, P.oc, P.c[s].mc, WA.s[s], cur, st);
+    maxN = max(maxN, WA.s[s].nN);
+    maxNc = max(maxNc, WA.s[s].Nc);
+  }
+  size_t smem = um_smem_bytes(maxNc);
+  dim3 grid(cdiv(P.Q, 128), maxN, P.na);
+  ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
+               2.0 * P.Q * (double)P.MC * P.oc, st);
+  if (P.act == TFNAS_ACT_RELU) {
+    cudaFuncSetAttribute(k_um_project<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_um_project<TFNAS_ACT_RELU><<<grid, NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
+  } else {
+    cudaFuncSetAttribute(k_um_project<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_um_project<TFNAS_ACT_SWISH><<<grid, NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
+  }
+}
+
+void umma_dc(const Plan& P, const float* G, const float* Zb, const float* bn3, const float4* dzc, const float* D,
+             const float* bn2, float* DC, float* dg, double* sD, float* prep_buf, cudaStream_t st) {
+  UmWAll WA;
+  float* cur = prep_buf;
+  int maxN = 0, maxNc = 0;
+  for (int s = 0; s < P.na; ++s) {
+    // logical weight (row = mid channel c, k = out channel o) = W3[o][c]
+    prep(P.c[s].w3, 1, P.c[s].mc, P.c[s].mc, P.oc, WA.s[s], cur, st);
+    maxN = max(maxN, WA.s[s].nN);
+    maxNc = max(maxNc, WA.s[s].Nc);
+  }
+  size_t smem = um_smem_bytes(maxNc);
+  dim3 grid(cdiv(P.Q, 128), maxN, P.na);
+  ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
+               2.0 * P.Q * (double)P.MC * P.oc, st);
+  if (P.act == TFNAS_ACT_RELU) {
+    cudaFuncSetAttribute(k_um_dc<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_um_dc<TFNAS_ACT_RELU><<<grid, NT, smem, st>>>(P, WA, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
+  } else {
+    cudaFuncSetAttribute(k_um_dc<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_um_dc<TFNAS_ACT_SWISH><<<grid, NT, smem, st>>>(P, WA, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
+  }
+}
+
+void umma_dx(const Plan& P, const float* DA, const float* UH, const float* bn1, float* dx, double* sU, float* prep_buf,
+             cudaStream_t st) {
+  UmW W;
+  um_tile(P.ic, W.Nc, W.nN);    // ic <= 192 -> one N chunk
+  W.Nout = P.ic;
+  W.wp = prep_buf;
+  DxChunks CH;
+  CH.first[0] = 0;
+  float* cur = prep_buf;
+  for (int s = 0; s < P.na; ++s) {
+    // logical weight (row = input channel k', k = mid channel c) = W1[c][k'], chunks never straddle candidates
+    UmW Ws;
+    prep(P.c[s].w1, 1, P.ic, P.ic, P.c[s].mc, Ws, cur, st);
+    CH.first[s + 1] = CH.first[s] + Ws.nK;
+  }
+  CH.total = CH.first[P.na];
+  W.nK = CH.total;
+  const int tiles = cdiv(P.P, 128);
+  int ksplit = max(1, min(CH.total, cdiv(2 * sm_count(), tiles)));
+  if (ksplit > 1) cudaMemsetAsync(dx, 0, (size_t)P.P * P.ic * sizeof(float), st);
+  size_t smem = um_smem_bytes(W.Nc);
+  dim3 grid(tiles, ksplit);
+  ProfScope ps("dx", 4.0 * P.P * (2.0 * P.MC + P.ic) + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
+  if (P.act == TFNAS_ACT_RELU) {
+    cudaFuncSetAttribute(k_um_dx<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_um_dx<TFNAS_ACT_RELU><<<grid, NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
+  } else {
+    cudaFuncSetAttribute(k_um_dx<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_um_dx<TFNAS_ACT_SWISH><<<grid, NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
+  }
+}
