@@ -44,7 +44,7 @@ CASES = [
     (112, 192, 2, 'swish', 7, 3, True, None),
     (192, 320, 1, 'swish', 7, 2, False, None),
     (8, 8, 1, 'relu', 5, 1, True, 3),       # N=1, tiny odd plane
-    (8, 12, 2, 'relu', 112, 1, False, None),  # large plane: row-tiled depthwise, 1 channel per CTA
+    (8, 12, 2, 'swish', 112, 1, False, None),  # large plane: row-tiled depthwise, 1 channel per CTA
     (8, 8, 1, 'swish', 40, 2, True, None),    # mid plane: 2 channels per CTA
 ]
 

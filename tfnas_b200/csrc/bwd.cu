@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NT) k_dw_bwd(Plan P, DwWork Wk, DwCfg cfg, con
                                                 float* __restrict__ DA, DwGrads gw) {
   extern __shared__ __align__(16) float dds[];   // [CPB][IR][WP] (+16 slack)
   constexpr int pad = KS / 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.z;
+  const int tid = threadIdx.x, n = blockIdx.z;
   int e = 0;
   while (e + 1 < Wk.n && (int)blockIdx.y >= Wk.gstart[e + 1]) ++e;
   const Cand& cd = P.c[Wk.slot[e]];
@@ -311,19 +311,30 @@ __global__ void __launch_bounds__(NT) k_dw_bwd(Plan P, DwWork Wk, DwCfg cfg, con
   const double invQ = 1.0 / (double)P.Q;
   for (int i = tid; i < (CPB * IR * WP + 16) / 4; i += NT) ((float4*)dds)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  // stage dd = r2 (dd-hat - m1 - d-hat m2): one warp per (channel, output row)
-  for (int rho = warp; rho < nc * IR; rho += NT / 32) {
-    const int c = rho / IR, lr = rho - c * IR;
-    const int oy = row0 + lr;
-    if (oy < 0 || oy >= Ho) continue;
-    const int cst = cd.coff + cbase + c;
-    const float mu = bn2[cst], r = bn2[P.MC + cst];
-    const float m1 = (float)(sD[2 * cst] * invQ), m2 = (float)(sD[2 * cst + 1] * invQ);
-    const size_t a = (((size_t)n * P.MC + cst) * Ho + oy) * Wo;
-    float* dst = dds + ((size_t)c * IR + lr) * WP + pad;
-    for (int ox = lane; ox < Wo; ox += 32) {
-      const float dh = (D[a + ox] - mu) * r;
-      dst[ox] = r * (DC[a + ox] - m1 - dh * m2);
+  // stage dd = r2 (dd-hat - m1 - d-hat m2) for the output rows this tile touches.  The BN2-backward
+  // coefficients of the CTA's channels go to smem first: dd = ca*ddh + cb*d + cc.
+  __shared__ float coef[3][32];
+  if (tid < CPB) {
+    float ca = 0.f, cb = 0.f, cc = 0.f;
+    if (tid < nc) {
+      const int cst = cd.coff + cbase + tid;
+      const float mu = bn2[cst], r = bn2[P.MC + cst];
+      const float m1 = (float)(sD[2 * cst] * invQ), m2 = (float)(sD[2 * cst + 1] * invQ);
+      // r*(ddh - m1 - (d-mu)*r*m2) = r*ddh - r*r*m2*d + r*(mu*r*m2 - m1)
+      ca = r; cb = -r * r * m2; cc = r * (mu * r * m2 - m1);
+    }
+    coef[0][tid] = ca; coef[1][tid] = cb; coef[2][tid] = cc;
+  }
+  __syncthreads();
+  {
+    const int vo_lo = max(row0, 0), vo_hi = min(row0 + IR - 1, oy_hi);
+    if (vo_hi >= vo_lo) {
+      const size_t off = (((size_t)n * P.MC + cd.coff + cbase) * Ho + vo_lo) * Wo;
+      const float* dcp = DC + off;
+      const ptrdiff_t d_minus_dc = D - DC;      // both tensors share the indexing
+      // the functor receives the DC value; it fetches the matching D value itself (same address + delta)
+      stage_planes2(dds, dcp, d_minus_dc, (size_t)Ho * Wo, nc, vo_hi - vo_lo + 1, Wo, IR, WP, vo_lo - row0, pad,
+                    [&](float g, float d, int c) { return coef[0][c] * g + coef[1][c] * d + coef[2][c]; });
     }
   }
   __syncthreads();
@@ -341,8 +352,9 @@ __global__ void __launch_bounds__(NT) k_dw_bwd(Plan P, DwWork Wk, DwCfg cfg, con
     const size_t pbase = (((size_t)n * P.MC + cst) * H + r0) * W;
     const int gpr = (W + 3) >> 2;
     const int ngroups = (r1 - r0) * gpr;
+    const float inv_gpr = 1.f / (float)gpr;
     for (int g = jl; g < ngroups; g += TPC) {
-      const int rl = g / gpr, col0 = (g - rl * gpr) * 4;
+      const int rl = fast_div(g, gpr, inv_gpr), col0 = (g - rl * gpr) * 4;
       const int r = r0 + rl;
       float a[4] = {0.f, 0.f, 0.f, 0.f};
       if (WG) {

@@ -44,16 +44,16 @@ struct DwGrads { float* p[4]; };   // depthwise weight-grad pointers per DwWork 
 template <int ACT>
 __device__ __forceinline__ float act_f(float x) {
   if (ACT == TFNAS_ACT_RELU) return fmaxf(x, 0.f);
-  return x / (1.f + __expf(-x));
+  return __fdividef(x, 1.f + __expf(-x));
 }
 // derivative of the activation at pre-activation x
 template <int ACT>
 __device__ __forceinline__ float act_df(float x) {
   if (ACT == TFNAS_ACT_RELU) return x > 0.f ? 1.f : 0.f;
-  float s = 1.f / (1.f + __expf(-x));
+  float s = __fdividef(1.f, 1.f + __expf(-x));
   return s * (1.f + x * (1.f - s));
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -65,6 +65,23 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Sum 16 per-lane values across the 32 lanes with 16 shuffles (instead of 80): afterwards lane l holds the
+// total of v[l & 15] (lanes l and l+16 hold the same channel).
+__device__ __forceinline__ float warp_sum16(float (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? v[i] : v[i + w];
+      const float keep = up ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 // sum over aligned groups of `width` lanes (width power of two <= 32)
 __device__ __forceinline__ float group_sum(float v, int width) {
   for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -94,6 +111,92 @@ __device__ __forceinline__ void dw_row4(float (&o)[4], const float* ap, int WP, 
     for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] += wr[ky * KS + kx] * v[j * S + kx];
+  }
+}
+
+// a / b for 0 <= a < 2^22 via a float reciprocal (3-4 instructions instead of ~20)
+__device__ __forceinline__ int fast_div(int a, int b, float inv_b) {
+  int q = __float2int_rz(((float)a + 0.5f) * inv_b);
+  q -= (q * b > a);
+  return q;
+}
+
+// Stage `nch` channel planes (each `rows` x W floats, contiguous rows; consecutive channels `plane_stride`
+// floats apart) into a zero-haloed smem tile [c][IR][WP] at (row_off + r, pad + col), applying f(value, c).
+// When the planes are whole and contiguous (plane_stride == rows*W) the copy is one flat vectorised stream.
+template <class F>
+__device__ __forceinline__ void stage_planes(float* tile, const float* __restrict__ src, size_t plane_stride, int nch,
+                                             int rows, int W, int IR, int WP, int row_off, int pad, F f) {
+  const int tid = threadIdx.x;
+  const int hw = rows * W;
+  const float inv_w = 1.f / (float)W, inv_hw = 1.f / (float)hw;
+  const bool flat = plane_stride == (size_t)hw;
+  const bool vec = ((hw & 3) == 0) && ((plane_stride & 3) == 0) && ((((uintptr_t)src) & 15) == 0);
+  if (vec) {
+    const int nv = hw >> 2;
+    const int total = flat ? nch * nv : nv;
+    for (int c0 = 0; c0 < (flat ? 1 : nch); ++c0) {
+      for (int i = tid; i < total; i += NT) {
+        int c = c0, v = i;
+        if (flat) { c = fast_div(i, nv, 1.f / (float)nv); v = i - c * nv; }
+        const float4 t = *(const float4*)(src + (size_t)c * plane_stride + (size_t)v * 4);
+        int r = fast_div(v * 4, W, inv_w), col = v * 4 - r * W;
+        const float x[4] = {t.x, t.y, t.z, t.w};
+        float* base = tile + ((size_t)c * IR + row_off) * WP + pad;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          base[r * WP + col] = f(x[e], c);
+          if (++col == W) { col = 0; ++r; }
+        }
+      }
+    }
+  } else {
+    const int total = nch * hw;
+    for (int i = tid; i < total; i += NT) {
+      const int c = fast_div(i, hw, inv_hw), p = i - c * hw;
+      const int r = fast_div(p, W, inv_w), col = p - r * W;
+      tile[((size_t)c * IR + row_off + r) * WP + pad + col] = f(src[(size_t)c * plane_stride + p], c);
+    }
+  }
+}
+
+// Same as stage_planes with a second tensor that shares the indexing (src2 = src + delta): f(v1, v2, c).
+template <class F>
+__device__ __forceinline__ void stage_planes2(float* tile, const float* __restrict__ src, ptrdiff_t delta, size_t plane_stride,
+                                              int nch, int rows, int W, int IR, int WP, int row_off, int pad, F f) {
+  const int tid = threadIdx.x;
+  const int hw = rows * W;
+  const float inv_w = 1.f / (float)W, inv_hw = 1.f / (float)hw;
+  const bool flat = plane_stride == (size_t)hw;
+  const bool vec = ((hw & 3) == 0) && ((plane_stride & 3) == 0) && ((((uintptr_t)src) & 15) == 0) &&
+                   ((((uintptr_t)(src + delta)) & 15) == 0);
+  if (vec) {
+    const int nv = hw >> 2;
+    const int total = flat ? nch * nv : nv;
+    for (int c0 = 0; c0 < (flat ? 1 : nch); ++c0) {
+      for (int i = tid; i < total; i += NT) {
+        int c = c0, v = i;
+        if (flat) { c = fast_div(i, nv, 1.f / (float)nv); v = i - c * nv; }
+        const float* q = src + (size_t)c * plane_stride + (size_t)v * 4;
+        const float4 t = *(const float4*)q, u = *(const float4*)(q + delta);
+        int r = fast_div(v * 4, W, inv_w), col = v * 4 - r * W;
+        const float x[4] = {t.x, t.y, t.z, t.w}, y[4] = {u.x, u.y, u.z, u.w};
+        float* base = tile + ((size_t)c * IR + row_off) * WP + pad;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          base[r * WP + col] = f(x[e], y[e], c);
+          if (++col == W) { col = 0; ++r; }
+        }
+      }
+    }
+  } else {
+    const int total = nch * hw;
+    for (int i = tid; i < total; i += NT) {
+      const int c = fast_div(i, hw, inv_hw), p2 = i - c * hw;
+      const int r = fast_div(p2, W, inv_w), col = p2 - r * W;
+      const float* q = src + (size_t)c * plane_stride + p2;
+      tile[((size_t)c * IR + row_off + r) * WP + pad + col] = f(q[0], q[delta], c);
+    }
   }
 }
 

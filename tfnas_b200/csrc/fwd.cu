@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(NT) k_dw_fwd(Plan P, DwWork Wk, DwCfg cfg, con
                                                 float* __restrict__ D, double* __restrict__ st2) {
   extern __shared__ __align__(16) float as[];   // [CPB][IR][WP] (+16 slack)
   constexpr int pad = KS / 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.z;
+  const int tid = threadIdx.x, n = blockIdx.z;
   int e = 0;
   while (e + 1 < Wk.n && (int)blockIdx.y >= Wk.gstart[e + 1]) ++e;
   const Cand& cd = P.c[Wk.slot[e]];
@@ -294,24 +294,14 @@ __global__ void __launch_bounds__(NT) k_dw_fwd(Plan P, DwWork Wk, DwCfg cfg, con
   const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo;
   const int oy0 = blockIdx.x * cfg.R, oy1 = min(Ho, oy0 + cfg.R);
   const int r_lo = oy0 * S - pad;
-  // zero the tile (halo + slack), then stage act(UH) rows: one warp per (channel, row)
+  // zero the tile (halo + slack), then stage act(UH) for the rows this tile needs
   for (int i = tid; i < (CPB * IR * WP + 16) / 4; i += NT) ((float4*)as)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  for (int rho = warp; rho < nc * IR; rho += NT / 32) {
-    const int c = rho / IR, lr = rho - c * IR;
-    const int r = r_lo + lr;
-    if (r < 0 || r >= H) continue;
-    const float* src = UH + (((size_t)n * P.MC + cd.coff + cbase + c) * H + r) * W;
-    float* dst = as + ((size_t)c * IR + lr) * WP + pad;
-    if ((W & 3) == 0) {
-      for (int v = lane; v < (W >> 2); v += 32) {
-        float4 t = *(const float4*)(src + v * 4);
-        dst[v * 4] = act_f<ACT>(t.x); dst[v * 4 + 1] = act_f<ACT>(t.y);
-        dst[v * 4 + 2] = act_f<ACT>(t.z); dst[v * 4 + 3] = act_f<ACT>(t.w);
-      }
-    } else {
-      for (int col = lane; col < W; col += 32) dst[col] = act_f<ACT>(src[col]);
-    }
+  {
+    const int vr_lo = max(r_lo, 0), vr_hi = min((oy1 - 1) * S - pad + KS - 1, H - 1);
+    const float* src = UH + (((size_t)n * P.MC + cd.coff + cbase) * H + vr_lo) * W;
+    stage_planes(as, src, (size_t)H * W, nc, vr_hi - vr_lo + 1, W, IR, WP, vr_lo - r_lo, pad,
+                 [](float v, int) { return act_f<ACT>(v); });
   }
   __syncthreads();
   const int TPC = NT / CPB;
@@ -325,8 +315,9 @@ __global__ void __launch_bounds__(NT) k_dw_fwd(Plan P, DwWork Wk, DwCfg cfg, con
     float* dp = D + (((size_t)n * P.MC + cd.coff + cbase + cl) * Ho + oy0) * Wo;
     const int gpr = (Wo + 3) >> 2;                 // groups of 4 outputs per row
     const int ngroups = (oy1 - oy0) * gpr;
+    const float inv_gpr = 1.f / (float)gpr;
     for (int g = jl; g < ngroups; g += TPC) {
-      const int oyl = g / gpr, ox0 = (g - oyl * gpr) * 4;
+      const int oyl = fast_div(g, gpr, inv_gpr), ox0 = (g - oyl * gpr) * 4;
       float o[4];
       dw_row4<KS, S>(o, ab + (size_t)(oyl * S) * WP + ox0 * S, WP, wr);
       float* q = dp + oyl * Wo + ox0;

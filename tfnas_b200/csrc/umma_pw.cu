@@ -21,7 +21,7 @@
 using namespace umma;
 
 #define UM_KC 32                 // K rows per chunk (one 128 B swizzle row of the weights)
-#define UM_STAGES 2
+#define UM_STAGES 1              // one smem stage per CTA: 2-3 CTAs/SM overlap each other's load / MMA / epilogue phases
 
 // One GEMM's weight-side geometry for one candidate slot
 struct UmW {
@@ -120,7 +120,7 @@ __device__ __forceinline__ void um_mainloop(F& f, const UmSmem& S, int Nc, uint3
   const int n = f.nchunks();
   float4 ra[4], rb[4];
   if (n > 0) f.load(0, ra, rb);
-  uint32_t ph_b[UM_STAGES] = {0, 0}, ph_m[UM_STAGES] = {0, 0};
+  uint32_t ph_b[UM_STAGES] = {0}, ph_m[UM_STAGES] = {0};
   for (int c = 0; c < n; ++c) {
     const int s = c & (UM_STAGES - 1);
     if (c >= UM_STAGES) {           // the MMAs that read this stage two chunks ago must have retired
@@ -313,20 +313,20 @@ __global__ void __launch_bounds__(NT) k_um_project(Plan P, UmWAll WA, const floa
   int c_lo, c_hi;
   epi_cols(W.Nc, c_lo, c_hi);
   for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-    float v[16];
+    float v[16], q[16];
     tmem_ld16(epi_taddr(tmem, c0), v);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int o = nc * W.Nc + c0 + j;          // warp-uniform
-      if (o < oc) {
-        const float z = e.v ? v[j] : 0.f;
-        if (e.v) Zb[((size_t)e.n * P.na * oc + slot * oc + o) * P.HWo + e.hw] = z;
-        const float s1 = warp_sum(z), s2 = warp_sum(z * z);
-        if (lane == 0) {
-          atomicAdd(&st3[2 * (slot * oc + o)], (double)s1);
-          atomicAdd(&st3[2 * (slot * oc + o) + 1], (double)s2);
-        }
-      }
+      const int o = nc * W.Nc + c0 + j;
+      v[j] = (e.v && o < oc) ? v[j] : 0.f;
+      if (e.v && o < oc) Zb[((size_t)e.n * P.na * oc + slot * oc + o) * P.HWo + e.hw] = v[j];
+      q[j] = v[j] * v[j];
+    }
+    const float s1 = warp_sum16(v), s2 = warp_sum16(q);
+    const int o = nc * W.Nc + c0 + (lane & 15);
+    if (lane < 16 && o < oc) {
+      atomicAdd(&st3[2 * (slot * oc + o)], (double)s1);
+      atomicAdd(&st3[2 * (slot * oc + o) + 1], (double)s2);
     }
   }
   um_teardown(tmem, W.Nc);
@@ -387,39 +387,63 @@ __global__ void __launch_bounds__(NT) k_um_dc(Plan P, UmWAll WA, const float* __
   um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
   const EpiPx e = epi_px(blockIdx.x * 128, P.Q, P.HWo);
   const bool gated = cd.se > 0;
+  // images covered by this warp's 32 consecutive pixels: at most two when HWo >= 32
   const int n_first = __shfl_sync(0xffffffffu, e.n, 0);
-  const bool one_img = __all_sync(0xffffffffu, (!e.v) || e.n == n_first);
+  int n_last = e.v ? e.n : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_last = max(n_last, __shfl_xor_sync(0xffffffffu, n_last, o));
+  const bool two_img = __all_sync(0xffffffffu, (!e.v) || e.n == n_first || e.n == n_last);
   int c_lo, c_hi;
   epi_cols(W.Nc, c_lo, c_hi);
   for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-    float v[16];
-    tmem_ld16(epi_taddr(tmem, c0), v);
+    float v[16], d[16];
+    // issue all 16 D loads before the TMEM read so they overlap
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int c = nc * W.Nc + c0 + j;      // warp-uniform
-      if (c < cd.mc) {
-        const int cst = cd.coff + c;
-        const size_t a = ((size_t)e.n * P.MC + cst) * P.HWo + e.hw;
-        const float d = e.v ? D[a] : 0.f;
-        const float dh = (d - bn2[cst]) * bn2[P.MC + cst];
-        if (gated) {
-          if (e.v) DC[a] = v[j];
-          float part = e.v ? v[j] * act_f<ACT>(dh) : 0.f;
-          if (one_img) {
-            part = warp_sum(part);
-            if (lane == 0) atomicAdd(&dg[(size_t)n_first * P.MCse + cd.soff + c], part);
-          } else if (e.v) {
-            atomicAdd(&dg[(size_t)e.n * P.MCse + cd.soff + c], part);
-          }
-        } else {
-          const float o = e.v ? v[j] * act_df<ACT>(dh) : 0.f;
-          if (e.v) DC[a] = o;
-          const float s1 = warp_sum(o), s2 = warp_sum(o * dh);
-          if (lane == 0) {
-            atomicAdd(&sD[2 * cst], (double)s1);
-            atomicAdd(&sD[2 * cst + 1], (double)s2);
-          }
+      const int c = nc * W.Nc + c0 + j;
+      d[j] = (e.v && c < cd.mc) ? D[((size_t)e.n * P.MC + cd.coff + c) * P.HWo + e.hw] : 0.f;
+    }
+    tmem_ld16(epi_taddr(tmem, c0), v);
+    if (gated) {
+      float pa[16], pb[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = nc * W.Nc + c0 + j;
+        const bool ok = e.v && c < cd.mc;
+        const int cst = cd.coff + min(c, cd.mc - 1);
+        const float b = act_f<ACT>((d[j] - bn2[cst]) * bn2[P.MC + cst]);
+        if (ok) DC[((size_t)e.n * P.MC + cst) * P.HWo + e.hw] = v[j];
+        const float part = ok ? v[j] * b : 0.f;
+        pa[j] = (e.n == n_first) ? part : 0.f;
+        pb[j] = (e.n == n_first) ? 0.f : part;
+        if (!two_img && ok) atomicAdd(&dg[(size_t)e.n * P.MCse + cd.soff + c], part);
+      }
+      if (two_img) {
+        const float sa = warp_sum16(pa), sb = warp_sum16(pb);
+        const int c = nc * W.Nc + c0 + (lane & 15);
+        if (lane < 16 && c < cd.mc) {
+          atomicAdd(&dg[(size_t)n_first * P.MCse + cd.soff + c], sa);
+          if (n_last > n_first) atomicAdd(&dg[(size_t)n_last * P.MCse + cd.soff + c], sb);
         }
+      }
+    } else {
+      float o1[16], o2[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = nc * W.Nc + c0 + j;
+        const bool ok = e.v && c < cd.mc;
+        const int cst = cd.coff + min(c, cd.mc - 1);
+        const float dh = (d[j] - bn2[cst]) * bn2[P.MC + cst];
+        const float o = ok ? v[j] * act_df<ACT>(dh) : 0.f;
+        if (ok) DC[((size_t)e.n * P.MC + cst) * P.HWo + e.hw] = o;
+        o1[j] = o;
+        o2[j] = o * dh;
+      }
+      const float s1 = warp_sum16(o1), s2 = warp_sum16(o2);
+      const int c = nc * W.Nc + c0 + (lane & 15);
+      if (lane < 16 && c < cd.mc) {
+        atomicAdd(&sD[2 * (cd.coff + c)], (double)s1);
+        atomicAdd(&sD[2 * (cd.coff + c) + 1], (double)s2);
       }
     }
   }
@@ -464,6 +488,9 @@ struct DxF {
     int slot, k0;
     locate(c, slot, k0);
     const Cand& cd = P.c[slot];
+    float st[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int kk = warp + i * 8, k = k0 + kk;
@@ -472,22 +499,21 @@ struct DxF {
         const int cst = cd.coff + k;
         const float r1 = bn1[P.MC + cst];
         const float da[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, uh[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
-        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float du = px.v[e] ? da[e] * act_df<ACT>(uh[e]) : 0.f;
-          s1 += du;
-          s2 += du * uh[e];
+          st[2 * i] += du;
+          st[2 * i + 1] += du * uh[e];
           v[e] = du * r1;
-        }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) {
-          atomicAdd(&sU[2 * cst], (double)s1);
-          atomicAdd(&sU[2 * cst + 1], (double)s2);
         }
       }
       um_put(ah, al, lane, kk, v);
+    }
+    // 8 statistics (4 rows x {sum du, sum du*uh}) reduced together; lane l < 8 ends up owning statistic l
+    const float tot = warp_sum16(st);
+    if (lane < 8) {
+      const int k = k0 + warp + (lane >> 1) * 8;
+      if (k < cd.mc) atomicAdd(&sU[2 * (cd.coff + k) + (lane & 1)], (double)tot);
     }
   }
   __device__ const void* wsrc(int c) const { return (const char*)W.wp + (size_t)(ch0 + c) * 2 * W.Nc * 128; }
@@ -559,25 +585,57 @@ size_t umma_bwd_prep_bytes(const Plan& P) {
   return b + (size_t)chunks * 2 * Nc * 128 + 1024;
 }
 
-static void prep(const float* src, int ld_r, int ld_k, int nrows, int K, UmW& W, float*& cursor, cudaStream_t st) {
+struct PrepJob { const float* src; float* dst; int ld_r, ld_k, nrows, K, Nc, nN, nK; };
+struct PrepJobs { int n; PrepJob j[TFNAS_MAX_OPS]; };
+
+// grid (max nK, max nN, jobs): all candidates' weights of one GEMM in ONE launch
+__global__ void __launch_bounds__(256) k_umma_prep_all(PrepJobs J) {
+  const PrepJob& q = J.j[blockIdx.z];
+  const int kc = blockIdx.x, nc = blockIdx.y;
+  if (kc >= q.nK || nc >= q.nN) return;
+  char* base = (char*)q.dst + ((size_t)nc * q.nK + kc) * 2 * q.Nc * 128;
+  for (int i = threadIdx.x; i < q.Nc * UM_KC; i += blockDim.x) {
+    int r, kk;
+    if (q.ld_k == 1) { r = i / UM_KC; kk = i - r * UM_KC; }
+    else { kk = i / q.Nc; r = i - kk * q.Nc; }
+    const int gr = nc * q.Nc + r, k = kc * UM_KC + kk;
+    float x = (gr < q.nrows && k < q.K) ? q.src[(size_t)gr * q.ld_r + (size_t)k * q.ld_k] : 0.f;
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    *(float*)(base + k_elem_off(r, kk)) = hi;
+    *(float*)(base + (size_t)q.Nc * 128 + k_elem_off(r, kk)) = lo;
+  }
+}
+
+static void prep(PrepJobs& J, const float* src, int ld_r, int ld_k, int nrows, int K, UmW& W, float*& cursor) {
   um_tile(nrows, W.Nc, W.nN);
   W.nK = cdiv(K, UM_KC);
   W.Nout = nrows;
   W.wp = cursor;
-  { ProfScope ps("um_prep_w", 4.0 * nrows * K * 3, 0, st);
-    k_umma_prep_w<<<dim3(W.nK, W.nN), 256, 0, st>>>(src, ld_r, ld_k, nrows, K, W.Nc, W.nN, W.nK, cursor); }
+  PrepJob& q = J.j[J.n++];
+  q.src = src; q.dst = cursor; q.ld_r = ld_r; q.ld_k = ld_k; q.nrows = nrows; q.K = K; q.Nc = W.Nc; q.nN = W.nN; q.nK = W.nK;
   cursor += (size_t)W.nN * W.nK * 2 * W.Nc * 32;
+}
+static void prep_launch(const PrepJobs& J, cudaStream_t st) {
+  int mk = 0, mn = 0;
+  double bytes = 0;
+  for (int i = 0; i < J.n; ++i) { mk = max(mk, J.j[i].nK); mn = max(mn, J.j[i].nN); bytes += 12.0 * J.j[i].nrows * J.j[i].K; }
+  ProfScope ps("um_prep_w", bytes, 0, st);
+  k_umma_prep_all<<<dim3(mk, mn, J.n), 256, 0, st>>>(J);
 }
 
 void umma_expand(const Plan& P, const float* x, const float* bn1, float* UH, float* prep_buf, cudaStream_t st) {
   UmWAll WA;
+  PrepJobs J;
+  J.n = 0;
   float* cur = prep_buf;
   int maxN = 0, maxNc = 0;
   for (int s = 0; s < P.na; ++s) {
-    prep(P.c[s].w1, P.ic, 1, P.c[s].mc, P.ic, WA.s[s], cur, st);
+    prep(J, P.c[s].w1, P.ic, 1, P.c[s].mc, P.ic, WA.s[s], cur);
     maxN = max(maxN, WA.s[s].nN);
     maxNc = max(maxNc, WA.s[s].Nc);
   }
+  prep_launch(J, st);
   size_t smem = um_smem_bytes(maxNc);
   cudaFuncSetAttribute(k_um_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
@@ -587,13 +645,16 @@ void umma_expand(const Plan& P, const float* x, const float* bn1, float* UH, flo
 void umma_project(const Plan& P, const float* D, const float* bn2, const float* seg, float* Zb, double* st3,
                   float* prep_buf, cudaStream_t st) {
   UmWAll WA;
+  PrepJobs J;
+  J.n = 0;
   float* cur = prep_buf;
   int maxN = 0, maxNc = 0;
   for (int s = 0; s < P.na; ++s) {
-    prep(P.c[s].w3, P.c[s].mc, 1, P.oc, P.c[s].mc, WA.s[s], cur, st);
+    prep(J, P.c[s].w3, P.c[s].mc, 1, P.oc, P.c[s].mc, WA.s[s], cur);
     maxN = max(maxN, WA.s[s].nN);
     maxNc = max(maxNc, WA.s[s].Nc);
   }
+  prep_launch(J, st);
   size_t smem = um_smem_bytes(maxNc);
   dim3 grid(cdiv(P.Q, 128), maxN, P.na);
   ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
@@ -610,14 +671,17 @@ void umma_project(const Plan& P, const float* D, const float* bn2, const float* 
 void umma_dc(const Plan& P, const float* G, const float* Zb, const float* bn3, const float4* dzc, const float* D,
              const float* bn2, float* DC, float* dg, double* sD, float* prep_buf, cudaStream_t st) {
   UmWAll WA;
+  PrepJobs J;
+  J.n = 0;
   float* cur = prep_buf;
   int maxN = 0, maxNc = 0;
   for (int s = 0; s < P.na; ++s) {
     // logical weight (row = mid channel c, k = out channel o) = W3[o][c]
-    prep(P.c[s].w3, 1, P.c[s].mc, P.c[s].mc, P.oc, WA.s[s], cur, st);
+    prep(J, P.c[s].w3, 1, P.c[s].mc, P.c[s].mc, P.oc, WA.s[s], cur);
     maxN = max(maxN, WA.s[s].nN);
     maxNc = max(maxNc, WA.s[s].Nc);
   }
+  prep_launch(J, st);
   size_t smem = um_smem_bytes(maxNc);
   dim3 grid(cdiv(P.Q, 128), maxN, P.na);
   ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
@@ -640,12 +704,15 @@ void umma_dx(const Plan& P, const float* DA, const float* UH, const float* bn1, 
   DxChunks CH;
   CH.first[0] = 0;
   float* cur = prep_buf;
+  PrepJobs J;
+  J.n = 0;
   for (int s = 0; s < P.na; ++s) {
     // logical weight (row = input channel k', k = mid channel c) = W1[c][k'], chunks never straddle candidates
     UmW Ws;
-    prep(P.c[s].w1, 1, P.ic, P.ic, P.c[s].mc, Ws, cur, st);
+    prep(J, P.c[s].w1, 1, P.ic, P.ic, P.c[s].mc, Ws, cur);
     CH.first[s + 1] = CH.first[s] + Ws.nK;
   }
+  prep_launch(J, st);
   CH.total = CH.first[P.na];
   W.nK = CH.total;
   const int tiles = cdiv(P.P, 128);
