@@ -148,7 +148,7 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
   size_t dmix = take(TFNAS_MAX_OPS * 4);
   size_t dg = take((size_t)P.N * P.MCse * 4);
   size_t sede = want_wgrad ? take((size_t)P.N * P.MCse * 4) : 0;
-  size_t sedt = want_wgrad ? take((size_t)P.N * P.SEH * 4) : 0;
+  size_t sedt = take((size_t)P.N * P.SEH * 4 + 16);
   size_t Smat = want_wgrad ? take((size_t)P.MC * P.ic * 4) : 0;
   size_t DC = take((size_t)P.N * P.MC * P.HWo * 4);
   size_t DA = take((size_t)P.N * P.MC * P.HW * 4);
@@ -166,7 +166,7 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
     S.dmix = (float*)(base + dmix);
     S.dg = (float*)(base + dg);
     S.sede = want_wgrad ? (float*)(base + sede) : nullptr;
-    S.sedt = want_wgrad ? (float*)(base + sedt) : nullptr;
+    S.sedt = (float*)(base + sedt);
     S.Smat = want_wgrad ? (float*)(base + Smat) : nullptr;
     S.DC = (float*)(base + DC);
     S.DA = (float*)(base + DA);

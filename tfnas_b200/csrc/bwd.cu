@@ -172,63 +172,36 @@ __global__ void __launch_bounds__(NT) k_dc(Plan P, const float* __restrict__ G, 
   }
 }
 
-// SE backward through sigmoid / expand FC / act / reduce FC.  grid (ceil(N/SE_NB), na).  dg -> dp in place.
+// SE backward, FC by FC (tiled small GEMMs, see fc_tile):
+//   de = dg * g (1-g)                         (on load; optionally saved for the weight grads)
+//   dt[n][j] = act'(t) * sum_c We[c][j] de[n][c]        k_se_bwd1  grid (N/32, se/64, na)
+//   dp[n][c] = sum_j Wr[j][c] dt[n][j]  -> dg in place  k_se_bwd2  grid (N/32, mc/64, na)
 template <int ACT>
-__global__ void __launch_bounds__(NT) k_se_bwd(Plan P, const float* __restrict__ seg, const float* __restrict__ set,
-                                                float* __restrict__ dg, float* __restrict__ sede,
-                                                float* __restrict__ sedt) {
-  extern __shared__ float sm[];
-  const Cand& cd = P.c[blockIdx.y];
-  if (cd.se == 0) return;
-  const int n0 = blockIdx.x * SE_NB, nb = min(SE_NB, P.N - n0), mc = cd.mc, se = cd.se, tid = threadIdx.x;
-  float* des = sm;                 // [SE_NB][mc]
-  float* dts = sm + SE_NB * mc;    // [SE_NB][se]
-  for (int i = tid; i < SE_NB * mc; i += NT) {
-    int b = i / mc, c = i - b * mc;
-    float de = 0.f;
-    if (b < nb) {
-      size_t gi = (size_t)(n0 + b) * P.MCse + cd.soff + c;
-      float g = seg[gi];
-      de = dg[gi] * g * (1.f - g);
-      if (sede) sede[gi] = de;
-    }
-    des[i] = de;
-  }
-  __syncthreads();
-  for (int j = tid; j < se; j += NT) {
-    float a[SE_NB];
-#pragma unroll
-    for (int b = 0; b < SE_NB; ++b) a[b] = 0.f;
-    for (int c = 0; c < mc; ++c) {
-      const float wv = cd.ew[(size_t)c * se + j];
-#pragma unroll
-      for (int b = 0; b < SE_NB; ++b) a[b] += wv * des[b * mc + c];
-    }
-#pragma unroll
-    for (int b = 0; b < SE_NB; ++b) {
-      float dt = 0.f;
-      if (b < nb) {
-        size_t ti = (size_t)(n0 + b) * P.SEH + cd.hoff + j;
-        dt = a[b] * act_df<ACT>(set[ti]);
-        if (sedt) sedt[ti] = dt;
-      }
-      dts[b * se + j] = dt;
-    }
-  }
-  __syncthreads();
-  for (int c = tid; c < mc; c += NT) {
-    float a[SE_NB];
-#pragma unroll
-    for (int b = 0; b < SE_NB; ++b) a[b] = 0.f;
-    for (int j = 0; j < se; ++j) {
-      const float wv = cd.rw[(size_t)j * mc + c];
-#pragma unroll
-      for (int b = 0; b < SE_NB; ++b) a[b] += wv * dts[b * se + j];
-    }
-#pragma unroll
-    for (int b = 0; b < SE_NB; ++b)
-      if (b < nb) dg[(size_t)(n0 + b) * P.MCse + cd.soff + c] = a[b];
-  }
+__global__ void __launch_bounds__(NT) k_se_bwd1(Plan P, const float* __restrict__ seg, const float* __restrict__ set,
+                                                 const float* __restrict__ dg, float* __restrict__ sede,
+                                                 float* __restrict__ sedt) {
+  const Cand& cd = P.c[blockIdx.z];
+  if (cd.se == 0 || (int)blockIdx.y * FC_TO >= cd.se) return;
+  const bool keep = sede != nullptr && blockIdx.y == 0;
+  fc_tile<true>(P.N, cd.se, cd.mc, cd.ew,
+                [&](int n, int k) {
+                  const size_t gi = (size_t)n * P.MCse + cd.soff + k;
+                  const float g = seg[gi];
+                  const float de = dg[gi] * g * (1.f - g);
+                  if (keep) sede[gi] = de;
+                  return de;
+                },
+                [&](int n, int o, float a) {
+                  const size_t ti = (size_t)n * P.SEH + cd.hoff + o;
+                  sedt[ti] = a * act_df<ACT>(set[ti]);
+                });
+}
+__global__ void __launch_bounds__(NT) k_se_bwd2(Plan P, const float* __restrict__ sedt, float* __restrict__ dg) {
+  const Cand& cd = P.c[blockIdx.z];
+  if (cd.se == 0 || (int)blockIdx.y * FC_TO >= cd.mc) return;
+  fc_tile<true>(P.N, cd.mc, cd.se, cd.rw,
+                [&](int n, int k) { return sedt[(size_t)n * P.SEH + cd.hoff + k]; },
+                [&](int n, int o, float a) { dg[(size_t)n * P.MCse + cd.soff + o] = a; });
 }
 
 // SE candidates: db = dc*g + dp/HWo ; dd-hat = db*act'(d-hat) in place ; BN2-backward sums.  warp per plane.
@@ -896,19 +869,14 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     double fcw = 0;
     for (int s = 0; s < P.na; ++s)
       if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); fcw += 2.0 * P.c[s].mc * P.c[s].se; }
-    size_t smem = (size_t)SE_NB * (maxmc + maxse) * 4;
     float* sede = dweights ? S.sede : nullptr;
-    float* sedt = dweights ? S.sedt : nullptr;
     dim3 gpl(cdiv(P.MCse * 32, NT), P.N);
     { ProfScope ps("se_bwd", 4.0 * fcw + 12.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
-      dim3 g(cdiv(P.N, SE_NB), P.na);
-      if (relu) {
-        cudaFuncSetAttribute(k_se_bwd<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_se_bwd<TFNAS_ACT_RELU><<<g, NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
-      } else {
-        cudaFuncSetAttribute(k_se_bwd<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_se_bwd<TFNAS_ACT_SWISH><<<g, NT, smem, st>>>(P, seg, set, S.dg, sede, sedt);
-      } }
+      dim3 g1(cdiv(P.N, FC_TN), cdiv(maxse, FC_TO), P.na);
+      if (relu) k_se_bwd1<TFNAS_ACT_RELU><<<g1, NT, 0, st>>>(P, seg, set, S.dg, sede, S.sedt);
+      else k_se_bwd1<TFNAS_ACT_SWISH><<<g1, NT, 0, st>>>(P, seg, set, S.dg, sede, S.sedt);
+      k_se_bwd2<<<dim3(cdiv(P.N, FC_TN), cdiv(maxmc, FC_TO), P.na), NT, 0, st>>>(P, S.sedt, S.dg);
+      count_launch(1); }
     { ProfScope ps("b2b", 12.0 * P.Q * P.MCse, 8.0 * P.Q * P.MCse, st);
       if (relu) k_b2b<TFNAS_ACT_RELU><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
       else k_b2b<TFNAS_ACT_SWISH><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD); }

@@ -364,61 +364,22 @@ __global__ void __launch_bounds__(NT) k_se_pool(Plan P, const float* __restrict_
   if (lane == 0) sep[(size_t)n * P.MCse + widx] = acc / (float)P.HWo;
 }
 
-// grid (ceil(N/SE_NB), na): t = Wr p + br ; h = act(t) ; g = sigmoid(We h + be), SE_NB images per CTA so
-// that each weight row is read once per SE_NB images.
+// SE FC 1: t = Wr p + br  (hidden pre-activation, saved).  grid (N/32, se/64, na)
+__global__ void __launch_bounds__(NT) k_se_fc1(Plan P, const float* __restrict__ sep, float* __restrict__ set) {
+  const Cand& cd = P.c[blockIdx.z];
+  if (cd.se == 0 || (int)blockIdx.y * FC_TO >= cd.se) return;
+  fc_tile<false>(P.N, cd.se, cd.mc, cd.rw,
+                 [&](int n, int k) { return sep[(size_t)n * P.MCse + cd.soff + k]; },
+                 [&](int n, int o, float a) { set[(size_t)n * P.SEH + cd.hoff + o] = a + cd.rb[o]; });
+}
+// SE FC 2: g = sigmoid(We act(t) + be).  grid (N/32, mc/64, na)
 template <int ACT>
-__global__ void __launch_bounds__(NT) k_se_fc(Plan P, const float* __restrict__ sep, float* __restrict__ set,
-                                               float* __restrict__ seg) {
-  extern __shared__ float sm[];
-  const Cand& cd = P.c[blockIdx.y];
-  if (cd.se == 0) return;
-  const int n0 = blockIdx.x * SE_NB, nb = min(SE_NB, P.N - n0), mc = cd.mc, se = cd.se;
-  float* ps = sm;               // [SE_NB][mc]
-  float* hs = sm + SE_NB * mc;  // [SE_NB][se]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < SE_NB * mc; i += NT) {
-    int b = i / mc, c = i - b * mc;
-    ps[i] = b < nb ? sep[(size_t)(n0 + b) * P.MCse + cd.soff + c] : 0.f;
-  }
-  __syncthreads();
-  for (int j = warp; j < se; j += NT / 32) {
-    const float* w = cd.rw + (size_t)j * mc;
-    float a[SE_NB];
-#pragma unroll
-    for (int b = 0; b < SE_NB; ++b) a[b] = 0.f;
-    for (int i = lane; i < mc; i += 32) {
-      const float wv = w[i];
-#pragma unroll
-      for (int b = 0; b < SE_NB; ++b) a[b] += wv * ps[b * mc + i];
-    }
-    const float bias = cd.rb[j];
-#pragma unroll
-    for (int b = 0; b < SE_NB; ++b) {
-      float t = warp_sum(a[b]) + bias;
-      if (lane == 0 && b < nb) {
-        set[(size_t)(n0 + b) * P.SEH + cd.hoff + j] = t;
-        hs[b * se + j] = act_f<ACT>(t);
-      }
-    }
-  }
-  __syncthreads();
-  for (int c = warp; c < mc; c += NT / 32) {
-    const float* w = cd.ew + (size_t)c * se;
-    float a[SE_NB];
-#pragma unroll
-    for (int b = 0; b < SE_NB; ++b) a[b] = 0.f;
-    for (int j = lane; j < se; j += 32) {
-      const float wv = w[j];
-#pragma unroll
-      for (int b = 0; b < SE_NB; ++b) a[b] += wv * hs[b * se + j];
-    }
-    const float bias = cd.eb[c];
-#pragma unroll
-    for (int b = 0; b < SE_NB; ++b) {
-      float t = warp_sum(a[b]);
-      if (lane == 0 && b < nb) seg[(size_t)(n0 + b) * P.MCse + cd.soff + c] = sigmoid_f(t + bias);
-    }
-  }
+__global__ void __launch_bounds__(NT) k_se_fc2(Plan P, const float* __restrict__ set, float* __restrict__ seg) {
+  const Cand& cd = P.c[blockIdx.z];
+  if (cd.se == 0 || (int)blockIdx.y * FC_TO >= cd.mc) return;
+  fc_tile<false>(P.N, cd.mc, cd.se, cd.ew,
+                 [&](int n, int k) { return act_f<ACT>(set[(size_t)n * P.SEH + cd.hoff + k]); },
+                 [&](int n, int o, float a) { seg[(size_t)n * P.MCse + cd.soff + o] = sigmoid_f(a + cd.eb[o]); });
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -678,21 +639,17 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
     double fcw = 0;
     for (int s = 0; s < P.na; ++s)
       if (P.c[s].se > 0) { maxmc = max(maxmc, P.c[s].mc); maxse = max(maxse, P.c[s].se); fcw += 2.0 * P.c[s].mc * P.c[s].se; }
-    size_t smem = (size_t)SE_NB * (maxmc + maxse) * 4;
     const bool relu = P.act == TFNAS_ACT_RELU;
     { ProfScope ps("se_pool", 4.0 * P.Q * P.MCse, 4.0 * P.Q * P.MCse, st);
       dim3 g(cdiv(P.MCse * 32, NT), P.N);
       if (relu) k_se_pool<TFNAS_ACT_RELU><<<g, NT, 0, st>>>(P, D, bn2, sep);
       else k_se_pool<TFNAS_ACT_SWISH><<<g, NT, 0, st>>>(P, D, bn2, sep); }
     { ProfScope ps("se_fc", 4.0 * fcw + 8.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
-      dim3 g(cdiv(P.N, SE_NB), P.na);
-      if (relu) {
-        cudaFuncSetAttribute(k_se_fc<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_se_fc<TFNAS_ACT_RELU><<<g, NT, smem, st>>>(P, sep, set, seg);
-      } else {
-        cudaFuncSetAttribute(k_se_fc<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_se_fc<TFNAS_ACT_SWISH><<<g, NT, smem, st>>>(P, sep, set, seg);
-      } }
+      k_se_fc1<<<dim3(cdiv(P.N, FC_TN), cdiv(maxse, FC_TO), P.na), NT, 0, st>>>(P, sep, set);
+      dim3 g2(cdiv(P.N, FC_TN), cdiv(maxmc, FC_TO), P.na);
+      if (relu) k_se_fc2<TFNAS_ACT_RELU><<<g2, NT, 0, st>>>(P, set, seg);
+      else k_se_fc2<TFNAS_ACT_SWISH><<<g2, NT, 0, st>>>(P, set, seg);
+      count_launch(1); }
   }
   // F3
   if (umma_enabled()) {
