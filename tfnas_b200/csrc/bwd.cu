@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(NT) k_wgrad(Plan P, int slot, const float* __r
 }
 
 // dW1[c][k] = r1 ( S[c][k] - m1 P mu_x[k] - m2 r1 P (W1 cov)[c][k] ).  one warp per channel c
-__global__ void __launch_bounds__(NT) k_w1fin(Plan P, int slot, const float* __restrict__ Smat,
+__global__ void __launch_bounds__(NT) k_w1fin(Plan P, int slot, const float* __restrict__ Smat, int smat_t,
                                                const float* __restrict__ bn1, const double* __restrict__ sU,
                                                const double* __restrict__ xmom, float* __restrict__ gw1) {
   const Cand& cd = P.c[slot];
@@ -699,7 +699,8 @@ __global__ void __launch_bounds__(NT) k_w1fin(Plan P, int slot, const float* __r
   for (int k = lane; k < ic; k += 32) {
     double wc = 0.0;
     for (int kp = 0; kp < ic; ++kp) wc += (double)w[kp] * cov[kp * ic + k];
-    gw1[(size_t)c * ic + k] = (float)(r1 * ((double)Smat[(size_t)c * ic + k] - s1 * mean[k] - s2 * r1 * wc));
+    const double sm = (double)(smat_t ? Smat[(size_t)k * cd.mc + c] : Smat[(size_t)c * ic + k]);
+    gw1[(size_t)c * ic + k] = (float)(r1 * (sm - s1 * mean[k] - s2 * r1 * wc));
   }
 }
 
@@ -856,11 +857,15 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       const Cand& cd = P.c[s];
       float* gw3 = dweights[cd.id].w3;
       cudaMemsetAsync(gw3, 0, (size_t)oc * cd.mc * sizeof(float), st);
-      int nsplit = max(1, min(cdiv(P.Q, 2048), cdiv(6 * sm_count(), cdiv(oc, WG_T) * cdiv(cd.mc, WG_T))));
-      dim3 grid(cdiv(oc, WG_T), cdiv(cd.mc, WG_T), nsplit);
-      ProfScope ps("wgrad_w3", 4.0 * P.Q * (2.0 * oc + cd.mc), 2.0 * P.Q * (double)oc * cd.mc, st);
-      if (relu) k_wgrad<0, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, dout, Zb, D, bn3, dzc, bn2, seg, gw3);
-      else k_wgrad<0, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, dout, Zb, D, bn3, dzc, bn2, seg, gw3);
+      if (umma_enabled()) {
+        umma_wgrad(P, s, 0, D, nullptr, dout, Zb, bn2, seg, bn3, dzc, gw3, st);
+      } else {
+        int nsplit = max(1, min(cdiv(P.Q, 2048), cdiv(6 * sm_count(), cdiv(oc, WG_T) * cdiv(cd.mc, WG_T))));
+        dim3 grid(cdiv(oc, WG_T), cdiv(cd.mc, WG_T), nsplit);
+        ProfScope ps("wgrad_w3", 4.0 * P.Q * (2.0 * oc + cd.mc), 2.0 * P.Q * (double)oc * cd.mc, st);
+        if (relu) k_wgrad<0, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, dout, Zb, D, bn3, dzc, bn2, seg, gw3);
+        else k_wgrad<0, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, dout, Zb, D, bn3, dzc, bn2, seg, gw3);
+      }
     }
   }
   // SE backward + B2b
@@ -930,13 +935,18 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       const Cand& cd = P.c[s];
       float* Sm = S.Smat + (size_t)cd.coff * ic;
       cudaMemsetAsync(Sm, 0, (size_t)cd.mc * ic * sizeof(float), st);
-      int nsplit = max(1, min(cdiv(P.P, 2048), cdiv(6 * sm_count(), cdiv(cd.mc, WG_T) * cdiv(ic, WG_T))));
-      dim3 grid(cdiv(cd.mc, WG_T), cdiv(ic, WG_T), nsplit);
-      { ProfScope ps("wgrad_w1", 4.0 * P.P * (2.0 * cd.mc + ic), 2.0 * P.P * (double)ic * cd.mc, st);
+      const int smat_t = umma_enabled();     // tensor-core path writes Smat transposed [ic][mc]
+      if (smat_t) {
+        umma_wgrad(P, s, 1, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, nullptr, Sm, st);
+      } else {
+        int nsplit = max(1, min(cdiv(P.P, 2048), cdiv(6 * sm_count(), cdiv(cd.mc, WG_T) * cdiv(ic, WG_T))));
+        dim3 grid(cdiv(cd.mc, WG_T), cdiv(ic, WG_T), nsplit);
+        ProfScope ps("wgrad_w1", 4.0 * P.P * (2.0 * cd.mc + ic), 2.0 * P.P * (double)ic * cd.mc, st);
         if (relu) k_wgrad<1, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
-        else k_wgrad<1, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm); }
+        else k_wgrad<1, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
+      }
       { ProfScope ps("w1fin", 12.0 * cd.mc * ic, 2.0 * cd.mc * ic * ic, st);
-        k_w1fin<<<cdiv(cd.mc * 32, NT), NT, 0, st>>>(P, s, Sm, bn1, S.sU, xmom, dweights[cd.id].w1); }
+        k_w1fin<<<cdiv(cd.mc * 32, NT), NT, 0, st>>>(P, s, Sm, smat_t, bn1, S.sU, xmom, dweights[cd.id].w1); }
     }
   }
   // B4

@@ -58,6 +58,9 @@ void umma_project(const Plan& P, const float* D, const float* bn2, const float* 
                   float* prep_buf, cudaStream_t st);
 void umma_dc(const Plan& P, const float* G, const float* Zb, const float* bn3, const float4* dzc, const float* D,
              const float* bn2, float* DC, float* dg, double* sD, float* prep_buf, cudaStream_t st);
+// MODE 0: dW3[o][c] += sum_p dz c~ ; MODE 1: SmatT[k][c] += sum_p du-hat x   (out must be zeroed by the caller)
+void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float* A1, const float* B0, const float* B1,
+                const float* bn2, const float* seg, const float* bn3, const float4* dzc, float* out, cudaStream_t st);
 void umma_dx(const Plan& P, const float* DA, const float* UH, const float* bn1, float* dx, double* sU, float* prep_buf,
              cudaStream_t st);
 

@@ -729,3 +729,178 @@ void umma_dx(const Plan& P, const float* DA, const float* UH, const float* bn1, 
     k_um_dx<TFNAS_ACT_SWISH><<<grid, NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
   }
 }
+
+// -------------------------------------------------------------------------------------------------
+// Weight gradients on the tensor cores (sampled w-step):  Out[a][b] += sum_p U[a][p] * V[b][p]
+//   MODE 0 (W3): a = mid channel c (U = c-tilde = act(BN2(d))*gate), b = out channel o (V = dz)   -> dW3[o][c]
+//   MODE 1 (W1): a = mid channel c (U = du-hat = DA*act'(UH)),        b = in  channel k (V = x)    -> SmatT[k][c]
+// Both operands are K-major (pixels contiguous), staged by the CTA's threads with the tf32 split.
+// grid (mc/128, N chunks, K splits over the pixel axis); fp32 atomics combine the K splits.
+// -------------------------------------------------------------------------------------------------
+struct WgArgs {
+  const float* A0; const float* A1;   // MODE 0: D, -      MODE 1: DA, UH
+  const float* B0; const float* B1;   // MODE 0: G, Z      MODE 1: x, -
+  const float* bn2; const float* seg; const float* bn3; const float4* dzc;
+  float* out;                         // MODE 0: dW3 [oc][mc]   MODE 1: SmatT [ic][mc]
+  int Nc, nN;                         // N chunking of the b axis
+};
+
+template <int MODE, int ACT>
+__global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
+  extern __shared__ __align__(1024) unsigned char um_raw[];
+  unsigned char* sm = (unsigned char*)(((uintptr_t)um_raw + 1023) & ~(uintptr_t)1023);
+  const int Nc = g.Nc;
+  unsigned char* a_hi = sm;
+  unsigned char* a_lo = sm + 16384;
+  unsigned char* b_hi = sm + 32768;
+  unsigned char* b_lo = b_hi + Nc * 128;
+  uint64_t* bar_mma = (uint64_t*)(b_lo + Nc * 128);
+  uint32_t* tmem_slot = (uint32_t*)(bar_mma + 1);
+  const Cand& cd = P.c[slot];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * Nc;
+  const int nb_total = MODE == 0 ? P.oc : P.ic;
+  const int HWp = MODE == 0 ? P.HWo : P.HW;
+  const int total = MODE == 0 ? P.Q : P.P;
+  const int nsplit = gridDim.z;
+  int p_lo = (int)((long long)total * blockIdx.z / nsplit) / 32 * 32;
+  int p_hi = (int)blockIdx.z + 1 < nsplit ? (int)((long long)total * (blockIdx.z + 1) / nsplit) / 32 * 32 : total;
+  if (tid == 0) { mbar_init(bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols(Nc));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t idesc = idesc_tf32(128, Nc, 0, 0);
+  const int q = tid & 7;               // 16 B chunk (4 pixels) of the 32-pixel K chunk owned by this thread
+  const int r_base = tid >> 3;         // rows r_base + 32 i
+  uint32_t phase = 0;
+  bool first = true;
+  for (int p0 = p_lo; p0 < p_hi; p0 += 32) {
+    // pixel decomposition of this thread's 4 pixels
+    Px4 px;
+    px_decomp(px, p0 + q * 4, p_hi, HWp);
+    if (!first) {                       // previous chunk's MMAs must have consumed the tiles
+      mbar_wait(bar_mma, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+    // ---- A rows: mid channels m0 .. m0+127 ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r_base + 32 * i, c = m0 + r;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c < cd.mc) {
+        const int cst = cd.coff + c;
+        float d[4];
+        load4(d, g.A0, px, P.MC, cst, HWp);
+        if (MODE == 0) {
+          const float mu = g.bn2[cst], rr = g.bn2[P.MC + cst];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float b = act_f<ACT>((d[e] - mu) * rr);
+            if (cd.se > 0) b *= g.seg[(size_t)px.n[e] * P.MCse + cd.soff + c];
+            v[e] = px.v[e] ? b : 0.f;
+          }
+        } else {
+          float u[4];
+          load4(u, g.A1, px, P.MC, cst, HWp);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? d[e] * act_df<ACT>(u[e]) : 0.f;
+        }
+      }
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
+      const uint32_t off = r * 128u + ((uint32_t)(q ^ (r & 7)) << 4);
+      *(float4*)(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *(float4*)(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    // ---- B rows: n0 .. n0+Nc-1 ----
+    for (int r = r_base; r < Nc; r += 32) {
+      const int b = n0 + r;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (b < nb_total) {
+        if (MODE == 0) {
+          const float4 cf = g.dzc[slot * P.oc + b];
+          const float mu3 = g.bn3[slot * P.oc + b], r3 = g.bn3[P.na * P.oc + slot * P.oc + b];
+          float gg[4], z[4];
+          load4(gg, g.B0, px, P.oc, b, HWp);
+          load4(z, g.B1, px, P.na * P.oc, slot * P.oc + b, HWp);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? cf.x * (gg[e] - cf.y - (z[e] - mu3) * r3 * cf.z) : 0.f;
+        } else {
+          load4(v, g.B0, px, P.ic, b, HWp);
+        }
+      }
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
+      const uint32_t off = r * 128u + ((uint32_t)(q ^ (r & 7)) << 4);
+      *(float4*)(b_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *(float4*)(b_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const uint64_t dah = smem_desc(ah + s * 32, 16, 1024, SWIZZLE_128B);
+        const uint64_t dal = smem_desc(al + s * 32, 16, 1024, SWIZZLE_128B);
+        const uint64_t dbh = smem_desc(bh + s * 32, 16, 1024, SWIZZLE_128B);
+        const uint64_t dbl = smem_desc(bl + s * 32, 16, 1024, SWIZZLE_128B);
+        mma_tf32(tmem, dah, dbh, idesc, (first && s == 0) ? 0u : 1u);
+        mma_tf32(tmem, dal, dbh, idesc, 1u);
+        mma_tf32(tmem, dah, dbl, idesc, 1u);
+      }
+      mma_commit(bar_mma);
+    }
+    first = false;
+  }
+  if (!first) {
+    mbar_wait(bar_mma, phase);
+    tc_fence_after();
+    // epilogue: lane = mid channel row, 16 b-columns per TMEM load; coalesced atomics along c
+    const int c = m0 + (warp & 3) * 32 + lane;
+    int c_lo, c_hi;
+    epi_cols(Nc, c_lo, c_hi);
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+      float v[16];
+      tmem_ld16(epi_taddr(tmem, c0), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int b = n0 + c0 + j;
+        if (b < nb_total && c < cd.mc) atomicAdd(&g.out[(size_t)b * cd.mc + c], v[j]);
+      }
+    }
+  }
+  um_teardown(tmem, Nc);
+}
+
+void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float* A1, const float* B0, const float* B1,
+                const float* bn2, const float* seg, const float* bn3, const float4* dzc, float* out, cudaStream_t st) {
+  const Cand& cd = P.c[slot];
+  WgArgs g;
+  g.A0 = A0; g.A1 = A1; g.B0 = B0; g.B1 = B1; g.bn2 = bn2; g.seg = seg; g.bn3 = bn3; g.dzc = dzc; g.out = out;
+  const int nb = mode == 0 ? P.oc : P.ic;
+  um_tile(nb, g.Nc, g.nN);
+  const int total = mode == 0 ? P.Q : P.P;
+  const int mt = cdiv(cd.mc, 128);
+  int nsplit = max(1, min(cdiv(total, 1024), cdiv(3 * sm_count(), mt * g.nN)));
+  size_t smem = 1024 + 32768 + (size_t)2 * g.Nc * 128 + 64;
+  dim3 grid(mt, g.nN, nsplit);
+  const bool relu = P.act == TFNAS_ACT_RELU;
+  if (mode == 0) {
+    ProfScope ps("wgrad_w3", 4.0 * P.Q * (2.0 * P.oc + cd.mc), 2.0 * P.Q * (double)P.oc * cd.mc, st);
+    auto k = relu ? k_um_wgrad<0, TFNAS_ACT_RELU> : k_um_wgrad<0, TFNAS_ACT_SWISH>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, NT, smem, st>>>(P, slot, g);
+  } else {
+    ProfScope ps("wgrad_w1", 4.0 * P.P * (2.0 * cd.mc + P.ic), 2.0 * P.P * (double)P.ic * cd.mc, st);
+    auto k = relu ? k_um_wgrad<1, TFNAS_ACT_RELU> : k_um_wgrad<1, TFNAS_ACT_SWISH>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, NT, smem, st>>>(P, slot, g);
+  }
+}
