@@ -121,6 +121,18 @@ int tfnas_stage_sink_bwd(int K, size_t numel, const float* const* res, const flo
  * {xmom, bn1, bn2, bn3, mixw, lat, se_p, se_t, se_g, UH, D, Z, total} (13 entries). */
 int tfnas_debug_saved_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, size_t* out13);
 
+/*
+ * Batch-statistic BatchNorm (no affine, biased variance, eps 1e-5, no running stats) fused with the activation:
+ * the BN + act of the reference's ConvLayer / second stem (models/layers.py:90-110, 469-477 with affine=False as in
+ * models/model_search.py:219-220,275).  x, y, dy, dx: [N, C, HW] fp32.  act: TFNAS_ACT_RELU, TFNAS_ACT_SWISH or
+ * TFNAS_ACT_NONE.  mean_rstd: device [2*C] (written by fwd, read by bwd).  workspace: >= 16*C bytes.
+ */
+#define TFNAS_ACT_NONE 2
+int tfnas_bn_act_fwd(int N, int C, int HW, int act, const float* x, float* y, float* mean_rstd, void* workspace,
+                     size_t ws_bytes, void* stream);
+int tfnas_bn_act_bwd(int N, int C, int HW, int act, const float* x, const float* mean_rstd, const float* dy, float* dx,
+                     void* workspace, size_t ws_bytes, void* stream);
+
 /* Test helper: byte offsets of the backward workspace regions
  * {sG, sGY, sD, sU, cvec2, Mm, dg, DC, DA, total} (10 entries). */
 int tfnas_debug_bwd_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, int want_wgrad, size_t* out10);

@@ -172,3 +172,22 @@ def test_stage_sink(K, shape, with_lat):
         assert H.rel_l2(a.grad, b.grad) < 1e-6
     if with_lat:
         assert H.rel_l2(cum.grad, c2.grad) < 1e-6
+
+
+@pytest.mark.parametrize('shape,act', [((4, 32, 12, 12), 'relu'), ((3, 16, 7, 5), None), ((2, 40, 6, 6), 'swish'),
+                                       ((128, 32, 28, 28), 'relu')])
+def test_bn_act_kernels(shape, act):
+    """BN(batch stats, no affine) + act of the stems / feature-mix layer vs torch fp64."""
+    from tfnas_b200.ops import bn_act
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(shape, generator=g) * 1.7 + 0.4)
+    gy = torch.randn(shape, generator=g)
+    xg = x.cuda().requires_grad_(True)
+    y = bn_act(xg, act)
+    (y * gy.cuda()).sum().backward()
+    xr = x.double().requires_grad_(True)
+    yr = torch.nn.functional.batch_norm(xr, None, None, None, None, True, 0.0, 1e-5)
+    yr = torch.relu(yr) if act == 'relu' else (yr * torch.sigmoid(yr) if act == 'swish' else yr)
+    (yr * gy.double()).sum().backward()
+    assert H.rel_l2(y, yr) < 1e-5
+    assert H.rel_l2(xg.grad, xr.grad) < (1e-3 if act == 'relu' else 1e-4)

@@ -8,7 +8,8 @@ import os
 
 MAX_OPS = 8
 ACT_RELU, ACT_SWISH = 0, 1
-ACT_CODE = {'relu': ACT_RELU, 'swish': ACT_SWISH}
+ACT_NONE = 2
+ACT_CODE = {'relu': ACT_RELU, 'swish': ACT_SWISH, None: ACT_NONE, 'none': ACT_NONE}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libtfnas_b200.so')
@@ -38,7 +39,7 @@ EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
            'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout', 'tfnas_debug_bwd_layout',
-           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest']
+           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd']
 
 _lib = None
 
@@ -79,6 +80,10 @@ def load():
     lib.tfnas_debug_saved_layout.argtypes = [dp, u32, ctypes.POINTER(sz)]
     lib.tfnas_debug_bwd_layout.restype = i32
     lib.tfnas_debug_bwd_layout.argtypes = [dp, u32, i32, ctypes.POINTER(sz)]
+    lib.tfnas_bn_act_fwd.restype = i32
+    lib.tfnas_bn_act_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.tfnas_bn_act_bwd.restype = i32
+    lib.tfnas_bn_act_bwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.tfnas_prof_enable.restype = i32
     lib.tfnas_prof_enable.argtypes = [i32]
     lib.tfnas_prof_collect.restype = i32

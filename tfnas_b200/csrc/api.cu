@@ -92,7 +92,7 @@ static int build_plan(const TfnasMixedOpDesc* d, uint32_t mask, const TfnasCandP
   P.HWo = P.Ho * P.Wo;
   long long Pn = (long long)d->N * P.HW, Qn = (long long)d->N * P.HWo;
   if (Pn * (long long)P.MC >= (1LL << 40)) return fail(TFNAS_E_UNSUPPORTED, "tensor too large");
-  if (Pn >= (1LL << 31) || Qn >= (1LL << 31)) return fail(TFNAS_E_UNSUPPORTED, "pixel count overflows int32");
+  if (Pn >= (1LL << 23) || Qn >= (1LL << 23)) return fail(TFNAS_E_UNSUPPORTED, "N*H*W >= 2^23 pixels per call not supported");
   P.P = (int)Pn; P.Q = (int)Qn;
   P.residual = (d->ic == d->oc && d->stride == 1);
   return TFNAS_OK;
@@ -263,6 +263,28 @@ int tfnas_mixedop_bwd(const TfnasMixedOpDesc* d, uint32_t cand_mask, const float
   launch_backward(P, x, dout, dlat, T, alpha_mode, (const char*)saved, L, S, dx, dlog_alphas, dweights,
                   (cudaStream_t)stream);
   return check_cuda("tfnas_mixedop_bwd");
+}
+
+int tfnas_bn_act_fwd(int N, int C, int HW, int act, const float* x, float* y, float* mean_rstd, void* workspace,
+                     size_t ws_bytes, void* stream) {
+  if (N < 1 || C < 1 || HW < 1 || act < 0 || act > 2) return fail(TFNAS_E_INVALID, "bn_act: bad shape / act");
+  if (!x || !y || !mean_rstd || !workspace) return fail(TFNAS_E_INVALID, "null pointer");
+  if ((long long)N * HW >= (1LL << 23)) return fail(TFNAS_E_UNSUPPORTED, "bn_act: N*HW >= 2^23");
+  if (ws_bytes < (size_t)2 * C * sizeof(double)) return fail(TFNAS_E_WORKSPACE, "bn_act workspace %zu < %zu", ws_bytes, (size_t)16 * C);
+  cudaGetLastError();
+  launch_bn_act_fwd(N, C, HW, act, x, y, mean_rstd, (double*)workspace, (cudaStream_t)stream);
+  return check_cuda("tfnas_bn_act_fwd");
+}
+
+int tfnas_bn_act_bwd(int N, int C, int HW, int act, const float* x, const float* mean_rstd, const float* dy, float* dx,
+                     void* workspace, size_t ws_bytes, void* stream) {
+  if (N < 1 || C < 1 || HW < 1 || act < 0 || act > 2) return fail(TFNAS_E_INVALID, "bn_act: bad shape / act");
+  if (!x || !dy || !dx || !mean_rstd || !workspace) return fail(TFNAS_E_INVALID, "null pointer");
+  if ((long long)N * HW >= (1LL << 23)) return fail(TFNAS_E_UNSUPPORTED, "bn_act: N*HW >= 2^23");
+  if (ws_bytes < (size_t)2 * C * sizeof(double)) return fail(TFNAS_E_WORKSPACE, "bn_act workspace %zu < %zu", ws_bytes, (size_t)16 * C);
+  cudaGetLastError();
+  launch_bn_act_bwd(N, C, HW, act, x, mean_rstd, dy, dx, (double*)workspace, (cudaStream_t)stream);
+  return check_cuda("tfnas_bn_act_bwd");
 }
 
 int tfnas_prof_enable(int on) {

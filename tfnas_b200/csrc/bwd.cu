@@ -683,24 +683,42 @@ __global__ void __launch_bounds__(NT) k_wgrad(Plan P, int slot, const float* __r
     }
 }
 
-// dW1[c][k] = r1 ( S[c][k] - m1 P mu_x[k] - m2 r1 P (W1 cov)[c][k] ).  one warp per channel c
+// dW1[c][k] = r1 ( S[c][k] - m1 P mu_x[k] - m2 r1 P (W1 cov)[c][k] ).  8 channels per CTA, thread = input channel k
+#define W1F_CH 8
 __global__ void __launch_bounds__(NT) k_w1fin(Plan P, int slot, const float* __restrict__ Smat, int smat_t,
                                                const float* __restrict__ bn1, const double* __restrict__ sU,
                                                const double* __restrict__ xmom, float* __restrict__ gw1) {
+  extern __shared__ float wsm[];     // [W1F_CH][ic]
   const Cand& cd = P.c[slot];
-  const int c = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= cd.mc) return;
-  const int ic = P.ic, cst = cd.coff + c;
-  const double r1 = (double)bn1[P.MC + cst];
-  const double s1 = sU[2 * cst], s2 = sU[2 * cst + 1];   // = m1*P, m2*P
+  const int ic = P.ic, tid = threadIdx.x;
+  const int c0 = blockIdx.x * W1F_CH;
+  for (int i = tid; i < W1F_CH * ic; i += NT) {
+    const int cc = i / ic, k = i - cc * ic;
+    wsm[i] = c0 + cc < cd.mc ? cd.w1[(size_t)(c0 + cc) * ic + k] : 0.f;
+  }
+  __syncthreads();
   const double* mean = xmom;
   const double* cov = xmom + ic;
-  const float* w = cd.w1 + (size_t)c * ic;
-  for (int k = lane; k < ic; k += 32) {
-    double wc = 0.0;
-    for (int kp = 0; kp < ic; ++kp) wc += (double)w[kp] * cov[kp * ic + k];
-    const double sm = (double)(smat_t ? Smat[(size_t)k * cd.mc + c] : Smat[(size_t)c * ic + k]);
-    gw1[(size_t)c * ic + k] = (float)(r1 * (sm - s1 * mean[k] - s2 * r1 * wc));
+  for (int k = tid; k < ic; k += NT) {
+    double wc[W1F_CH];
+#pragma unroll
+    for (int c = 0; c < W1F_CH; ++c) wc[c] = 0.0;
+    for (int kp = 0; kp < ic; ++kp) {
+      const double cv = cov[kp * ic + k];
+#pragma unroll
+      for (int c = 0; c < W1F_CH; ++c) wc[c] += (double)wsm[c * ic + kp] * cv;
+    }
+#pragma unroll
+    for (int c = 0; c < W1F_CH; ++c) {
+      const int cl = c0 + c;
+      if (cl < cd.mc) {
+        const int cst = cd.coff + cl;
+        const double r1 = (double)bn1[P.MC + cst];
+        const double s1 = sU[2 * cst], s2 = sU[2 * cst + 1];   // = m1*P, m2*P
+        const double smv = (double)(smat_t ? Smat[(size_t)k * cd.mc + cl] : Smat[(size_t)cl * ic + k]);
+        gw1[(size_t)cl * ic + k] = (float)(r1 * (smv - s1 * mean[k] - s2 * r1 * wc[c]));
+      }
+    }
   }
 }
 
@@ -946,7 +964,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
         else k_wgrad<1, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
       }
       { ProfScope ps("w1fin", 12.0 * cd.mc * ic, 2.0 * cd.mc * ic * ic, st);
-        k_w1fin<<<cdiv(cd.mc * 32, NT), NT, 0, st>>>(P, s, Sm, smat_t, bn1, S.sU, xmom, dweights[cd.id].w1); }
+        k_w1fin<<<cdiv(cd.mc, W1F_CH), NT, (size_t)W1F_CH * ic * 4, st>>>(P, s, Sm, smat_t, bn1, S.sU, xmom, dweights[cd.id].w1); }
     }
   }
   // B4

@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(NT) k_xsum(Plan P, const float* __restrict__ x
   }
 }
 
-// centred second moment; grid (chunks per image, N).  smem: xs[icp][XC_LD] + red
+// centred second moment over flattened pixels p = (n, hw); persistent CTAs walk tiles of XC_TPX pixels and keep
+// their partial ic x ic blocks in registers, so each CTA issues one double atomic per entry.
+// smem: xs[icp][XC_LD] + mean[icp] (+ red[nblk*16] when several thread groups share a block)
 #define XC_TPX 128
 #define XC_LD (XC_TPX + 4)
 __global__ void __launch_bounds__(NT) k_xcov(Plan P, const float* __restrict__ x,
@@ -47,35 +49,33 @@ __global__ void __launch_bounds__(NT) k_xcov(Plan P, const float* __restrict__ x
   const int ic = P.ic, nb = (ic + 3) >> 2, icp = nb * 4, nblk = nb * nb;
   float* xs = sm;                      // [icp][XC_LD]
   float* mean = xs + icp * XC_LD;      // [icp]
-  float* red = mean + icp;             // [nblk_local*16] when nsplit > 1
-  const int n = blockIdx.y;
-  const int chunks = gridDim.x;
-  const int px0 = (int)((long long)P.HW * blockIdx.x / chunks), px1 = (int)((long long)P.HW * (blockIdx.x + 1) / chunks);
+  float* red = mean + icp;             // [nblk*16] when nsplit > 1
   const int tid = threadIdx.x;
   for (int k = tid; k < icp; k += NT) mean[k] = k < ic ? (float)(xsum[k] / (double)P.P) : 0.f;
   const int nsplit = nblk >= NT ? 1 : NT / nblk;
   const int myblk = nsplit == 1 ? tid : tid % nblk;
   const int mysp = nsplit == 1 ? 0 : tid / nblk;
   const bool active = nsplit == 1 ? true : (tid < nblk * nsplit);
-  // per-thread accumulators for up to MAXB blocks when nsplit==1 would blow registers: loop blocks outermost
-  // and keep the pixel loop inside, re-reading xs (smem) — x stays resident per chunk step.
   const int nloops = nsplit == 1 ? (nblk + NT - 1) / NT : 1;
-  // accumulate across the pixel steps of this CTA in registers for ONE block at a time requires the
-  // pixel tile to stay resident; so for nloops>1 we flush per pixel step to smem-less global atomics.
-  // To keep it simple and exact: accumulate per (block) in a local array of nloops<=9 x 16 floats.
   float acc[9][16];
 #pragma unroll
   for (int l = 0; l < 9; ++l)
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[l][e] = 0.f;
-  for (int p0 = px0; p0 < px1; p0 += XC_TPX) {
-    const int np = min(XC_TPX, px1 - p0);
+  const int ntiles = (P.P + XC_TPX - 1) / XC_TPX;
+  const float inv_hw = 1.f / (float)P.HW;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * XC_TPX;
     __syncthreads();
-    for (int i = tid; i < icp * XC_TPX; i += NT) {
-      int k = i / XC_TPX, p = i - k * XC_TPX;
-      float v = 0.f;
-      if (k < ic && p < np) v = x[((size_t)n * ic + k) * P.HW + p0 + p] - mean[k];
-      xs[k * XC_LD + p] = v;
+    // thread -> pixel (tid & 127), channel rows (tid >> 7) + 2 i : coalesced along pixels
+    {
+      const int pp = tid & (XC_TPX - 1);
+      const int p = p0 + pp;
+      const bool pv = p < P.P;
+      const int n = pv ? fast_div(p, P.HW, inv_hw) : 0, hw = p - n * P.HW;
+      const float* src = x + (size_t)n * ic * P.HW + hw;
+      for (int k = tid >> 7; k < icp; k += NT / XC_TPX)
+        xs[k * XC_LD + pp] = (pv && k < ic) ? src[(size_t)k * P.HW] - mean[k] : 0.f;
     }
     __syncthreads();
     if (active) {
@@ -161,29 +161,53 @@ __global__ void k_xfin(int ic, int Pn, const double* __restrict__ xsum, const do
   if (i < ic * ic) xmom[ic + i] = xcov[i] * inv;
 }
 
-// analytic BN1 statistics, one warp per stacked mid channel
+// analytic BN1 statistics: mu1 = W1 mu_x, v1 = w^T cov w.  8 stacked mid channels per CTA; every thread walks its
+// share of the ic x ic covariance once (coalesced, fp64) for all 8 channels.
+#define BN1_CH 8
 __global__ void __launch_bounds__(NT) k_bn1(Plan P, const double* __restrict__ xmom, float* __restrict__ bn1) {
-  const int warp = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= P.MC) return;
-  int s = 0;
-  while (s + 1 < P.na && warp >= P.c[s + 1].coff) ++s;
-  const int ic = P.ic;
-  const float* w = P.c[s].w1 + (size_t)(warp - P.c[s].coff) * ic;
+  extern __shared__ float wsm[];       // [BN1_CH][ic]
+  const int ic = P.ic, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.x * BN1_CH;
+  for (int i = tid; i < BN1_CH * ic; i += NT) {
+    const int cc = i / ic, k = i - cc * ic, cst = c0 + cc;
+    float w = 0.f;
+    if (cst < P.MC) {
+      int s = 0;
+      while (s + 1 < P.na && cst >= P.c[s + 1].coff) ++s;
+      w = P.c[s].w1[(size_t)(cst - P.c[s].coff) * ic + k];
+    }
+    wsm[i] = w;
+  }
+  __syncthreads();
   const double* mean = xmom;
   const double* cov = xmom + ic;
-  double mu = 0.0, v = 0.0;
-  for (int j = lane; j < ic; j += 32) {
-    double t = 0.0;
-    for (int k = 0; k < ic; ++k) t += (double)w[k] * cov[k * ic + j];
-    double wj = (double)w[j];
-    v += t * wj;
-    mu += wj * mean[j];
+  double acc[BN1_CH];
+#pragma unroll
+  for (int c = 0; c < BN1_CH; ++c) acc[c] = 0.0;
+  const float inv_ic = 1.f / (float)ic;
+  for (int idx = tid; idx < ic * ic; idx += NT) {
+    const int k = fast_div(idx, ic, inv_ic), j = idx - k * ic;
+    const double cv = cov[idx];
+#pragma unroll
+    for (int c = 0; c < BN1_CH; ++c) acc[c] += (double)(wsm[c * ic + k] * wsm[c * ic + j]) * cv;
   }
-  mu = warp_sum_d(mu);
-  v = warp_sum_d(v);
-  if (lane == 0) {
-    bn1[warp] = (float)mu;
-    bn1[P.MC + warp] = (float)(1.0 / sqrt(fmax(v, 0.0) + (double)BN_EPS));
+  __shared__ double red[NT / 32][BN1_CH];
+#pragma unroll
+  for (int c = 0; c < BN1_CH; ++c) {
+    const double t = warp_sum_d(acc[c]);
+    if (lane == 0) red[warp][c] = t;
+  }
+  __syncthreads();
+  if (warp < BN1_CH && c0 + warp < P.MC) {      // warp c: finish channel c
+    double mu = 0.0;
+    for (int k = lane; k < ic; k += 32) mu += (double)wsm[warp * ic + k] * mean[k];
+    mu = warp_sum_d(mu);
+    if (lane == 0) {
+      double v = 0.0;
+      for (int w = 0; w < NT / 32; ++w) v += red[w][warp];
+      bn1[c0 + warp] = (float)mu;
+      bn1[P.MC + c0 + warp] = (float)(1.0 / sqrt(fmax(v, 0.0) + (double)BN_EPS));
+    }
   }
 }
 
@@ -598,15 +622,15 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
     { ProfScope ps("xsum", xbytes, 1.0 * P.P * ic, st);
       k_xsum<<<dim3(ic, split), NT, 0, st>>>(P, x, S.xsum); }
     int nb = (ic + 3) / 4, icp = nb * 4, nblk = nb * nb;
-    int chunks = max(1, min(cdiv(P.HW, XC_TPX), cdiv(4 * sm_count(), P.N)));
+    int ctas = max(1, min(cdiv(P.P, XC_TPX), 4 * sm_count()));
     size_t smem = (size_t)(icp * XC_LD + icp + (nblk < NT ? nblk * 16 : 0)) * 4;
     cudaFuncSetAttribute(k_xcov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     { ProfScope ps("xcov", xbytes, 1.0 * P.P * ic * ic, st);
-      k_xcov<<<dim3(chunks, P.N), NT, smem, st>>>(P, x, S.xsum, S.xcov); }
+      k_xcov<<<ctas, NT, smem, st>>>(P, x, S.xsum, S.xcov); }
     { ProfScope ps("xfin", 16.0 * ic * ic, 0, st);
       k_xfin<<<cdiv(ic * ic, 256), 256, 0, st>>>(ic, P.P, S.xsum, S.xcov, xmom); }
     { ProfScope ps("bn1", 4.0 * P.MC * ic + 8.0 * ic * ic, 2.0 * P.MC * ic * ic, st);
-      k_bn1<<<cdiv(P.MC * 32, NT), NT, 0, st>>>(P, xmom, bn1); }
+      k_bn1<<<cdiv(P.MC, BN1_CH), NT, (size_t)BN1_CH * ic * 4, st>>>(P, xmom, bn1); }
   }
   // F1a
   if (umma_enabled()) {

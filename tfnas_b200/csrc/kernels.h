@@ -78,6 +78,10 @@ void launch_sink_bwd(int K, size_t numel, const float* const* res, const float* 
                      const float* cumlat, const float* dout, const float* dlat, float* const* dres,
                      float* dbetas, float* dcumlat, double* ws, cudaStream_t st);
 
+void launch_bn_act_fwd(int N, int C, int HW, int act, const float* x, float* y, float* mr, double* ws, cudaStream_t st);
+void launch_bn_act_bwd(int N, int C, int HW, int act, const float* x, const float* mr, const float* dy, float* dx,
+                       double* ws, cudaStream_t st);
+
 void count_launch(int n);
 
 // RAII launch marker: counts the launch and, when profiling is enabled (tfnas_prof_enable), brackets

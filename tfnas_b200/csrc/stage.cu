@@ -110,3 +110,168 @@ void launch_sink_bwd(int K, size_t numel, const float* const* res, const float* 
   { ProfScope ps("sink_fin", 64, 0, st);
     k_sink_fin<<<1, 32, 0, st>>>(K, betas, cumlat, dlat, ws, dbetas, dcumlat); }
 }
+
+// -------------------------------------------------------------------------------------------------
+// Batch-statistic BatchNorm (no affine, biased variance, eps 1e-5) fused with the activation, for the
+// non-MixedOP layers of Network.forward (reference models/layers.py:90-110 BasicLayer with
+// nn.BatchNorm2d(affine=False, track_running_stats=False) + ReLU / Swish; models/model_search.py:219-220,275).
+// -------------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float bn_act(float v) {
+  if (ACT == TFNAS_ACT_RELU) return act_f<TFNAS_ACT_RELU>(v);
+  if (ACT == TFNAS_ACT_SWISH) return act_f<TFNAS_ACT_SWISH>(v);
+  return v;
+}
+template <int ACT>
+__device__ __forceinline__ float bn_dact(float v) {
+  if (ACT == TFNAS_ACT_RELU) return act_df<TFNAS_ACT_RELU>(v);
+  if (ACT == TFNAS_ACT_SWISH) return act_df<TFNAS_ACT_SWISH>(v);
+  return 1.f;
+}
+
+// grid (C, splits): per-channel sum and sum of squares over (n, hw)
+__global__ void __launch_bounds__(NT) k_bn_stats(int N, int C, int HW, const float* __restrict__ x, double* __restrict__ st) {
+  const int c = blockIdx.x;
+  const long long total = (long long)N * HW;
+  const long long i0 = total * blockIdx.y / gridDim.y, i1 = total * (blockIdx.y + 1) / gridDim.y;
+  float s1 = 0.f, s2 = 0.f;
+  const float inv_hw = 1.f / (float)HW;
+  if ((HW & 3) == 0) {
+    for (long long i = (i0 >> 2) + threadIdx.x; i < (i1 >> 2); i += NT) {
+      const int e = (int)(i << 2);
+      const int n = fast_div(e, HW, inv_hw), hw = e - n * HW;
+      const float4 v = *(const float4*)(x + ((size_t)n * C + c) * HW + hw);
+      s1 += v.x + v.y + v.z + v.w;
+      s2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (long long i = i0 + threadIdx.x; i < i1; i += NT) {
+      const int n = fast_div((int)i, HW, inv_hw), hw = (int)i - n * HW;
+      const float v = x[((size_t)n * C + c) * HW + hw];
+      s1 += v;
+      s2 += v * v;
+    }
+  }
+  __shared__ double red[2][NT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double a = warp_sum_d((double)s1), b = warp_sum_d((double)s2);
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0;
+    for (int w = 0; w < NT / 32; ++w) t += red[threadIdx.x][w];
+    atomicAdd(&st[2 * c + threadIdx.x], t);
+  }
+}
+
+__global__ void k_bn_fin(int C, double invM, const double* __restrict__ st, float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = st[2 * c] * invM;
+  double v = st[2 * c + 1] * invM - m * m;
+  out[c] = (float)m;
+  out[C + c] = (float)(1.0 / sqrt(fmax(v, 0.0) + (double)BN_EPS));
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_bn_apply(int C, int HW, size_t total, const float* __restrict__ x,
+                                                  const float* __restrict__ mr, float* __restrict__ y) {
+  const float inv_hw = 1.f / (float)HW;
+  const size_t stride = (size_t)gridDim.x * NT;
+  if ((HW & 3) == 0) {
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < (total >> 2); i += stride) {
+      const size_t e = i << 2;
+      const int plane = (int)(e / HW);
+      const int c = plane % C;
+      const float mu = mr[c], r = mr[C + c];
+      const float4 v = *(const float4*)(x + e);
+      *(float4*)(y + e) = make_float4(bn_act<ACT>((v.x - mu) * r), bn_act<ACT>((v.y - mu) * r),
+                                      bn_act<ACT>((v.z - mu) * r), bn_act<ACT>((v.w - mu) * r));
+    }
+  } else {
+    for (size_t e = (size_t)blockIdx.x * NT + threadIdx.x; e < total; e += stride) {
+      const int c = (int)((e / HW) % C);
+      y[e] = bn_act<ACT>((x[e] - mr[c]) * mr[C + c]);
+    }
+  }
+  (void)inv_hw;
+}
+
+// backward pass 1: g = dy * act'(xhat); sums of g and g*xhat per channel.  grid (C, splits)
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_bn_bwd_stats(int N, int C, int HW, const float* __restrict__ x,
+                                                      const float* __restrict__ mr, const float* __restrict__ dy,
+                                                      double* __restrict__ st) {
+  const int c = blockIdx.x;
+  const float mu = mr[c], r = mr[C + c];
+  const long long total = (long long)N * HW;
+  const long long i0 = total * blockIdx.y / gridDim.y, i1 = total * (blockIdx.y + 1) / gridDim.y;
+  const float inv_hw = 1.f / (float)HW;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += NT) {
+    const int n = fast_div((int)i, HW, inv_hw), hw = (int)i - n * HW;
+    const size_t a = ((size_t)n * C + c) * HW + hw;
+    const float xh = (x[a] - mu) * r;
+    const float g = dy[a] * bn_dact<ACT>(xh);
+    s1 += g;
+    s2 += g * xh;
+  }
+  __shared__ double red[2][NT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double a = warp_sum_d((double)s1), b = warp_sum_d((double)s2);
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0;
+    for (int w = 0; w < NT / 32; ++w) t += red[threadIdx.x][w];
+    atomicAdd(&st[2 * c + threadIdx.x], t);
+  }
+}
+
+// backward pass 2: dx = r (g - mean(g) - xhat mean(g xhat))
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_bn_bwd_apply(int C, int HW, size_t total, double invM, const float* __restrict__ x,
+                                                      const float* __restrict__ mr, const float* __restrict__ dy,
+                                                      const double* __restrict__ st, float* __restrict__ dx) {
+  const size_t stride = (size_t)gridDim.x * NT;
+  for (size_t e = (size_t)blockIdx.x * NT + threadIdx.x; e < total; e += stride) {
+    const int c = (int)((e / HW) % C);
+    const float mu = mr[c], r = mr[C + c];
+    const float m1 = (float)(st[2 * c] * invM), m2 = (float)(st[2 * c + 1] * invM);
+    const float xh = (x[e] - mu) * r;
+    const float g = dy[e] * bn_dact<ACT>(xh);
+    dx[e] = r * (g - m1 - xh * m2);
+  }
+}
+
+void launch_bn_act_fwd(int N, int C, int HW, int act, const float* x, float* y, float* mr, double* ws, cudaStream_t st) {
+  const size_t total = (size_t)N * C * HW;
+  cudaMemsetAsync(ws, 0, (size_t)2 * C * sizeof(double), st);
+  int splits = max(1, min((int)(((long long)N * HW + 4095) / 4096), cdiv(4 * sm_count(), C)));
+  { ProfScope ps("bn_stats", 4.0 * total, 3.0 * total, st);
+    k_bn_stats<<<dim3(C, splits), NT, 0, st>>>(N, C, HW, x, ws); }
+  { ProfScope ps("bn_fin", 24.0 * C, 0, st);
+    k_bn_fin<<<cdiv(C, 256), 256, 0, st>>>(C, 1.0 / ((double)N * HW), ws, mr); }
+  int blocks = (int)min((size_t)(8 * sm_count()), (total / 4 + NT - 1) / NT);
+  ProfScope ps("bn_apply", 8.0 * total, 4.0 * total, st);
+  if (act == TFNAS_ACT_RELU) k_bn_apply<TFNAS_ACT_RELU><<<max(blocks, 1), NT, 0, st>>>(C, HW, total, x, mr, y);
+  else if (act == TFNAS_ACT_SWISH) k_bn_apply<TFNAS_ACT_SWISH><<<max(blocks, 1), NT, 0, st>>>(C, HW, total, x, mr, y);
+  else k_bn_apply<2><<<max(blocks, 1), NT, 0, st>>>(C, HW, total, x, mr, y);
+}
+
+void launch_bn_act_bwd(int N, int C, int HW, int act, const float* x, const float* mr, const float* dy, float* dx,
+                       double* ws, cudaStream_t st) {
+  const size_t total = (size_t)N * C * HW;
+  cudaMemsetAsync(ws, 0, (size_t)2 * C * sizeof(double), st);
+  int splits = max(1, min((int)(((long long)N * HW + 4095) / 4096), cdiv(4 * sm_count(), C)));
+  int blocks = (int)min((size_t)(8 * sm_count()), (total + NT - 1) / NT);
+  const double invM = 1.0 / ((double)N * HW);
+  { ProfScope ps("bn_bwd_stats", 8.0 * total, 6.0 * total, st);
+    if (act == TFNAS_ACT_RELU) k_bn_bwd_stats<TFNAS_ACT_RELU><<<dim3(C, splits), NT, 0, st>>>(N, C, HW, x, mr, dy, ws);
+    else if (act == TFNAS_ACT_SWISH) k_bn_bwd_stats<TFNAS_ACT_SWISH><<<dim3(C, splits), NT, 0, st>>>(N, C, HW, x, mr, dy, ws);
+    else k_bn_bwd_stats<2><<<dim3(C, splits), NT, 0, st>>>(N, C, HW, x, mr, dy, ws); }
+  ProfScope ps("bn_bwd_apply", 12.0 * total, 8.0 * total, st);
+  if (act == TFNAS_ACT_RELU) k_bn_bwd_apply<TFNAS_ACT_RELU><<<max(blocks, 1), NT, 0, st>>>(C, HW, total, invM, x, mr, dy, ws, dx);
+  else if (act == TFNAS_ACT_SWISH) k_bn_bwd_apply<TFNAS_ACT_SWISH><<<max(blocks, 1), NT, 0, st>>>(C, HW, total, invM, x, mr, dy, ws, dx);
+  else k_bn_bwd_apply<2><<<max(blocks, 1), NT, 0, st>>>(C, HW, total, invM, x, mr, dy, ws, dx);
+}

@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .config import CAND_SPEC, PRIMITIVES, lut_key
-from .ops import MixedOpCall, MixedOpFn, StageSinkFn
+from .ops import MixedOpCall, MixedOpFn, StageSinkFn, bn_act
 
 __all__ = ['PRIMITIVES', 'OPS', 'MixedOP', 'MixedStage', 'Network', 'MBInvertedResBlock', 'ConvLayer',
            'LinearLayer', 'NoisePlan', 'injected', 'seed_noise', 'draw_gumbel']
@@ -303,8 +303,7 @@ class ConvLayer(nn.Module):
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, kernel_size // 2, bias=False)
 
     def forward(self, x):
-        x = F.batch_norm(self.conv(x), None, None, None, None, True, 0.0, 1e-5)
-        return F.relu(x) if self.act_func == 'relu' else x * torch.sigmoid(x)
+        return bn_act(self.conv(x), self.act_func)
 
 
 class LinearLayer(nn.Module):
@@ -321,12 +320,11 @@ class _StemBlock(MBInvertedResBlock):
     Runs on stock torch ops for now ('next')."""
 
     def forward(self, x):
-        bn = lambda t: F.batch_norm(t, None, None, None, None, True, 0.0, 1e-5)
-        x = F.relu(bn(self.depth_conv.conv(x)))
+        x = bn_act(self.depth_conv.conv(x), 'relu')
         g = F.adaptive_avg_pool2d(x, 1)
         g = self.squeeze_excite.conv_expand(F.relu(self.squeeze_excite.conv_reduce(g)))
         x = x * torch.sigmoid(g)
-        return bn(self.point_linear.conv(x))
+        return bn_act(self.point_linear.conv(x), None)
 
 
 class Network(nn.Module):

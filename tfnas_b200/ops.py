@@ -166,3 +166,39 @@ class StageSinkFn(torch.autograd.Function):
         check(lib.tfnas_stage_sink_bwd(K, gout.numel(), ptrs, _ptr(betas), _ptr(cl), _ptr(gout), _ptr(gl), dptrs,
                                        _ptr(dbetas), _ptr(dcum), _ptr(ws), 64, _stream()))
         return (dbetas, dcum) + tuple(dres)
+
+
+class BnActFn(torch.autograd.Function):
+    """y = act(BN_batchstats(x)) (no affine, eps 1e-5): the BN + activation of the stems / feature-mix layer."""
+
+    @staticmethod
+    def forward(ctx, x, act):
+        lib = _lib.load()
+        _require_cuda_f32(x, 'x')
+        x = x.contiguous()
+        N, C = x.shape[0], x.shape[1]
+        HW = x.numel() // (N * C)
+        y = torch.empty_like(x)
+        mr = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        ws = torch.empty(16 * C, dtype=torch.uint8, device=x.device)
+        check(lib.tfnas_bn_act_fwd(N, C, HW, _lib.ACT_CODE[act], _ptr(x), _ptr(y), _ptr(mr), _ptr(ws), 16 * C, _stream()))
+        ctx.act = act
+        ctx.save_for_backward(x, mr)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, mr = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, C = x.shape[0], x.shape[1]
+        HW = x.numel() // (N * C)
+        dx = torch.empty_like(x)
+        ws = torch.empty(16 * C, dtype=torch.uint8, device=x.device)
+        check(lib.tfnas_bn_act_bwd(N, C, HW, _lib.ACT_CODE[ctx.act], _ptr(x), _ptr(mr), _ptr(gy), _ptr(dx), _ptr(ws),
+                                   16 * C, _stream()))
+        return dx, None
+
+
+def bn_act(x, act):
+    return BnActFn.apply(x, act)
