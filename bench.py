@@ -257,7 +257,7 @@ def run_b200(args, rank, local, world):
                 'kernel_ms_per_step': tot_ms / args.steps,
                 'kernels': [{'name': r['name'], 'share': r['ms'] / tot_ms, 'ms_per_step': r['ms'] / args.steps,
                              'GBps': r['bytes'] / r['ms'] / 1e6, 'TFLOPs': r['flops'] / r['ms'] / 1e9,
-                             'launches_per_step': r['launches'] / args.steps} for r in recs[:12]]}
+                             'launches_per_step': r['launches'] / args.steps} for r in recs[:48]]}
     if rank != 0:
         return
     h2d = 3 * (BS * 3 * 224 * 224 * 4 + BS * 8)

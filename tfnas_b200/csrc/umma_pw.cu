@@ -21,6 +21,8 @@
 using namespace umma;
 
 #define UM_KC 32                 // K rows per chunk (one 128 B swizzle row of the weights)
+#define UM_NT 512                // threads per CTA of the pointwise tcgen05 kernels (16 warps, 2 K rows per warp per chunk)
+#define UM_RW (UM_KC / (UM_NT / 32))   // K rows per warp per chunk
 #define UM_STAGES 1              // one smem stage per CTA: 2-3 CTAs/SM overlap each other's load / MMA / epilogue phases
 
 // One GEMM's weight-side geometry for one candidate slot
@@ -111,14 +113,14 @@ __device__ __forceinline__ void um_issue(const UmSmem& S, int s, int Nc, uint32_
 
 // Generic main loop.  F supplies:
 //   int   nchunks()                                   K chunks this CTA walks
-//   void  load(int c, float4 (&ra)[4], float4 (&rb)[4])     global loads of chunk c (rows warp+8i, 4 px / lane)
+//   void  load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW])     global loads of chunk c (rows warp+8i, 4 px / lane)
 //   void  emit(int c, ra, rb, a_hi, a_lo)                   prologue math + hi/lo split + st.shared
 //   const void* wsrc(int c)                                 prepped weight block of chunk c (2*Nc*128 bytes)
 template <class F>
 __device__ __forceinline__ void um_mainloop(F& f, const UmSmem& S, int Nc, uint32_t tmem, uint32_t idesc) {
   const int tid = threadIdx.x;
   const int n = f.nchunks();
-  float4 ra[4], rb[4];
+  float4 ra[UM_RW], rb[UM_RW];
   if (n > 0) f.load(0, ra, rb);
   uint32_t ph_b[UM_STAGES] = {0}, ph_m[UM_STAGES] = {0};
   for (int c = 0; c < n; ++c) {
@@ -185,10 +187,11 @@ __device__ __forceinline__ EpiPx epi_px(int tile0, int total, int HW) {
 }
 // column range of this warp: warps w and w+4 split the Nc columns in halves (multiples of 16)
 __device__ __forceinline__ void epi_cols(int Nc, int& c_lo, int& c_hi) {
-  const int half = (threadIdx.x >> 5) >> 2;
-  const int h = (Nc / 2 + 15) / 16 * 16;
-  c_lo = half * h;
-  c_hi = min(Nc, (half + 1) * h);
+  const int parts = blockDim.x >> 7;                  // warps / 4
+  const int part = (threadIdx.x >> 5) >> 2;
+  const int h = ((Nc + parts - 1) / parts + 15) / 16 * 16;
+  c_lo = min(Nc, part * h);
+  c_hi = min(Nc, (part + 1) * h);
 }
 __device__ __forceinline__ uint32_t epi_taddr(uint32_t tmem, int col) {
   return tmem + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16) + (uint32_t)col;
@@ -207,24 +210,24 @@ __device__ __forceinline__ float4 ld4(const float* __restrict__ T, const Px4& px
 struct ExpandF {
   const Plan& P; const UmW& W; const float* x; Px4 px; int nc; int lane, warp;
   __device__ int nchunks() const { return W.nK; }
-  __device__ void load(int c, float4 (&ra)[4], float4 (&rb)[4]) const {
+  __device__ void load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW]) const {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = c * UM_KC + warp + i * 8;
+    for (int i = 0; i < UM_RW; ++i) {
+      const int k = c * UM_KC + warp + i * (UM_NT / 32);
       ra[i] = k < P.ic ? ld4(x, px, P.ic, k, P.HW) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  __device__ void emit(int c, const float4 (&ra)[4], const float4 (&rb)[4], unsigned char* ah, unsigned char* al) const {
+  __device__ void emit(int c, const float4 (&ra)[UM_RW], const float4 (&rb)[UM_RW], unsigned char* ah, unsigned char* al) const {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < UM_RW; ++i) {
       const float v[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
-      um_put(ah, al, lane, warp + i * 8, v);
+      um_put(ah, al, lane, warp + i * (UM_NT / 32), v);
     }
   }
   __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
 };
 
-__global__ void __launch_bounds__(NT) k_um_expand(Plan P, UmWAll WA, const float* __restrict__ x,
+__global__ void __launch_bounds__(UM_NT, 2) k_um_expand(Plan P, UmWAll WA, const float* __restrict__ x,
                                                    const float* __restrict__ bn1, float* __restrict__ UH) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
   const int slot = blockIdx.z, nc = blockIdx.y;
@@ -263,17 +266,17 @@ template <int ACT>
 struct ProjectF {
   const Plan& P; const UmW& W; const Cand& cd; const float* D; const float* bn2; const float* seg; Px4 px; int nc; int lane, warp;
   __device__ int nchunks() const { return W.nK; }
-  __device__ void load(int c, float4 (&ra)[4], float4 (&rb)[4]) const {
+  __device__ void load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW]) const {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = c * UM_KC + warp + i * 8;
+    for (int i = 0; i < UM_RW; ++i) {
+      const int k = c * UM_KC + warp + i * (UM_NT / 32);
       ra[i] = k < cd.mc ? ld4(D, px, P.MC, cd.coff + k, P.HWo) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  __device__ void emit(int c, const float4 (&ra)[4], const float4 (&rb)[4], unsigned char* ah, unsigned char* al) const {
+  __device__ void emit(int c, const float4 (&ra)[UM_RW], const float4 (&rb)[UM_RW], unsigned char* ah, unsigned char* al) const {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int kk = warp + i * 8, k = c * UM_KC + kk;
+    for (int i = 0; i < UM_RW; ++i) {
+      const int kk = warp + i * (UM_NT / 32), k = c * UM_KC + kk;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (k < cd.mc) {
         const int cst = cd.coff + k;
@@ -293,7 +296,7 @@ struct ProjectF {
 };
 
 template <int ACT>
-__global__ void __launch_bounds__(NT) k_um_project(Plan P, UmWAll WA, const float* __restrict__ D,
+__global__ void __launch_bounds__(UM_NT, 2) k_um_project(Plan P, UmWAll WA, const float* __restrict__ D,
                                                     const float* __restrict__ bn2, const float* __restrict__ seg,
                                                     float* __restrict__ Zb, double* __restrict__ st3) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
@@ -338,10 +341,10 @@ __global__ void __launch_bounds__(NT) k_um_project(Plan P, UmWAll WA, const floa
 struct DcF {
   const Plan& P; const UmW& W; const float* G; const float* Zb; const float* bn3; const float4* dzc; Px4 px; int nc, slot; int lane, warp;
   __device__ int nchunks() const { return W.nK; }
-  __device__ void load(int c, float4 (&ra)[4], float4 (&rb)[4]) const {
+  __device__ void load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW]) const {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int o = c * UM_KC + warp + i * 8;
+    for (int i = 0; i < UM_RW; ++i) {
+      const int o = c * UM_KC + warp + i * (UM_NT / 32);
       if (o < P.oc) {
         ra[i] = ld4(G, px, P.oc, o, P.HWo);
         rb[i] = ld4(Zb, px, P.na * P.oc, slot * P.oc + o, P.HWo);
@@ -350,10 +353,10 @@ struct DcF {
       }
     }
   }
-  __device__ void emit(int c, const float4 (&ra)[4], const float4 (&rb)[4], unsigned char* ah, unsigned char* al) const {
+  __device__ void emit(int c, const float4 (&ra)[UM_RW], const float4 (&rb)[UM_RW], unsigned char* ah, unsigned char* al) const {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int kk = warp + i * 8, o = c * UM_KC + kk;
+    for (int i = 0; i < UM_RW; ++i) {
+      const int kk = warp + i * (UM_NT / 32), o = c * UM_KC + kk;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (o < P.oc) {
         const float4 cf = dzc[slot * P.oc + o];
@@ -369,7 +372,7 @@ struct DcF {
 };
 
 template <int ACT>
-__global__ void __launch_bounds__(NT) k_um_dc(Plan P, UmWAll WA, const float* __restrict__ G, const float* __restrict__ Zb,
+__global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const float* __restrict__ G, const float* __restrict__ Zb,
                                                const float* __restrict__ bn3, const float4* __restrict__ dzc,
                                                const float* __restrict__ D, const float* __restrict__ bn2,
                                                float* __restrict__ DC, float* __restrict__ dg, double* __restrict__ sD) {
@@ -469,13 +472,13 @@ struct DxF {
     while (slot + 1 < P.na && g >= CH.first[slot + 1]) ++slot;
     k0 = (g - CH.first[slot]) * UM_KC;
   }
-  __device__ void load(int c, float4 (&ra)[4], float4 (&rb)[4]) const {
+  __device__ void load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW]) const {
     int slot, k0;
     locate(c, slot, k0);
     const Cand& cd = P.c[slot];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = k0 + warp + i * 8;
+    for (int i = 0; i < UM_RW; ++i) {
+      const int k = k0 + warp + i * (UM_NT / 32);
       if (k < cd.mc) {
         ra[i] = ld4(DA, px, P.MC, cd.coff + k, P.HW);
         rb[i] = ld4(UH, px, P.MC, cd.coff + k, P.HW);
@@ -484,7 +487,7 @@ struct DxF {
       }
     }
   }
-  __device__ void emit(int c, const float4 (&ra)[4], const float4 (&rb)[4], unsigned char* ah, unsigned char* al) const {
+  __device__ void emit(int c, const float4 (&ra)[UM_RW], const float4 (&rb)[UM_RW], unsigned char* ah, unsigned char* al) const {
     int slot, k0;
     locate(c, slot, k0);
     const Cand& cd = P.c[slot];
@@ -492,8 +495,8 @@ struct DxF {
 #pragma unroll
     for (int i = 0; i < 16; ++i) st[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int kk = warp + i * 8, k = k0 + kk;
+    for (int i = 0; i < UM_RW; ++i) {
+      const int kk = warp + i * (UM_NT / 32), k = k0 + kk;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (k < cd.mc) {     // warp-uniform
         const int cst = cd.coff + k;
@@ -511,8 +514,8 @@ struct DxF {
     }
     // 8 statistics (4 rows x {sum du, sum du*uh}) reduced together; lane l < 8 ends up owning statistic l
     const float tot = warp_sum16(st);
-    if (lane < 8) {
-      const int k = k0 + warp + (lane >> 1) * 8;
+    if (lane < 2 * UM_RW) {
+      const int k = k0 + warp + (lane >> 1) * (UM_NT / 32);
       if (k < cd.mc) atomicAdd(&sU[2 * (cd.coff + k) + (lane & 1)], (double)tot);
     }
   }
@@ -520,7 +523,7 @@ struct DxF {
 };
 
 template <int ACT>
-__global__ void __launch_bounds__(NT) k_um_dx(Plan P, UmW W, DxChunks CH, int ksplit, const float* __restrict__ DA,
+__global__ void __launch_bounds__(UM_NT, 2) k_um_dx(Plan P, UmW W, DxChunks CH, int ksplit, const float* __restrict__ DA,
                                                const float* __restrict__ UH, const float* __restrict__ bn1,
                                                float* __restrict__ dx, double* __restrict__ sU) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
@@ -639,7 +642,7 @@ void umma_expand(const Plan& P, const float* x, const float* bn1, float* UH, flo
   size_t smem = um_smem_bytes(maxNc);
   cudaFuncSetAttribute(k_um_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
-  k_um_expand<<<dim3(cdiv(P.P, 128), maxN, P.na), NT, smem, st>>>(P, WA, x, bn1, UH);
+  k_um_expand<<<dim3(cdiv(P.P, 128), maxN, P.na), UM_NT, smem, st>>>(P, WA, x, bn1, UH);
 }
 
 void umma_project(const Plan& P, const float* D, const float* bn2, const float* seg, float* Zb, double* st3,
@@ -661,10 +664,10 @@ void umma_project(const Plan& P, const float* D, const float* bn2, const float* 
                2.0 * P.Q * (double)P.MC * P.oc, st);
   if (P.act == TFNAS_ACT_RELU) {
     cudaFuncSetAttribute(k_um_project<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_project<TFNAS_ACT_RELU><<<grid, NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
+    k_um_project<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
   } else {
     cudaFuncSetAttribute(k_um_project<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_project<TFNAS_ACT_SWISH><<<grid, NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
+    k_um_project<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
   }
 }
 
@@ -688,10 +691,10 @@ void umma_dc(const Plan& P, const float* G, const float* Zb, const float* bn3, c
                2.0 * P.Q * (double)P.MC * P.oc, st);
   if (P.act == TFNAS_ACT_RELU) {
     cudaFuncSetAttribute(k_um_dc<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_dc<TFNAS_ACT_RELU><<<grid, NT, smem, st>>>(P, WA, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
+    k_um_dc<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
   } else {
     cudaFuncSetAttribute(k_um_dc<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_dc<TFNAS_ACT_SWISH><<<grid, NT, smem, st>>>(P, WA, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
+    k_um_dc<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
   }
 }
 
@@ -723,10 +726,10 @@ void umma_dx(const Plan& P, const float* DA, const float* UH, const float* bn1, 
   ProfScope ps("dx", 4.0 * P.P * (2.0 * P.MC + P.ic) + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   if (P.act == TFNAS_ACT_RELU) {
     cudaFuncSetAttribute(k_um_dx<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_dx<TFNAS_ACT_RELU><<<grid, NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
+    k_um_dx<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
   } else {
     cudaFuncSetAttribute(k_um_dx<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_dx<TFNAS_ACT_SWISH><<<grid, NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
+    k_um_dx<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
   }
 }
 
