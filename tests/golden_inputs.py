@@ -19,15 +19,8 @@ NET = dict(N=2, size=224, seed=7, noise_seed=123, wstep_noise_seed=77, py_seed=5
 
 def load_lut():
     """LUT fixture -> the same dict-of-dicts structure as the reference pickle."""
-    z = np.load(os.path.join(GOLDEN_DIR, 'lut_gpu.npz'))
-    lut = OrderedDict()
-    lut['base'] = float(z['base'])
-    pos = 0
-    for k, n in zip(z['keys'], z['lens']):
-        vals = z['vals'][pos:pos + int(n)]
-        lut[str(k)] = OrderedDict((m + 1, float(v)) for m, v in enumerate(vals))
-        pos += int(n)
-    return lut
+    from tfnas_b200.lut import load_lut as _load
+    return _load(os.path.join(GOLDEN_DIR, 'lut_gpu.npz'))
 
 
 def patched_lut_cfg1(lut):

@@ -12,7 +12,6 @@ import argparse
 import copy
 import logging
 import os
-import pickle
 import random
 import sys
 import time
@@ -28,6 +27,7 @@ sys.path.insert(0, ROOT)
 
 from tfnas_b200 import config as cfg  # noqa: E402
 from tfnas_b200 import elastic, model_search, parallel, parsing, search_loop  # noqa: E402
+from tfnas_b200.lut import load_lut  # noqa: E402
 
 
 def build_parser():
@@ -131,8 +131,7 @@ def main(argv=None):
         model_search.seed_noise(args.seed)     # identical sampling on all ranks
     logging.info('args = %s', args)
 
-    with open(args.lookup_path, 'rb') as f:
-        lat_lookup = pickle.load(f)
+    lat_lookup = load_lut(args.lookup_path)
     mc_mask_dddict = cfg.make_mc_mask_dddict()
     keys = cfg.lat_lookup_key_dddict
     mc_maxnum_dddict = cfg.get_mc_num_dddict(mc_mask_dddict, is_max=True)
