@@ -85,7 +85,7 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit=print):
     """CPU oracle port, one search unit per step on a bounded sample (bs REF_BS)."""
     if rank != 0:
         return
@@ -109,7 +109,7 @@ def run_reference(args, rank, world):
     dt = time.time() - t0
     val = n_img / dt
     sample = 'search unit at bs %d on CPU (%d threads), fp32, same supernet / LUT / losses' % (REF_BS, torch.get_num_threads())
-    print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+    emit(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
                       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * dt / args.steps,
                       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                       'data': 'synthetic', 'config': base_config(max(world, 1)),
@@ -143,7 +143,7 @@ def cpu_baseline_sample():
 
 
 # ------------------------------------------------------------------------------------------------
-def run_b200(args, rank, local, world):
+def run_b200(args, rank, local, world, emit=print):
     import torch
     import torch.distributed as dist
     import torch.nn as nn
@@ -269,13 +269,28 @@ def run_b200(args, rank, local, world):
             'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_sample()
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+class StdoutGuard(object):
+    """Route everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr; the JSON line is the
+    only thing that reaches the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + '\n').encode())
 
 
 def main():
+    guard = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
@@ -285,7 +300,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, guard.emit)
         return
     from tfnas_b200.parallel import init_from_env
     rank, local, world = init_from_env()
@@ -293,8 +308,9 @@ def main():
         # launched without torchrun: re-exec under torch.distributed.run
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', '29531', os.path.abspath(__file__)] + sys.argv[1:]
+        os.dup2(guard.real, 1)
         raise SystemExit(subprocess.call(cmd))
-    run_b200(args, rank, local, world)
+    run_b200(args, rank, local, world, guard.emit)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -1,0 +1,96 @@
+"""2-GPU NCCL check of the data-parallel search step (skipped with < 2 GPUs): after GradSync every rank holds
+the MEAN of the per-shard gradients (SURVEY 8e parity definition), ranks sample identical sub-networks, and
+weights stay bit-identical across ranks after an optimiser step."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world)
+    try:
+        from tests import golden_inputs as gi
+        from tfnas_b200 import config, model_search
+        from tfnas_b200.model_search import Network
+        from tfnas_b200.parallel import GradSync, SearchParallel
+        from tfnas_b200.search_loop import make_optimizers, w_step
+        mcs = config.get_mc_num_dddict(config.mc_mask_dddict)
+        torch.manual_seed(2)
+        net = Network(100, mcs, gi.load_lut())
+        net.set_temperature(5.0)
+        model = SearchParallel(net).cuda().train()
+        crit = nn.CrossEntropyLoss().cuda()
+        g = torch.Generator().manual_seed(5)
+        xs = torch.randn(world, 4, 3, 64, 64, generator=g)
+        ts = torch.randint(0, 100, (world, 4), generator=g)
+
+        def grads_for(shard):
+            model_search.seed_noise(11)
+            for p in net.parameters():
+                p.grad = None
+            for p in net.weight_parameters():
+                p.requires_grad = True
+            for p in net.arch_parameters():
+                p.requires_grad = False
+            lg, _ = model(xs[shard].cuda(), sampling=True, mode='gumbel')
+            lr, _ = model(xs[shard].cuda(), sampling=True, mode='random')
+            (crit(lg, ts[shard].cuda()) + crit(lr, ts[shard].cuda())).backward()
+            return {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+
+        per = [grads_for(s) for s in range(world)]                 # every rank computes all shards (reference for the mean)
+        mine = grads_for(rank)
+        for n, p in net.named_parameters():
+            p.grad = mine.get(n)
+        nbytes = GradSync()(net.weight_parameters())
+        worst = 0.0
+        for n, p in net.named_parameters():
+            if n in per[0]:
+                ref = sum(per[s][n] for s in range(world)) / world
+                worst = max(worst, float((p.grad - ref).norm() / (ref.norm() + 1e-20)))
+        same_keys = all(set(per[0]) == set(per[s]) for s in range(world))
+        # one real optimiser step through the public loop, then compare weights across ranks
+        model_search.seed_noise(3)
+        opt_w, _ = make_optimizers(net)
+        w_step(model, xs[rank].cuda(), ts[rank].cuda(), crit, opt_w, 5.0, GradSync(), bisample=True)
+        flat = torch.cat([p.detach().reshape(-1) for p in net.weight_parameters()])
+        lo, hi = flat.clone(), flat.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        q.put((rank, worst, same_keys, nbytes, bool((lo == hi).all().item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_gpu_nccl_grad_mean_and_weight_sync():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, worst, same_keys, nbytes, synced in res:
+        print('rank', rank, 'worst rel err of all-reduced grads vs mean of shard grads', worst, 'bucket bytes', nbytes)
+        assert worst < 1e-5 and same_keys and nbytes > 1e6 and synced

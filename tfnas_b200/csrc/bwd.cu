@@ -23,7 +23,9 @@ __global__ void __launch_bounds__(NT) k_b1(Plan P, const float* __restrict__ G, 
                                             double* __restrict__ sGY) {
   const int c = blockIdx.x, oc = P.oc, na = P.na, HWo = P.HWo;
   const int nsplit = gridDim.y;
-  const int i0 = (int)((long long)P.Q * blockIdx.y / nsplit), i1 = (int)((long long)P.Q * (blockIdx.y + 1) / nsplit);
+  // split boundaries on multiples of 4 so the vector path never straddles them
+  const int i0 = (int)((long long)(P.Q >> 2) * blockIdx.y / nsplit) << 2;
+  const int i1 = (int)blockIdx.y + 1 == nsplit ? P.Q : ((int)((long long)(P.Q >> 2) * (blockIdx.y + 1) / nsplit) << 2);
   float mu[TFNAS_MAX_OPS], r[TFNAS_MAX_OPS], acc[TFNAS_MAX_OPS], sg = 0.f;
 #pragma unroll
   for (int s = 0; s < TFNAS_MAX_OPS; ++s) {
@@ -31,13 +33,29 @@ __global__ void __launch_bounds__(NT) k_b1(Plan P, const float* __restrict__ G, 
     mu[s] = s < na ? bn3[s * oc + c] : 0.f;
     r[s] = s < na ? bn3[na * oc + s * oc + c] : 0.f;
   }
-  for (int i = i0 + threadIdx.x; i < i1; i += NT) {
-    int n = i / HWo, hw = i - n * HWo;
-    float g = G[((size_t)n * oc + c) * HWo + hw];
-    sg += g;
+  const float inv_hwo = 1.f / (float)HWo;
+  if ((HWo & 3) == 0) {
+    for (int i = (i0 >> 2) + threadIdx.x; i < (i1 >> 2); i += NT) {
+      const int e0 = i << 2;
+      const int n = fast_div(e0, HWo, inv_hwo), hw = e0 - n * HWo;
+      const float4 g = *(const float4*)(G + ((size_t)n * oc + c) * HWo + hw);
+      sg += g.x + g.y + g.z + g.w;
 #pragma unroll
-    for (int s = 0; s < TFNAS_MAX_OPS; ++s)
-      if (s < na) acc[s] += g * (Zb[((size_t)(n * na + s) * oc + c) * HWo + hw] - mu[s]) * r[s];
+      for (int s = 0; s < TFNAS_MAX_OPS; ++s)
+        if (s < na) {
+          const float4 z = *(const float4*)(Zb + ((size_t)(n * na + s) * oc + c) * HWo + hw);
+          acc[s] += (g.x * (z.x - mu[s]) + g.y * (z.y - mu[s]) + g.z * (z.z - mu[s]) + g.w * (z.w - mu[s])) * r[s];
+        }
+    }
+  } else {
+    for (int i = i0 + threadIdx.x; i < i1; i += NT) {
+      const int n = fast_div(i, HWo, inv_hwo), hw = i - n * HWo;
+      const float g = G[((size_t)n * oc + c) * HWo + hw];
+      sg += g;
+#pragma unroll
+      for (int s = 0; s < TFNAS_MAX_OPS; ++s)
+        if (s < na) acc[s] += g * (Zb[((size_t)(n * na + s) * oc + c) * HWo + hw] - mu[s]) * r[s];
+    }
   }
   __shared__ double red[NT / 32][TFNAS_MAX_OPS + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -486,42 +504,72 @@ __global__ void k_b4coef(int MC, double invP, const float* __restrict__ bn1, con
   a12[MC + c] = (float)(r1 * r1 * sU[2 * c + 1] * invP);
 }
 
-// grid (ic, nsplit): partial row k of Mm[k][k'] = sum_c W1[c][k] a2_c W1[c][k'] and cvec[k] = sum_c W1[c][k] a1_c over
-// this block's share of the stacked channels; float atomics into the zeroed Mm / cvec.
+// Mm[k][k'] = sum_c W1[c][k] a2_c W1[c][k'] as a tiled CUDA-core GEMM over the stacked channels:
+// grid (ic/64, ic/64, c-splits); 64x64 tile, 4x4 per thread, 32 channels per smem chunk; float atomics into Mm.
+#define B4_T 64
+#define B4_KC 32
 __global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ a12, float* __restrict__ Mm,
                                               float* __restrict__ cvec) {
-  const int k = blockIdx.x, ic = P.ic, tid = threadIdx.x;
-  const int KP = ((ic + 31) / 32) * 32;       // threads along k'
-  const int parts = NT / KP;                  // thread groups striding over channels (ic <= 192 -> parts >= 1)
-  const int kp = tid % KP, part = tid / KP;
-  const int c_lo = (int)((long long)P.MC * blockIdx.y / gridDim.y), c_hi = (int)((long long)P.MC * (blockIdx.y + 1) / gridDim.y);
-  float m = 0.f, cv = 0.f;
-  if (part < parts) {
+  __shared__ __align__(16) float As[B4_KC][B4_T + 4];   // a2_c * W1[c][k0 + .]
+  __shared__ __align__(16) float Bs[B4_KC][B4_T + 4];   // W1[c][kp0 + .]
+  const int ic = P.ic, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k0 = blockIdx.x * B4_T, kp0 = blockIdx.y * B4_T;
+  const int c_lo = (int)((long long)P.MC * blockIdx.z / gridDim.z), c_hi = (int)((long long)P.MC * (blockIdx.z + 1) / gridDim.z);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int cb = c_lo; cb < c_hi; cb += B4_KC) {
+    __syncthreads();
+    for (int i = tid; i < B4_KC * B4_T; i += NT) {
+      const int cc = i / B4_T, kk = i - cc * B4_T;
+      const int cst = cb + cc;
+      float wa = 0.f, wb = 0.f;
+      if (cst < c_hi) {
+        int s = 0;
+        while (s + 1 < P.na && cst >= P.c[s + 1].coff) ++s;
+        const float* w = P.c[s].w1 + (size_t)(cst - P.c[s].coff) * ic;
+        if (k0 + kk < ic) wa = w[k0 + kk] * a12[P.MC + cst];
+        if (kp0 + kk < ic) wb = w[kp0 + kk];
+      }
+      As[cc][kk] = wa;
+      Bs[cc][kk] = wb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int cc = 0; cc < B4_KC; ++cc) {
+      const float4 a = *(const float4*)&As[cc][ty * 4];
+      const float4 bq = *(const float4*)&Bs[cc][tx * 4];
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + ty * 4 + i, kp = kp0 + tx * 4 + j;
+      if (k < ic && kp < ic) atomicAdd(&Mm[k * ic + kp], acc[i][j]);
+    }
+  (void)cvec;
+}
+
+// cvec[k] = sum_c W1[c][k] a1_c : grid (c-splits), thread = k, coalesced rows, float atomics
+__global__ void __launch_bounds__(NT) k_b4cvec(Plan P, const float* __restrict__ a12, float* __restrict__ cvec) {
+  const int ic = P.ic;
+  const int c_lo = (int)((long long)P.MC * blockIdx.x / gridDim.x), c_hi = (int)((long long)P.MC * (blockIdx.x + 1) / gridDim.x);
+  for (int k = threadIdx.x; k < ic; k += NT) {
+    float cv = 0.f;
     for (int s = 0; s < P.na; ++s) {
       const Cand& cd = P.c[s];
       const int lo = max(c_lo, cd.coff), hi = min(c_hi, cd.coff + cd.mc);
-      for (int cst = lo + part; cst < hi; cst += parts) {
-        const float* w = cd.w1 + (size_t)(cst - cd.coff) * ic;
-        const float wk = w[k];
-        if (kp < ic) m += wk * a12[P.MC + cst] * w[kp];
-        if (kp == 0) cv += wk * a12[cst];
-      }
+      for (int cst = lo; cst < hi; ++cst) cv += cd.w1[(size_t)(cst - cd.coff) * ic + k] * a12[cst];
     }
-  }
-  __shared__ float red[NT];
-  red[tid] = m;
-  __syncthreads();
-  if (part == 0 && kp < ic) {
-    for (int q = 1; q < parts; ++q) m += red[q * KP + kp];
-    atomicAdd(&Mm[k * ic + kp], m);
-  }
-  __syncthreads();
-  red[tid] = (kp == 0 && part < parts) ? cv : 0.f;
-  __syncthreads();
-  if (tid == 0) {
-    float t = 0.f;
-    for (int q = 0; q < parts; ++q) t += red[q * KP];
-    atomicAdd(&cvec[k], t);
+    atomicAdd(&cvec[k], cv);
   }
 }
 
@@ -862,8 +910,12 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     return;
   }
   // B2
+  UmWAll WD;
+  UmW WX;
+  DxChunks CHX;
   if (umma_enabled()) {
-    umma_dc(P, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, S.umprep, st);
+    umma_prep_bwd(P, S.umprep, WD, WX, CHX, st);
+    umma_dc(P, WD, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
   } else {
     int maxmc = 0;
     for (int s = 0; s < P.na; ++s) maxmc = max(maxmc, P.c[s].mc);
@@ -928,12 +980,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   // B3b
   OcTile Tx = oc_tile(ic, 24);
   if (umma_enabled()) {
-    size_t off = 0;     // the dx weights follow the dc weights in the prep buffer
-    for (int s = 0; s < P.na; ++s) {
-      int nN = cdiv(P.c[s].mc, 256), Nc = cdiv(cdiv(P.c[s].mc, nN), 16) * 16;
-      off += (size_t)nN * cdiv(oc, 32) * 2 * Nc * 32;
-    }
-    umma_dx(P, S.DA, UH, bn1, dx, S.sU, S.umprep + off, st);
+    umma_dx(P, WX, CHX, S.DA, UH, bn1, dx, S.sU, st);
   } else {
     int tiles = cdiv(P.P, PW_TPX);
     int total_chunks = 0;
@@ -974,8 +1021,11 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     { ProfScope ps("b4coef", 24.0 * P.MC, 0, st);
       k_b4coef<<<cdiv(P.MC, 256), 256, 0, st>>>(P.MC, 1.0 / (double)P.P, bn1, S.sU, S.a12); }
     { ProfScope ps("b4mm", 4.0 * P.MC * ic, 2.0 * P.MC * ic * ic, st);
-      int nsplit = max(1, min(cdiv(P.MC, 64), cdiv(4 * sm_count(), ic)));
-      k_b4mm<<<dim3(ic, nsplit), NT, 0, st>>>(P, S.a12, S.Mm, S.cvec2); }
+      const int kt = cdiv(ic, B4_T);
+      int nsplit = max(1, min(cdiv(P.MC, 2 * B4_KC), cdiv(2 * sm_count(), kt * kt)));
+      k_b4mm<<<dim3(kt, kt, nsplit), NT, 0, st>>>(P, S.a12, S.Mm, S.cvec2);
+      k_b4cvec<<<max(1, min(cdiv(P.MC, 64), 2 * sm_count())), NT, 0, st>>>(P, S.a12, S.cvec2);
+      count_launch(1); }
     { ProfScope ps("b4fin", 4.0 * ic * ic, 2.0 * ic * ic, st);
       k_b4fin<<<cdiv(ic, 64), 64, 0, st>>>(ic, S.Mm, xmom, S.cvec2); }
     switch (Tx.TC) {

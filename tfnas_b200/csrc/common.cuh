@@ -208,7 +208,7 @@ __device__ __forceinline__ void stage_planes2(float* tile, const float* __restri
 // load(n, k) -> input value and store(n, o, acc).
 #define FC_TN 32
 #define FC_TO 64
-#define FC_KC 32
+#define FC_KC 64
 template <bool WKN, class LoadF, class StoreF>
 __device__ __forceinline__ void fc_tile(int N, int Nout, int K, const float* __restrict__ Wg, LoadF load, StoreF store) {
   __shared__ float ins[FC_KC][FC_TN + 1];

@@ -633,8 +633,10 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
       k_bn1<<<cdiv(P.MC, BN1_CH), NT, (size_t)BN1_CH * ic * 4, st>>>(P, xmom, bn1); }
   }
   // F1a
+  UmWAll WE, WP;
   if (umma_enabled()) {
-    umma_expand(P, x, bn1, UH, S.umprep, st);
+    umma_prep_fwd(P, S.umprep, WE, WP, st);
+    umma_expand(P, WE, x, bn1, UH, st);
   } else {
     int maxmc = 0;
     for (int s = 0; s < P.na; ++s) maxmc = max(maxmc, P.c[s].mc);
@@ -677,13 +679,7 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
   }
   // F3
   if (umma_enabled()) {
-    // the project weights follow the expand weights in the prep buffer
-    size_t off = 0;
-    for (int s = 0; s < P.na; ++s) {
-      int nN = cdiv(P.c[s].mc, 256), Nc = cdiv(cdiv(P.c[s].mc, nN), 16) * 16;
-      off += (size_t)nN * cdiv(P.ic, 32) * 2 * Nc * 32;
-    }
-    umma_project(P, D, bn2, seg, Zb, S.st3, S.umprep + off, st);
+    umma_project(P, WP, D, bn2, seg, Zb, S.st3, st);
   } else {
     OcTile T3 = oc_tile(P.oc, 16);
     switch (T3.TC) {

@@ -53,16 +53,33 @@ int sm_count();
 int umma_enabled();
 size_t umma_fwd_prep_bytes(const Plan& P);
 size_t umma_bwd_prep_bytes(const Plan& P);
-void umma_expand(const Plan& P, const float* x, const float* bn1, float* UH, float* prep_buf, cudaStream_t st);
-void umma_project(const Plan& P, const float* D, const float* bn2, const float* seg, float* Zb, double* st3,
-                  float* prep_buf, cudaStream_t st);
-void umma_dc(const Plan& P, const float* G, const float* Zb, const float* bn3, const float4* dzc, const float* D,
-             const float* bn2, float* DC, float* dg, double* sD, float* prep_buf, cudaStream_t st);
+// One GEMM's weight-side geometry for one candidate slot
+struct UmW {
+  const float* wp;   // prepped weights: [nN][nK][2][Nc*128 B]
+  int Nout;          // true output channels
+  int Nc;            // channels per N chunk (multiple of 16, <= 256)
+  int nN;            // number of N chunks
+  int nK;            // number of K chunks (of 32)
+};
+struct UmWAll { UmW s[TFNAS_MAX_OPS]; };
+
+struct DxChunks {            // chunk c of the stacked K axis -> (slot, first local channel)
+  int total;
+  int first[TFNAS_MAX_OPS + 1];   // first chunk index of each slot
+};
+
+void umma_prep_fwd(const Plan& P, float* prep_buf, UmWAll& WE, UmWAll& WP, cudaStream_t st);
+void umma_prep_bwd(const Plan& P, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks& CH, cudaStream_t st);
+void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1, float* UH, cudaStream_t st);
+void umma_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn2, const float* seg, float* Zb,
+                  double* st3, cudaStream_t st);
+void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, const float* bn3, const float4* dzc,
+             const float* D, const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st);
 // MODE 0: dW3[o][c] += sum_p dz c~ ; MODE 1: SmatT[k][c] += sum_p du-hat x   (out must be zeroed by the caller)
 void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float* A1, const float* B0, const float* B1,
                 const float* bn2, const float* seg, const float* bn3, const float4* dzc, float* out, cudaStream_t st);
-void umma_dx(const Plan& P, const float* DA, const float* UH, const float* bn1, float* dx, double* sU, float* prep_buf,
-             cudaStream_t st);
+void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, const float* bn1,
+             float* dx, double* sU, cudaStream_t st);
 
 void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
                     const float* lat8, float T, int alpha_mode, float* out, float* out_lat,

@@ -25,16 +25,6 @@ using namespace umma;
 #define UM_RW (UM_KC / (UM_NT / 32))   // K rows per warp per chunk
 #define UM_STAGES 1              // one smem stage per CTA: 2-3 CTAs/SM overlap each other's load / MMA / epilogue phases
 
-// One GEMM's weight-side geometry for one candidate slot
-struct UmW {
-  const float* wp;   // prepped weights: [nN][nK][2][Nc*128 B]
-  int Nout;          // true output channels
-  int Nc;            // channels per N chunk (multiple of 16, <= 256)
-  int nN;            // number of N chunks
-  int nK;            // number of K chunks (of 32)
-};
-struct UmWAll { UmW s[TFNAS_MAX_OPS]; };
-
 static inline void um_tile(int Nout, int& Nc, int& nN) {
   nN = cdiv(Nout, 256);
   Nc = cdiv(cdiv(Nout, nN), 16) * 16;
@@ -456,11 +446,6 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const flo
 // -------------------------------------------------------------------------------------------------
 // B3b: dx_main = sum_i W1_i^T (r1 * du-hat), K = stacked mid channels (per-candidate chunks of 32)
 // -------------------------------------------------------------------------------------------------
-struct DxChunks {            // chunk c of the stacked K axis -> (slot, first local channel)
-  int total;
-  int first[TFNAS_MAX_OPS + 1];   // first chunk index of each slot
-};
-
 template <int ACT>
 struct DxF {
   const Plan& P; const UmW& W; const DxChunks& CH; const float* DA; const float* UH; const float* bn1; double* sU; Px4 px;
@@ -589,7 +574,7 @@ size_t umma_bwd_prep_bytes(const Plan& P) {
 }
 
 struct PrepJob { const float* src; float* dst; int ld_r, ld_k, nrows, K, Nc, nN, nK; };
-struct PrepJobs { int n; PrepJob j[TFNAS_MAX_OPS]; };
+struct PrepJobs { int n; PrepJob j[2 * TFNAS_MAX_OPS]; };
 
 // grid (max nK, max nN, jobs): all candidates' weights of one GEMM in ONE launch
 __global__ void __launch_bounds__(256) k_umma_prep_all(PrepJobs J) {
@@ -627,37 +612,34 @@ static void prep_launch(const PrepJobs& J, cudaStream_t st) {
   k_umma_prep_all<<<dim3(mk, mn, J.n), 256, 0, st>>>(J);
 }
 
-void umma_expand(const Plan& P, const float* x, const float* bn1, float* UH, float* prep_buf, cudaStream_t st) {
-  UmWAll WA;
+// all forward weights (expand W1, project W3) of the active candidates in one prep launch
+void umma_prep_fwd(const Plan& P, float* prep_buf, UmWAll& WE, UmWAll& WP, cudaStream_t st) {
   PrepJobs J;
   J.n = 0;
   float* cur = prep_buf;
-  int maxN = 0, maxNc = 0;
-  for (int s = 0; s < P.na; ++s) {
-    prep(J, P.c[s].w1, P.ic, 1, P.c[s].mc, P.ic, WA.s[s], cur);
-    maxN = max(maxN, WA.s[s].nN);
-    maxNc = max(maxNc, WA.s[s].Nc);
-  }
+  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w1, P.ic, 1, P.c[s].mc, P.ic, WE.s[s], cur);
+  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w3, P.c[s].mc, 1, P.oc, P.c[s].mc, WP.s[s], cur);
   prep_launch(J, st);
+}
+
+static void um_max(const Plan& P, const UmWAll& WA, int& maxN, int& maxNc) {
+  maxN = 0; maxNc = 0;
+  for (int s = 0; s < P.na; ++s) { maxN = max(maxN, WA.s[s].nN); maxNc = max(maxNc, WA.s[s].Nc); }
+}
+
+void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1, float* UH, cudaStream_t st) {
+  int maxN, maxNc;
+  um_max(P, WA, maxN, maxNc);
   size_t smem = um_smem_bytes(maxNc);
   cudaFuncSetAttribute(k_um_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   k_um_expand<<<dim3(cdiv(P.P, 128), maxN, P.na), UM_NT, smem, st>>>(P, WA, x, bn1, UH);
 }
 
-void umma_project(const Plan& P, const float* D, const float* bn2, const float* seg, float* Zb, double* st3,
-                  float* prep_buf, cudaStream_t st) {
-  UmWAll WA;
-  PrepJobs J;
-  J.n = 0;
-  float* cur = prep_buf;
-  int maxN = 0, maxNc = 0;
-  for (int s = 0; s < P.na; ++s) {
-    prep(J, P.c[s].w3, P.c[s].mc, 1, P.oc, P.c[s].mc, WA.s[s], cur);
-    maxN = max(maxN, WA.s[s].nN);
-    maxNc = max(maxNc, WA.s[s].Nc);
-  }
-  prep_launch(J, st);
+void umma_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn2, const float* seg, float* Zb,
+                  double* st3, cudaStream_t st) {
+  int maxN, maxNc;
+  um_max(P, WA, maxN, maxNc);
   size_t smem = um_smem_bytes(maxNc);
   dim3 grid(cdiv(P.Q, 128), maxN, P.na);
   ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
@@ -671,20 +653,32 @@ void umma_project(const Plan& P, const float* D, const float* bn2, const float* 
   }
 }
 
-void umma_dc(const Plan& P, const float* G, const float* Zb, const float* bn3, const float4* dzc, const float* D,
-             const float* bn2, float* DC, float* dg, double* sD, float* prep_buf, cudaStream_t st) {
-  UmWAll WA;
+// all backward weights (dc: W3^T, dx: W1^T with per-candidate K chunks) in one prep launch
+void umma_prep_bwd(const Plan& P, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks& CH, cudaStream_t st) {
   PrepJobs J;
   J.n = 0;
   float* cur = prep_buf;
-  int maxN = 0, maxNc = 0;
+  // logical weight (row = mid channel c, k = out channel o) = W3[o][c]
+  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w3, 1, P.c[s].mc, P.c[s].mc, P.oc, WD.s[s], cur);
+  um_tile(P.ic, WX.Nc, WX.nN);    // ic <= 192 -> one N chunk
+  WX.Nout = P.ic;
+  WX.wp = cur;
+  CH.first[0] = 0;
   for (int s = 0; s < P.na; ++s) {
-    // logical weight (row = mid channel c, k = out channel o) = W3[o][c]
-    prep(J, P.c[s].w3, 1, P.c[s].mc, P.c[s].mc, P.oc, WA.s[s], cur);
-    maxN = max(maxN, WA.s[s].nN);
-    maxNc = max(maxNc, WA.s[s].Nc);
+    // logical weight (row = input channel k', k = mid channel c) = W1[c][k'], chunks never straddle candidates
+    UmW Ws;
+    prep(J, P.c[s].w1, 1, P.ic, P.ic, P.c[s].mc, Ws, cur);
+    CH.first[s + 1] = CH.first[s] + Ws.nK;
   }
+  CH.total = CH.first[P.na];
+  WX.nK = CH.total;
   prep_launch(J, st);
+}
+
+void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, const float* bn3, const float4* dzc,
+             const float* D, const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st) {
+  int maxN, maxNc;
+  um_max(P, WA, maxN, maxNc);
   size_t smem = um_smem_bytes(maxNc);
   dim3 grid(cdiv(P.Q, 128), maxN, P.na);
   ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
@@ -698,26 +692,8 @@ void umma_dc(const Plan& P, const float* G, const float* Zb, const float* bn3, c
   }
 }
 
-void umma_dx(const Plan& P, const float* DA, const float* UH, const float* bn1, float* dx, double* sU, float* prep_buf,
-             cudaStream_t st) {
-  UmW W;
-  um_tile(P.ic, W.Nc, W.nN);    // ic <= 192 -> one N chunk
-  W.Nout = P.ic;
-  W.wp = prep_buf;
-  DxChunks CH;
-  CH.first[0] = 0;
-  float* cur = prep_buf;
-  PrepJobs J;
-  J.n = 0;
-  for (int s = 0; s < P.na; ++s) {
-    // logical weight (row = input channel k', k = mid channel c) = W1[c][k'], chunks never straddle candidates
-    UmW Ws;
-    prep(J, P.c[s].w1, 1, P.ic, P.ic, P.c[s].mc, Ws, cur);
-    CH.first[s + 1] = CH.first[s] + Ws.nK;
-  }
-  prep_launch(J, st);
-  CH.total = CH.first[P.na];
-  W.nK = CH.total;
+void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, const float* bn1,
+             float* dx, double* sU, cudaStream_t st) {
   const int tiles = cdiv(P.P, 128);
   int ksplit = max(1, min(CH.total, cdiv(2 * sm_count(), tiles)));
   if (ksplit > 1) cudaMemsetAsync(dx, 0, (size_t)P.P * P.ic * sizeof(float), st);
