@@ -12,7 +12,8 @@ ACT_NONE = 2
 ACT_CODE = {'relu': ACT_RELU, 'swish': ACT_SWISH, None: ACT_NONE, 'none': ACT_NONE}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libtfnas_b200.so')
+# TFNAS_B200_LIB selects another build of the same ABI (e.g. the phase-trace debug variant)
+LIB_PATH = os.environ.get('TFNAS_B200_LIB') or os.path.join(_HERE, 'lib', 'libtfnas_b200.so')
 
 
 class MixedOpDesc(ctypes.Structure):

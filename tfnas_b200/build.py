@@ -32,18 +32,23 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=True):
+TRACE_LIB = os.path.join(LIBDIR, 'libtfnas_b200_trace.so')
+
+
+def build(force=False, verbose=True, trace=False):
+    """trace=True builds the debug variant with the in-kernel phase trace (-DUM_TRACE) next to the product library."""
     os.makedirs(LIBDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, 'libtfnas_b200.digest')
+    stamp = os.path.join(LIBDIR, 'libtfnas_b200%s.digest' % ('_trace' if trace else ''))
     dg = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dg:
-        return LIB
+    lib = TRACE_LIB if trace else LIB
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == dg:
+        return lib
     nvcc = _nvcc()
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        obj = os.path.join(LIBDIR, src.replace('.cu', '_trace.o' if trace else '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + (['-DUM_TRACE'] if trace else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             print(' '.join(cmd), file=sys.stderr)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -54,12 +59,12 @@ def build(force=False, verbose=True):
             sys.stderr.write(out.decode(errors='replace'))
         if p.returncode != 0:
             raise RuntimeError('nvcc failed on %s:\n%s' % (src, out.decode(errors='replace')))
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [nvcc, '-shared', '-o', lib] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     with open(stamp, 'w') as f:
         f.write(dg)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv))
+    print(build(force='--force' in sys.argv, trace='--trace' in sys.argv))

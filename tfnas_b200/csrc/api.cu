@@ -142,6 +142,7 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
   size_t nd = (size_t)P.oc + (size_t)P.na * P.oc + 4 * (size_t)P.MC;
   size_t acc = take(nd * sizeof(double));
   size_t dzc = take((size_t)P.na * P.oc * sizeof(float4));
+  size_t dzc2 = take((size_t)P.na * P.oc * sizeof(float4));
   size_t cvec2 = take((size_t)P.ic * 4);
   size_t Mm = take((size_t)P.ic * P.ic * 4);
   size_t a12 = take((size_t)2 * P.MC * 4);
@@ -160,6 +161,7 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
     S.sD = S.sGY + (size_t)P.na * P.oc;
     S.sU = S.sD + 2 * (size_t)P.MC;
     S.dzc = (float4*)(base + dzc);
+    S.dzc2 = (float4*)(base + dzc2);
     S.cvec2 = (float*)(base + cvec2);
     S.Mm = (float*)(base + Mm);
     S.a12 = (float*)(base + a12);

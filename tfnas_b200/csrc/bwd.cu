@@ -78,13 +78,17 @@ __global__ void __launch_bounds__(NT) k_b1(Plan P, const float* __restrict__ G, 
 // dzc[slot*oc + o] = {A = w_i*r3, B = sG/Q, C = sGY/Q, 0}; dmix[id] = sum_c sGY
 __global__ void k_b2prep(Plan P, const float* __restrict__ mixw, const float* __restrict__ bn3,
                          const double* __restrict__ sG, const double* __restrict__ sGY, float4* __restrict__ dzc,
-                         float* __restrict__ dmix) {
+                         float4* __restrict__ dzc2, float* __restrict__ dmix) {
   const int oc = P.oc, na = P.na;
   const double invQ = 1.0 / (double)P.Q;
   for (int i = threadIdx.x; i < na * oc; i += blockDim.x) {
     int s = i / oc, o = i - s * oc;
     float w = mixw[P.c[s].id];
-    dzc[i] = make_float4(w * bn3[na * oc + i], (float)(sG[o] * invQ), (float)(sGY[i] * invQ), 0.f);
+    const double r3 = bn3[na * oc + i], mu3 = bn3[i];
+    const double A = (double)w * r3, B = sG[o] * invQ, C = sGY[i] * invQ;
+    dzc[i] = make_float4(w * bn3[na * oc + i], (float)B, (float)C, 0.f);
+    // dz = A*(g - B - (z - mu3)*r3*C) = A*g + (-A*C*r3)*z + A*(C*r3*mu3 - B)
+    dzc2[i] = make_float4((float)A, (float)(-A * C * r3), (float)(A * (C * r3 * mu3 - B)), 0.f);
   }
   if (threadIdx.x < TFNAS_MAX_OPS) dmix[threadIdx.x] = 0.f;
   __syncthreads();
@@ -899,7 +903,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     { ProfScope ps("b1", 4.0 * P.Q * oc * (1 + P.na), 3.0 * P.Q * oc * P.na, st);
       k_b1<<<dim3(oc, nsplit), NT, 0, st>>>(P, dout, Zb, bn3, S.sG, S.sGY); }
     { ProfScope ps("b2prep", 32.0 * P.na * oc, 0, st);
-      k_b2prep<<<1, 256, 0, st>>>(P, mixw, bn3, S.sG, S.sGY, S.dzc, S.dmix); }
+      k_b2prep<<<1, 256, 0, st>>>(P, mixw, bn3, S.sG, S.sGY, S.dzc, S.dzc2, S.dmix); }
   }
   const float4* dzc = S.dzc;
   if (!dx) {   // input needs no gradient (first MixedOP of the alpha step): only dL/dlog_alpha
@@ -914,8 +918,8 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   UmW WX;
   DxChunks CHX;
   if (umma_enabled()) {
-    umma_prep_bwd(P, S.umprep, WD, WX, CHX, st);
-    umma_dc(P, WD, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
+    umma_prep_bwd(P, bn1, S.umprep, WD, WX, CHX, st);
+    umma_dc(P, WD, dout, Zb, S.dzc2, D, bn2, S.DC, S.dg, S.sD, st);
   } else {
     int maxmc = 0;
     for (int s = 0; s < P.na; ++s) maxmc = max(maxmc, P.c[s].mc);

@@ -41,19 +41,24 @@ struct DwWork {
 struct DwCfg { int CPB, R, IR, WP, tiles; size_t smem; };
 struct DwGrads { float* p[4]; };   // depthwise weight-grad pointers per DwWork entry
 
+// MUFU-backed exp2 / reciprocal with flush-to-zero (one instruction each; no denormal-range fix-up code)
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1 / (1 + e^-x): e^-x overflows to +inf for x < -88 -> 0, underflows to 0 for large x -> 1
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.f + ex2_ftz(x * -1.4426950408889634f)); }
+
 template <int ACT>
 __device__ __forceinline__ float act_f(float x) {
   if (ACT == TFNAS_ACT_RELU) return fmaxf(x, 0.f);
-  return __fdividef(x, 1.f + __expf(-x));
+  return x * sigmoid_f(x);
 }
 // derivative of the activation at pre-activation x
 template <int ACT>
 __device__ __forceinline__ float act_df(float x) {
   if (ACT == TFNAS_ACT_RELU) return x > 0.f ? 1.f : 0.f;
-  float s = __fdividef(1.f, 1.f + __expf(-x));
+  const float s = sigmoid_f(x);
   return s * (1.f + x * (1.f - s));
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

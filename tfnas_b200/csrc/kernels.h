@@ -36,7 +36,8 @@ struct BwdScratch {
   float* dg;      // [N*MCse]    SE: sum_hw dc*b, then dp in place
   double* sD;     // [2*MC]
   double* sU;     // [2*MC]
-  float4* dzc;    // [na*oc]  per (slot, out channel) BN3-backward coefficients
+  float4* dzc;    // [na*oc]  per (slot, out channel) BN3-backward coefficients {A, B, C}: dz = A*(g - B - yhat*C)
+  float4* dzc2;   // [na*oc]  the same folded into dz = a*g + b*z + c (tcgen05 dc prologue: two FMAs per element)
   float* cvec2;   // [ic]        (cvec2 and Mm adjacent: zeroed by one memset)
   float* Mm;      // [ic*ic]
   float* a12;     // [2*MC]  BN1-backward per-channel coefficients
@@ -69,11 +70,11 @@ struct DxChunks {            // chunk c of the stacked K axis -> (slot, first lo
 };
 
 void umma_prep_fwd(const Plan& P, float* prep_buf, UmWAll& WE, UmWAll& WP, cudaStream_t st);
-void umma_prep_bwd(const Plan& P, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks& CH, cudaStream_t st);
+void umma_prep_bwd(const Plan& P, const float* bn1, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks& CH, cudaStream_t st);
 void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1, float* UH, cudaStream_t st);
 void umma_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn2, const float* seg, float* Zb,
                   double* st3, cudaStream_t st);
-void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, const float* bn3, const float4* dzc,
+void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, const float4* dzc2,
              const float* D, const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st);
 // MODE 0: dW3[o][c] += sum_p dz c~ ; MODE 1: SmatT[k][c] += sum_p du-hat x   (out must be zeroed by the caller)
 void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float* A1, const float* B0, const float* B1,

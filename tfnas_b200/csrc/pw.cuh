@@ -22,13 +22,15 @@ struct Px4 {
 };
 
 __device__ __forceinline__ void px_decomp(Px4& px, int p0, int total, int HW) {
+  // one reciprocal division for the first pixel, the other three follow incrementally (p0 < 2^23)
+  int n = 0, hw = 0;
+  if (p0 < total) { n = fast_div(p0, HW, __frcp_rn((float)HW)); hw = p0 - n * HW; }
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    int p = p0 + e;
-    px.v[e] = p < total;
-    int nn = px.v[e] ? p / HW : 0;
-    px.n[e] = nn;
-    px.hw[e] = px.v[e] ? p - nn * HW : 0;
+    px.v[e] = p0 + e < total;
+    px.n[e] = px.v[e] ? n : 0;
+    px.hw[e] = px.v[e] ? hw : 0;
+    if (++hw == HW) { hw = 0; ++n; }
   }
   px.vec = ((HW & 3) == 0) && px.v[0];   // p0 % 4 == 0 and total % 4 == 0 then
 }

@@ -25,8 +25,8 @@ using namespace umma;
 #define UM_RW (UM_KC / (UM_NT / 32))   // K rows per warp per chunk
 #define UM_STAGES 1              // one smem stage per CTA: 2-3 CTAs/SM overlap each other's load / MMA / epilogue phases
 
-static inline void um_tile(int Nout, int& Nc, int& nN) {
-  nN = cdiv(Nout, 256);
+static inline void um_tile(int Nout, int& Nc, int& nN, int cap = 256) {
+  nN = cdiv(Nout, cap);
   Nc = cdiv(cdiv(Nout, nN), 16) * 16;
 }
 
@@ -58,10 +58,13 @@ struct UmSmem {
   uint64_t* bar_b;                  // [UM_STAGES]
   uint64_t* bar_mma;                // [UM_STAGES]
   uint32_t* tmem_slot;
+  float2* cf;                       // [256] per-column epilogue coefficients (e.g. BN mean / rstd)
+  unsigned char* ring;              // cp.async staging ring of raw input rows (thread-private 16 B slots)
 };
 
 __device__ __forceinline__ void um_carve(unsigned char* raw, int Nc, UmSmem& S) {
-  unsigned char* sm = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  // align by OFFSET so the pointer keeps its shared address space (STS/LDS instead of generic ST/LD)
+  unsigned char* sm = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   const size_t stage = 32768 + (size_t)2 * Nc * 128;     // multiple of 1024 because Nc % 16 == 0 -> 2*Nc*128 % 4096 == 0
 #pragma unroll
   for (int s = 0; s < UM_STAGES; ++s) {
@@ -72,8 +75,14 @@ __device__ __forceinline__ void um_carve(unsigned char* raw, int Nc, UmSmem& S) 
   S.bar_b = (uint64_t*)(sm + UM_STAGES * stage);
   S.bar_mma = S.bar_b + UM_STAGES;
   S.tmem_slot = (uint32_t*)(S.bar_mma + UM_STAGES);
+  S.cf = (float2*)(sm + UM_STAGES * stage + 64);
+  S.ring = sm + UM_STAGES * stage + 64 + 256 * sizeof(float2);
 }
-static inline size_t um_smem_bytes(int Nc) { return 1024 + UM_STAGES * (32768 + (size_t)2 * Nc * 128) + 64; }
+// one ring stage holds, for each of `ntens` input tensors, UM_RW rows x 4 pixels (16 B) per thread
+__host__ __device__ inline size_t um_ring_stage_bytes(int ntens) { return (size_t)ntens * UM_RW * UM_NT * 16; }
+static inline size_t um_smem_bytes(int Nc, size_t ring_bytes = 0) {
+  return 1024 + UM_STAGES * (32768 + (size_t)2 * Nc * 128) + 64 + 256 * sizeof(float2) + ring_bytes;
+}
 
 // write 4 pixels (one 16 B chunk) of row kk, split into hi / lo
 __device__ __forceinline__ void um_put(unsigned char* a_hi, unsigned char* a_lo, int lane, int kk, const float (&v)[4]) {
@@ -103,46 +112,196 @@ __device__ __forceinline__ void um_issue(const UmSmem& S, int s, int Nc, uint32_
 
 // Generic main loop.  F supplies:
 //   int   nchunks()                                   K chunks this CTA walks
-//   void  load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW])     global loads of chunk c (rows warp+8i, 4 px / lane)
-//   void  emit(int c, ra, rb, a_hi, a_lo)                   prologue math + hi/lo split + st.shared
+//   struct Regs                                             registers carried from load(c) to emit(c)
+//   void  load(int c, Regs&)                                global loads of chunk c (rows warp+16i, 4 px / lane)
+//   void  emit(int c, const Regs&, a_hi, a_lo)              prologue math + hi/lo split + st.shared
 //   const void* wsrc(int c)                                 prepped weight block of chunk c (2*Nc*128 bytes)
+// ---- optional in-kernel phase trace (debug; tfnas_debug_um_trace) -------------------------------------
+// Thread 0 of each traced CTA accumulates clock64() deltas per phase: [0] total, [1] setup, [2] wait MMA,
+// [3] weights TMA issue, [4] cp.async wait, [5] emit, [6] fence + barrier, [7] weights wait + MMA issue,
+// [8] epilogue, [9] chunks, [10] kernel id.
+#define UM_TRACE_SLOTS 16
+__device__ unsigned long long* g_um_trace = nullptr;
+__device__ int g_um_trace_n = 0;
+#ifdef UM_TRACE
+struct UmTrace {
+  unsigned long long* out;
+  long long t0, tstart;
+  long long acc[UM_TRACE_SLOTS];
+  __device__ __forceinline__ void begin() {
+    out = nullptr;
+    if (threadIdx.x == 0 && g_um_trace) {
+      const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      if (cta < g_um_trace_n) out = g_um_trace + (size_t)cta * UM_TRACE_SLOTS;
+    }
+    if (out) {
+#pragma unroll
+      for (int i = 0; i < UM_TRACE_SLOTS; ++i) acc[i] = 0;
+      t0 = tstart = clock64();
+    }
+  }
+  __device__ __forceinline__ void mark(int slot) {
+    if (out) { const long long t = clock64(); acc[slot] += t - t0; t0 = t; }
+  }
+  __device__ __forceinline__ void end(int kernel_id, int chunks) {
+    if (out) {
+      acc[0] = clock64() - tstart; acc[9] = chunks; acc[10] = kernel_id;
+#pragma unroll
+      for (int i = 0; i < UM_TRACE_SLOTS; ++i) out[i] = (unsigned long long)acc[i];
+    }
+  }
+};
+#else      // production build: the trace compiles to nothing
+struct UmTrace {
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void end(int, int) {}
+};
+#endif
+
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 template <class F>
 __device__ __forceinline__ void um_mainloop(F& f, const UmSmem& S, int Nc, uint32_t tmem, uint32_t idesc) {
-  const int tid = threadIdx.x;
+  const int warp = threadIdx.x >> 5;
   const int n = f.nchunks();
-  float4 ra[UM_RW], rb[UM_RW];
-  if (n > 0) f.load(0, ra, rb);
+  typename F::Regs rg;
+  if (n > 0) f.load(0, rg);
   uint32_t ph_b[UM_STAGES] = {0}, ph_m[UM_STAGES] = {0};
   for (int c = 0; c < n; ++c) {
     const int s = c & (UM_STAGES - 1);
-    if (c >= UM_STAGES) {           // the MMAs that read this stage two chunks ago must have retired
+    if (c >= UM_STAGES) {           // the MMAs that read this stage must have retired
       mbar_wait(&S.bar_mma[s], ph_m[s]);
       ph_m[s] ^= 1;
       tc_fence_after();
     }
-    if (tid == 0) {
-      mbar_expect_tx(&S.bar_b[s], 2 * Nc * 128);
-      bulk_g2s(S.b[s], f.wsrc(c), 2 * Nc * 128, &S.bar_b[s]);
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(&S.bar_b[s], 2 * Nc * 128);
+        bulk_g2s(S.b[s], f.wsrc(c), 2 * Nc * 128, &S.bar_b[s]);
+      }
+      __syncwarp();
     }
-    f.emit(c, ra, rb, S.a_hi[s], S.a_lo[s]);
-    if (c + 1 < n) f.load(c + 1, ra, rb);      // in flight while the tensor core works on chunk c
+    f.emit(c, rg, S.a_hi[s], S.a_lo[s]);
+    if (c + 1 < n) f.load(c + 1, rg);          // in flight while the tensor core works on chunk c
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&S.bar_b[s], ph_b[s]);
-      tc_fence_after();
-      um_issue(S, s, Nc, tmem, idesc, c == 0);
-      mma_commit(&S.bar_mma[s]);
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_wait(&S.bar_b[s], ph_b[s]);
+        tc_fence_after();
+        um_issue(S, s, Nc, tmem, idesc, c == 0);
+        mma_commit(&S.bar_mma[s]);
+      }
+      __syncwarp();
     }
     ph_b[s] ^= 1;
   }
-  // drain: wait for the last (up to two) commits
+  // drain: wait for the last commits
   for (int c = max(0, n - UM_STAGES); c < n; ++c) {
     const int s = c & (UM_STAGES - 1);
     mbar_wait(&S.bar_mma[s], ph_m[s]);
     ph_m[s] ^= 1;
   }
   tc_fence_after();
+}
+
+// ---- cp.async staging ring -----------------------------------------------------------------------
+// The single-stage loop above keeps at most ONE K chunk of global loads in flight per CTA (they live in registers),
+// which leaves the kernels latency-bound.  The ring variant parks the raw rows of the next RS-1 chunks in shared
+// memory with cp.async (no registers): every thread copies, waits for and reads back only ITS OWN 16-byte slots, so
+// no extra barrier is needed.  F supplies:
+//   void issue(int c, unsigned char* slot)                  cp.async of chunk c's raw rows into ring stage `slot`
+//   struct Regs; void consts(int c, Regs&)                  per-row constants of chunk c (registers, one chunk ahead)
+//   void emit(int c, const unsigned char* slot, const Regs&, a_hi, a_lo)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;          // src-size 0: nothing is read, the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 4u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 4 pixels of row `ch` of an [N][C][HW] tensor -> this thread's 16 B ring slot (zero-filled when !rowok / invalid pixel)
+__device__ __forceinline__ void ring_row(unsigned char* dst, const float* __restrict__ T, const float* __restrict__ Tb,
+                                         const Px4& px, int C, int ch, int HW, bool rowok) {
+  if (px.vec) {
+    cp_async16(dst, rowok ? Tb + (size_t)ch * HW : T, rowok);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool ok = rowok && px.v[e];
+      cp_async4(dst + 4 * e, ok ? T + ((size_t)px.n[e] * C + ch) * HW + px.hw[e] : T, ok);
+    }
+  }
+}
+
+template <int RS, class F>
+__device__ __forceinline__ void um_mainloop_ring(F& f, const UmSmem& S, size_t stage_bytes, int Nc, uint32_t tmem, uint32_t idesc,
+                                                 UmTrace& tr) {
+  const int warp = threadIdx.x >> 5;
+  const int n = f.nchunks();
+  typename F::Regs rg;
+#pragma unroll
+  for (int c = 0; c < RS - 1; ++c) {
+    if (c < n) f.issue(c, S.ring + (size_t)c * stage_bytes);
+    cp_async_commit();
+  }
+  if (n > 0) f.consts(0, rg);
+  uint32_t ph_b = 0, ph_m = 0;
+  int slot = 0, slot_issue = RS - 1;        // ring stage of chunk c / of chunk c + RS - 1
+  tr.mark(1);
+  for (int c = 0; c < n; ++c) {
+    if (c + RS - 1 < n) f.issue(c + RS - 1, S.ring + (size_t)slot_issue * stage_bytes);
+    cp_async_commit();                      // one group per iteration (possibly empty) keeps the group count uniform
+    if (c > 0) {                            // the MMAs that read the operand tiles must have retired
+      mbar_wait(&S.bar_mma[0], ph_m);
+      ph_m ^= 1;
+      tc_fence_after();
+    }
+    tr.mark(2);
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(&S.bar_b[0], 2 * Nc * 128);
+        bulk_g2s(S.b[0], f.wsrc(c), 2 * Nc * 128, &S.bar_b[0]);
+      }
+      __syncwarp();
+    }
+    tr.mark(3);
+    cp_async_wait<RS - 1>();                // this thread's copies of chunk c have landed
+    tr.mark(4);
+    f.emit(c, S.ring + (size_t)slot * stage_bytes, rg, S.a_hi[0], S.a_lo[0]);
+    if (c + 1 < n) f.consts(c + 1, rg);
+    tr.mark(5);
+    fence_proxy_async();
+    __syncthreads();
+    tr.mark(6);
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_wait(&S.bar_b[0], ph_b);
+        tc_fence_after();
+        um_issue(S, 0, Nc, tmem, idesc, c == 0);
+        mma_commit(&S.bar_mma[0]);
+      }
+      __syncwarp();
+    }
+    tr.mark(7);
+    ph_b ^= 1;
+    slot = slot + 1 == RS ? 0 : slot + 1;
+    slot_issue = slot_issue + 1 == RS ? 0 : slot_issue + 1;
+  }
+  if (n > 0) mbar_wait(&S.bar_mma[0], ph_m);
+  tc_fence_after();
+  tr.mark(2);
 }
 
 __device__ __forceinline__ uint32_t um_setup(const UmSmem& S, int Nc) {
@@ -171,7 +330,7 @@ __device__ __forceinline__ EpiPx epi_px(int tile0, int total, int HW) {
   EpiPx e;
   e.p = tile0 + (warp & 3) * 32 + lane;
   e.v = e.p < total;
-  e.n = e.v ? e.p / HW : 0;
+  e.n = e.v ? fast_div(e.p, HW, __frcp_rn((float)HW)) : 0;
   e.hw = e.v ? e.p - e.n * HW : 0;
   return e;
 }
@@ -198,25 +357,27 @@ __device__ __forceinline__ float4 ld4(const float* __restrict__ T, const Px4& px
 // F1a: expand
 // -------------------------------------------------------------------------------------------------
 struct ExpandF {
-  const Plan& P; const UmW& W; const float* x; Px4 px; int nc; int lane, warp;
+  const Plan& P; const UmW& W; const float* x; const float* xb; Px4 px; int nc; int lane, warp;
+  struct Regs { float4 a[UM_RW]; };
   __device__ int nchunks() const { return W.nK; }
-  __device__ void load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW]) const {
+  __device__ void load(int c, Regs& g) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
       const int k = c * UM_KC + warp + i * (UM_NT / 32);
-      ra[i] = k < P.ic ? ld4(x, px, P.ic, k, P.HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k >= P.ic) g.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      else if (px.vec) g.a[i] = *(const float4*)(xb + (size_t)k * P.HW);
+      else g.a[i] = ld4(x, px, P.ic, k, P.HW);
     }
   }
-  __device__ void emit(int c, const float4 (&ra)[UM_RW], const float4 (&rb)[UM_RW], unsigned char* ah, unsigned char* al) const {
+  __device__ void emit(int c, const Regs& g, unsigned char* ah, unsigned char* al) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
-      const float v[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+      const float v[4] = {g.a[i].x, g.a[i].y, g.a[i].z, g.a[i].w};
       um_put(ah, al, lane, warp + i * (UM_NT / 32), v);
     }
   }
   __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
 };
-
 __global__ void __launch_bounds__(UM_NT, 2) k_um_expand(Plan P, UmWAll WA, const float* __restrict__ x,
                                                    const float* __restrict__ bn1, float* __restrict__ UH) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
@@ -226,24 +387,34 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_expand(Plan P, UmWAll WA, const
   const Cand& cd = P.c[slot];
   UmSmem S;
   um_carve(um_raw, W.Nc, S);
+  const int ncol = min(W.Nc, cd.mc - nc * W.Nc);        // valid output columns of this chunk
+  const int cst0 = cd.coff + nc * W.Nc;                 // stacked channel of column 0
+  for (int i = threadIdx.x; i < ncol; i += UM_NT) S.cf[i] = make_float2(bn1[cst0 + i], bn1[P.MC + cst0 + i]);
   const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  ExpandF f{P, W, x, Px4(), nc, lane, warp};
+  ExpandF f{P, W, x, x, Px4(), nc, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.P, P.HW);
+  f.xb = x + (size_t)f.px.n[0] * P.ic * P.HW + f.px.hw[0];
   um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
   const EpiPx e = epi_px(blockIdx.x * 128, P.P, P.HW);
   int c_lo, c_hi;
   epi_cols(W.Nc, c_lo, c_hi);
+  c_hi = min(c_hi, ncol);
+  const size_t HW = (size_t)P.HW;
+  float* ob = UH + ((size_t)e.n * P.MC + cst0) * HW + e.hw;
   for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
     float v[16];
     tmem_ld16(epi_taddr(tmem, c0), v);
+    if (!e.v) continue;
+    float* q = ob + (size_t)c0 * HW;
+    const float2* cf = S.cf + c0;
+    if (c0 + 16 <= c_hi) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = nc * W.Nc + c0 + j;
-      if (c < cd.mc && e.v) {
-        const int cst = cd.coff + c;
-        UH[((size_t)e.n * P.MC + cst) * P.HW + e.hw] = (v[j] - bn1[cst]) * bn1[P.MC + cst];
-      }
+      for (int j = 0; j < 16; ++j) { const float2 m = cf[j]; *q = (v[j] - m.x) * m.y; q += HW; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c0 + j < c_hi) { const float2 m = cf[j]; *q = (v[j] - m.x) * m.y; q += HW; }
     }
   }
   um_teardown(tmem, W.Nc);
@@ -254,29 +425,47 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_expand(Plan P, UmWAll WA, const
 // -------------------------------------------------------------------------------------------------
 template <int ACT>
 struct ProjectF {
-  const Plan& P; const UmW& W; const Cand& cd; const float* D; const float* bn2; const float* seg; Px4 px; int nc; int lane, warp;
+  const Plan& P; const UmW& W; const Cand& cd; const float* D; const float* Db; const float* bn2; const float* seg; Px4 px; int nc; int lane, warp;
   __device__ int nchunks() const { return W.nK; }
-  __device__ void load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW]) const {
+  // mu / r = BN2 mean / rstd of the row; gt = SE gate of the first pixel's image (1 without SE)
+  struct Regs { float mu[UM_RW], r[UM_RW], gt[UM_RW]; };
+  __device__ void issue(int c, unsigned char* slot) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
       const int k = c * UM_KC + warp + i * (UM_NT / 32);
-      ra[i] = k < cd.mc ? ld4(D, px, P.MC, cd.coff + k, P.HWo) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ring_row(slot + ((size_t)i * UM_NT + threadIdx.x) * 16, D, Db, px, P.MC, cd.coff + k, P.HWo, k < cd.mc);
     }
   }
-  __device__ void emit(int c, const float4 (&ra)[UM_RW], const float4 (&rb)[UM_RW], unsigned char* ah, unsigned char* al) const {
+  __device__ void consts(int c, Regs& g) const {
+#pragma unroll
+    for (int i = 0; i < UM_RW; ++i) {
+      const int k = c * UM_KC + warp + i * (UM_NT / 32);
+      if (k >= cd.mc) { g.mu[i] = g.r[i] = g.gt[i] = 0.f; continue; }
+      const int cst = cd.coff + k;
+      g.mu[i] = bn2[cst];
+      g.r[i] = bn2[P.MC + cst];
+      g.gt[i] = cd.se > 0 ? seg[(size_t)px.n[0] * P.MCse + cd.soff + k] : 1.f;
+    }
+  }
+  __device__ void emit(int c, const unsigned char* slot, const Regs& g, unsigned char* ah, unsigned char* al) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
       const int kk = warp + i * (UM_NT / 32), k = c * UM_KC + kk;
+      const float4 a = *(const float4*)(slot + ((size_t)i * UM_NT + threadIdx.x) * 16);
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (k < cd.mc) {
-        const int cst = cd.coff + k;
-        const float mu = bn2[cst], r = bn2[P.MC + cst];
-        const float d[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w};
+        const float mu = g.mu[i], r = g.r[i];
+        const float d[4] = {a.x, a.y, a.z, a.w};
+        if (px.vec) {        // 4 valid pixels of one image
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float b = act_f<ACT>((d[e] - mu) * r);
-          if (cd.se > 0) b *= seg[(size_t)px.n[e] * P.MCse + cd.soff + k];
-          v[e] = px.v[e] ? b : 0.f;
+          for (int e = 0; e < 4; ++e) v[e] = act_f<ACT>((d[e] - mu) * r) * g.gt[i];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float b = act_f<ACT>((d[e] - mu) * r);
+            if (cd.se > 0) b *= seg[(size_t)px.n[e] * P.MCse + cd.soff + k];
+            v[e] = px.v[e] ? b : 0.f;
+          }
         }
       }
       um_put(ah, al, lane, kk, v);
@@ -285,7 +474,7 @@ struct ProjectF {
   __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
 };
 
-template <int ACT>
+template <int ACT, int RS>
 __global__ void __launch_bounds__(UM_NT, 2) k_um_project(Plan P, UmWAll WA, const float* __restrict__ D,
                                                     const float* __restrict__ bn2, const float* __restrict__ seg,
                                                     float* __restrict__ Zb, double* __restrict__ st3) {
@@ -294,34 +483,54 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_project(Plan P, UmWAll WA, cons
   const UmW& W = WA.s[slot];
   if (nc >= W.nN) return;
   const Cand& cd = P.c[slot];
+  UmTrace tr;
+  tr.begin();
   UmSmem S;
   um_carve(um_raw, W.Nc, S);
   const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  ProjectF<ACT> f{P, W, cd, D, bn2, seg, Px4(), nc, lane, warp};
+  ProjectF<ACT> f{P, W, cd, D, D, bn2, seg, Px4(), nc, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.Q, P.HWo);
-  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
+  f.Db = D + (size_t)f.px.n[0] * P.MC * P.HWo + f.px.hw[0];
+  um_mainloop_ring<RS>(f, S, um_ring_stage_bytes(1), W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0), tr);
   const EpiPx e = epi_px(blockIdx.x * 128, P.Q, P.HWo);
   const int oc = P.oc;
+  const int ncol = min(W.Nc, oc - nc * W.Nc);
   int c_lo, c_hi;
   epi_cols(W.Nc, c_lo, c_hi);
+  c_hi = min(c_hi, ncol);
+  const size_t HWo = (size_t)P.HWo;
+  const int o0 = slot * oc + nc * W.Nc;                  // Z / BN3 channel of column 0
+  float* zb = Zb + ((size_t)e.n * P.na * oc + o0) * HWo + e.hw;
+  // Rows of invalid pixels and weight rows past oc are zero in the operands, so their accumulators are exactly 0:
+  // the BN3 sums need no masking, only the stores do.
   for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
     float v[16], q[16];
     tmem_ld16(epi_taddr(tmem, c0), v);
+    if (e.v) {
+      float* zp = zb + (size_t)c0 * HWo;
+      if (c0 + 16 <= c_hi) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int o = nc * W.Nc + c0 + j;
-      v[j] = (e.v && o < oc) ? v[j] : 0.f;
-      if (e.v && o < oc) Zb[((size_t)e.n * P.na * oc + slot * oc + o) * P.HWo + e.hw] = v[j];
-      q[j] = v[j] * v[j];
+        for (int j = 0; j < 16; ++j) { *zp = v[j]; zp += HWo; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < c_hi) *zp = v[j];
+          zp += HWo;
+        }
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) q[j] = v[j] * v[j];
     const float s1 = warp_sum16(v), s2 = warp_sum16(q);
-    const int o = nc * W.Nc + c0 + (lane & 15);
-    if (lane < 16 && o < oc) {
-      atomicAdd(&st3[2 * (slot * oc + o)], (double)s1);
-      atomicAdd(&st3[2 * (slot * oc + o) + 1], (double)s2);
+    const int col = c0 + (lane & 15);
+    if (lane < 16 && col < c_hi) {
+      atomicAdd(&st3[2 * (o0 + col)], (double)s1);
+      atomicAdd(&st3[2 * (o0 + col) + 1], (double)s2);
     }
   }
+  tr.mark(8);
+  tr.end(1, W.nK);
   um_teardown(tmem, W.Nc);
 }
 
@@ -329,32 +538,37 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_project(Plan P, UmWAll WA, cons
 // B2: dc = W3^T dz
 // -------------------------------------------------------------------------------------------------
 struct DcF {
-  const Plan& P; const UmW& W; const float* G; const float* Zb; const float* bn3; const float4* dzc; Px4 px; int nc, slot; int lane, warp;
+  const Plan& P; const UmW& W; const float* G; const float* Zb; const float* Gb; const float* Zbb; const float4* dzc2; Px4 px; int nc, slot; int lane, warp;
+  // a = G row, b = Z row, cf = (A, B, C): dz = A*g + B*z + C  (BN3 backward folded, k_b2prep)
+  struct Regs { float4 a[UM_RW], b[UM_RW], cf[UM_RW]; };
   __device__ int nchunks() const { return W.nK; }
-  __device__ void load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW]) const {
+  __device__ void load(int c, Regs& g) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
       const int o = c * UM_KC + warp + i * (UM_NT / 32);
       if (o < P.oc) {
-        ra[i] = ld4(G, px, P.oc, o, P.HWo);
-        rb[i] = ld4(Zb, px, P.na * P.oc, slot * P.oc + o, P.HWo);
+        if (px.vec) {
+          g.a[i] = *(const float4*)(Gb + (size_t)o * P.HWo);
+          g.b[i] = *(const float4*)(Zbb + (size_t)o * P.HWo);
+        } else {
+          g.a[i] = ld4(G, px, P.oc, o, P.HWo);
+          g.b[i] = ld4(Zb, px, P.na * P.oc, slot * P.oc + o, P.HWo);
+        }
+        g.cf[i] = dzc2[slot * P.oc + o];
       } else {
-        ra[i] = rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g.a[i] = g.b[i] = g.cf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
-  __device__ void emit(int c, const float4 (&ra)[UM_RW], const float4 (&rb)[UM_RW], unsigned char* ah, unsigned char* al) const {
+  __device__ void emit(int c, const Regs& g, unsigned char* ah, unsigned char* al) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
-      const int kk = warp + i * (UM_NT / 32), o = c * UM_KC + kk;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (o < P.oc) {
-        const float4 cf = dzc[slot * P.oc + o];
-        const float mu3 = bn3[slot * P.oc + o], r3 = bn3[P.na * P.oc + slot * P.oc + o];
-        const float g[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, z[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+      const int kk = warp + i * (UM_NT / 32);
+      const float4 cf = g.cf[i];      // zero for rows >= oc
+      const float gg[4] = {g.a[i].x, g.a[i].y, g.a[i].z, g.a[i].w}, z[4] = {g.b[i].x, g.b[i].y, g.b[i].z, g.b[i].w};
+      float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? cf.x * (g[e] - cf.y - (z[e] - mu3) * r3 * cf.z) : 0.f;
-      }
+      for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? fmaf(cf.x, gg[e], fmaf(cf.y, z[e], cf.z)) : 0.f;
       um_put(ah, al, lane, kk, v);
     }
   }
@@ -363,7 +577,7 @@ struct DcF {
 
 template <int ACT>
 __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const float* __restrict__ G, const float* __restrict__ Zb,
-                                               const float* __restrict__ bn3, const float4* __restrict__ dzc,
+                                               const float4* __restrict__ dzc2,
                                                const float* __restrict__ D, const float* __restrict__ bn2,
                                                float* __restrict__ DC, float* __restrict__ dg, double* __restrict__ sD) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
@@ -373,10 +587,15 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const flo
   const Cand& cd = P.c[slot];
   UmSmem S;
   um_carve(um_raw, W.Nc, S);
+  const int ncol = min(W.Nc, cd.mc - nc * W.Nc);        // valid output columns (mid channels) of this chunk
+  const int cst0 = cd.coff + nc * W.Nc;                 // stacked channel of column 0
+  for (int i = threadIdx.x; i < ncol; i += UM_NT) S.cf[i] = make_float2(bn2[cst0 + i], bn2[P.MC + cst0 + i]);
   const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  DcF f{P, W, G, Zb, bn3, dzc, Px4(), nc, slot, lane, warp};
+  DcF f{P, W, G, Zb, G, Zb, dzc2, Px4(), nc, slot, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.Q, P.HWo);
+  f.Gb = G + (size_t)f.px.n[0] * P.oc * P.HWo + f.px.hw[0];
+  f.Zbb = Zb + ((size_t)f.px.n[0] * P.na + slot) * P.oc * P.HWo + f.px.hw[0];
   um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
   const EpiPx e = epi_px(blockIdx.x * 128, P.Q, P.HWo);
   const bool gated = cd.se > 0;
@@ -388,55 +607,104 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const flo
   const bool two_img = __all_sync(0xffffffffu, (!e.v) || e.n == n_first || e.n == n_last);
   int c_lo, c_hi;
   epi_cols(W.Nc, c_lo, c_hi);
+  c_hi = min(c_hi, ncol);
+  const size_t HWo = (size_t)P.HWo;
+  const size_t eoff = ((size_t)e.n * P.MC + cst0) * HWo + e.hw;
+  const int soff0 = cd.soff + nc * W.Nc;                // SE-gated stacked channel of column 0
+  // Rows of invalid pixels and weight rows past mc are zero in the operands, so their accumulators are exactly 0
+  // and (with d loaded as 0) contribute 0 to every sum below: only loads and stores are masked.
   for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
     float v[16], d[16];
-    // issue all 16 D loads before the TMEM read so they overlap
+    const int nv = min(16, c_hi - c0);                  // valid columns of this group (uniform)
+    {                                                   // D loads issued before the TMEM read so they overlap
+      const float* dp = D + eoff + (size_t)c0 * HWo;
+      if (nv == 16) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = nc * W.Nc + c0 + j;
-      d[j] = (e.v && c < cd.mc) ? D[((size_t)e.n * P.MC + cd.coff + c) * P.HWo + e.hw] : 0.f;
+        for (int j = 0; j < 16; ++j) { d[j] = e.v ? *dp : 0.f; dp += HWo; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { d[j] = (e.v && j < nv) ? *dp : 0.f; dp += HWo; }
+      }
     }
     tmem_ld16(epi_taddr(tmem, c0), v);
-    if (gated) {
-      float pa[16], pb[16];
+    const float2* cf = S.cf + c0;
+    const int col = c0 + (lane & 15);
+    if (e.v) {
+      float* qp = DC + eoff + (size_t)c0 * HWo;
+      if (gated) {
+        // DC = dc (raw); v <- dc * act(BN2(d)) = this pixel's contribution to dL/dgate
+        if (nv == 16) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int c = nc * W.Nc + c0 + j;
-        const bool ok = e.v && c < cd.mc;
-        const int cst = cd.coff + min(c, cd.mc - 1);
-        const float b = act_f<ACT>((d[j] - bn2[cst]) * bn2[P.MC + cst]);
-        if (ok) DC[((size_t)e.n * P.MC + cst) * P.HWo + e.hw] = v[j];
-        const float part = ok ? v[j] * b : 0.f;
-        pa[j] = (e.n == n_first) ? part : 0.f;
-        pb[j] = (e.n == n_first) ? 0.f : part;
-        if (!two_img && ok) atomicAdd(&dg[(size_t)e.n * P.MCse + cd.soff + c], part);
+          for (int j = 0; j < 16; ++j) {
+            const float2 m = cf[j];
+            *qp = v[j];
+            qp += HWo;
+            v[j] *= act_f<ACT>((d[j] - m.x) * m.y);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < nv) {
+              const float2 m = cf[j];
+              *qp = v[j];
+              v[j] *= act_f<ACT>((d[j] - m.x) * m.y);
+            }
+            qp += HWo;
+          }
+        }
+      } else {
+        // DC = dd-hat = dc * act'(d-hat); v <- dd-hat, d <- dd-hat * d-hat (BN2-backward sums)
+        if (nv == 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 m = cf[j];
+            const float dh = (d[j] - m.x) * m.y;
+            const float o = v[j] * act_df<ACT>(dh);
+            *qp = o;
+            qp += HWo;
+            v[j] = o;
+            d[j] = o * dh;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < nv) {
+              const float2 m = cf[j];
+              const float dh = (d[j] - m.x) * m.y;
+              const float o = v[j] * act_df<ACT>(dh);
+              *qp = o;
+              v[j] = o;
+              d[j] = o * dh;
+            }
+            qp += HWo;
+          }
+        }
       }
-      if (two_img) {
-        const float sa = warp_sum16(pa), sb = warp_sum16(pb);
-        const int c = nc * W.Nc + c0 + (lane & 15);
-        if (lane < 16 && c < cd.mc) {
-          atomicAdd(&dg[(size_t)n_first * P.MCse + cd.soff + c], sa);
-          if (n_last > n_first) atomicAdd(&dg[(size_t)n_last * P.MCse + cd.soff + c], sb);
+    }
+    if (gated) {
+      if (!two_img) {                    // tiny planes (HWo < 32): more than two images per warp
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (e.v && j < nv) atomicAdd(&dg[(size_t)e.n * P.MCse + soff0 + c0 + j], v[j]);
+      } else if (n_last <= n_first) {    // the usual case: all 32 pixels belong to one image
+        const float sa = warp_sum16(v);
+        if (lane < 16 && col < c_hi) atomicAdd(&dg[(size_t)n_first * P.MCse + soff0 + col], sa);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) d[j] = (e.n == n_first) ? 0.f : v[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (e.n == n_first) ? v[j] : 0.f;
+        const float sa = warp_sum16(v), sb = warp_sum16(d);
+        if (lane < 16 && col < c_hi) {
+          atomicAdd(&dg[(size_t)n_first * P.MCse + soff0 + col], sa);
+          atomicAdd(&dg[(size_t)n_last * P.MCse + soff0 + col], sb);
         }
       }
     } else {
-      float o1[16], o2[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int c = nc * W.Nc + c0 + j;
-        const bool ok = e.v && c < cd.mc;
-        const int cst = cd.coff + min(c, cd.mc - 1);
-        const float dh = (d[j] - bn2[cst]) * bn2[P.MC + cst];
-        const float o = ok ? v[j] * act_df<ACT>(dh) : 0.f;
-        if (ok) DC[((size_t)e.n * P.MC + cst) * P.HWo + e.hw] = o;
-        o1[j] = o;
-        o2[j] = o * dh;
-      }
-      const float s1 = warp_sum16(o1), s2 = warp_sum16(o2);
-      const int c = nc * W.Nc + c0 + (lane & 15);
-      if (lane < 16 && c < cd.mc) {
-        atomicAdd(&sD[2 * (cd.coff + c)], (double)s1);
-        atomicAdd(&sD[2 * (cd.coff + c) + 1], (double)s2);
+      const float s1 = warp_sum16(v), s2 = warp_sum16(d);
+      if (lane < 16 && col < c_hi) {
+        atomicAdd(&sD[2 * (cst0 + col)], (double)s1);
+        atomicAdd(&sD[2 * (cst0 + col) + 1], (double)s2);
       }
     }
   }
@@ -448,31 +716,38 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const flo
 // -------------------------------------------------------------------------------------------------
 template <int ACT>
 struct DxF {
-  const Plan& P; const UmW& W; const DxChunks& CH; const float* DA; const float* UH; const float* bn1; double* sU; Px4 px;
+  const Plan& P; const UmW& W; const DxChunks& CH; const float* DA; const float* UH; const float* DAb; const float* UHb; double* sU; Px4 px;
   int ch0, ch1; int lane, warp;
+  struct Regs {};
   __device__ int nchunks() const { return ch1 - ch0; }
   __device__ void locate(int c, int& slot, int& k0) const {
+    // static indices only: a dynamically indexed by-value parameter would be copied to local memory
     const int g = ch0 + c;
+    int f0 = 0;
     slot = 0;
-    while (slot + 1 < P.na && g >= CH.first[slot + 1]) ++slot;
-    k0 = (g - CH.first[slot]) * UM_KC;
+#pragma unroll
+    for (int s = 1; s < TFNAS_MAX_OPS; ++s)
+      if (s < P.na && g >= CH.first[s]) { slot = s; f0 = CH.first[s]; }
+    k0 = (g - f0) * UM_KC;
   }
-  __device__ void load(int c, float4 (&ra)[UM_RW], float4 (&rb)[UM_RW]) const {
+  // ring stage: [DA rows | UH rows], each UM_RW x UM_NT x 16 B
+  __device__ void issue(int c, unsigned char* slot_p) const {
     int slot, k0;
     locate(c, slot, k0);
     const Cand& cd = P.c[slot];
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
       const int k = k0 + warp + i * (UM_NT / 32);
-      if (k < cd.mc) {
-        ra[i] = ld4(DA, px, P.MC, cd.coff + k, P.HW);
-        rb[i] = ld4(UH, px, P.MC, cd.coff + k, P.HW);
-      } else {
-        ra[i] = rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      const bool ok = k < cd.mc;
+      const int cst = cd.coff + k;
+      ring_row(slot_p + ((size_t)i * UM_NT + threadIdx.x) * 16, DA, DAb, px, P.MC, cst, P.HW, ok);
+      ring_row(slot_p + ((size_t)(UM_RW + i) * UM_NT + threadIdx.x) * 16, UH, UHb, px, P.MC, cst, P.HW, ok);
     }
   }
-  __device__ void emit(int c, const float4 (&ra)[UM_RW], const float4 (&rb)[UM_RW], unsigned char* ah, unsigned char* al) const {
+  __device__ void consts(int, Regs&) const {}
+  // Rows past the candidate's width and invalid pixels are zero-filled in the ring, so du = 0 * act'(0) = 0 there.
+  // BN1's rstd is folded into the prepped weights (umma_prep_bwd), the operand is plain du-hat.
+  __device__ void emit(int c, const unsigned char* slot_p, const Regs&, unsigned char* ah, unsigned char* al) const {
     int slot, k0;
     locate(c, slot, k0);
     const Cand& cd = P.c[slot];
@@ -481,63 +756,72 @@ struct DxF {
     for (int i = 0; i < 16; ++i) st[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
-      const int kk = warp + i * (UM_NT / 32), k = k0 + kk;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (k < cd.mc) {     // warp-uniform
-        const int cst = cd.coff + k;
-        const float r1 = bn1[P.MC + cst];
-        const float da[4] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w}, uh[4] = {rb[i].x, rb[i].y, rb[i].z, rb[i].w};
+      const int kk = warp + i * (UM_NT / 32);
+      const float4 a = *(const float4*)(slot_p + ((size_t)i * UM_NT + threadIdx.x) * 16);
+      const float4 b = *(const float4*)(slot_p + ((size_t)(UM_RW + i) * UM_NT + threadIdx.x) * 16);
+      const float da[4] = {a.x, a.y, a.z, a.w}, uh[4] = {b.x, b.y, b.z, b.w};
+      float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float du = px.v[e] ? da[e] * act_df<ACT>(uh[e]) : 0.f;
-          st[2 * i] += du;
-          st[2 * i + 1] += du * uh[e];
-          v[e] = du * r1;
-        }
+      for (int e = 0; e < 4; ++e) {
+        v[e] = da[e] * act_df<ACT>(uh[e]);
+        st[2 * i] += v[e];
+        st[2 * i + 1] += v[e] * uh[e];
       }
       um_put(ah, al, lane, kk, v);
     }
-    // 8 statistics (4 rows x {sum du, sum du*uh}) reduced together; lane l < 8 ends up owning statistic l
+    // 2*UM_RW statistics (rows x {sum du, sum du*uh}) reduced together; lane l < 2*UM_RW ends up owning statistic l
     const float tot = warp_sum16(st);
-    if (lane < 2 * UM_RW) {
-      const int k = k0 + warp + (lane >> 1) * (UM_NT / 32);
-      if (k < cd.mc) atomicAdd(&sU[2 * (cd.coff + k) + (lane & 1)], (double)tot);
-    }
+    static_assert(UM_RW == 2, "statistic ownership below assumes two rows per warp per chunk");
+    const int k = k0 + warp + ((lane & 2) ? UM_NT / 32 : 0);
+    if (lane < 2 * UM_RW && k < cd.mc) atomicAdd(&sU[2 * (cd.coff + k) + (lane & 1)], (double)tot);
   }
   __device__ const void* wsrc(int c) const { return (const char*)W.wp + (size_t)(ch0 + c) * 2 * W.Nc * 128; }
 };
 
-template <int ACT>
+template <int ACT, int RS>
 __global__ void __launch_bounds__(UM_NT, 2) k_um_dx(Plan P, UmW W, DxChunks CH, int ksplit, const float* __restrict__ DA,
-                                               const float* __restrict__ UH, const float* __restrict__ bn1,
+                                               const float* __restrict__ UH,
                                                float* __restrict__ dx, double* __restrict__ sU) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
+  UmTrace tr;
+  tr.begin();
   UmSmem S;
   um_carve(um_raw, W.Nc, S);
   const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch0 = (int)((long long)CH.total * blockIdx.y / ksplit), ch1 = (int)((long long)CH.total * (blockIdx.y + 1) / ksplit);
-  DxF<ACT> f{P, W, CH, DA, UH, bn1, sU, Px4(), ch0, ch1, lane, warp};
+  DxF<ACT> f{P, W, CH, DA, UH, DA, UH, sU, Px4(), ch0, ch1, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.P, P.HW);
-  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
+  {
+    const size_t o = (size_t)f.px.n[0] * P.MC * P.HW + f.px.hw[0];
+    f.DAb = DA + o;
+    f.UHb = UH + o;
+  }
+  um_mainloop_ring<RS>(f, S, um_ring_stage_bytes(2), W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0), tr);
   const EpiPx e = epi_px(blockIdx.x * 128, P.P, P.HW);
   int c_lo, c_hi;
   epi_cols(W.Nc, c_lo, c_hi);
+  c_hi = min(c_hi, P.ic);
   if (ch1 > ch0) {
+    const size_t HW = (size_t)P.HW;
+    float* ob = dx + (size_t)e.n * P.ic * HW + e.hw;
     for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
       float v[16];
       tmem_ld16(epi_taddr(tmem, c0), v);
+      if (!e.v) continue;
+      float* q = ob + (size_t)c0 * HW;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int k = c0 + j;
-        if (k < P.ic && e.v) {
-          float* q = dx + ((size_t)e.n * P.ic + k) * P.HW + e.hw;
+        if (c0 + j < c_hi) {
           if (ksplit == 1) *q = v[j];
           else atomicAdd(q, v[j]);
         }
+        q += HW;
       }
     }
   }
+  tr.mark(8);
+  tr.end(2, ch1 - ch0);
   um_teardown(tmem, W.Nc);
 }
 
@@ -554,14 +838,15 @@ int umma_enabled() {
 }
 
 // bytes of prepped weights for a [Nout x K] GEMM
-static size_t um_prep_bytes(int Nout, int K) {
+#define UM_EXPAND_NCAP 256
+static size_t um_prep_bytes(int Nout, int K, int cap = 256) {
   int Nc, nN;
-  um_tile(Nout, Nc, nN);
+  um_tile(Nout, Nc, nN, cap);
   return (size_t)nN * cdiv(K, UM_KC) * 2 * Nc * 128;
 }
 size_t umma_fwd_prep_bytes(const Plan& P) {
   size_t b = 0;
-  for (int s = 0; s < P.na; ++s) b += um_prep_bytes(P.c[s].mc, P.ic) + um_prep_bytes(P.oc, P.c[s].mc);
+  for (int s = 0; s < P.na; ++s) b += um_prep_bytes(P.c[s].mc, P.ic, UM_EXPAND_NCAP) + um_prep_bytes(P.oc, P.c[s].mc);
   return b + 1024;
 }
 size_t umma_bwd_prep_bytes(const Plan& P) {
@@ -573,7 +858,7 @@ size_t umma_bwd_prep_bytes(const Plan& P) {
   return b + (size_t)chunks * 2 * Nc * 128 + 1024;
 }
 
-struct PrepJob { const float* src; float* dst; int ld_r, ld_k, nrows, K, Nc, nN, nK; };
+struct PrepJob { const float* src; const float* kscale; float* dst; int ld_r, ld_k, nrows, K, Nc, nN, nK; };   // kscale: optional per-k factor
 struct PrepJobs { int n; PrepJob j[2 * TFNAS_MAX_OPS]; };
 
 // grid (max nK, max nN, jobs): all candidates' weights of one GEMM in ONE launch
@@ -588,6 +873,7 @@ __global__ void __launch_bounds__(256) k_umma_prep_all(PrepJobs J) {
     else { kk = i / q.Nc; r = i - kk * q.Nc; }
     const int gr = nc * q.Nc + r, k = kc * UM_KC + kk;
     float x = (gr < q.nrows && k < q.K) ? q.src[(size_t)gr * q.ld_r + (size_t)k * q.ld_k] : 0.f;
+    if (q.kscale && k < q.K) x *= q.kscale[k];
     float hi, lo;
     split_tf32(x, hi, lo);
     *(float*)(base + k_elem_off(r, kk)) = hi;
@@ -595,13 +881,14 @@ __global__ void __launch_bounds__(256) k_umma_prep_all(PrepJobs J) {
   }
 }
 
-static void prep(PrepJobs& J, const float* src, int ld_r, int ld_k, int nrows, int K, UmW& W, float*& cursor) {
-  um_tile(nrows, W.Nc, W.nN);
+static void prep(PrepJobs& J, const float* src, int ld_r, int ld_k, int nrows, int K, UmW& W, float*& cursor,
+                 int cap = 256, const float* kscale = nullptr) {
+  um_tile(nrows, W.Nc, W.nN, cap);
   W.nK = cdiv(K, UM_KC);
   W.Nout = nrows;
   W.wp = cursor;
   PrepJob& q = J.j[J.n++];
-  q.src = src; q.dst = cursor; q.ld_r = ld_r; q.ld_k = ld_k; q.nrows = nrows; q.K = K; q.Nc = W.Nc; q.nN = W.nN; q.nK = W.nK;
+  q.src = src; q.kscale = kscale; q.dst = cursor; q.ld_r = ld_r; q.ld_k = ld_k; q.nrows = nrows; q.K = K; q.Nc = W.Nc; q.nN = W.nN; q.nK = W.nK;
   cursor += (size_t)W.nN * W.nK * 2 * W.Nc * 32;
 }
 static void prep_launch(const PrepJobs& J, cudaStream_t st) {
@@ -617,7 +904,7 @@ void umma_prep_fwd(const Plan& P, float* prep_buf, UmWAll& WE, UmWAll& WP, cudaS
   PrepJobs J;
   J.n = 0;
   float* cur = prep_buf;
-  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w1, P.ic, 1, P.c[s].mc, P.ic, WE.s[s], cur);
+  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w1, P.ic, 1, P.c[s].mc, P.ic, WE.s[s], cur, UM_EXPAND_NCAP);
   for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w3, P.c[s].mc, 1, P.oc, P.c[s].mc, WP.s[s], cur);
   prep_launch(J, st);
 }
@@ -626,6 +913,8 @@ static void um_max(const Plan& P, const UmWAll& WA, int& maxN, int& maxNc) {
   maxN = 0; maxNc = 0;
   for (int s = 0; s < P.na; ++s) { maxN = max(maxN, WA.s[s].nN); maxNc = max(maxNc, WA.s[s].Nc); }
 }
+
+#define UM_SMEM_2CTA 115712   // (228 KB - 2 x 1 KB reserved) / 2
 
 void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1, float* UH, cudaStream_t st) {
   int maxN, maxNc;
@@ -636,25 +925,35 @@ void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* b
   k_um_expand<<<dim3(cdiv(P.P, 128), maxN, P.na), UM_NT, smem, st>>>(P, WA, x, bn1, UH);
 }
 
+template <int ACT, int RS>
+static void launch_um_project(const Plan& P, const UmWAll& WA, dim3 grid, size_t smem, const float* D, const float* bn2,
+                              const float* seg, float* Zb, double* st3, cudaStream_t st) {
+  cudaFuncSetAttribute(k_um_project<ACT, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_um_project<ACT, RS><<<grid, UM_NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
+}
+
 void umma_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn2, const float* seg, float* Zb,
                   double* st3, cudaStream_t st) {
   int maxN, maxNc;
   um_max(P, WA, maxN, maxNc);
-  size_t smem = um_smem_bytes(maxNc);
+  // 3 ring stages when two CTAs per SM still fit, else one CTA per SM with a deeper ring
+  const bool two = um_smem_bytes(maxNc, 3 * um_ring_stage_bytes(1)) <= UM_SMEM_2CTA;
+  const size_t smem = um_smem_bytes(maxNc, (two ? 3 : 5) * um_ring_stage_bytes(1));
   dim3 grid(cdiv(P.Q, 128), maxN, P.na);
   ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
-  if (P.act == TFNAS_ACT_RELU) {
-    cudaFuncSetAttribute(k_um_project<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_project<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
+  const bool relu = P.act == TFNAS_ACT_RELU;
+  if (two) {
+    if (relu) launch_um_project<TFNAS_ACT_RELU, 3>(P, WA, grid, smem, D, bn2, seg, Zb, st3, st);
+    else launch_um_project<TFNAS_ACT_SWISH, 3>(P, WA, grid, smem, D, bn2, seg, Zb, st3, st);
   } else {
-    cudaFuncSetAttribute(k_um_project<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_project<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
+    if (relu) launch_um_project<TFNAS_ACT_RELU, 5>(P, WA, grid, smem, D, bn2, seg, Zb, st3, st);
+    else launch_um_project<TFNAS_ACT_SWISH, 5>(P, WA, grid, smem, D, bn2, seg, Zb, st3, st);
   }
 }
 
 // all backward weights (dc: W3^T, dx: W1^T with per-candidate K chunks) in one prep launch
-void umma_prep_bwd(const Plan& P, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks& CH, cudaStream_t st) {
+void umma_prep_bwd(const Plan& P, const float* bn1, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks& CH, cudaStream_t st) {
   PrepJobs J;
   J.n = 0;
   float* cur = prep_buf;
@@ -667,7 +966,8 @@ void umma_prep_bwd(const Plan& P, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks
   for (int s = 0; s < P.na; ++s) {
     // logical weight (row = input channel k', k = mid channel c) = W1[c][k'], chunks never straddle candidates
     UmW Ws;
-    prep(J, P.c[s].w1, 1, P.ic, P.ic, P.c[s].mc, Ws, cur);
+    // BN1's rstd (per mid channel = per k) is folded in here, so the dx prologue emits plain du-hat
+    prep(J, P.c[s].w1, 1, P.ic, P.ic, P.c[s].mc, Ws, cur, 256, bn1 + P.MC + P.c[s].coff);
     CH.first[s + 1] = CH.first[s] + Ws.nK;
   }
   CH.total = CH.first[P.na];
@@ -675,7 +975,7 @@ void umma_prep_bwd(const Plan& P, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks
   prep_launch(J, st);
 }
 
-void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, const float* bn3, const float4* dzc,
+void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, const float4* dzc2,
              const float* D, const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st) {
   int maxN, maxNc;
   um_max(P, WA, maxN, maxNc);
@@ -685,27 +985,38 @@ void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, c
                2.0 * P.Q * (double)P.MC * P.oc, st);
   if (P.act == TFNAS_ACT_RELU) {
     cudaFuncSetAttribute(k_um_dc<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_dc<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
+    k_um_dc<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD);
   } else {
     cudaFuncSetAttribute(k_um_dc<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_dc<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, bn3, dzc, D, bn2, DC, dg, sD);
+    k_um_dc<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD);
   }
+}
+
+template <int ACT, int RS>
+static void launch_um_dx(const Plan& P, const UmW& W, const DxChunks& CH, dim3 grid, int ksplit, size_t smem, const float* DA,
+                         const float* UH, float* dx, double* sU, cudaStream_t st) {
+  cudaFuncSetAttribute(k_um_dx<ACT, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_um_dx<ACT, RS><<<grid, UM_NT, smem, st>>>(P, W, CH, ksplit, DA, UH, dx, sU);
 }
 
 void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, const float* bn1,
              float* dx, double* sU, cudaStream_t st) {
+  (void)bn1;   // folded into the prepped weights
   const int tiles = cdiv(P.P, 128);
-  int ksplit = max(1, min(CH.total, cdiv(2 * sm_count(), tiles)));
+  // 2 ring stages (64 KB) with two CTAs per SM when that fits, else one CTA per SM with 4 stages
+  const bool two = um_smem_bytes(W.Nc, 2 * um_ring_stage_bytes(2)) <= UM_SMEM_2CTA;
+  const size_t smem = um_smem_bytes(W.Nc, (two ? 2 : 4) * um_ring_stage_bytes(2));
+  int ksplit = max(1, min(CH.total, cdiv((two ? 2 : 1) * sm_count(), tiles)));
   if (ksplit > 1) cudaMemsetAsync(dx, 0, (size_t)P.P * P.ic * sizeof(float), st);
-  size_t smem = um_smem_bytes(W.Nc);
   dim3 grid(tiles, ksplit);
   ProfScope ps("dx", 4.0 * P.P * (2.0 * P.MC + P.ic) + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
-  if (P.act == TFNAS_ACT_RELU) {
-    cudaFuncSetAttribute(k_um_dx<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_dx<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
+  const bool relu = P.act == TFNAS_ACT_RELU;
+  if (two) {
+    if (relu) launch_um_dx<TFNAS_ACT_RELU, 2>(P, W, CH, grid, ksplit, smem, DA, UH, dx, sU, st);
+    else launch_um_dx<TFNAS_ACT_SWISH, 2>(P, W, CH, grid, ksplit, smem, DA, UH, dx, sU, st);
   } else {
-    cudaFuncSetAttribute(k_um_dx<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_um_dx<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, W, CH, ksplit, DA, UH, bn1, dx, sU);
+    if (relu) launch_um_dx<TFNAS_ACT_RELU, 4>(P, W, CH, grid, ksplit, smem, DA, UH, dx, sU, st);
+    else launch_um_dx<TFNAS_ACT_SWISH, 4>(P, W, CH, grid, ksplit, smem, DA, UH, dx, sU, st);
   }
 }
 
@@ -727,7 +1038,7 @@ struct WgArgs {
 template <int MODE, int ACT>
 __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
-  unsigned char* sm = (unsigned char*)(((uintptr_t)um_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sm = um_raw + ((1024u - (smem_u32(um_raw) & 1023u)) & 1023u);
   const int Nc = g.Nc;
   unsigned char* a_hi = sm;
   unsigned char* a_lo = sm + 16384;
@@ -882,4 +1193,12 @@ void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float*
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<grid, NT, smem, st>>>(P, slot, g);
   }
+}
+
+// debug: enable / disable the in-kernel phase trace (buf: device memory, n_ctas * UM_TRACE_SLOTS u64; nullptr disables)
+extern "C" int tfnas_debug_um_trace(void* buf, int n_ctas) {
+  unsigned long long* p = (unsigned long long*)buf;
+  if (cudaMemcpyToSymbol(g_um_trace, &p, sizeof(p)) != cudaSuccess) return TFNAS_E_CUDA;
+  if (cudaMemcpyToSymbol(g_um_trace_n, &n_ctas, sizeof(n_ctas)) != cudaSuccess) return TFNAS_E_CUDA;
+  return TFNAS_OK;
 }
