@@ -51,53 +51,67 @@ __global__ void __launch_bounds__(256) k_umma_prep_w(const float* __restrict__ s
 // -------------------------------------------------------------------------------------------------
 // shared skeleton
 // -------------------------------------------------------------------------------------------------
+#define UM_MAXB 8                 // weight (B operand) slots: chunk c lives in slot c % nb, fetched nb-1 chunks ahead
 struct UmSmem {
   unsigned char* a_hi[UM_STAGES];
   unsigned char* a_lo[UM_STAGES];
-  unsigned char* b[UM_STAGES];      // hi block followed by lo block
-  uint64_t* bar_b;                  // [UM_STAGES]
+  unsigned char* b[UM_STAGES];      // first weight slot: hi block followed by lo block; slot j at b + j * 2*Nc*128
+  uint64_t* bar_b;                  // [UM_MAXB]
   uint64_t* bar_mma;                // [UM_STAGES]
   uint32_t* tmem_slot;
   float2* cf;                       // [256] per-column epilogue coefficients (e.g. BN mean / rstd)
   unsigned char* ring;              // cp.async staging ring of raw input rows (thread-private 16 B slots)
+  int nb;
 };
 
-__device__ __forceinline__ void um_carve(unsigned char* raw, int Nc, UmSmem& S) {
+// layout: [a_hi 16K | a_lo 16K | nb weight slots | barriers 128 B | cf 2 KB | ring]
+__device__ __forceinline__ void um_carve(unsigned char* raw, int Nc, UmSmem& S, int nb = 1) {
   // align by OFFSET so the pointer keeps its shared address space (STS/LDS instead of generic ST/LD)
   unsigned char* sm = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
-  const size_t stage = 32768 + (size_t)2 * Nc * 128;     // multiple of 1024 because Nc % 16 == 0 -> 2*Nc*128 % 4096 == 0
-#pragma unroll
-  for (int s = 0; s < UM_STAGES; ++s) {
-    S.a_hi[s] = sm + s * stage;
-    S.a_lo[s] = S.a_hi[s] + 16384;
-    S.b[s] = S.a_hi[s] + 32768;
-  }
-  S.bar_b = (uint64_t*)(sm + UM_STAGES * stage);
-  S.bar_mma = S.bar_b + UM_STAGES;
+  const size_t wslot = (size_t)2 * Nc * 128;             // multiple of 4096 because Nc % 16 == 0
+  S.a_hi[0] = sm;
+  S.a_lo[0] = sm + 16384;
+  S.b[0] = sm + 32768;
+  unsigned char* tail = sm + 32768 + nb * wslot;
+  S.bar_b = (uint64_t*)tail;
+  S.bar_mma = S.bar_b + UM_MAXB;
   S.tmem_slot = (uint32_t*)(S.bar_mma + UM_STAGES);
-  S.cf = (float2*)(sm + UM_STAGES * stage + 64);
-  S.ring = sm + UM_STAGES * stage + 64 + 256 * sizeof(float2);
+  S.cf = (float2*)(tail + 128);
+  S.ring = tail + 128 + 256 * sizeof(float2);
+  S.nb = nb;
 }
 // one ring stage holds, for each of `ntens` input tensors, UM_RW rows x 4 pixels (16 B) per thread
 __host__ __device__ inline size_t um_ring_stage_bytes(int ntens) { return (size_t)ntens * UM_RW * UM_NT * 16; }
-static inline size_t um_smem_bytes(int Nc, size_t ring_bytes = 0) {
-  return 1024 + UM_STAGES * (32768 + (size_t)2 * Nc * 128) + 64 + 256 * sizeof(float2) + ring_bytes;
+static inline size_t um_smem_bytes(int Nc, size_t ring_bytes = 0, int nb = 1) {
+  return 1024 + 32768 + (size_t)nb * 2 * Nc * 128 + 128 + 256 * sizeof(float2) + ring_bytes;
 }
 
-// write 4 pixels (one 16 B chunk) of row kk, split into hi / lo
-__device__ __forceinline__ void um_put(unsigned char* a_hi, unsigned char* a_lo, int lane, int kk, const float (&v)[4]) {
+// One thread's share of a K chunk of the pixel operand: UM_RW rows x 4 pixels, already split into tf32 hi / lo.
+// The prologue math fills it BEFORE the wait for the previous chunk's MMAs (so that math overlaps the tensor core's
+// ~850-cycle issue -> commit -> mbarrier round trip); only the stores happen after the wait.
+struct UmTile { float4 hi[UM_RW], lo[UM_RW]; };
+__device__ __forceinline__ void um_split(UmTile& t, int i, const float (&v)[4]) {
   float h[4], l[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
-  const uint32_t off = mn_chunk_off(lane * 4, kk, UM_KC * 128);
-  *(float4*)(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-  *(float4*)(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+  t.hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+  t.lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+}
+// row kk = warp + i * (UM_NT / 32) of the chunk, 16 B chunk of pixels 4*lane .. 4*lane+3
+__device__ __forceinline__ void um_store(const UmTile& t, unsigned char* a_hi, unsigned char* a_lo) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < UM_RW; ++i) {
+    const uint32_t off = mn_chunk_off(lane * 4, warp + i * (UM_NT / 32), UM_KC * 128);
+    *(float4*)(a_hi + off) = t.hi[i];
+    *(float4*)(a_lo + off) = t.lo[i];
+  }
 }
 
 // issue the 12 MMAs of one K chunk (one thread)
-__device__ __forceinline__ void um_issue(const UmSmem& S, int s, int Nc, uint32_t tmem, uint32_t idesc, bool first) {
+__device__ __forceinline__ void um_issue(const UmSmem& S, int s, int Nc, uint32_t tmem, uint32_t idesc, bool first, int bslot = 0) {
   const uint32_t ah = smem_u32(S.a_hi[s]), al = smem_u32(S.a_lo[s]);
-  const uint32_t bh = smem_u32(S.b[s]), bl = bh + Nc * 128;
+  const uint32_t bh = smem_u32(S.b[0]) + bslot * 2 * Nc * 128, bl = bh + Nc * 128;
 #pragma unroll
   for (int q = 0; q < UM_KC / 8; ++q) {
     const uint64_t dah = smem_desc(ah + q * 1024, UM_KC * 128, 512, SWIZZLE_128B_BASE32B);
@@ -172,42 +186,38 @@ __device__ __forceinline__ void um_mainloop(F& f, const UmSmem& S, int Nc, uint3
   const int n = f.nchunks();
   typename F::Regs rg;
   if (n > 0) f.load(0, rg);
-  uint32_t ph_b[UM_STAGES] = {0}, ph_m[UM_STAGES] = {0};
+  uint32_t ph_b = 0, ph_m = 0;
   for (int c = 0; c < n; ++c) {
-    const int s = c & (UM_STAGES - 1);
-    if (c >= UM_STAGES) {           // the MMAs that read this stage must have retired
-      mbar_wait(&S.bar_mma[s], ph_m[s]);
-      ph_m[s] ^= 1;
+    UmTile t;
+    f.compute(c, rg, t);                       // prologue math of chunk c while chunk c-1 is still on the tensor core
+    if (c + 1 < n) f.load(c + 1, rg);          // next chunk's global loads in flight across the wait
+    if (c > 0) {                               // the MMAs that read the operand tiles must have retired
+      mbar_wait(&S.bar_mma[0], ph_m);
+      ph_m ^= 1;
       tc_fence_after();
     }
     if (warp == 0) {
       if (elect_one()) {
-        mbar_expect_tx(&S.bar_b[s], 2 * Nc * 128);
-        bulk_g2s(S.b[s], f.wsrc(c), 2 * Nc * 128, &S.bar_b[s]);
+        mbar_expect_tx(&S.bar_b[0], 2 * Nc * 128);
+        bulk_g2s(S.b[0], f.wsrc(c), 2 * Nc * 128, &S.bar_b[0]);
       }
       __syncwarp();
     }
-    f.emit(c, rg, S.a_hi[s], S.a_lo[s]);
-    if (c + 1 < n) f.load(c + 1, rg);          // in flight while the tensor core works on chunk c
+    um_store(t, S.a_hi[0], S.a_lo[0]);
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {
       if (elect_one()) {
-        mbar_wait(&S.bar_b[s], ph_b[s]);
+        mbar_wait(&S.bar_b[0], ph_b);
         tc_fence_after();
-        um_issue(S, s, Nc, tmem, idesc, c == 0);
-        mma_commit(&S.bar_mma[s]);
+        um_issue(S, 0, Nc, tmem, idesc, c == 0);
+        mma_commit(&S.bar_mma[0]);
       }
       __syncwarp();
     }
-    ph_b[s] ^= 1;
+    ph_b ^= 1;
   }
-  // drain: wait for the last commits
-  for (int c = max(0, n - UM_STAGES); c < n; ++c) {
-    const int s = c & (UM_STAGES - 1);
-    mbar_wait(&S.bar_mma[s], ph_m[s]);
-    ph_m[s] ^= 1;
-  }
+  if (n > 0) mbar_wait(&S.bar_mma[0], ph_m);
   tc_fence_after();
 }
 
@@ -257,47 +267,63 @@ __device__ __forceinline__ void um_mainloop_ring(F& f, const UmSmem& S, size_t s
     cp_async_commit();
   }
   if (n > 0) f.consts(0, rg);
-  uint32_t ph_b = 0, ph_m = 0;
+  const int nb = S.nb;
+  const uint32_t wbytes = 2 * Nc * 128;
+  if (warp == 0) {                          // weights of the first nb-1 chunks
+    if (elect_one()) {
+      for (int j = 0; j < nb - 1 && j < n; ++j) {
+        mbar_expect_tx(&S.bar_b[j], wbytes);
+        bulk_g2s(S.b[0] + (size_t)j * wbytes, f.wsrc(j), wbytes, &S.bar_b[j]);
+      }
+    }
+    __syncwarp();
+  }
+  uint32_t ph_m = 0;
   int slot = 0, slot_issue = RS - 1;        // ring stage of chunk c / of chunk c + RS - 1
+  int bslot = 0, bslot_issue = nb - 1;      // weight slot of chunk c / of chunk c + nb - 1
+  uint32_t ph_b = 0;                        // parity of chunk c's weight barrier = (c / nb) & 1
   tr.mark(1);
   for (int c = 0; c < n; ++c) {
     if (c + RS - 1 < n) f.issue(c + RS - 1, S.ring + (size_t)slot_issue * stage_bytes);
     cp_async_commit();                      // one group per iteration (possibly empty) keeps the group count uniform
-    if (c > 0) {                            // the MMAs that read the operand tiles must have retired
+    cp_async_wait<RS - 1>();                // this thread's copies of chunk c have landed
+    tr.mark(4);
+    UmTile t;
+    f.compute(c, S.ring + (size_t)slot * stage_bytes, rg, t);    // overlaps chunk c-1 on the tensor core
+    if (c + 1 < n) f.consts(c + 1, rg);
+    tr.mark(5);
+    if (c > 0) {                            // the MMAs that read the operand tiles (and weight slot (c-1) % nb) must have retired
       mbar_wait(&S.bar_mma[0], ph_m);
       ph_m ^= 1;
       tc_fence_after();
     }
     tr.mark(2);
     if (warp == 0) {
-      if (elect_one()) {
-        mbar_expect_tx(&S.bar_b[0], 2 * Nc * 128);
-        bulk_g2s(S.b[0], f.wsrc(c), 2 * Nc * 128, &S.bar_b[0]);
+      if (c + nb - 1 < n && elect_one()) {  // weights of chunk c + nb - 1 into the slot chunk c - 1 just released
+        mbar_expect_tx(&S.bar_b[bslot_issue], wbytes);
+        bulk_g2s(S.b[0] + (size_t)bslot_issue * wbytes, f.wsrc(c + nb - 1), wbytes, &S.bar_b[bslot_issue]);
       }
       __syncwarp();
     }
     tr.mark(3);
-    cp_async_wait<RS - 1>();                // this thread's copies of chunk c have landed
-    tr.mark(4);
-    f.emit(c, S.ring + (size_t)slot * stage_bytes, rg, S.a_hi[0], S.a_lo[0]);
-    if (c + 1 < n) f.consts(c + 1, rg);
-    tr.mark(5);
+    um_store(t, S.a_hi[0], S.a_lo[0]);
     fence_proxy_async();
     __syncthreads();
     tr.mark(6);
     if (warp == 0) {
       if (elect_one()) {
-        mbar_wait(&S.bar_b[0], ph_b);
+        mbar_wait(&S.bar_b[bslot], ph_b);
         tc_fence_after();
-        um_issue(S, 0, Nc, tmem, idesc, c == 0);
+        um_issue(S, 0, Nc, tmem, idesc, c == 0, bslot);
         mma_commit(&S.bar_mma[0]);
       }
       __syncwarp();
     }
     tr.mark(7);
-    ph_b ^= 1;
     slot = slot + 1 == RS ? 0 : slot + 1;
     slot_issue = slot_issue + 1 == RS ? 0 : slot_issue + 1;
+    if (++bslot == nb) { bslot = 0; ph_b ^= 1; }
+    bslot_issue = bslot_issue + 1 == nb ? 0 : bslot_issue + 1;
   }
   if (n > 0) mbar_wait(&S.bar_mma[0], ph_m);
   tc_fence_after();
@@ -308,7 +334,8 @@ __device__ __forceinline__ uint32_t um_setup(const UmSmem& S, int Nc) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < UM_STAGES; ++s) { mbar_init(&S.bar_b[s], 1); mbar_init(&S.bar_mma[s], 1); }
+    for (int s = 0; s < UM_MAXB; ++s) mbar_init(&S.bar_b[s], 1);
+    for (int s = 0; s < UM_STAGES; ++s) mbar_init(&S.bar_mma[s], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(S.tmem_slot, tmem_cols(Nc));
@@ -369,11 +396,11 @@ struct ExpandF {
       else g.a[i] = ld4(x, px, P.ic, k, P.HW);
     }
   }
-  __device__ void emit(int c, const Regs& g, unsigned char* ah, unsigned char* al) const {
+  __device__ void compute(int c, const Regs& g, UmTile& t) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
       const float v[4] = {g.a[i].x, g.a[i].y, g.a[i].z, g.a[i].w};
-      um_put(ah, al, lane, warp + i * (UM_NT / 32), v);
+      um_split(t, i, v);
     }
   }
   __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
@@ -447,7 +474,7 @@ struct ProjectF {
       g.gt[i] = cd.se > 0 ? seg[(size_t)px.n[0] * P.MCse + cd.soff + k] : 1.f;
     }
   }
-  __device__ void emit(int c, const unsigned char* slot, const Regs& g, unsigned char* ah, unsigned char* al) const {
+  __device__ void compute(int c, const unsigned char* slot, const Regs& g, UmTile& t) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
       const int kk = warp + i * (UM_NT / 32), k = c * UM_KC + kk;
@@ -468,7 +495,7 @@ struct ProjectF {
           }
         }
       }
-      um_put(ah, al, lane, kk, v);
+      um_split(t, i, v);
     }
   }
   __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
@@ -477,7 +504,7 @@ struct ProjectF {
 template <int ACT, int RS>
 __global__ void __launch_bounds__(UM_NT, 2) k_um_project(Plan P, UmWAll WA, const float* __restrict__ D,
                                                     const float* __restrict__ bn2, const float* __restrict__ seg,
-                                                    float* __restrict__ Zb, double* __restrict__ st3) {
+                                                    float* __restrict__ Zb, double* __restrict__ st3, int nb) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
   const int slot = blockIdx.z, nc = blockIdx.y;
   const UmW& W = WA.s[slot];
@@ -486,7 +513,7 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_project(Plan P, UmWAll WA, cons
   UmTrace tr;
   tr.begin();
   UmSmem S;
-  um_carve(um_raw, W.Nc, S);
+  um_carve(um_raw, W.Nc, S, nb);
   const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   ProjectF<ACT> f{P, W, cd, D, D, bn2, seg, Px4(), nc, lane, warp};
@@ -538,9 +565,9 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_project(Plan P, UmWAll WA, cons
 // B2: dc = W3^T dz
 // -------------------------------------------------------------------------------------------------
 struct DcF {
-  const Plan& P; const UmW& W; const float* G; const float* Zb; const float* Gb; const float* Zbb; const float4* dzc2; Px4 px; int nc, slot; int lane, warp;
-  // a = G row, b = Z row, cf = (A, B, C): dz = A*g + B*z + C  (BN3 backward folded, k_b2prep)
-  struct Regs { float4 a[UM_RW], b[UM_RW], cf[UM_RW]; };
+  const Plan& P; const UmW& W; const float* G; const float* Zb; const float* Gb; const float* Zbb; const float4* cft; Px4 px; int nc, slot; int lane, warp;
+  // a = G row, b = Z row; cft[o] = (A, B, C) in shared memory: dz = A*g + B*z + C  (BN3 backward folded, k_b2prep)
+  struct Regs { float4 a[UM_RW], b[UM_RW]; };
   __device__ int nchunks() const { return W.nK; }
   __device__ void load(int c, Regs& g) const {
 #pragma unroll
@@ -554,22 +581,21 @@ struct DcF {
           g.a[i] = ld4(G, px, P.oc, o, P.HWo);
           g.b[i] = ld4(Zb, px, P.na * P.oc, slot * P.oc + o, P.HWo);
         }
-        g.cf[i] = dzc2[slot * P.oc + o];
       } else {
-        g.a[i] = g.b[i] = g.cf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g.a[i] = g.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
-  __device__ void emit(int c, const Regs& g, unsigned char* ah, unsigned char* al) const {
+  __device__ void compute(int c, const Regs& g, UmTile& t) const {
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
-      const int kk = warp + i * (UM_NT / 32);
-      const float4 cf = g.cf[i];      // zero for rows >= oc
+      const int o = c * UM_KC + warp + i * (UM_NT / 32);
+      const float4 cf = o < P.oc ? cft[o] : make_float4(0.f, 0.f, 0.f, 0.f);
       const float gg[4] = {g.a[i].x, g.a[i].y, g.a[i].z, g.a[i].w}, z[4] = {g.b[i].x, g.b[i].y, g.b[i].z, g.b[i].w};
       float v[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? fmaf(cf.x, gg[e], fmaf(cf.y, z[e], cf.z)) : 0.f;
-      um_put(ah, al, lane, kk, v);
+      um_split(t, i, v);
     }
   }
   __device__ const void* wsrc(int c) const { return (const char*)W.wp + ((size_t)nc * W.nK + c) * 2 * W.Nc * 128; }
@@ -590,9 +616,11 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const flo
   const int ncol = min(W.Nc, cd.mc - nc * W.Nc);        // valid output columns (mid channels) of this chunk
   const int cst0 = cd.coff + nc * W.Nc;                 // stacked channel of column 0
   for (int i = threadIdx.x; i < ncol; i += UM_NT) S.cf[i] = make_float2(bn2[cst0 + i], bn2[P.MC + cst0 + i]);
+  float4* cft = (float4*)S.ring;                        // [oc] BN3-backward coefficients of this slot
+  for (int i = threadIdx.x; i < P.oc; i += UM_NT) cft[i] = dzc2[slot * P.oc + i];
   const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  DcF f{P, W, G, Zb, G, Zb, dzc2, Px4(), nc, slot, lane, warp};
+  DcF f{P, W, G, Zb, G, Zb, cft, Px4(), nc, slot, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.Q, P.HWo);
   f.Gb = G + (size_t)f.px.n[0] * P.oc * P.HWo + f.px.hw[0];
   f.Zbb = Zb + ((size_t)f.px.n[0] * P.na + slot) * P.oc * P.HWo + f.px.hw[0];
@@ -747,7 +775,7 @@ struct DxF {
   __device__ void consts(int, Regs&) const {}
   // Rows past the candidate's width and invalid pixels are zero-filled in the ring, so du = 0 * act'(0) = 0 there.
   // BN1's rstd is folded into the prepped weights (umma_prep_bwd), the operand is plain du-hat.
-  __device__ void emit(int c, const unsigned char* slot_p, const Regs&, unsigned char* ah, unsigned char* al) const {
+  __device__ void compute(int c, const unsigned char* slot_p, const Regs&, UmTile& t) const {
     int slot, k0;
     locate(c, slot, k0);
     const Cand& cd = P.c[slot];
@@ -767,7 +795,7 @@ struct DxF {
         st[2 * i] += v[e];
         st[2 * i + 1] += v[e] * uh[e];
       }
-      um_put(ah, al, lane, kk, v);
+      um_split(t, i, v);
     }
     // 2*UM_RW statistics (rows x {sum du, sum du*uh}) reduced together; lane l < 2*UM_RW ends up owning statistic l
     const float tot = warp_sum16(st);
@@ -781,12 +809,12 @@ struct DxF {
 template <int ACT, int RS>
 __global__ void __launch_bounds__(UM_NT, 2) k_um_dx(Plan P, UmW W, DxChunks CH, int ksplit, const float* __restrict__ DA,
                                                const float* __restrict__ UH,
-                                               float* __restrict__ dx, double* __restrict__ sU) {
+                                               float* __restrict__ dx, double* __restrict__ sU, int nb) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
   UmTrace tr;
   tr.begin();
   UmSmem S;
-  um_carve(um_raw, W.Nc, S);
+  um_carve(um_raw, W.Nc, S, nb);
   const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch0 = (int)((long long)CH.total * blockIdx.y / ksplit), ch1 = (int)((long long)CH.total * (blockIdx.y + 1) / ksplit);
@@ -925,31 +953,49 @@ void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* b
   k_um_expand<<<dim3(cdiv(P.P, 128), maxN, P.na), UM_NT, smem, st>>>(P, WA, x, bn1, UH);
 }
 
+#define UM_SMEM_1CTA 232448   // 227 KB opt-in maximum
+
+// largest weight-slot count nb in [1, want] whose smem footprint stays within `limit` (0: not even one fits)
+static int um_fit_nb(int Nc, size_t ring_bytes, int want, size_t limit) {
+  for (int nb = want; nb >= 1; --nb)
+    if (um_smem_bytes(Nc, ring_bytes, nb) <= limit) return nb;
+  return 0;
+}
+
 template <int ACT, int RS>
-static void launch_um_project(const Plan& P, const UmWAll& WA, dim3 grid, size_t smem, const float* D, const float* bn2,
+static void launch_um_project(const Plan& P, const UmWAll& WA, dim3 grid, size_t smem, int nb, const float* D, const float* bn2,
                               const float* seg, float* Zb, double* st3, cudaStream_t st) {
   cudaFuncSetAttribute(k_um_project<ACT, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_um_project<ACT, RS><<<grid, UM_NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3);
+  k_um_project<ACT, RS><<<grid, UM_NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3, nb);
 }
 
 void umma_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn2, const float* seg, float* Zb,
                   double* st3, cudaStream_t st) {
-  int maxN, maxNc;
+  int maxN, maxNc, maxK = 1;
   um_max(P, WA, maxN, maxNc);
-  // 3 ring stages when two CTAs per SM still fit, else one CTA per SM with a deeper ring
-  const bool two = um_smem_bytes(maxNc, 3 * um_ring_stage_bytes(1)) <= UM_SMEM_2CTA;
-  const size_t smem = um_smem_bytes(maxNc, (two ? 3 : 5) * um_ring_stage_bytes(1));
+  for (int s = 0; s < P.na; ++s) maxK = max(maxK, WA.s[s].nK);
+  const int want = min(4, maxK);
+  const size_t rs1 = um_ring_stage_bytes(1);
+  // preference: two CTAs per SM with weights fetched >= 1 chunk ahead (nb >= 2) and 3, else 2 ring stages; else one CTA
+  // per SM with a 5-stage ring; last resort two CTAs with a single weight slot
+  int RS = 3, nb = um_fit_nb(maxNc, 3 * rs1, want, UM_SMEM_2CTA);
+  if (nb < min(2, want)) {
+    const int nb2 = um_fit_nb(maxNc, 2 * rs1, want, UM_SMEM_2CTA);
+    if (nb2 >= min(2, want)) { RS = 2; nb = nb2; }
+    else { RS = 5; nb = um_fit_nb(maxNc, 5 * rs1, want, UM_SMEM_1CTA); }
+  }
+  const size_t smem = um_smem_bytes(maxNc, RS * rs1, nb);
   dim3 grid(cdiv(P.Q, 128), maxN, P.na);
   ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
   const bool relu = P.act == TFNAS_ACT_RELU;
-  if (two) {
-    if (relu) launch_um_project<TFNAS_ACT_RELU, 3>(P, WA, grid, smem, D, bn2, seg, Zb, st3, st);
-    else launch_um_project<TFNAS_ACT_SWISH, 3>(P, WA, grid, smem, D, bn2, seg, Zb, st3, st);
-  } else {
-    if (relu) launch_um_project<TFNAS_ACT_RELU, 5>(P, WA, grid, smem, D, bn2, seg, Zb, st3, st);
-    else launch_um_project<TFNAS_ACT_SWISH, 5>(P, WA, grid, smem, D, bn2, seg, Zb, st3, st);
-  }
+#define UM_PROJ(RS_) \
+  (relu ? launch_um_project<TFNAS_ACT_RELU, RS_>(P, WA, grid, smem, nb, D, bn2, seg, Zb, st3, st) \
+        : launch_um_project<TFNAS_ACT_SWISH, RS_>(P, WA, grid, smem, nb, D, bn2, seg, Zb, st3, st))
+  if (RS == 3) UM_PROJ(3);
+  else if (RS == 2) UM_PROJ(2);
+  else UM_PROJ(5);
+#undef UM_PROJ
 }
 
 // all backward weights (dc: W3^T, dx: W1^T with per-candidate K chunks) in one prep launch
@@ -979,7 +1025,7 @@ void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, c
              const float* D, const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st) {
   int maxN, maxNc;
   um_max(P, WA, maxN, maxNc);
-  size_t smem = um_smem_bytes(maxNc);
+  size_t smem = um_smem_bytes(maxNc, (size_t)P.oc * sizeof(float4));     // + the per-row coefficient table
   dim3 grid(cdiv(P.Q, 128), maxN, P.na);
   ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
@@ -993,30 +1039,33 @@ void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, c
 }
 
 template <int ACT, int RS>
-static void launch_um_dx(const Plan& P, const UmW& W, const DxChunks& CH, dim3 grid, int ksplit, size_t smem, const float* DA,
-                         const float* UH, float* dx, double* sU, cudaStream_t st) {
+static void launch_um_dx(const Plan& P, const UmW& W, const DxChunks& CH, dim3 grid, int ksplit, size_t smem, int nb,
+                         const float* DA, const float* UH, float* dx, double* sU, cudaStream_t st) {
   cudaFuncSetAttribute(k_um_dx<ACT, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_um_dx<ACT, RS><<<grid, UM_NT, smem, st>>>(P, W, CH, ksplit, DA, UH, dx, sU);
+  k_um_dx<ACT, RS><<<grid, UM_NT, smem, st>>>(P, W, CH, ksplit, DA, UH, dx, sU, nb);
 }
 
 void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, const float* bn1,
              float* dx, double* sU, cudaStream_t st) {
   (void)bn1;   // folded into the prepped weights
   const int tiles = cdiv(P.P, 128);
+  const size_t rs2 = um_ring_stage_bytes(2);
   // 2 ring stages (64 KB) with two CTAs per SM when that fits, else one CTA per SM with 4 stages
-  const bool two = um_smem_bytes(W.Nc, 2 * um_ring_stage_bytes(2)) <= UM_SMEM_2CTA;
-  const size_t smem = um_smem_bytes(W.Nc, (two ? 2 : 4) * um_ring_stage_bytes(2));
+  int nb = um_fit_nb(W.Nc, 2 * rs2, 4, UM_SMEM_2CTA);
+  const bool two = nb >= 1;
+  if (!two) nb = um_fit_nb(W.Nc, 4 * rs2, 4, UM_SMEM_1CTA);
+  const size_t smem = um_smem_bytes(W.Nc, (two ? 2 : 4) * rs2, nb);
   int ksplit = max(1, min(CH.total, cdiv((two ? 2 : 1) * sm_count(), tiles)));
   if (ksplit > 1) cudaMemsetAsync(dx, 0, (size_t)P.P * P.ic * sizeof(float), st);
   dim3 grid(tiles, ksplit);
   ProfScope ps("dx", 4.0 * P.P * (2.0 * P.MC + P.ic) + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   const bool relu = P.act == TFNAS_ACT_RELU;
   if (two) {
-    if (relu) launch_um_dx<TFNAS_ACT_RELU, 2>(P, W, CH, grid, ksplit, smem, DA, UH, dx, sU, st);
-    else launch_um_dx<TFNAS_ACT_SWISH, 2>(P, W, CH, grid, ksplit, smem, DA, UH, dx, sU, st);
+    if (relu) launch_um_dx<TFNAS_ACT_RELU, 2>(P, W, CH, grid, ksplit, smem, nb, DA, UH, dx, sU, st);
+    else launch_um_dx<TFNAS_ACT_SWISH, 2>(P, W, CH, grid, ksplit, smem, nb, DA, UH, dx, sU, st);
   } else {
-    if (relu) launch_um_dx<TFNAS_ACT_RELU, 4>(P, W, CH, grid, ksplit, smem, DA, UH, dx, sU, st);
-    else launch_um_dx<TFNAS_ACT_SWISH, 4>(P, W, CH, grid, ksplit, smem, DA, UH, dx, sU, st);
+    if (relu) launch_um_dx<TFNAS_ACT_RELU, 4>(P, W, CH, grid, ksplit, smem, nb, DA, UH, dx, sU, st);
+    else launch_um_dx<TFNAS_ACT_SWISH, 4>(P, W, CH, grid, ksplit, smem, nb, DA, UH, dx, sU, st);
   }
 }
 

@@ -152,3 +152,64 @@ extern "C" int tfnas_umma_selftest(int M, int N, int K, const float* A, const fl
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? TFNAS_OK : TFNAS_E_CUDA;
 }
+
+// ---- microbenchmark: cycles per round of 12 kind::tf32 MMAs (one K=32 chunk of the hi/lo split) ----------------
+//   mode 0: A MN-major (128B swizzle, 32B base) as in the pointwise kernels; mode 1: A K-major (128B swizzle) as in
+//   the weight-gradient kernel.  Operand contents are irrelevant (zeros).  out[cta] = cycles per round.
+__global__ void __launch_bounds__(128) k_umma_bench(int mode, int Npad, int rounds, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* a_hi = sm;
+  unsigned char* a_lo = sm + 16384;
+  unsigned char* b_hi = sm + 32768;
+  unsigned char* b_lo = b_hi + Npad * 128;
+  uint64_t* bar_mma = (uint64_t*)(b_lo + Npad * 128);
+  uint32_t* tmem_slot = (uint32_t*)(bar_mma + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (32768 + 2 * Npad * 128) / 16; i += blockDim.x) ((float4*)sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t ncols = tmem_cols(Npad);
+  if (tid == 0) { mbar_init(bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, ncols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_tf32(128, Npad, mode == 0 ? 1 : 0, 0);
+    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+    uint32_t phase = 0;
+    const long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const uint64_t dah = mode == 0 ? smem_desc(ah + s * 1024, ST_KC * 128, 512, SWIZZLE_128B_BASE32B)
+                                       : smem_desc(ah + s * 32, 16, 1024, SWIZZLE_128B);
+        const uint64_t dal = mode == 0 ? smem_desc(al + s * 1024, ST_KC * 128, 512, SWIZZLE_128B_BASE32B)
+                                       : smem_desc(al + s * 32, 16, 1024, SWIZZLE_128B);
+        const uint64_t dbh = smem_desc(bh + s * 32, 16, 1024, SWIZZLE_128B);
+        const uint64_t dbl = smem_desc(bl + s * 32, 16, 1024, SWIZZLE_128B);
+        mma_tf32(tmem, dah, dbh, idesc, (r | s) ? 1u : 0u);
+        mma_tf32(tmem, dal, dbh, idesc, 1u);
+        mma_tf32(tmem, dah, dbl, idesc, 1u);
+      }
+      mma_commit(bar_mma);
+      mbar_wait(bar_mma, phase);
+      phase ^= 1;
+    }
+    out[blockIdx.x] = (clock64() - t0) / rounds;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+// out: device [ctas] int64.  Returns 0 on launch success.
+extern "C" int tfnas_umma_bench(int mode, int N, int rounds, int ctas, long long* out, void* stream) {
+  const int Npad = (N + 15) / 16 * 16;
+  if (Npad > 256 || N < 1) return TFNAS_E_INVALID;
+  size_t smem = 1024 + 32768 + 2 * (size_t)Npad * 128 + 64;
+  cudaFuncSetAttribute(k_umma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_umma_bench<<<ctas, 128, smem, (cudaStream_t)stream>>>(mode, Npad, rounds, out);
+  return cudaGetLastError() == cudaSuccess ? TFNAS_OK : TFNAS_E_CUDA;
+}
