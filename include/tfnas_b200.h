@@ -133,6 +133,16 @@ int tfnas_bn_act_fwd(int N, int C, int HW, int act, const float* x, float* y, fl
 int tfnas_bn_act_bwd(int N, int C, int HW, int act, const float* x, const float* mean_rstd, const float* dy, float* dx,
                      void* workspace, size_t ws_bytes, void* stream);
 
+/*
+ * Depthwise KxK convolution (groups = C, padding K/2, no bias) of the second stem: the reference's
+ * MBInvertedResBlock.depth_conv when mid_channels == in_channels (models/layers.py:479-489, built by
+ * models/model_search.py:220).  K in {3, 5}; stride 1 only.  x, y, dy, dx: [N, C, H, W]; w, dw: [C, K*K].
+ * bwd: dx (input gradient) and dw (weight gradient, written not accumulated) may each be NULL.
+ */
+int tfnas_dwconv_fwd(int N, int C, int H, int W, int K, int stride, const float* x, const float* w, float* y, void* stream);
+int tfnas_dwconv_bwd(int N, int C, int H, int W, int K, int stride, const float* x, const float* w, const float* dy,
+                     float* dx, float* dw, void* stream);
+
 /* Test helper: byte offsets of the backward workspace regions
  * {sG, sGY, sD, sU, cvec2, Mm, dg, DC, DA, total} (10 entries). */
 int tfnas_debug_bwd_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, int want_wgrad, size_t* out10);

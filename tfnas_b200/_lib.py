@@ -40,7 +40,8 @@ EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
            'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout', 'tfnas_debug_bwd_layout',
-           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd']
+           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd',
+           'tfnas_dwconv_fwd', 'tfnas_dwconv_bwd']
 
 _lib = None
 
@@ -85,6 +86,10 @@ def load():
     lib.tfnas_bn_act_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.tfnas_bn_act_bwd.restype = i32
     lib.tfnas_bn_act_bwd.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    lib.tfnas_dwconv_fwd.restype = i32
+    lib.tfnas_dwconv_fwd.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.tfnas_dwconv_bwd.restype = i32
+    lib.tfnas_dwconv_bwd.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.tfnas_prof_enable.restype = i32
     lib.tfnas_prof_enable.argtypes = [i32]
     lib.tfnas_prof_collect.restype = i32

@@ -289,6 +289,27 @@ int tfnas_bn_act_bwd(int N, int C, int HW, int act, const float* x, const float*
   return check_cuda("tfnas_bn_act_bwd");
 }
 
+int tfnas_dwconv_fwd(int N, int C, int H, int W, int K, int stride, const float* x, const float* w, float* y, void* stream) {
+  if (N < 1 || C < 1 || H < 1 || W < 1 || (K != 3 && K != 5)) return fail(TFNAS_E_INVALID, "dwconv: bad shape / kernel size");
+  if (stride != 1) return fail(TFNAS_E_UNSUPPORTED, "dwconv: only stride 1 (the second stem) is implemented");
+  if ((long long)N * C > 65535) return fail(TFNAS_E_UNSUPPORTED, "dwconv: N*C > 65535 planes");
+  if (!x || !w || !y) return fail(TFNAS_E_INVALID, "null pointer");
+  cudaGetLastError();
+  launch_dwconv_fwd(N, C, H, W, K, x, w, y, (cudaStream_t)stream);
+  return check_cuda("tfnas_dwconv_fwd");
+}
+
+int tfnas_dwconv_bwd(int N, int C, int H, int W, int K, int stride, const float* x, const float* w, const float* dy,
+                     float* dx, float* dw, void* stream) {
+  if (N < 1 || C < 1 || H < 1 || W < 1 || (K != 3 && K != 5)) return fail(TFNAS_E_INVALID, "dwconv: bad shape / kernel size");
+  if (stride != 1) return fail(TFNAS_E_UNSUPPORTED, "dwconv: only stride 1 (the second stem) is implemented");
+  if ((long long)N * C > 65535) return fail(TFNAS_E_UNSUPPORTED, "dwconv: N*C > 65535 planes");
+  if (!w || !dy || (dw && !x)) return fail(TFNAS_E_INVALID, "null pointer");
+  cudaGetLastError();
+  launch_dwconv_bwd(N, C, H, W, K, x, w, dy, dx, dw, (cudaStream_t)stream);
+  return check_cuda("tfnas_dwconv_bwd");
+}
+
 int tfnas_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_recs) { g_pool.push_back(r.e0); g_pool.push_back(r.e1); }

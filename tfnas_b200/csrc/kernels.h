@@ -100,6 +100,10 @@ void launch_bn_act_fwd(int N, int C, int HW, int act, const float* x, float* y, 
 void launch_bn_act_bwd(int N, int C, int HW, int act, const float* x, const float* mr, const float* dy, float* dx,
                        double* ws, cudaStream_t st);
 
+void launch_dwconv_fwd(int N, int C, int H, int W, int KS, const float* x, const float* w, float* y, cudaStream_t st);
+void launch_dwconv_bwd(int N, int C, int H, int W, int KS, const float* x, const float* w, const float* dy, float* dx,
+                       float* dw, cudaStream_t st);
+
 void count_launch(int n);
 
 // RAII launch marker: counts the launch and, when profiling is enabled (tfnas_prof_enable), brackets

@@ -275,3 +275,128 @@ void launch_bn_act_bwd(int N, int C, int HW, int act, const float* x, const floa
   else if (act == TFNAS_ACT_SWISH) k_bn_bwd_apply<TFNAS_ACT_SWISH><<<max(blocks, 1), NT, 0, st>>>(C, HW, total, invM, x, mr, dy, ws, dx);
   else k_bn_bwd_apply<2><<<max(blocks, 1), NT, 0, st>>>(C, HW, total, invM, x, mr, dy, ws, dx);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Plain depthwise KxK convolution, stride 1, padding K/2 (the second stem's depth_conv, models/layers.py:486-489
+// with the widths of models/model_search.py:220): forward, input gradient and weight gradient.
+// Direct kernels: a thread owns 4 consecutive outputs of one row, the KxK taps live in registers, inputs come
+// through the read-only path (each input element is re-read from L1, never staged).
+// ------------------------------------------------------------------------------------------------
+// FLIP = false: y[r][c] = sum w[ky][kx] x[r+ky-p][c+kx-p]     (forward)
+// FLIP = true : correlation with the flipped filter             (input gradient of the same convolution)
+template <int KS, bool FLIP>
+__global__ void __launch_bounds__(NT) k_dwc_s1(int C, int H, int W, const float* __restrict__ x, const float* __restrict__ w,
+                                               float* __restrict__ y) {
+  constexpr int pad = KS / 2;
+  const int plane = blockIdx.y;                 // n * C + c
+  const int c = plane % C;
+  const int gpr = (W + 3) >> 2;                 // groups of 4 outputs per row
+  const int g = blockIdx.x * NT + threadIdx.x;
+  if (g >= H * gpr) return;
+  const int r = g / gpr, c0 = (g - r * gpr) * 4;
+  float wr[KS * KS];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) wr[i] = w[(size_t)c * KS * KS + (FLIP ? KS * KS - 1 - i : i)];
+  const float* xp = x + (size_t)plane * H * W;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ky = 0; ky < KS; ++ky) {
+    const int rr = r + ky - pad;
+    if (rr < 0 || rr >= H) continue;
+    float v[4 + KS - 1];
+#pragma unroll
+    for (int j = 0; j < 4 + KS - 1; ++j) {
+      const int cc = c0 + j - pad;
+      v[j] = (cc >= 0 && cc < W) ? __ldg(xp + (size_t)rr * W + cc) : 0.f;
+    }
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] += wr[ky * KS + kx] * v[j + kx];
+  }
+  float* q = y + (size_t)plane * H * W + (size_t)r * W + c0;
+  if ((W & 3) == 0) {
+    *(float4*)q = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c0 + j < W) q[j] = o[j];
+  }
+}
+
+// dw[c][ky][kx] = sum_{n,r,col} dy[n,c,r,col] * x[n,c,r+ky-p,col+kx-p].  grid (C, splits over images)
+template <int KS>
+__global__ void __launch_bounds__(NT) k_dwc_wgrad(int N, int C, int H, int W, const float* __restrict__ x,
+                                                  const float* __restrict__ dy, float* __restrict__ dw) {
+  constexpr int pad = KS / 2;
+  const int c = blockIdx.x;
+  const int n0 = (int)((long long)N * blockIdx.y / gridDim.y), n1 = (int)((long long)N * (blockIdx.y + 1) / gridDim.y);
+  float acc[KS * KS];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) acc[i] = 0.f;
+  const int gpr = (W + 3) >> 2, groups = H * gpr;
+  for (int n = n0; n < n1; ++n) {
+    const float* xp = x + ((size_t)n * C + c) * H * W;
+    const float* gp = dy + ((size_t)n * C + c) * H * W;
+    for (int g = threadIdx.x; g < groups; g += NT) {
+      const int r = g / gpr, c0 = (g - r * gpr) * 4;
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = c0 + j < W ? __ldg(gp + (size_t)r * W + c0 + j) : 0.f;
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+        const int rr = r + ky - pad;
+        if (rr < 0 || rr >= H) continue;
+        float v[4 + KS - 1];
+#pragma unroll
+        for (int j = 0; j < 4 + KS - 1; ++j) {
+          const int cc = c0 + j - pad;
+          v[j] = (cc >= 0 && cc < W) ? __ldg(xp + (size_t)rr * W + cc) : 0.f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[ky * KS + kx] += d[j] * v[j + kx];
+      }
+    }
+  }
+  __shared__ float red[NT / 32][KS * KS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) {
+    const float t = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < KS * KS) {
+    float t = 0.f;
+    for (int wq = 0; wq < NT / 32; ++wq) t += red[wq][threadIdx.x];
+    atomicAdd(&dw[(size_t)c * KS * KS + threadIdx.x], t);
+  }
+}
+
+void launch_dwconv_fwd(int N, int C, int H, int W, int KS, const float* x, const float* w, float* y, cudaStream_t st) {
+  const double total = (double)N * C * H * W;
+  dim3 grid(cdiv(H * ((W + 3) >> 2), NT), N * C);
+  ProfScope ps("stem_dw_fwd", 8.0 * total, 2.0 * KS * KS * total, st);
+  if (KS == 3) k_dwc_s1<3, false><<<grid, NT, 0, st>>>(C, H, W, x, w, y);
+  else k_dwc_s1<5, false><<<grid, NT, 0, st>>>(C, H, W, x, w, y);
+}
+
+void launch_dwconv_bwd(int N, int C, int H, int W, int KS, const float* x, const float* w, const float* dy, float* dx,
+                       float* dw, cudaStream_t st) {
+  const double total = (double)N * C * H * W;
+  if (dx) {
+    dim3 grid(cdiv(H * ((W + 3) >> 2), NT), N * C);
+    ProfScope ps("stem_dw_bwd", 8.0 * total, 2.0 * KS * KS * total, st);
+    if (KS == 3) k_dwc_s1<3, true><<<grid, NT, 0, st>>>(C, H, W, dy, w, dx);
+    else k_dwc_s1<5, true><<<grid, NT, 0, st>>>(C, H, W, dy, w, dx);
+  }
+  if (dw) {
+    cudaMemsetAsync(dw, 0, (size_t)C * KS * KS * sizeof(float), st);
+    const int splits = max(1, min(N, cdiv(4 * sm_count(), C)));
+    ProfScope ps("stem_dw_wgrad", 8.0 * total, 2.0 * KS * KS * total, st);
+    if (KS == 3) k_dwc_wgrad<3><<<dim3(C, splits), NT, 0, st>>>(N, C, H, W, x, dy, dw);
+    else k_dwc_wgrad<5><<<dim3(C, splits), NT, 0, st>>>(N, C, H, W, x, dy, dw);
+  }
+}

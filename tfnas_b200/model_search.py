@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .config import CAND_SPEC, PRIMITIVES, lut_key
-from .ops import MixedOpCall, MixedOpFn, StageSinkFn, bn_act
+from .ops import MixedOpCall, MixedOpFn, StageSinkFn, bn_act, dwconv
 
 __all__ = ['PRIMITIVES', 'OPS', 'MixedOP', 'MixedStage', 'Network', 'MBInvertedResBlock', 'ConvLayer',
            'LinearLayer', 'NoisePlan', 'injected', 'seed_noise', 'draw_gumbel']
@@ -317,10 +317,10 @@ class LinearLayer(nn.Module):
 
 class _StemBlock(MBInvertedResBlock):
     """second_stem: MBConv(32,32,se 8,16,k3,s1,relu) without expand conv (models/model_search.py:220).
-    Runs on stock torch ops for now ('next')."""
+    Depthwise conv and both BN(+act) run in the library; the tiny SE FCs and the 32->16 1x1 conv stay on torch."""
 
     def forward(self, x):
-        x = bn_act(self.depth_conv.conv(x), 'relu')
+        x = bn_act(dwconv(x, self.depth_conv.conv.weight), 'relu')
         g = F.adaptive_avg_pool2d(x, 1)
         g = self.squeeze_excite.conv_expand(F.relu(self.squeeze_excite.conv_reduce(g)))
         x = x * torch.sigmoid(g)

@@ -202,3 +202,39 @@ class BnActFn(torch.autograd.Function):
 
 def bn_act(x, act):
     return BnActFn.apply(x, act)
+
+
+class DwConvFn(torch.autograd.Function):
+    """Depthwise KxK, stride 1, padding K//2, no bias: the second stem's depth_conv (models/layers.py:486-489)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        lib = _lib.load()
+        _require_cuda_f32(x, 'x')
+        _require_cuda_f32(weight, 'weight')
+        x = x.contiguous()
+        w = weight.contiguous()
+        N, C, H, W = x.shape
+        K = w.shape[-1]
+        if w.shape[0] != C or w.shape[1] != 1 or w.shape[2] != K:
+            raise ValueError('depthwise weight must be [C, 1, K, K]')
+        y = torch.empty_like(x)
+        check(lib.tfnas_dwconv_fwd(N, C, H, W, K, 1, _ptr(x), _ptr(w), _ptr(y), _stream()))
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, C, H, W = x.shape
+        K = w.shape[-1]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        check(lib.tfnas_dwconv_bwd(N, C, H, W, K, 1, _ptr(x), _ptr(w), _ptr(gy), _ptr(dx), _ptr(dw), _stream()))
+        return dx, dw
+
+
+def dwconv(x, weight):
+    return DwConvFn.apply(x, weight)
