@@ -932,7 +932,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       float* gw3 = dweights[cd.id].w3;
       cudaMemsetAsync(gw3, 0, (size_t)oc * cd.mc * sizeof(float), st);
       if (umma_enabled()) {
-        umma_wgrad(P, s, 0, D, nullptr, dout, Zb, bn2, seg, bn3, dzc, gw3, st);
+        umma_wgrad(P, s, 0, D, nullptr, dout, Zb, bn2, seg, bn3, S.dzc2, gw3, st);
       } else {
         int nsplit = max(1, min(cdiv(P.Q, 2048), cdiv(6 * sm_count(), cdiv(oc, WG_T) * cdiv(cd.mc, WG_T))));
         dim3 grid(cdiv(oc, WG_T), cdiv(cd.mc, WG_T), nsplit);

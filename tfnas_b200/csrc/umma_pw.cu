@@ -784,7 +784,7 @@ struct DxF {
     for (int i = 0; i < 16; ++i) st[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < UM_RW; ++i) {
-      const int kk = warp + i * (UM_NT / 32);
+      (void)0;
       const float4 a = *(const float4*)(slot_p + ((size_t)i * UM_NT + threadIdx.x) * 16);
       const float4 b = *(const float4*)(slot_p + ((size_t)(UM_RW + i) * UM_NT + threadIdx.x) * 16);
       const float da[4] = {a.x, a.y, a.z, a.w}, uh[4] = {b.x, b.y, b.z, b.w};
@@ -1084,7 +1084,10 @@ struct WgArgs {
   int Nc, nN;                         // N chunking of the b axis
 };
 
-template <int MODE, int ACT>
+// NBR = B rows per thread (Nc <= 32 * NBR).  Software pipeline per 32-pixel K chunk: the raw rows of chunk c+1 are
+// loaded into registers right after chunk c's operands are stored, so they fly during the barrier, the MMA issue and
+// the tensor core's round trip; per-row constants (BN2 mean / rstd, BN3-backward coefficients) are hoisted.
+template <int MODE, int ACT, int NBR>
 __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
   unsigned char* sm = um_raw + ((1024u - (smem_u32(um_raw) & 1023u)) & 1023u);
@@ -1102,8 +1105,8 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
   const int HWp = MODE == 0 ? P.HWo : P.HW;
   const int total = MODE == 0 ? P.Q : P.P;
   const int nsplit = gridDim.z;
-  int p_lo = (int)((long long)total * blockIdx.z / nsplit) / 32 * 32;
-  int p_hi = (int)blockIdx.z + 1 < nsplit ? (int)((long long)total * (blockIdx.z + 1) / nsplit) / 32 * 32 : total;
+  const int p_lo = (int)((long long)total * blockIdx.z / nsplit) / 32 * 32;
+  const int p_hi = (int)blockIdx.z + 1 < nsplit ? (int)((long long)total * (blockIdx.z + 1) / nsplit) / 32 * 32 : total;
   if (tid == 0) { mbar_init(bar_mma, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols(Nc));
   tc_fence_before();
@@ -1113,12 +1116,72 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
   const uint32_t idesc = idesc_tf32(128, Nc, 0, 0);
   const int q = tid & 7;               // 16 B chunk (4 pixels) of the 32-pixel K chunk owned by this thread
   const int r_base = tid >> 3;         // rows r_base + 32 i
+  // ---- per-thread row constants ----
+  int a_cst[4];                        // stacked mid channel of A row i, -1 past the candidate's width
+  float a_mu[4], a_r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = m0 + r_base + 32 * i;
+    a_cst[i] = c < cd.mc ? cd.coff + c : -1;
+    a_mu[i] = a_r[i] = 0.f;
+    if (MODE == 0 && a_cst[i] >= 0) { a_mu[i] = g.bn2[a_cst[i]]; a_r[i] = g.bn2[P.MC + a_cst[i]]; }
+  }
+  int b_row[NBR];                      // B channel of row j, -1 when absent
+  float4 b_cf[MODE == 0 ? NBR : 1];    // MODE 0: dz = cf.x*g + cf.y*z + cf.z
+#pragma unroll
+  for (int j = 0; j < NBR; ++j) {
+    const int r = r_base + 32 * j, b = n0 + r;
+    b_row[j] = (r < Nc && b < nb_total) ? b : -1;
+    if (MODE == 0) b_cf[j] = b_row[j] >= 0 ? g.dzc[slot * P.oc + b] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const bool vecshape = (HWp & 3) == 0;
+  const bool gated = MODE == 0 && cd.se > 0;
+  // ---- raw registers of one chunk ----
+  float4 ra0[4], ra1[MODE == 1 ? 4 : 1], rb0[NBR], rb1[MODE == 0 ? NBR : 1];
+  float rgt[4];                        // MODE 0: SE gate per A row (vector path: one image per 4 pixels)
+  Px4 px;
+  int p = p_lo + q * 4, n = 0, hw = 0;
+  if (p < p_hi) { n = fast_div(p, HWp, __frcp_rn((float)HWp)); hw = p - n * HWp; }
+  auto load_chunk = [&]() {
+    if (vecshape) {                    // 4 valid pixels of one image (p, p_hi are multiples of 4)
+      px.vec = p < p_hi;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { px.v[e] = px.vec; px.n[e] = px.vec ? n : 0; px.hw[e] = px.vec ? hw + e : 0; }
+    } else {
+      px_decomp(px, p, p_hi, HWp);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a_cst[i] >= 0) load4(d, g.A0, px, P.MC, a_cst[i], HWp);
+      ra0[i] = make_float4(d[0], d[1], d[2], d[3]);
+      if (MODE == 1) {
+        float u[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a_cst[i] >= 0) load4(u, g.A1, px, P.MC, a_cst[i], HWp);
+        ra1[i] = make_float4(u[0], u[1], u[2], u[3]);
+      }
+      rgt[i] = 1.f;
+      if (gated && a_cst[i] >= 0) rgt[i] = g.seg[(size_t)px.n[0] * P.MCse + cd.soff + (a_cst[i] - cd.coff)];
+    }
+#pragma unroll
+    for (int j = 0; j < NBR; ++j) {
+      float v0[4] = {0.f, 0.f, 0.f, 0.f}, v1[4] = {0.f, 0.f, 0.f, 0.f};
+      if (b_row[j] >= 0) {
+        if (MODE == 0) {
+          load4(v0, g.B0, px, P.oc, b_row[j], HWp);
+          load4(v1, g.B1, px, P.na * P.oc, slot * P.oc + b_row[j], HWp);
+        } else {
+          load4(v0, g.B0, px, P.ic, b_row[j], HWp);
+        }
+      }
+      rb0[j] = make_float4(v0[0], v0[1], v0[2], v0[3]);
+      if (MODE == 0) rb1[j] = make_float4(v1[0], v1[1], v1[2], v1[3]);
+    }
+  };
   uint32_t phase = 0;
   bool first = true;
+  if (p_lo < p_hi) load_chunk();
   for (int p0 = p_lo; p0 < p_hi; p0 += 32) {
-    // pixel decomposition of this thread's 4 pixels
-    Px4 px;
-    px_decomp(px, p0 + q * 4, p_hi, HWp);
     if (!first) {                       // previous chunk's MMAs must have consumed the tiles
       mbar_wait(bar_mma, phase);
       phase ^= 1;
@@ -1127,23 +1190,19 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
     // ---- A rows: mid channels m0 .. m0+127 ----
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int r = r_base + 32 * i, c = m0 + r;
+      const int r = r_base + 32 * i;
+      const float d[4] = {ra0[i].x, ra0[i].y, ra0[i].z, ra0[i].w};
       float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (c < cd.mc) {
-        const int cst = cd.coff + c;
-        float d[4];
-        load4(d, g.A0, px, P.MC, cst, HWp);
+      if (a_cst[i] >= 0) {
         if (MODE == 0) {
-          const float mu = g.bn2[cst], rr = g.bn2[P.MC + cst];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float b = act_f<ACT>((d[e] - mu) * rr);
-            if (cd.se > 0) b *= g.seg[(size_t)px.n[e] * P.MCse + cd.soff + c];
+            float b = act_f<ACT>((d[e] - a_mu[i]) * a_r[i]);
+            if (gated) b *= px.vec ? rgt[i] : g.seg[(size_t)px.n[e] * P.MCse + cd.soff + (a_cst[i] - cd.coff)];
             v[e] = px.v[e] ? b : 0.f;
           }
         } else {
-          float u[4];
-          load4(u, g.A1, px, P.MC, cst, HWp);
+          const float u[4] = {ra1[i].x, ra1[i].y, ra1[i].z, ra1[i].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? d[e] * act_df<ACT>(u[e]) : 0.f;
         }
@@ -1156,45 +1215,55 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
       *(float4*)(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
     // ---- B rows: n0 .. n0+Nc-1 ----
-    for (int r = r_base; r < Nc; r += 32) {
-      const int b = n0 + r;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (b < nb_total) {
-        if (MODE == 0) {
-          const float4 cf = g.dzc[slot * P.oc + b];
-          const float mu3 = g.bn3[slot * P.oc + b], r3 = g.bn3[P.na * P.oc + slot * P.oc + b];
-          float gg[4], z[4];
-          load4(gg, g.B0, px, P.oc, b, HWp);
-          load4(z, g.B1, px, P.na * P.oc, slot * P.oc + b, HWp);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? cf.x * (gg[e] - cf.y - (z[e] - mu3) * r3 * cf.z) : 0.f;
-        } else {
-          load4(v, g.B0, px, P.ic, b, HWp);
+    for (int j = 0; j < NBR; ++j) {
+      const int r = r_base + 32 * j;
+      if (r < Nc) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (b_row[j] >= 0) {
+          const float x0[4] = {rb0[j].x, rb0[j].y, rb0[j].z, rb0[j].w};
+          if (MODE == 0) {
+            const float z[4] = {rb1[j].x, rb1[j].y, rb1[j].z, rb1[j].w};
+            const float4 cf = b_cf[j];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? fmaf(cf.x, x0[e], fmaf(cf.y, z[e], cf.z)) : 0.f;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = x0[e];      // invalid pixels were loaded as 0
+          }
         }
-      }
-      float h[4], l[4];
+        float h[4], l[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
-      const uint32_t off = r * 128u + ((uint32_t)(q ^ (r & 7)) << 4);
-      *(float4*)(b_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-      *(float4*)(b_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
+        const uint32_t off = r * 128u + ((uint32_t)(q ^ (r & 7)) << 4);
+        *(float4*)(b_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *(float4*)(b_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+      }
     }
+    // next chunk's raw rows: in flight across the barrier, the MMA issue and the tensor core's round trip
+    p += 32;
+    hw += 32;
+    while (hw >= HWp) { hw -= HWp; ++n; }      // planes smaller than 32 pixels wrap more than once
+    if (p0 + 32 < p_hi) load_chunk();
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const uint64_t dah = smem_desc(ah + s * 32, 16, 1024, SWIZZLE_128B);
-        const uint64_t dal = smem_desc(al + s * 32, 16, 1024, SWIZZLE_128B);
-        const uint64_t dbh = smem_desc(bh + s * 32, 16, 1024, SWIZZLE_128B);
-        const uint64_t dbl = smem_desc(bl + s * 32, 16, 1024, SWIZZLE_128B);
-        mma_tf32(tmem, dah, dbh, idesc, (first && s == 0) ? 0u : 1u);
-        mma_tf32(tmem, dal, dbh, idesc, 1u);
-        mma_tf32(tmem, dah, dbl, idesc, 1u);
+        for (int s = 0; s < 4; ++s) {
+          const uint64_t dah = smem_desc(ah + s * 32, 16, 1024, SWIZZLE_128B);
+          const uint64_t dal = smem_desc(al + s * 32, 16, 1024, SWIZZLE_128B);
+          const uint64_t dbh = smem_desc(bh + s * 32, 16, 1024, SWIZZLE_128B);
+          const uint64_t dbl = smem_desc(bl + s * 32, 16, 1024, SWIZZLE_128B);
+          mma_tf32(tmem, dah, dbh, idesc, (first && s == 0) ? 0u : 1u);
+          mma_tf32(tmem, dal, dbh, idesc, 1u);
+          mma_tf32(tmem, dah, dbl, idesc, 1u);
+        }
+        mma_commit(bar_mma);
       }
-      mma_commit(bar_mma);
+      __syncwarp();
     }
     first = false;
   }
@@ -1218,6 +1287,18 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
   um_teardown(tmem, Nc);
 }
 
+template <int MODE, int ACT>
+static void launch_um_wgrad(int nbr, dim3 grid, size_t smem, const Plan& P, int slot, const WgArgs& g, cudaStream_t st) {
+#define UM_WG(NBR_) do { \
+    cudaFuncSetAttribute(k_um_wgrad<MODE, ACT, NBR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    k_um_wgrad<MODE, ACT, NBR_><<<grid, NT, smem, st>>>(P, slot, g); } while (0)
+  if (nbr <= 2) UM_WG(2);
+  else if (nbr <= 4) UM_WG(4);
+  else UM_WG(8);
+#undef UM_WG
+}
+
+// dzc: the FOLDED BN3-backward coefficients (BwdScratch::dzc2): dz = A*g + B*z + C
 void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float* A1, const float* B0, const float* B1,
                 const float* bn2, const float* seg, const float* bn3, const float4* dzc, float* out, cudaStream_t st) {
   const Cand& cd = P.c[slot];
@@ -1231,16 +1312,15 @@ void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float*
   size_t smem = 1024 + 32768 + (size_t)2 * g.Nc * 128 + 64;
   dim3 grid(mt, g.nN, nsplit);
   const bool relu = P.act == TFNAS_ACT_RELU;
+  const int nbr = cdiv(g.Nc, 32);
   if (mode == 0) {
     ProfScope ps("wgrad_w3", 4.0 * P.Q * (2.0 * P.oc + cd.mc), 2.0 * P.Q * (double)P.oc * cd.mc, st);
-    auto k = relu ? k_um_wgrad<0, TFNAS_ACT_RELU> : k_um_wgrad<0, TFNAS_ACT_SWISH>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, NT, smem, st>>>(P, slot, g);
+    if (relu) launch_um_wgrad<0, TFNAS_ACT_RELU>(nbr, grid, smem, P, slot, g, st);
+    else launch_um_wgrad<0, TFNAS_ACT_SWISH>(nbr, grid, smem, P, slot, g, st);
   } else {
     ProfScope ps("wgrad_w1", 4.0 * P.P * (2.0 * cd.mc + P.ic), 2.0 * P.P * (double)P.ic * cd.mc, st);
-    auto k = relu ? k_um_wgrad<1, TFNAS_ACT_RELU> : k_um_wgrad<1, TFNAS_ACT_SWISH>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, NT, smem, st>>>(P, slot, g);
+    if (relu) launch_um_wgrad<1, TFNAS_ACT_RELU>(nbr, grid, smem, P, slot, g, st);
+    else launch_um_wgrad<1, TFNAS_ACT_SWISH>(nbr, grid, smem, P, slot, g, st);
   }
 }
 
