@@ -12,6 +12,8 @@
 #include "kernels.h"
 #include "pw.cuh"
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 // ----------------------------------------------------------------------------------------------
 // F0: input moments
@@ -650,7 +652,10 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
     }
   }
   // F1b
-  if (P.stride == 1) {
+  static const bool dw_tile = getenv("TFNAS_DW") && strcmp(getenv("TFNAS_DW"), "tile") == 0;
+  if (!dw_tile && dws_supported(P)) {
+    launch_dws_fwd(P, UH, D, S.st2, st);
+  } else if (P.stride == 1) {
     launch_dw_fwd<3, 1>(P, UH, D, S.st2, st);
     launch_dw_fwd<5, 1>(P, UH, D, S.st2, st);
   } else {

@@ -82,6 +82,12 @@ void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float*
 void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, const float* bn1,
              float* dx, double* sU, cudaStream_t st);
 
+// register sliding-window depthwise kernels (dws.cu): stride-1 MixedOPs; TFNAS_DW=tile forces the smem-tile kernels
+bool dws_supported(const Plan& P);
+void launch_dws_fwd(const Plan& P, const float* UH, float* D, double* st2, cudaStream_t st);
+void launch_dws_bwd(const Plan& P, const float* DC, const float* D, const float* bn2, const double* sD, const float* UH,
+                    float* DA, const TfnasCandPtrs* dweights, cudaStream_t st);
+
 void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
                     const float* lat8, float T, int alpha_mode, float* out, float* out_lat,
                     char* saved, const SavedLayout& L, const FwdScratch& S, cudaStream_t st);
