@@ -162,6 +162,17 @@ __global__ void k_xfin(int ic, int Pn, const double* __restrict__ xsum, const do
   if (i < ic) xmom[i] = xsum[i] * inv;
   if (i < ic * ic) xmom[ic + i] = xcov[i] * inv;
 }
+// same from UNCENTRED sums (tensor-core one-pass moments): cov = E[x x^T] - mean mean^T, in double
+__global__ void k_xfin_raw(int ic, int Pn, const double* __restrict__ xsum, const double* __restrict__ xx,
+                           double* __restrict__ xmom) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double inv = 1.0 / (double)Pn;
+  if (i < ic) xmom[i] = xsum[i] * inv;
+  if (i < ic * ic) {
+    const int r = i / ic, c = i - r * ic;
+    xmom[ic + i] = xx[i] * inv - (xsum[r] * inv) * (xsum[c] * inv);
+  }
+}
 
 // analytic BN1 statistics: mu1 = W1 mu_x, v1 = w^T cov w.  8 stacked mid channels per CTA; every thread walks its
 // share of the ic x ic covariance once (coalesced, fp64) for all 8 channels.
@@ -619,7 +630,16 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
   size_t zbytes = (size_t)(ic + ic * ic + 2 * P.MC + 2 * P.na * P.oc) * sizeof(double);
   cudaMemsetAsync(S.xsum, 0, zbytes, st);
   // F0
-  {
+  if (umma_enabled()) {
+    int split = max(1, min(P.N, 4 * sm_count() / max(ic, 1)));
+    { ProfScope ps("xsum", xbytes, 1.0 * P.P * ic, st);
+      k_xsum<<<dim3(ic, split), NT, 0, st>>>(P, x, S.xsum); }
+    umma_covariance(P, x, S.xsum, st);
+    { ProfScope ps("xfin", 16.0 * ic * ic, 0, st);
+      k_xfin<<<cdiv(ic * ic, 256), 256, 0, st>>>(ic, P.P, S.xsum, S.xcov, xmom); }
+    { ProfScope ps("bn1", 4.0 * P.MC * ic + 8.0 * ic * ic, 2.0 * P.MC * ic * ic, st);
+      k_bn1<<<cdiv(P.MC, BN1_CH), NT, (size_t)BN1_CH * ic * 4, st>>>(P, xmom, bn1); }
+  } else {
     int split = max(1, min(P.N, 4 * sm_count() / max(ic, 1)));
     { ProfScope ps("xsum", xbytes, 1.0 * P.P * ic, st);
       k_xsum<<<dim3(ic, split), NT, 0, st>>>(P, x, S.xsum); }

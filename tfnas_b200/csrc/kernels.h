@@ -79,6 +79,8 @@ void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, c
 // MODE 0: dW3[o][c] += sum_p dz c~ ; MODE 1: SmatT[k][c] += sum_p du-hat x   (out must be zeroed by the caller)
 void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float* A1, const float* B0, const float* B1,
                 const float* bn2, const float* seg, const float* bn3, const float4* dzc, float* out, cudaStream_t st);
+// input covariance on the tensor cores: acc = [sum x (ic, input) | centred second moments (ic*ic, accumulated)] doubles
+void umma_covariance(const Plan& P, const float* x, double* acc, cudaStream_t st);
 void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, const float* bn1,
              float* dx, double* sU, cudaStream_t st);
 

@@ -1073,6 +1073,8 @@ void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, c
 // Weight gradients on the tensor cores (sampled w-step):  Out[a][b] += sum_p U[a][p] * V[b][p]
 //   MODE 0 (W3): a = mid channel c (U = c-tilde = act(BN2(d))*gate), b = out channel o (V = dz)   -> dW3[o][c]
 //   MODE 1 (W1): a = mid channel c (U = du-hat = DA*act'(UH)),        b = in  channel k (V = x)    -> SmatT[k][c]
+//   MODE 2 (input covariance, F0): a, b = in channels, U = V = x - mean (means from the k_xsum pass)
+//                 -> double accumulators  sum_p (x_a - m_a)(x_b - m_b)   (ic x ic)
 // Both operands are K-major (pixels contiguous), staged by the CTA's threads with the tf32 split.
 // grid (mc/128, N chunks, K splits over the pixel axis); fp32 atomics combine the K splits.
 // -------------------------------------------------------------------------------------------------
@@ -1080,7 +1082,7 @@ struct WgArgs {
   const float* A0; const float* A1;   // MODE 0: D, -      MODE 1: DA, UH
   const float* B0; const float* B1;   // MODE 0: G, Z      MODE 1: x, -
   const float* bn2; const float* seg; const float* bn3; const float4* dzc;
-  float* out;                         // MODE 0: dW3 [oc][mc]   MODE 1: SmatT [ic][mc]
+  float* out;                         // MODE 0: dW3 [oc][mc]   MODE 1: SmatT [ic][mc]   MODE 2: double [ic + ic*ic]
   int Nc, nN;                         // N chunking of the b axis
 };
 
@@ -1104,6 +1106,9 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
   const int nb_total = MODE == 0 ? P.oc : P.ic;
   const int HWp = MODE == 0 ? P.HWo : P.HW;
   const int total = MODE == 0 ? P.Q : P.P;
+  const int am = MODE == 2 ? P.ic : cd.mc;          // valid A rows
+  const int acoff = MODE == 2 ? 0 : cd.coff;        // channel offset of A row 0 in its tensor
+  const int CA = MODE == 2 ? P.ic : P.MC;           // channels of the A tensor
   const int nsplit = gridDim.z;
   const int p_lo = (int)((long long)total * blockIdx.z / nsplit) / 32 * 32;
   const int p_hi = (int)blockIdx.z + 1 < nsplit ? (int)((long long)total * (blockIdx.z + 1) / nsplit) / 32 * 32 : total;
@@ -1122,17 +1127,19 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = m0 + r_base + 32 * i;
-    a_cst[i] = c < cd.mc ? cd.coff + c : -1;
+    a_cst[i] = c < am ? acoff + c : -1;
     a_mu[i] = a_r[i] = 0.f;
     if (MODE == 0 && a_cst[i] >= 0) { a_mu[i] = g.bn2[a_cst[i]]; a_r[i] = g.bn2[P.MC + a_cst[i]]; }
+    if (MODE == 2 && a_cst[i] >= 0) a_mu[i] = (float)(((const double*)g.out)[a_cst[i]] / (double)P.P);   // channel mean
   }
   int b_row[NBR];                      // B channel of row j, -1 when absent
-  float4 b_cf[MODE == 0 ? NBR : 1];    // MODE 0: dz = cf.x*g + cf.y*z + cf.z
+  float4 b_cf[MODE != 1 ? NBR : 1];    // MODE 0: dz = cf.x*g + cf.y*z + cf.z ; MODE 2: cf.x = channel mean
 #pragma unroll
   for (int j = 0; j < NBR; ++j) {
     const int r = r_base + 32 * j, b = n0 + r;
     b_row[j] = (r < Nc && b < nb_total) ? b : -1;
     if (MODE == 0) b_cf[j] = b_row[j] >= 0 ? g.dzc[slot * P.oc + b] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 2) b_cf[j] = make_float4(b_row[j] >= 0 ? (float)(((const double*)g.out)[b] / (double)P.P) : 0.f, 0.f, 0.f, 0.f);
   }
   const bool vecshape = (HWp & 3) == 0;
   const bool gated = MODE == 0 && cd.se > 0;
@@ -1153,7 +1160,7 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float d[4] = {0.f, 0.f, 0.f, 0.f};
-      if (a_cst[i] >= 0) load4(d, g.A0, px, P.MC, a_cst[i], HWp);
+      if (a_cst[i] >= 0) load4(d, g.A0, px, CA, a_cst[i], HWp);
       ra0[i] = make_float4(d[0], d[1], d[2], d[3]);
       if (MODE == 1) {
         float u[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1201,10 +1208,13 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
             if (gated) b *= px.vec ? rgt[i] : g.seg[(size_t)px.n[e] * P.MCse + cd.soff + (a_cst[i] - cd.coff)];
             v[e] = px.v[e] ? b : 0.f;
           }
-        } else {
+        } else if (MODE == 1) {
           const float u[4] = {ra1[i].x, ra1[i].y, ra1[i].z, ra1[i].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? d[e] * act_df<ACT>(u[e]) : 0.f;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? d[e] - a_mu[i] : 0.f;      // centred
         }
       }
       float h[4], l[4];
@@ -1227,9 +1237,12 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
             const float4 cf = b_cf[j];
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? fmaf(cf.x, x0[e], fmaf(cf.y, z[e], cf.z)) : 0.f;
-          } else {
+          } else if (MODE == 1) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = x0[e];      // invalid pixels were loaded as 0
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? x0[e] - b_cf[j].x : 0.f;
           }
         }
         float h[4], l[4];
@@ -1280,7 +1293,12 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int b = n0 + c0 + j;
-        if (b < nb_total && c < cd.mc) atomicAdd(&g.out[(size_t)b * cd.mc + c], v[j]);
+        if (MODE == 2) {
+          double* od = (double*)g.out;               // [ic] sums (input), then [ic][ic] centred second moments
+          if (b < nb_total && c < am) atomicAdd(&od[P.ic + (size_t)c * P.ic + b], (double)v[j]);
+        } else {
+          if (b < nb_total && c < cd.mc) atomicAdd(&g.out[(size_t)b * cd.mc + c], v[j]);
+        }
       }
     }
   }
@@ -1322,6 +1340,23 @@ void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float*
     if (relu) launch_um_wgrad<1, TFNAS_ACT_RELU>(nbr, grid, smem, P, slot, g, st);
     else launch_um_wgrad<1, TFNAS_ACT_SWISH>(nbr, grid, smem, P, slot, g, st);
   }
+}
+
+// F0 on the tensor cores: acc = [sum_p x_k (ic, INPUT: from k_xsum) | sum_p (x_k - m_k)(x_l - m_l) (ic x ic, accumulated)]
+// doubles.  Each CTA accumulates at most ~1.5k pixels in TMEM (fp32) before its partial goes to the double
+// accumulators, so the rounding of the tensor core's fp32 accumulation stays ~1e-5 relative on the variances; the
+// means (which decide ReLU gates) come from the fp64 k_xsum pass.
+void umma_covariance(const Plan& P, const float* x, double* acc, cudaStream_t st) {
+  WgArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A0 = x; g.B0 = x; g.out = (float*)acc;
+  um_tile(P.ic, g.Nc, g.nN);
+  const int mt = cdiv(P.ic, 128);
+  int nsplit = max(1, min(cdiv(P.P, 256), 1024));
+  size_t smem = 1024 + 32768 + (size_t)2 * g.Nc * 128 + 64;
+  dim3 grid(mt, g.nN, nsplit);
+  ProfScope ps("xcov", 4.0 * P.P * P.ic, 2.0 * P.P * (double)P.ic * P.ic, st);
+  launch_um_wgrad<2, TFNAS_ACT_RELU>(cdiv(g.Nc, 32), grid, smem, P, 0, g, st);
 }
 
 // debug: enable / disable the in-kernel phase trace (buf: device memory, n_ctas * UM_TRACE_SLOTS u64; nullptr disables)
