@@ -45,6 +45,17 @@ ProfScope::~ProfScope() {
   delete r;
 }
 
+void ensure_smem_impl(const void* kern, size_t smem) {
+  static std::map<const void*, size_t> limits;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = limits[kern];
+  if (smem > cur) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cur = smem;
+  }
+}
+
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

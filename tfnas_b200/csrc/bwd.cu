@@ -196,16 +196,22 @@ __global__ void __launch_bounds__(NT) k_dc(Plan P, const float* __restrict__ G, 
   }
 }
 
-// SE backward, FC by FC (tiled small GEMMs, see fc_tile):
+// SE backward, FC by FC (tiled small GEMMs, see fc_tile_g):
 //   de = dg * g (1-g)                         (on load; optionally saved for the weight grads)
-//   dt[n][j] = act'(t) * sum_c We[c][j] de[n][c]        k_se_bwd1  grid (N/32, se/64, na)
+//   du[n][j] = sum_c We[c][j] de[n][c]                  k_se_bwd1  grid (N/32, se/64, na*ksplit)  split-K, atomics
+//   dt = act'(t) * du                                   applied by the consumers (k_se_bwd2, k_se_wgrad)
 //   dp[n][c] = sum_j Wr[j][c] dt[n][j]  -> dg in place  k_se_bwd2  grid (N/32, mc/64, na)
 template <int ACT>
-__global__ void __launch_bounds__(NT) k_se_bwd1(Plan P, const float* __restrict__ seg, const float* __restrict__ set,
+__global__ void __launch_bounds__(NT) k_se_bwd1(Plan P, int ksplit, const float* __restrict__ seg,
                                                  const float* __restrict__ dg, float* __restrict__ sede,
-                                                 float* __restrict__ sedt) {
-  const Cand& cd = P.c[blockIdx.z];
+                                                 float* __restrict__ sedu) {
+  const int slot = blockIdx.z / ksplit, part = blockIdx.z - slot * ksplit;
+  const Cand& cd = P.c[slot];
   if (cd.se == 0 || (int)blockIdx.y * FC_TO >= cd.se) return;
+  const int chunks = (cd.mc + FC_KC - 1) / FC_KC;
+  const int ks = min(ksplit, chunks);               // this candidate's split: every part < ks owns at least one chunk
+  if (part >= ks) return;
+  const int k0 = (chunks * part / ks) * FC_KC, k1 = min(cd.mc, (chunks * (part + 1) / ks) * FC_KC);
   const bool keep = sede != nullptr && blockIdx.y == 0;
   fc_tile<true>(P.N, cd.se, cd.mc, cd.ew,
                 [&](int n, int k) {
@@ -215,16 +221,19 @@ __global__ void __launch_bounds__(NT) k_se_bwd1(Plan P, const float* __restrict_
                   if (keep) sede[gi] = de;
                   return de;
                 },
-                [&](int n, int o, float a) {
-                  const size_t ti = (size_t)n * P.SEH + cd.hoff + o;
-                  sedt[ti] = a * act_df<ACT>(set[ti]);
-                });
+                [&](int n, int o, float a) { atomicAdd(&sedu[(size_t)n * P.SEH + cd.hoff + o], a); },
+                k0, k1);
 }
-__global__ void __launch_bounds__(NT) k_se_bwd2(Plan P, const float* __restrict__ sedt, float* __restrict__ dg) {
+template <int ACT>
+__global__ void __launch_bounds__(NT) k_se_bwd2(Plan P, const float* __restrict__ sedu, const float* __restrict__ set,
+                                                 float* __restrict__ dg) {
   const Cand& cd = P.c[blockIdx.z];
   if (cd.se == 0 || (int)blockIdx.y * FC_TO >= cd.mc) return;
   fc_tile<true>(P.N, cd.mc, cd.se, cd.rw,
-                [&](int n, int k) { return sedt[(size_t)n * P.SEH + cd.hoff + k]; },
+                [&](int n, int k) {
+                  const size_t ti = (size_t)n * P.SEH + cd.hoff + k;
+                  return sedu[ti] * act_df<ACT>(set[ti]);
+                },
                 [&](int n, int o, float a) { dg[(size_t)n * P.MCse + cd.soff + o] = a; });
 }
 
@@ -776,39 +785,48 @@ __global__ void __launch_bounds__(NT) k_w1fin(Plan P, int slot, const float* __r
   }
 }
 
-// SE weight grads: sums over the batch
+// SE weight grads: two small GEMMs over the batch axis (K = N images) plus the bias column sums.
+//   blockIdx.z == 0:  dWe[c][j] = sum_n de[n][c] * act(t[n][j])      rows c (mc), outputs j (se);  dbe[c] = sum_n de[n][c]
+//   blockIdx.z == 1:  dWr[j][c] = sum_n dt[n][j] * p[n][c]           rows j (se), outputs c (mc);  dbr[j] = sum_n dt[n][j]
+// with dt = du * act'(t).  grid (max(mc, se)/32, max(mc, se)/64, 2)
 template <int ACT>
 __global__ void __launch_bounds__(NT) k_se_wgrad(Plan P, int slot, const float* __restrict__ sede,
-                                                  const float* __restrict__ sedt, const float* __restrict__ sep,
+                                                  const float* __restrict__ sedu, const float* __restrict__ sep,
                                                   const float* __restrict__ set, TfnasCandPtrs gw) {
   const Cand& cd = P.c[slot];
   const int mc = cd.mc, se = cd.se, N = P.N;
-  const int i = blockIdx.x * NT + threadIdx.x;
-  if (i < mc * se) {
-    {   // conv_expand.weight [mc][se]
-      int c = i / se, j = i - c * se;
-      float a = 0.f;
-      for (int n = 0; n < N; ++n)
-        a += sede[(size_t)n * P.MCse + cd.soff + c] * act_f<ACT>(set[(size_t)n * P.SEH + cd.hoff + j]);
-      gw.se_ew[i] = a;
+  __shared__ __align__(16) FcSmem sm;
+  if (blockIdx.z == 0) {
+    if ((int)blockIdx.x * FC_TN >= mc || (int)blockIdx.y * FC_TO >= se) return;
+    fc_tile_g<true, true>(sm, mc, se, 0, N,
+                          [&](int c, int n) { return sede[(size_t)n * P.MCse + cd.soff + c]; },
+                          [&](int j, int n) { return act_f<ACT>(set[(size_t)n * P.SEH + cd.hoff + j]); },
+                          [&](int c, int j, float a) { gw.se_ew[(size_t)c * se + j] = a; });
+    if (blockIdx.y == 0) {
+      const int c = blockIdx.x * FC_TN + threadIdx.x;
+      if ((int)threadIdx.x < FC_TN && c < mc) {
+        float a = 0.f;
+        for (int n = 0; n < N; ++n) a += sede[(size_t)n * P.MCse + cd.soff + c];
+        gw.se_eb[c] = a;
+      }
     }
-    {   // conv_reduce.weight [se][mc]
-      int j = i / mc, c = i - j * mc;
-      float a = 0.f;
-      for (int n = 0; n < N; ++n)
-        a += sedt[(size_t)n * P.SEH + cd.hoff + j] * sep[(size_t)n * P.MCse + cd.soff + c];
-      gw.se_rw[i] = a;
+  } else {
+    if ((int)blockIdx.x * FC_TN >= se || (int)blockIdx.y * FC_TO >= mc) return;
+    auto dt = [&](int j, int n) {
+      const size_t ti = (size_t)n * P.SEH + cd.hoff + j;
+      return sedu[ti] * act_df<ACT>(set[ti]);
+    };
+    fc_tile_g<true, true>(sm, se, mc, 0, N, dt,
+                          [&](int c, int n) { return sep[(size_t)n * P.MCse + cd.soff + c]; },
+                          [&](int j, int c, float a) { gw.se_rw[(size_t)j * mc + c] = a; });
+    if (blockIdx.y == 0) {
+      const int j = blockIdx.x * FC_TN + threadIdx.x;
+      if ((int)threadIdx.x < FC_TN && j < se) {
+        float a = 0.f;
+        for (int n = 0; n < N; ++n) a += dt(j, n);
+        gw.se_rb[j] = a;
+      }
     }
-  }
-  if (i < mc) {
-    float a = 0.f;
-    for (int n = 0; n < N; ++n) a += sede[(size_t)n * P.MCse + cd.soff + i];
-    gw.se_eb[i] = a;
-  }
-  if (i < se) {
-    float a = 0.f;
-    for (int n = 0; n < N; ++n) a += sedt[(size_t)n * P.SEH + cd.hoff + i];
-    gw.se_rb[i] = a;
   }
 }
 
@@ -852,11 +870,11 @@ static void launch_dw_bwd(const Plan& P, const float* DC, const float* D, const 
                2.0 * KS * KS * mck * P.Q * (dweights ? 2 : 1), st);
   if (dweights) {
     auto kern = relu ? k_dw_bwd<KS, S, TFNAS_ACT_RELU, true> : k_dw_bwd<KS, S, TFNAS_ACT_SWISH, true>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    ensure_smem(kern, (size_t)(cfg.smem));
     kern<<<grid, NT, cfg.smem, st>>>(P, w, cfg, DC, D, bn2, sD, UH, DA, gw);
   } else {
     auto kern = relu ? k_dw_bwd<KS, S, TFNAS_ACT_RELU, false> : k_dw_bwd<KS, S, TFNAS_ACT_SWISH, false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    ensure_smem(kern, (size_t)(cfg.smem));
     kern<<<grid, NT, cfg.smem, st>>>(P, w, cfg, DC, D, bn2, sD, UH, DA, gw);
   }
 }
@@ -953,10 +971,14 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     float* sede = dweights ? S.sede : nullptr;
     dim3 gpl(cdiv(P.MCse * 32, NT), P.N);
     { ProfScope ps("se_bwd", 4.0 * fcw + 12.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
-      dim3 g1(cdiv(P.N, FC_TN), cdiv(maxse, FC_TO), P.na);
-      if (relu) k_se_bwd1<TFNAS_ACT_RELU><<<g1, NT, 0, st>>>(P, seg, set, S.dg, sede, S.sedt);
-      else k_se_bwd1<TFNAS_ACT_SWISH><<<g1, NT, 0, st>>>(P, seg, set, S.dg, sede, S.sedt);
-      k_se_bwd2<<<dim3(cdiv(P.N, FC_TN), cdiv(maxmc, FC_TO), P.na), NT, 0, st>>>(P, S.sedt, S.dg);
+      const int ksplit = max(1, min(8, cdiv(maxmc, 2 * FC_KC)));
+      cudaMemsetAsync(S.sedt, 0, (size_t)P.N * P.SEH * sizeof(float), st);
+      dim3 g1(cdiv(P.N, FC_TN), cdiv(maxse, FC_TO), P.na * ksplit);
+      if (relu) k_se_bwd1<TFNAS_ACT_RELU><<<g1, NT, 0, st>>>(P, ksplit, seg, S.dg, sede, S.sedt);
+      else k_se_bwd1<TFNAS_ACT_SWISH><<<g1, NT, 0, st>>>(P, ksplit, seg, S.dg, sede, S.sedt);
+      dim3 g2(cdiv(P.N, FC_TN), cdiv(maxmc, FC_TO), P.na);
+      if (relu) k_se_bwd2<TFNAS_ACT_RELU><<<g2, NT, 0, st>>>(P, S.sedt, set, S.dg);
+      else k_se_bwd2<TFNAS_ACT_SWISH><<<g2, NT, 0, st>>>(P, S.sedt, set, S.dg);
       count_launch(1); }
     { ProfScope ps("b2b", 12.0 * P.Q * P.MCse, 8.0 * P.Q * P.MCse, st);
       if (relu) k_b2b<TFNAS_ACT_RELU><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
@@ -965,10 +987,11 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       for (int s = 0; s < P.na; ++s) {
         const Cand& cd = P.c[s];
         if (!cd.se) continue;
-        int tot = max(cd.mc * cd.se, max(cd.mc, cd.se));
+        const int big = max(cd.mc, cd.se);
+        dim3 gwg(cdiv(big, FC_TN), cdiv(big, FC_TO), 2);
         ProfScope ps("se_wgrad", 8.0 * cd.mc * cd.se, 4.0 * P.N * cd.mc * cd.se, st);
-        if (relu) k_se_wgrad<TFNAS_ACT_RELU><<<cdiv(tot, NT), NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
-        else k_se_wgrad<TFNAS_ACT_SWISH><<<cdiv(tot, NT), NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
+        if (relu) k_se_wgrad<TFNAS_ACT_RELU><<<gwg, NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
+        else k_se_wgrad<TFNAS_ACT_SWISH><<<gwg, NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
       }
     }
   }

@@ -206,42 +206,44 @@ __device__ __forceinline__ void stage_planes2(float* tile, const float* __restri
   }
 }
 
-// Small batched fully-connected layer used by the squeeze-excite path:
-//   Out[n][o] = sum_k In[n][k] * W(o,k)      n < N images, one candidate per blockIdx.z
-// CTA tile 32 images x 64 outputs, K streamed through smem in chunks of 32; thread (ty, tx) owns 2 images x 4
-// outputs.  `WKN` = weights stored [k][o] (o contiguous) instead of [o][k].  The caller supplies
-// load(n, k) -> input value and store(n, o, acc).
+// Small tiled GEMM used by the squeeze-excite path (FCs and their weight gradients):
+//   Out[r][o] = sum_{k in [k_begin, k_end)} In(r, k) * W(o, k)        r < R rows, o < Nout outputs
+// CTA tile 32 rows x 64 outputs (blockIdx.x, blockIdx.y), K streamed through smem in chunks of 64; thread (ty, tx)
+// owns 2 rows x 4 outputs.  The caller supplies in(r, k), w(o, k) and store(r, o, acc).  IN_ROWFAST / W_OFAST say
+// which index consecutive threads should walk when staging (pick the one that is contiguous in memory).
 #define FC_TN 32
 #define FC_TO 64
 #define FC_KC 64
-template <bool WKN, class LoadF, class StoreF>
-__device__ __forceinline__ void fc_tile(int N, int Nout, int K, const float* __restrict__ Wg, LoadF load, StoreF store) {
-  __shared__ float ins[FC_KC][FC_TN + 1];
-  __shared__ __align__(16) float ws[FC_KC][FC_TO + 4];
+struct FcSmem {
+  float ins[FC_KC][FC_TN + 1];
+  __align__(16) float ws[FC_KC][FC_TO + 4];
+};
+template <bool IN_ROWFAST, bool W_OFAST, class InF, class WF, class StoreF>
+__device__ __forceinline__ void fc_tile_g(FcSmem& sm, int R, int Nout, int k_begin, int k_end, InF in, WF w, StoreF store) {
+  float (*ins)[FC_TN + 1] = sm.ins;
+  float (*ws)[FC_TO + 4] = sm.ws;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int n0 = blockIdx.x * FC_TN, o0 = blockIdx.y * FC_TO;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int k0 = 0; k0 < K; k0 += FC_KC) {
+  for (int k0 = k_begin; k0 < k_end; k0 += FC_KC) {
     __syncthreads();
     for (int i = tid; i < FC_TN * FC_KC; i += NT) {
-      const int nn = i / FC_KC, kk = i - nn * FC_KC;       // consecutive threads -> consecutive k
-      ins[kk][nn] = (n0 + nn < N && k0 + kk < K) ? load(n0 + nn, k0 + kk) : 0.f;
+      int nn, kk;
+      if (IN_ROWFAST) { kk = i / FC_TN; nn = i - kk * FC_TN; } else { nn = i / FC_KC; kk = i - nn * FC_KC; }
+      ins[kk][nn] = (n0 + nn < R && k0 + kk < k_end) ? in(n0 + nn, k0 + kk) : 0.f;
     }
     for (int i = tid; i < FC_TO * FC_KC; i += NT) {
       int oo, kk;
-      if (WKN) { kk = i / FC_TO; oo = i - kk * FC_TO; } else { oo = i / FC_KC; kk = i - oo * FC_KC; }
-      float w = 0.f;
-      if (o0 + oo < Nout && k0 + kk < K)
-        w = WKN ? Wg[(size_t)(k0 + kk) * Nout + o0 + oo] : Wg[(size_t)(o0 + oo) * K + k0 + kk];
-      ws[kk][oo] = w;
+      if (W_OFAST) { kk = i / FC_TO; oo = i - kk * FC_TO; } else { oo = i / FC_KC; kk = i - oo * FC_KC; }
+      ws[kk][oo] = (o0 + oo < Nout && k0 + kk < k_end) ? w(o0 + oo, k0 + kk) : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
     for (int kk = 0; kk < FC_KC; ++kk) {
       const float a0 = ins[kk][ty * 2], a1 = ins[kk][ty * 2 + 1];
-      const float4 w = *(const float4*)&ws[kk][tx * 4];
-      acc[0][0] += a0 * w.x; acc[0][1] += a0 * w.y; acc[0][2] += a0 * w.z; acc[0][3] += a0 * w.w;
-      acc[1][0] += a1 * w.x; acc[1][1] += a1 * w.y; acc[1][2] += a1 * w.z; acc[1][3] += a1 * w.w;
+      const float4 wv = *(const float4*)&ws[kk][tx * 4];
+      acc[0][0] += a0 * wv.x; acc[0][1] += a0 * wv.y; acc[0][2] += a0 * wv.z; acc[0][3] += a0 * wv.w;
+      acc[1][0] += a1 * wv.x; acc[1][1] += a1 * wv.y; acc[1][2] += a1 * wv.z; acc[1][3] += a1 * wv.w;
     }
   }
 #pragma unroll
@@ -249,8 +251,17 @@ __device__ __forceinline__ void fc_tile(int N, int Nout, int K, const float* __r
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + ty * 2 + i, o = o0 + tx * 4 + j;
-      if (n < N && o < Nout) store(n, o, acc[i][j]);
+      if (n < R && o < Nout) store(n, o, acc[i][j]);
     }
+}
+// weights from a dense matrix: WKN = stored [k][o] (o contiguous) instead of [o][k]
+template <bool WKN, class LoadF, class StoreF>
+__device__ __forceinline__ void fc_tile(int N, int Nout, int K, const float* __restrict__ Wg, LoadF load, StoreF store,
+                                        int k_begin = 0, int k_end = -1) {
+  if (k_end < 0) k_end = K;
+  __shared__ __align__(16) FcSmem sm;
+  fc_tile_g<false, WKN>(sm, N, Nout, k_begin, k_end, load,
+                        [&](int o, int k) { return WKN ? Wg[(size_t)k * Nout + o] : Wg[(size_t)o * K + k]; }, store);
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

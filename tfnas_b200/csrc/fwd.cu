@@ -401,13 +401,20 @@ __global__ void __launch_bounds__(NT) k_se_pool(Plan P, const float* __restrict_
   if (lane == 0) sep[(size_t)n * P.MCse + widx] = acc / (float)P.HWo;
 }
 
-// SE FC 1: t = Wr p + br  (hidden pre-activation, saved).  grid (N/32, se/64, na)
-__global__ void __launch_bounds__(NT) k_se_fc1(Plan P, const float* __restrict__ sep, float* __restrict__ set) {
-  const Cand& cd = P.c[blockIdx.z];
+// SE FC 1: t = Wr p + br  (hidden pre-activation, saved).  K = mc is long and the output narrow, so the K axis is
+// split over blockIdx.z = slot * ksplit + part and combined with atomics into the zeroed `set` (bias added by part 0).
+__global__ void __launch_bounds__(NT) k_se_fc1(Plan P, int ksplit, const float* __restrict__ sep, float* __restrict__ set) {
+  const int slot = blockIdx.z / ksplit, part = blockIdx.z - slot * ksplit;
+  const Cand& cd = P.c[slot];
   if (cd.se == 0 || (int)blockIdx.y * FC_TO >= cd.se) return;
+  const int chunks = (cd.mc + FC_KC - 1) / FC_KC;
+  const int ks = min(ksplit, chunks);               // this candidate's split: every part < ks owns at least one chunk
+  if (part >= ks) return;
+  const int k0 = (chunks * part / ks) * FC_KC, k1 = min(cd.mc, (chunks * (part + 1) / ks) * FC_KC);
   fc_tile<false>(P.N, cd.se, cd.mc, cd.rw,
                  [&](int n, int k) { return sep[(size_t)n * P.MCse + cd.soff + k]; },
-                 [&](int n, int o, float a) { set[(size_t)n * P.SEH + cd.hoff + o] = a + cd.rb[o]; });
+                 [&](int n, int o, float a) { atomicAdd(&set[(size_t)n * P.SEH + cd.hoff + o], part == 0 ? a + cd.rb[o] : a); },
+                 k0, k1);
 }
 // SE FC 2: g = sigmoid(We act(t) + be).  grid (N/32, mc/64, na)
 template <int ACT>
@@ -592,7 +599,7 @@ static void launch_dw_fwd(const Plan& P, const float* UH, float* D, double* st2,
   for (int i = 0; i < w.n; ++i) mck += P.c[w.slot[i]].mc;
   dim3 grid(cfg.tiles, w.gstart[w.n], P.N);
   auto kern = P.act == TFNAS_ACT_RELU ? k_dw_fwd<KS, S, TFNAS_ACT_RELU> : k_dw_fwd<KS, S, TFNAS_ACT_SWISH>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+  ensure_smem(kern, (size_t)(cfg.smem));
   ProfScope ps(KS == 3 ? "dw_fwd_k3" : "dw_fwd_k5", 4.0 * mck * ((double)P.P + P.Q), 2.0 * KS * KS * mck * P.Q, st);
   kern<<<grid, NT, cfg.smem, st>>>(P, w, cfg, UH, D, st2);
 }
@@ -646,7 +653,7 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
     int nb = (ic + 3) / 4, icp = nb * 4, nblk = nb * nb;
     int ctas = max(1, min(cdiv(P.P, XC_TPX), 4 * sm_count()));
     size_t smem = (size_t)(icp * XC_LD + icp + (nblk < NT ? nblk * 16 : 0)) * 4;
-    cudaFuncSetAttribute(k_xcov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_smem(k_xcov, (size_t)(smem));
     { ProfScope ps("xcov", xbytes, 1.0 * P.P * ic * ic, st);
       k_xcov<<<ctas, NT, smem, st>>>(P, x, S.xsum, S.xcov); }
     { ProfScope ps("xfin", 16.0 * ic * ic, 0, st);
@@ -696,7 +703,9 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
       if (relu) k_se_pool<TFNAS_ACT_RELU><<<g, NT, 0, st>>>(P, D, bn2, sep);
       else k_se_pool<TFNAS_ACT_SWISH><<<g, NT, 0, st>>>(P, D, bn2, sep); }
     { ProfScope ps("se_fc", 4.0 * fcw + 8.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
-      k_se_fc1<<<dim3(cdiv(P.N, FC_TN), cdiv(maxse, FC_TO), P.na), NT, 0, st>>>(P, sep, set);
+      const int ksplit = max(1, min(8, cdiv(maxmc, 2 * FC_KC)));
+      cudaMemsetAsync(set, 0, (size_t)P.N * P.SEH * sizeof(float), st);
+      k_se_fc1<<<dim3(cdiv(P.N, FC_TN), cdiv(maxse, FC_TO), P.na * ksplit), NT, 0, st>>>(P, ksplit, sep, set);
       dim3 g2(cdiv(P.N, FC_TN), cdiv(maxmc, FC_TO), P.na);
       if (relu) k_se_fc2<TFNAS_ACT_RELU><<<g2, NT, 0, st>>>(P, set, seg);
       else k_se_fc2<TFNAS_ACT_SWISH><<<g2, NT, 0, st>>>(P, set, seg);

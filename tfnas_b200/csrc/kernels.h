@@ -114,6 +114,12 @@ void launch_dwconv_bwd(int N, int C, int H, int W, int KS, const float* x, const
 
 void count_launch(int n);
 
+// Raise a kernel's dynamic shared-memory limit only when a launch needs more than any launch before it did
+// (cudaFuncSetAttribute costs about a microsecond of host time per call).  Keyed by the kernel's address.
+void ensure_smem_impl(const void* kern, size_t smem);
+template <class K>
+static inline void ensure_smem(K kern, size_t smem) { ensure_smem_impl((const void*)kern, smem); }
+
 // RAII launch marker: counts the launch and, when profiling is enabled (tfnas_prof_enable), brackets
 // it with CUDA events on the launching stream and records its algorithmic bytes / flops.
 struct ProfScope {

@@ -948,7 +948,7 @@ void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* b
   int maxN, maxNc;
   um_max(P, WA, maxN, maxNc);
   size_t smem = um_smem_bytes(maxNc);
-  cudaFuncSetAttribute(k_um_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ensure_smem(k_um_expand, (size_t)(smem));
   ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   k_um_expand<<<dim3(cdiv(P.P, 128), maxN, P.na), UM_NT, smem, st>>>(P, WA, x, bn1, UH);
 }
@@ -965,7 +965,7 @@ static int um_fit_nb(int Nc, size_t ring_bytes, int want, size_t limit) {
 template <int ACT, int RS>
 static void launch_um_project(const Plan& P, const UmWAll& WA, dim3 grid, size_t smem, int nb, const float* D, const float* bn2,
                               const float* seg, float* Zb, double* st3, cudaStream_t st) {
-  cudaFuncSetAttribute(k_um_project<ACT, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ensure_smem(k_um_project<ACT, RS>, (size_t)(smem));
   k_um_project<ACT, RS><<<grid, UM_NT, smem, st>>>(P, WA, D, bn2, seg, Zb, st3, nb);
 }
 
@@ -1030,10 +1030,10 @@ void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, c
   ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
   if (P.act == TFNAS_ACT_RELU) {
-    cudaFuncSetAttribute(k_um_dc<TFNAS_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_smem(k_um_dc<TFNAS_ACT_RELU>, (size_t)(smem));
     k_um_dc<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD);
   } else {
-    cudaFuncSetAttribute(k_um_dc<TFNAS_ACT_SWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_smem(k_um_dc<TFNAS_ACT_SWISH>, (size_t)(smem));
     k_um_dc<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD);
   }
 }
@@ -1041,7 +1041,7 @@ void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, c
 template <int ACT, int RS>
 static void launch_um_dx(const Plan& P, const UmW& W, const DxChunks& CH, dim3 grid, int ksplit, size_t smem, int nb,
                          const float* DA, const float* UH, float* dx, double* sU, cudaStream_t st) {
-  cudaFuncSetAttribute(k_um_dx<ACT, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ensure_smem(k_um_dx<ACT, RS>, (size_t)(smem));
   k_um_dx<ACT, RS><<<grid, UM_NT, smem, st>>>(P, W, CH, ksplit, DA, UH, dx, sU, nb);
 }
 
@@ -1308,7 +1308,7 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
 template <int MODE, int ACT>
 static void launch_um_wgrad(int nbr, dim3 grid, size_t smem, const Plan& P, int slot, const WgArgs& g, cudaStream_t st) {
 #define UM_WG(NBR_) do { \
-    cudaFuncSetAttribute(k_um_wgrad<MODE, ACT, NBR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    ensure_smem(k_um_wgrad<MODE, ACT, NBR_>, (size_t)(smem)); \
     k_um_wgrad<MODE, ACT, NBR_><<<grid, NT, smem, st>>>(P, slot, g); } while (0)
   if (nbr <= 2) UM_WG(2);
   else if (nbr <= 4) UM_WG(4);

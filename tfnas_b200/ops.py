@@ -19,7 +19,8 @@ def _ptr(t):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of the current stream of the current device (torch.cuda.current_stream() costs ~30 us per call)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def _require_cuda_f32(t, name):
