@@ -180,12 +180,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// rg must already hold chunk 0's loads (f.load(0, rg) issued before um_setup so they fly during the TMEM allocation)
 template <class F>
-__device__ __forceinline__ void um_mainloop(F& f, const UmSmem& S, int Nc, uint32_t tmem, uint32_t idesc) {
+__device__ __forceinline__ void um_mainloop(F& f, const UmSmem& S, int Nc, uint32_t tmem, uint32_t idesc, typename F::Regs& rg) {
   const int warp = threadIdx.x >> 5;
   const int n = f.nchunks();
-  typename F::Regs rg;
-  if (n > 0) f.load(0, rg);
   uint32_t ph_b = 0, ph_m = 0;
   for (int c = 0; c < n; ++c) {
     UmTile t;
@@ -255,18 +254,24 @@ __device__ __forceinline__ void ring_row(unsigned char* dst, const float* __rest
   }
 }
 
+// first RS-1 chunks' copies and chunk 0's constants: called BEFORE um_setup so that they fly during the TMEM
+// allocation / barrier initialisation (short-K CTAs spend a third of their life there otherwise)
 template <int RS, class F>
-__device__ __forceinline__ void um_mainloop_ring(F& f, const UmSmem& S, size_t stage_bytes, int Nc, uint32_t tmem, uint32_t idesc,
-                                                 UmTrace& tr) {
-  const int warp = threadIdx.x >> 5;
+__device__ __forceinline__ void um_ring_prefetch(F& f, const UmSmem& S, size_t stage_bytes, typename F::Regs& rg) {
   const int n = f.nchunks();
-  typename F::Regs rg;
 #pragma unroll
   for (int c = 0; c < RS - 1; ++c) {
     if (c < n) f.issue(c, S.ring + (size_t)c * stage_bytes);
     cp_async_commit();
   }
   if (n > 0) f.consts(0, rg);
+}
+
+template <int RS, class F>
+__device__ __forceinline__ void um_mainloop_ring(F& f, const UmSmem& S, size_t stage_bytes, int Nc, uint32_t tmem, uint32_t idesc,
+                                                 typename F::Regs& rg, UmTrace& tr) {
+  const int warp = threadIdx.x >> 5;
+  const int n = f.nchunks();
   const int nb = S.nb;
   const uint32_t wbytes = 2 * Nc * 128;
   if (warp == 0) {                          // weights of the first nb-1 chunks
@@ -417,12 +422,14 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_expand(Plan P, UmWAll WA, const
   const int ncol = min(W.Nc, cd.mc - nc * W.Nc);        // valid output columns of this chunk
   const int cst0 = cd.coff + nc * W.Nc;                 // stacked channel of column 0
   for (int i = threadIdx.x; i < ncol; i += UM_NT) S.cf[i] = make_float2(bn1[cst0 + i], bn1[P.MC + cst0 + i]);
-  const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   ExpandF f{P, W, x, x, Px4(), nc, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.P, P.HW);
   f.xb = x + (size_t)f.px.n[0] * P.ic * P.HW + f.px.hw[0];
-  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
+  ExpandF::Regs rg;
+  if (f.nchunks() > 0) f.load(0, rg);
+  const uint32_t tmem = um_setup(S, W.Nc);
+  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0), rg);
   const EpiPx e = epi_px(blockIdx.x * 128, P.P, P.HW);
   int c_lo, c_hi;
   epi_cols(W.Nc, c_lo, c_hi);
@@ -514,12 +521,14 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_project(Plan P, UmWAll WA, cons
   tr.begin();
   UmSmem S;
   um_carve(um_raw, W.Nc, S, nb);
-  const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   ProjectF<ACT> f{P, W, cd, D, D, bn2, seg, Px4(), nc, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.Q, P.HWo);
   f.Db = D + (size_t)f.px.n[0] * P.MC * P.HWo + f.px.hw[0];
-  um_mainloop_ring<RS>(f, S, um_ring_stage_bytes(1), W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0), tr);
+  typename ProjectF<ACT>::Regs rg;
+  um_ring_prefetch<RS>(f, S, um_ring_stage_bytes(1), rg);
+  const uint32_t tmem = um_setup(S, W.Nc);
+  um_mainloop_ring<RS>(f, S, um_ring_stage_bytes(1), W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0), rg, tr);
   const EpiPx e = epi_px(blockIdx.x * 128, P.Q, P.HWo);
   const int oc = P.oc;
   const int ncol = min(W.Nc, oc - nc * W.Nc);
@@ -618,13 +627,15 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const flo
   for (int i = threadIdx.x; i < ncol; i += UM_NT) S.cf[i] = make_float2(bn2[cst0 + i], bn2[P.MC + cst0 + i]);
   float4* cft = (float4*)S.ring;                        // [oc] BN3-backward coefficients of this slot
   for (int i = threadIdx.x; i < P.oc; i += UM_NT) cft[i] = dzc2[slot * P.oc + i];
-  const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   DcF f{P, W, G, Zb, G, Zb, cft, Px4(), nc, slot, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.Q, P.HWo);
   f.Gb = G + (size_t)f.px.n[0] * P.oc * P.HWo + f.px.hw[0];
   f.Zbb = Zb + ((size_t)f.px.n[0] * P.na + slot) * P.oc * P.HWo + f.px.hw[0];
-  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0));
+  DcF::Regs rg;
+  if (f.nchunks() > 0) f.load(0, rg);
+  const uint32_t tmem = um_setup(S, W.Nc);
+  um_mainloop(f, S, W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0), rg);
   const EpiPx e = epi_px(blockIdx.x * 128, P.Q, P.HWo);
   const bool gated = cd.se > 0;
   // images covered by this warp's 32 consecutive pixels: at most two when HWo >= 32
@@ -815,7 +826,6 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dx(Plan P, UmW W, DxChunks CH, 
   tr.begin();
   UmSmem S;
   um_carve(um_raw, W.Nc, S, nb);
-  const uint32_t tmem = um_setup(S, W.Nc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch0 = (int)((long long)CH.total * blockIdx.y / ksplit), ch1 = (int)((long long)CH.total * (blockIdx.y + 1) / ksplit);
   DxF<ACT> f{P, W, CH, DA, UH, DA, UH, sU, Px4(), ch0, ch1, lane, warp};
@@ -825,7 +835,10 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dx(Plan P, UmW W, DxChunks CH, 
     f.DAb = DA + o;
     f.UHb = UH + o;
   }
-  um_mainloop_ring<RS>(f, S, um_ring_stage_bytes(2), W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0), tr);
+  typename DxF<ACT>::Regs rg;
+  um_ring_prefetch<RS>(f, S, um_ring_stage_bytes(2), rg);
+  const uint32_t tmem = um_setup(S, W.Nc);
+  um_mainloop_ring<RS>(f, S, um_ring_stage_bytes(2), W.Nc, tmem, idesc_tf32(128, W.Nc, 1, 0), rg, tr);
   const EpiPx e = epi_px(blockIdx.x * 128, P.P, P.HW);
   int c_lo, c_hi;
   epi_cols(W.Nc, c_lo, c_hi);
