@@ -56,7 +56,12 @@ def _worker(rank, world, port, q):
             return {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
 
         per = [grads_for(s) for s in range(world)]                 # every rank computes all shards (reference for the mean)
-        mine = grads_for(rank)
+        # The collective is checked on the SAME gradients that enter the reference mean: the kernels accumulate their
+        # batch statistics with atomics, and at this tiny batch (4 images, 2x2 planes in the last stages) the BN
+        # backward is ill-conditioned enough that a second evaluation differs by ~1e-4 (checked separately below).
+        mine = {n: g.clone() for n, g in per[rank].items()}
+        again = grads_for(rank)
+        rerun = max(float((again[n] - mine[n]).norm() / (mine[n].norm() + 1e-20)) for n in mine)
         for n, p in net.named_parameters():
             p.grad = mine.get(n)
         nbytes = GradSync()(net.weight_parameters())
@@ -74,7 +79,7 @@ def _worker(rank, world, port, q):
         lo, hi = flat.clone(), flat.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        q.put((rank, worst, same_keys, nbytes, bool((lo == hi).all().item())))
+        q.put((rank, worst, same_keys, nbytes, bool((lo == hi).all().item()), rerun))
     finally:
         dist.destroy_process_group()
 
@@ -91,6 +96,8 @@ def test_two_gpu_nccl_grad_mean_and_weight_sync():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, worst, same_keys, nbytes, synced in res:
-        print('rank', rank, 'worst rel err of all-reduced grads vs mean of shard grads', worst, 'bucket bytes', nbytes)
+    for rank, worst, same_keys, nbytes, synced, rerun in res:
+        print('rank', rank, 'worst rel err of all-reduced grads vs mean of shard grads', worst, 'bucket bytes', nbytes,
+              'run-to-run', rerun)
         assert worst < 1e-5 and same_keys and nbytes > 1e6 and synced
+        assert rerun < 2e-3        # atomics-order noise of one rank's own gradients at bs 4 (north-star tolerance 1e-3 is at bs 128)

@@ -84,6 +84,17 @@ void umma_covariance(const Plan& P, const float* x, double* acc, cudaStream_t st
 void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, const float* bn1,
              float* dx, double* sU, cudaStream_t st);
 
+// persistent warp-specialised versions (umma_ws.cu); return false when the shape does not fit (caller falls back).
+// which: 0 expand, 1 project, 2 dc, 3 dx  (TFNAS_WS=comma list selects a subset, "none" disables)
+int ws_enabled(int which);
+bool ws_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1, float* UH, cudaStream_t st);
+bool ws_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn2, const float* seg, float* Zb, double* st3,
+                cudaStream_t st);
+bool ws_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, const float4* dzc2, const float* D,
+           const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st);
+bool ws_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, float* dx, double* sU,
+           cudaStream_t st);
+
 // register sliding-window depthwise kernels (dws.cu): stride-1 MixedOPs; TFNAS_DW=tile forces the smem-tile kernels
 bool dws_supported(const Plan& P);
 void launch_dws_fwd(const Plan& P, const float* UH, float* D, double* st2, cudaStream_t st);

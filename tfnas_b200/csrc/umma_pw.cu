@@ -879,7 +879,8 @@ int umma_enabled() {
 }
 
 // bytes of prepped weights for a [Nout x K] GEMM
-#define UM_EXPAND_NCAP 256
+#define UM_EXPAND_NCAP (ws_enabled(0) ? 192 : 256)   // the persistent kernels keep two weight slots + two accumulators on chip
+#define UM_DC_NCAP (ws_enabled(2) ? 128 : 256)
 static size_t um_prep_bytes(int Nout, int K, int cap = 256) {
   int Nc, nN;
   um_tile(Nout, Nc, nN, cap);
@@ -893,7 +894,7 @@ size_t umma_fwd_prep_bytes(const Plan& P) {
 size_t umma_bwd_prep_bytes(const Plan& P) {
   size_t b = 0;
   int chunks = 0;
-  for (int s = 0; s < P.na; ++s) { b += um_prep_bytes(P.c[s].mc, P.oc); chunks += cdiv(P.c[s].mc, UM_KC); }
+  for (int s = 0; s < P.na; ++s) { b += um_prep_bytes(P.c[s].mc, P.oc, UM_DC_NCAP); chunks += cdiv(P.c[s].mc, UM_KC); }
   int Nc, nN;
   um_tile(P.ic, Nc, nN);
   return b + (size_t)chunks * 2 * Nc * 128 + 1024;
@@ -958,6 +959,7 @@ static void um_max(const Plan& P, const UmWAll& WA, int& maxN, int& maxNc) {
 #define UM_SMEM_2CTA 115712   // (228 KB - 2 x 1 KB reserved) / 2
 
 void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1, float* UH, cudaStream_t st) {
+  if (ws_enabled(0) && ws_expand(P, WA, x, bn1, UH, st)) return;
   int maxN, maxNc;
   um_max(P, WA, maxN, maxNc);
   size_t smem = um_smem_bytes(maxNc);
@@ -984,6 +986,7 @@ static void launch_um_project(const Plan& P, const UmWAll& WA, dim3 grid, size_t
 
 void umma_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn2, const float* seg, float* Zb,
                   double* st3, cudaStream_t st) {
+  if (ws_enabled(1) && ws_project(P, WA, D, bn2, seg, Zb, st3, st)) return;
   int maxN, maxNc, maxK = 1;
   um_max(P, WA, maxN, maxNc);
   for (int s = 0; s < P.na; ++s) maxK = max(maxK, WA.s[s].nK);
@@ -1017,7 +1020,7 @@ void umma_prep_bwd(const Plan& P, const float* bn1, float* prep_buf, UmWAll& WD,
   J.n = 0;
   float* cur = prep_buf;
   // logical weight (row = mid channel c, k = out channel o) = W3[o][c]
-  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w3, 1, P.c[s].mc, P.c[s].mc, P.oc, WD.s[s], cur);
+  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w3, 1, P.c[s].mc, P.c[s].mc, P.oc, WD.s[s], cur, UM_DC_NCAP);
   um_tile(P.ic, WX.Nc, WX.nN);    // ic <= 192 -> one N chunk
   WX.Nout = P.ic;
   WX.wp = cur;
@@ -1036,6 +1039,7 @@ void umma_prep_bwd(const Plan& P, const float* bn1, float* prep_buf, UmWAll& WD,
 
 void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, const float4* dzc2,
              const float* D, const float* bn2, float* DC, float* dg, double* sD, cudaStream_t st) {
+  if (ws_enabled(2) && ws_dc(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD, st)) return;
   int maxN, maxNc;
   um_max(P, WA, maxN, maxNc);
   size_t smem = um_smem_bytes(maxNc, (size_t)P.oc * sizeof(float4));     // + the per-row coefficient table
@@ -1061,6 +1065,7 @@ static void launch_um_dx(const Plan& P, const UmW& W, const DxChunks& CH, dim3 g
 void umma_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, const float* UH, const float* bn1,
              float* dx, double* sU, cudaStream_t st) {
   (void)bn1;   // folded into the prepped weights
+  if (ws_enabled(3) && ws_dx(P, W, CH, DA, UH, dx, sU, st)) return;
   const int tiles = cdiv(P.P, 128);
   const size_t rs2 = um_ring_stage_bytes(2);
   // 2 ring stages (64 KB) with two CTAs per SM when that fits, else one CTA per SM with 4 stages
