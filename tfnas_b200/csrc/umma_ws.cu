@@ -2,16 +2,18 @@
 //
 //   Out[o][p] = sum_k W[o][k] * In[k][p],   p = flattened (n,h,w) pixel, 128 pixels per tile (MMA M = 128)
 //
-// One CTA per SM walks a static list of work items (candidate slot, N chunk, 128-pixel tile).  The CTA's 18 warps
+// One CTA per SM walks a static list of work items (candidate slot, N chunk, 128-pixel tile).  The CTA's warps
 // have fixed roles that meet only through mbarriers, so no phase of one tile ever waits for another phase:
-//   warps 0..7    EPILOGUE   tcgen05.ld of the finished accumulator (lane quarter = warp & 3, column half = warp >> 2),
+//   NE warps      EPILOGUE   tcgen05.ld of the finished accumulator (lane quarter = warp & 3, column part = warp >> 2),
 //                            BN statistics / SE partial sums / coalesced per-channel stores
-//   warps 8..15   PRODUCERS  cp.async of the raw input rows (and their per-row constants) RS-1 K chunks ahead into a
+//   NP warps      PRODUCERS  cp.async of the raw input rows (and their per-row constants) RS-1 K chunks ahead into a
 //                            thread-private ring; prologue math (BN / activation / SE gate / BN-backward on load),
 //                            tf32 hi/lo split, st.shared into one of S operand stages (MN-major, 128B swizzle)
-//   warp 16       MMA        one thread: waits operand stage + weight slot, issues the 12 kind::tf32 MMAs of the K chunk
+//   1 warp        MMA        one thread: waits operand stage + weight slot, issues the 12 kind::tf32 MMAs of the K chunk
 //                            (hi*hi + lo*hi + hi*lo per K=8 step), commits to the stage's / slot's "empty" barriers
-//   warp 17       WEIGHTS    one thread: bulk (TMA) copies of the pre-split, pre-swizzled weight blocks, NB-1 chunks ahead
+//   1 warp        WEIGHTS    one thread: bulk (TMA) copies of the pre-split, pre-swizzled weight blocks, NB-1 chunks ahead
+// (NE, NP) = (8, 16) for the prologue-bound kernels (project, dx), (16, 8) for the epilogue-bound ones (expand, dc):
+// the prologue / epilogue instruction streams are latency-bound per warp, so each side gets the warps it can use.
 // The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile j overlaps the main loop of
 // tile j+1.  Per-CTA set-up (TMEM allocation, barrier init) is paid once per SM instead of once per tile.
 //
@@ -19,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include "kernels.h"
 #include "pw.cuh"
 #include "umma.cuh"
@@ -26,16 +29,21 @@
 using namespace umma;
 
 #define WS_KC 32
-#define WS_NE 8
-#define WS_NP 8
-#define WS_RW (WS_KC / WS_NP)                 // K rows per producer warp per chunk
-#define WS_NPT (WS_NP * 32)
-#define WS_MMA_WARP (WS_NE + WS_NP)
-#define WS_TMA_WARP (WS_NE + WS_NP + 1)
-#define WS_NT (32 * (WS_NE + WS_NP + 2))
 #define WS_ACC_STRIDE 256                     // TMEM columns between the two accumulator buffers
-#define WS_ROWS_BYTES(ntens) ((ntens) * WS_RW * WS_NPT * 16)
+#define WS_ROWS_BYTES(ntens) ((ntens) * WS_KC * 128 * 4)      // one K chunk of raw rows: 32 rows x 128 pixels (16 KB) per tensor
 #define WS_WCONST 128                         // bytes of per-warp row constants in one ring stage
+// Warp split of a kernel: NE epilogue warps (multiple of 4: lane quarter = warp & 3, column part = warp >> 2),
+// NP producer warps (divides 32), then the MMA warp and the weight-copy warp.
+template <int NE_, int NP_>
+struct WsDim {
+  static constexpr int NE = NE_, NP = NP_;
+  static constexpr int RW = WS_KC / NP_;      // K rows per producer warp per chunk
+  static constexpr int NPT = NP_ * 32;
+  static constexpr int MMA_WARP = NE_ + NP_, TMA_WARP = NE_ + NP_ + 1;
+  static constexpr int NTHR = 32 * (NE_ + NP_ + 2);
+};
+typedef WsDim<8, 16> DimProd;                 // prologue-bound kernels (project, dx)
+typedef WsDim<16, 8> DimEpi;                  // epilogue-bound kernels (expand, dc)
 #define WS_MAXS 4
 #define WS_MAXB 4
 #define WS_SMEM_LIMIT 232448                  // 227 KB opt-in maximum
@@ -50,11 +58,12 @@ struct WsCfg { int S, NB, RS; uint32_t wslot, stage_bytes, cf_bytes; };
 struct WsSmem {
   unsigned char *a, *w, *ring;
   uint64_t *full, *empty, *wfull, *wempty, *accfull, *accempty;
+  uint64_t* rbar;          // bulk mode: [RS][NP] "rows landed" barriers, one per (ring stage, producer warp)
   uint32_t* tmem_slot;
   float2* cf;
 };
 
-// layout: [S operand stages x (hi 16K | lo 16K)] [NB weight slots] [barriers 256 B] [cf tables] [ring]
+// layout: [S operand stages x (hi 16K | lo 16K)] [NB weight slots] [barriers 1 KB] [cf tables] [ring]
 __device__ __forceinline__ void ws_carve(unsigned char* raw, const WsCfg& c, WsSmem& M) {
   unsigned char* sm = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   M.a = sm;
@@ -67,11 +76,12 @@ __device__ __forceinline__ void ws_carve(unsigned char* raw, const WsCfg& c, WsS
   M.accfull = M.wempty + WS_MAXB;
   M.accempty = M.accfull + 2;
   M.tmem_slot = (uint32_t*)(M.accempty + 2);
-  M.cf = (float2*)(tail + 256);
-  M.ring = tail + 256 + c.cf_bytes;
+  M.rbar = (uint64_t*)(tail + 256);           // 4 x 16 x 8 B
+  M.cf = (float2*)(tail + 1024);
+  M.ring = tail + 1024 + c.cf_bytes;
 }
 static size_t ws_smem_bytes(const WsCfg& c) {
-  return 1024 + (size_t)c.S * 32768 + (size_t)c.NB * c.wslot + 256 + c.cf_bytes + (size_t)c.RS * c.stage_bytes;
+  return 1024 + (size_t)c.S * 32768 + (size_t)c.NB * c.wslot + 1024 + c.cf_bytes + (size_t)c.RS * c.stage_bytes;
 }
 // deepest pipeline that fits: operand stages S, weight slots NB, ring stages RS
 static bool ws_fit(int maxNc, uint32_t stage_bytes, uint32_t cf_bytes, WsCfg& c) {
@@ -107,15 +117,14 @@ __device__ __forceinline__ void ws_cp4(void* dst, const void* src, bool valid) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
 }
 __device__ __forceinline__ void ws_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void ws_cp_wait(int pending) {
-  switch (pending) {      // wait_group needs an immediate
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-  }
+__device__ __forceinline__ void ws_cp_wait(int pending) {      // wait_group needs an immediate; pending is CTA-uniform
+  if (pending >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+  else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+  else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+  else asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void ws_bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(WS_NE * 32) : "memory"); }
+template <int NTHREADS>
+__device__ __forceinline__ void ws_bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 // 4 pixels of row `ch` of an [N][C][HW] tensor -> this thread's 16 B ring slot (zero-filled when !rowok / invalid pixel)
 __device__ __forceinline__ void ws_ring_row(unsigned char* dst, const float* __restrict__ T, const float* __restrict__ Tb,
@@ -131,19 +140,22 @@ __device__ __forceinline__ void ws_ring_row(unsigned char* dst, const float* __r
   }
 }
 
-struct WsTile { float4 hi[WS_RW], lo[WS_RW]; };
-__device__ __forceinline__ void ws_split(WsTile& t, int i, const float (&v)[4]) {
+template <class D>
+struct WsTile { float4 hi[D::RW], lo[D::RW]; };
+template <class D>
+__device__ __forceinline__ void ws_split(WsTile<D>& t, int i, const float (&v)[4]) {
   float h[4], l[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
   t.hi[i] = make_float4(h[0], h[1], h[2], h[3]);
   t.lo[i] = make_float4(l[0], l[1], l[2], l[3]);
 }
-// row kk = pw + i * WS_NP of the chunk, 16 B chunk of pixels 4*lane .. 4*lane+3
-__device__ __forceinline__ void ws_store(const WsTile& t, unsigned char* a_hi, int pw, int lane) {
+// row kk = pw + i * NP of the chunk, 16 B chunk of pixels 4*lane .. 4*lane+3
+template <class D>
+__device__ __forceinline__ void ws_store(const WsTile<D>& t, unsigned char* a_hi, int pw, int lane) {
 #pragma unroll
-  for (int i = 0; i < WS_RW; ++i) {
-    const uint32_t off = mn_chunk_off(lane * 4, pw + i * WS_NP, WS_KC * 128);
+  for (int i = 0; i < D::RW; ++i) {
+    const uint32_t off = mn_chunk_off(lane * 4, pw + i * D::NP, WS_KC * 128);
     *(float4*)(a_hi + off) = t.hi[i];
     *(float4*)(a_hi + 16384 + off) = t.lo[i];
   }
@@ -151,13 +163,14 @@ __device__ __forceinline__ void ws_store(const WsTile& t, unsigned char* a_hi, i
 
 // the 12 MMAs of one K chunk (one thread): operand stage at `a` (hi | lo), weights at `b` (hi block, lo block Nc*128 later)
 __device__ __forceinline__ void ws_issue(uint32_t a, uint32_t b, int Nc, uint32_t acc, uint32_t idesc, bool first) {
-  const uint32_t al = a + 16384, bl = b + Nc * 128;
+  // descriptor = constant fields | (shared address >> 4): stepping K only adds to the low word (addresses < 256 KB)
+  const uint64_t ca = smem_desc(0, WS_KC * 128, 512, SWIZZLE_128B_BASE32B), cb = smem_desc(0, 16, 1024, SWIZZLE_128B);
+  const uint64_t dah0 = ca | (a >> 4), dal0 = ca | ((a + 16384) >> 4);
+  const uint64_t dbh0 = cb | (b >> 4), dbl0 = cb | ((b + Nc * 128) >> 4);
 #pragma unroll
   for (int q = 0; q < WS_KC / 8; ++q) {
-    const uint64_t dah = smem_desc(a + q * 1024, WS_KC * 128, 512, SWIZZLE_128B_BASE32B);
-    const uint64_t dal = smem_desc(al + q * 1024, WS_KC * 128, 512, SWIZZLE_128B_BASE32B);
-    const uint64_t dbh = smem_desc(b + q * 32, 16, 1024, SWIZZLE_128B);
-    const uint64_t dbl = smem_desc(bl + q * 32, 16, 1024, SWIZZLE_128B);
+    const uint64_t dah = dah0 + q * 64, dal = dal0 + q * 64;       // + q * 1024 bytes
+    const uint64_t dbh = dbh0 + q * 2, dbl = dbl0 + q * 2;         // + q * 32 bytes
     mma_tf32(acc, dah, dbh, idesc, (first && q == 0) ? 0u : 1u);
     mma_tf32(acc, dal, dbh, idesc, 1u);
     mma_tf32(acc, dah, dbl, idesc, 1u);
@@ -166,13 +179,14 @@ __device__ __forceinline__ void ws_issue(uint32_t a, uint32_t b, int Nc, uint32_
 
 // epilogue geometry of one thread: pixel of its TMEM lane, column range of its warp
 struct WsEpi { int p, n, hw; bool v; int c_lo, c_hi; uint32_t taddr; };
+template <class D>
 __device__ __forceinline__ WsEpi ws_epi(int tile0, int total, int HW, int Nc, int ncol, uint32_t acc, int ew, int lane) {
   WsEpi e;
   e.p = tile0 + (ew & 3) * 32 + lane;
   e.v = e.p < total;
   e.n = e.v ? fast_div(e.p, HW, __frcp_rn((float)HW)) : 0;
   e.hw = e.v ? e.p - e.n * HW : 0;
-  const int parts = WS_NE / 4, part = ew >> 2;
+  const int parts = D::NE / 4, part = ew >> 2;
   const int h = ((Nc + parts - 1) / parts + 15) / 16 * 16;
   e.c_lo = min(Nc, part * h);
   e.c_hi = min(min(Nc, (part + 1) * h), ncol);
@@ -189,26 +203,62 @@ __device__ __forceinline__ WsEpi ws_epi(int tile0, int total, int HW, int Nc, in
 //   epi_prep(A, Sc, item, cf, etid)          fill the per-column coefficient table (epilogue warps, before the barrier)
 //   epi_run(A, Sc, item, acc, cf, ew, lane)  consume the accumulator
 // -------------------------------------------------------------------------------------------------
-template <class T>
+// ---- optional phase trace (debug build -DUM_TRACE; tfnas_debug_ws_trace) ------------------------------------
+// Producer warp 0 / the MMA thread of each traced CTA accumulate clock64() deltas per phase.
+//   producer slots: [0] iterations [1] issue [2] wait data [3] compute [4] wait empty [5] store [6] fence [7] arrive
+//   MMA slots:      [8] chunks [9] wait weights [10] wait operands [11] issue + commits [12] wait accumulator
+#define WS_TRACE_SLOTS 16
+__device__ unsigned long long* g_ws_trace = nullptr;
+__device__ int g_ws_trace_n = 0;
+#ifdef UM_TRACE
+struct WsTrace {
+  unsigned long long* out; long long t0; long long acc[8];
+  __device__ __forceinline__ void begin(bool on) {
+    out = (on && g_ws_trace && (int)blockIdx.x < g_ws_trace_n) ? g_ws_trace + (size_t)blockIdx.x * WS_TRACE_SLOTS : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0;
+    if (out) t0 = clock64();
+  }
+  __device__ __forceinline__ void mark(int slot) { if (out) { const long long t = clock64(); acc[slot] += t - t0; t0 = t; } }
+  __device__ __forceinline__ void count() { if (out) acc[0] += 1; }
+  __device__ __forceinline__ void end(int base) {
+    if (out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (base + i < WS_TRACE_SLOTS) out[base + i] = (unsigned long long)acc[i];
+    }
+  }
+};
+#else
+struct WsTrace {
+  __device__ __forceinline__ void begin(bool) {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void count() {}
+  __device__ __forceinline__ void end(int) {}
+};
+#endif
+
+template <class T, bool BULK>
 __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched& Sc, const WsCfg& cfg) {
+  using D = typename T::Dim;
   extern __shared__ __align__(1024) unsigned char ws_raw[];
   WsSmem M;
   ws_carve(ws_raw, cfg, M);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < WS_MAXS; ++s) { mbar_init(&M.full[s], WS_NPT); mbar_init(&M.empty[s], 1); }
+    for (int s = 0; s < WS_MAXS; ++s) { mbar_init(&M.full[s], D::NP); mbar_init(&M.empty[s], 1); }
     for (int s = 0; s < WS_MAXB; ++s) { mbar_init(&M.wfull[s], 1); mbar_init(&M.wempty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&M.accfull[s], 1); mbar_init(&M.accempty[s], WS_NE * 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&M.accfull[s], 1); mbar_init(&M.accempty[s], D::NE); }
+    for (int s = 0; s < WS_MAXS * D::NP; ++s) mbar_init(&M.rbar[s], 1);
     fence_barrier_init();
   }
-  if (warp == WS_MMA_WARP) tmem_alloc(M.tmem_slot, 512);
+  if (warp == D::MMA_WARP) tmem_alloc(M.tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *M.tmem_slot;
   const int item0 = blockIdx.x, istep = gridDim.x;
 
-  if (warp < WS_NE) {
+  if (warp < D::NE) {
     // ------------------------------ epilogue ------------------------------
     int jj = 0;
     for (int item = item0; item < Sc.n_items; item += istep, ++jj) {
@@ -216,23 +266,27 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
       const uint32_t au = (uint32_t)jj >> 1;
       float2* cf = M.cf + ab * 256;
       T::epi_prep(A, Sc, item, cf, tid);
-      ws_bar_epi();
+      if (T::CF) ws_bar_epi<D::NE * 32>();
       mbar_wait(&M.accfull[ab], au & 1);
       tc_fence_after();
       T::epi_run(A, Sc, item, tmem + ab * WS_ACC_STRIDE, cf, warp, lane);
       tc_fence_before();
-      mbar_arrive(&M.accempty[ab]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&M.accempty[ab]);
     }
-  } else if (warp < WS_NE + WS_NP) {
+  } else if (warp < D::NE + D::NP) {
     // ------------------------------ producers ------------------------------
-    const int ptid = tid - WS_NE * 32, pw = ptid >> 5;
-    typename T::Prod fi{A, ptid, pw, lane}, fc{A, ptid, pw, lane};
+    const int ptid = tid - D::NE * 32, pw = ptid >> 5;
+    typename std::conditional<BULK, typename T::ProdB, typename T::Prod>::type fi{A, ptid, pw, lane}, fc{A, ptid, pw, lane};
     int item_i = item0, ci = 0;
     bool vi = item_i < Sc.n_items;
     if (vi) fi.bind(Sc, item_i);
-    auto issue_next = [&](unsigned char* st) {
+    // fetch the next chunk of this warp's rows into ring stage `stg`.  Generic mode: per-thread cp.async into private
+    // slots.  Bulk mode: a few lanes issue bulk (TMA) copies of whole 512 B rows, completion on the warp's own mbarrier.
+    auto issue_next = [&](int stg) {
       if (vi) {
-        fi.issue(ci, st);
+        if (BULK) fi.issue(ci, M.ring + (size_t)stg * cfg.stage_bytes, &M.rbar[stg * D::NP + pw]);
+        else fi.issue(ci, M.ring + (size_t)stg * cfg.stage_bytes, nullptr);
         if (++ci == fi.nK) {
           ci = 0;
           item_i += istep;
@@ -240,62 +294,85 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
           if (vi) fi.bind(Sc, item_i);
         }
       }
-      ws_cp_commit();                          // one group per call (possibly empty) keeps the group count uniform
+      if (!BULK || T::WCONST) ws_cp_commit();  // one group per call (possibly empty) keeps the group count uniform
     };
     const int RS = cfg.RS, S = cfg.S;
-    for (int k = 0; k < RS - 1; ++k) issue_next(M.ring + (size_t)k * cfg.stage_bytes);
+    for (int k = 0; k < RS - 1; ++k) issue_next(k);
+    WsTrace tr;
+    tr.begin(pw == 0 && lane == 0);
     int rs = 0, rs_issue = RS - 1;             // ring stage of the chunk being emitted / being fetched
+    uint32_t rph = 0;                          // parity of the ring barriers of stage rs
     int s = 0;
     uint32_t eph = 1;                          // parity to wait for on empty[s]: passes on the first use of each stage
     for (int item = item0; item < Sc.n_items; item += istep) {
       fc.bind(Sc, item);
       const int n = fc.nK;
       for (int c = 0; c < n; ++c) {
-        __syncwarp();                          // every lane is done with the constants of the stage about to be refilled
-        issue_next(M.ring + (size_t)rs_issue * cfg.stage_bytes);
-        ws_cp_wait(RS - 1);                    // this thread's copies of the current chunk have landed
+        __syncwarp();                          // every lane is done with the ring stage about to be refilled
+        tr.count();
+        tr.mark(7);
+        issue_next(rs_issue);
+        tr.mark(1);
+        if (!BULK || T::WCONST) ws_cp_wait(RS - 1);      // this thread's cp.async copies of the current chunk have landed
+        if (BULK) mbar_wait(&M.rbar[rs * D::NP + pw], rph);
         __syncwarp();                          // ... and so have the warp-shared constants fetched by the other lanes
-        WsTile t;
+        tr.mark(2);
+        WsTile<D> t;
         fc.compute(c, M.ring + (size_t)rs * cfg.stage_bytes, t);
+        tr.mark(3);
         mbar_wait(&M.empty[s], eph);           // the MMAs that read this operand stage have retired
         tc_fence_after();
-        ws_store(t, M.a + (size_t)s * 32768, pw, lane);
+        tr.mark(4);
+        ws_store<D>(t, M.a + (size_t)s * 32768, pw, lane);
+        tr.mark(5);
         fence_proxy_async();
-        mbar_arrive(&M.full[s]);
-        rs = rs + 1 == RS ? 0 : rs + 1;
+        tr.mark(6);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&M.full[s]);
+        if (++rs == RS) { rs = 0; rph ^= 1; }
         rs_issue = rs_issue + 1 == RS ? 0 : rs_issue + 1;
         if (++s == S) { s = 0; eph ^= 1; }
       }
     }
-    ws_cp_wait(0);
-  } else if (warp == WS_MMA_WARP) {
+    if (!BULK || T::WCONST) ws_cp_wait(0);
+    tr.end(0);
+  } else if (warp == D::MMA_WARP) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       int s = 0, b = 0, jj = 0;
       uint32_t fph = 0, wph = 0;               // parities of full[s] / wfull[b]
       const uint32_t a0 = smem_u32(M.a), w0 = smem_u32(M.w);
+      WsTrace tr;
+      tr.begin(true);
       for (int item = item0; item < Sc.n_items; item += istep, ++jj) {
         int nK, Nc;
         const char* wb;
         T::geom(A, Sc, item, nK, Nc, wb);
         const int ab = jj & 1;
         const uint32_t au = (uint32_t)jj >> 1;
+        tr.mark(3);
         mbar_wait(&M.accempty[ab], (au & 1) ^ 1);     // the epilogue has drained this accumulator (passes for the first two)
         tc_fence_after();
+        tr.mark(4);
         const uint32_t idesc = idesc_tf32(128, Nc, 1, 0);
         const uint32_t acc = tmem + ab * WS_ACC_STRIDE;
         for (int c = 0; c < nK; ++c) {
+          tr.count();
           mbar_wait(&M.wfull[b], wph);
+          tr.mark(1);
           mbar_wait(&M.full[s], fph);
           tc_fence_after();
+          tr.mark(2);
           ws_issue(a0 + s * 32768, w0 + b * cfg.wslot, Nc, acc, idesc, c == 0);
           mma_commit(&M.empty[s]);
           mma_commit(&M.wempty[b]);
+          tr.mark(3);
           if (++s == cfg.S) { s = 0; fph ^= 1; }
           if (++b == cfg.NB) { b = 0; wph ^= 1; }
         }
         mma_commit(&M.accfull[ab]);
       }
+      tr.end(8);
     }
     __syncwarp();
   } else {
@@ -320,8 +397,27 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == WS_MMA_WARP) tmem_dealloc(tmem, 512);
+  if (warp == D::MMA_WARP) tmem_dealloc(tmem, 512);
 }
+
+
+// Bulk mode (HW % 4 == 0, HW >= 128, pixel count a multiple of 128): a 128-pixel tile is one contiguous 512 B run per
+// channel row, or two runs when it straddles an image boundary (len1 pixels in image n0, the rest at the start of n0+1).
+struct WsSeg { int n0, hw0, len1; };
+__device__ __forceinline__ WsSeg ws_seg(int tile0, int HW) {
+  WsSeg g;
+  g.n0 = fast_div(tile0, HW, __frcp_rn((float)HW));
+  g.hw0 = tile0 - g.n0 * HW;
+  g.len1 = min(128, HW - g.hw0);
+  return g;
+}
+// lane `l` of the issuing group copies run (l & 1) of row kk: src0 / src1 = start of the row's first / second run
+__device__ __forceinline__ void ws_bulk_row(unsigned char* row_dst, const float* src0, const float* src1, int seg, int len1,
+                                            bool rowok, uint64_t* bar) {
+  const int nbytes = seg ? (128 - len1) * 4 : len1 * 4;
+  if (rowok && nbytes > 0) bulk_g2s(row_dst + (seg ? len1 * 4 : 0), seg ? src1 : src0, (uint32_t)nbytes, bar);
+}
+static bool ws_bulk_ok(int HW, int total) { return (HW % 4) == 0 && HW >= 128 && (total % 128) == 0; }
 
 // images covered by a 128-pixel tile: first image and count
 __device__ __forceinline__ void ws_tile_images(int tile0, int total, int HW, int& n0, int& nimg) {
@@ -336,6 +432,7 @@ __device__ __forceinline__ void ws_tile_images(int tile0, int total, int HW, int
 struct WsExpandArgs { Plan P; UmWAll WA; const float* x; const float* bn1; float* UH; };
 struct WsExpandT {
   using Args = WsExpandArgs;
+  using Dim = DimEpi;
   static constexpr int NTENS = 1;
   static constexpr uint32_t STAGE = WS_ROWS_BYTES(1);
   static constexpr uint32_t CF = 2 * 256 * sizeof(float2);
@@ -356,29 +453,66 @@ struct WsExpandT {
       px_decomp(px, mt * 128 + lane * 4, A.P.P, A.P.HW);
       xb = A.x + (size_t)px.n[0] * A.P.ic * A.P.HW + px.hw[0];
     }
-    __device__ __forceinline__ void issue(int c, unsigned char* st) const {
+    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t*) const {
 #pragma unroll
-      for (int i = 0; i < WS_RW; ++i) {
-        const int k = c * WS_KC + pw + i * WS_NP;
-        ws_ring_row(st + ((size_t)i * WS_NPT + ptid) * 16, A.x, xb, px, A.P.ic, k, A.P.HW, k < A.P.ic);
+      for (int i = 0; i < DimEpi::RW; ++i) {
+        const int k = c * WS_KC + pw + i * DimEpi::NP;
+        ws_ring_row(st + ((size_t)i * DimEpi::NPT + ptid) * 16, A.x, xb, px, A.P.ic, k, A.P.HW, k < A.P.ic);
       }
     }
-    __device__ __forceinline__ void compute(int, const unsigned char* st, WsTile& t) const {
+    __device__ __forceinline__ void compute(int, const unsigned char* st, WsTile<DimEpi>& t) const {
 #pragma unroll
-      for (int i = 0; i < WS_RW; ++i) {
-        const float4 a = *(const float4*)(st + ((size_t)i * WS_NPT + ptid) * 16);
+      for (int i = 0; i < DimEpi::RW; ++i) {
+        const float4 a = *(const float4*)(st + ((size_t)i * DimEpi::NPT + ptid) * 16);
         const float v[4] = {a.x, a.y, a.z, a.w};
-        ws_split(t, i, v);
+        ws_split<DimEpi>(t, i, v);
       }
     }
   };
+  struct ProdB {
+    const Args& A; int ptid, pw, lane;
+    int nK, len1; size_t off0, off1;
+    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
+      int slot, nc, mt;
+      ws_decode(Sc, item, slot, nc, mt);
+      nK = A.WA.s[slot].nK;
+      const WsSeg g = ws_seg(mt * 128, A.P.HW);
+      len1 = g.len1;
+      off0 = (size_t)g.n0 * A.P.ic * A.P.HW + g.hw0;
+      off1 = (size_t)(g.n0 + 1) * A.P.ic * A.P.HW;
+    }
+    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t* bar) const {
+      if (lane < 2 * DimEpi::RW) {
+        const int kk = pw + (lane >> 1) * DimEpi::NP, k = c * WS_KC + kk;
+        const size_t ro = (size_t)k * A.P.HW;
+        ws_bulk_row(st + kk * 512, A.x + off0 + ro, A.x + off1 + ro, lane & 1, len1, k < A.P.ic, bar);
+      }
+      if (lane == 0) {
+        int nv = 0;
+#pragma unroll
+        for (int i = 0; i < DimEpi::RW; ++i) nv += (c * WS_KC + pw + i * DimEpi::NP < A.P.ic) ? 1 : 0;
+        mbar_expect_tx(bar, nv * 512);
+      }
+    }
+    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimEpi>& t) const {
+#pragma unroll
+      for (int i = 0; i < DimEpi::RW; ++i) {
+        const int kk = pw + i * DimEpi::NP;
+        const float4 a = *(const float4*)(st + kk * 512 + lane * 16);
+        const bool ok = c * WS_KC + kk < A.P.ic;
+        const float v[4] = {ok ? a.x : 0.f, ok ? a.y : 0.f, ok ? a.z : 0.f, ok ? a.w : 0.f};
+        ws_split<DimEpi>(t, i, v);
+      }
+    }
+  };
+  static constexpr bool WCONST = false;
   static __device__ __forceinline__ void epi_prep(const Args& A, const WsSched& Sc, int item, float2* cf, int etid) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const Cand& cd = A.P.c[slot];
     const int Nc = A.WA.s[slot].Nc;
     const int ncol = min(Nc, cd.mc - nc * Nc), cst0 = cd.coff + nc * Nc;
-    for (int i = etid; i < ncol; i += WS_NE * 32) cf[i] = make_float2(A.bn1[cst0 + i], A.bn1[A.P.MC + cst0 + i]);
+    for (int i = etid; i < ncol; i += DimEpi::NE * 32) cf[i] = make_float2(A.bn1[cst0 + i], A.bn1[A.P.MC + cst0 + i]);
   }
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2* cft,
                                                  int ew, int lane) {
@@ -387,7 +521,7 @@ struct WsExpandT {
     const Cand& cd = A.P.c[slot];
     const int Nc = A.WA.s[slot].Nc;
     const int ncol = min(Nc, cd.mc - nc * Nc), cst0 = cd.coff + nc * Nc;
-    const WsEpi e = ws_epi(mt * 128, A.P.P, A.P.HW, Nc, ncol, acc, ew, lane);
+    const WsEpi e = ws_epi<DimEpi>(mt * 128, A.P.P, A.P.HW, Nc, ncol, acc, ew, lane);
     const size_t HW = (size_t)A.P.HW;
     float* ob = A.UH + ((size_t)e.n * A.P.MC + cst0) * HW + e.hw;
     for (int c0 = e.c_lo; c0 < e.c_hi; c0 += 16) {
@@ -415,8 +549,9 @@ struct WsProjectArgs { Plan P; UmWAll WA; const float* D; const float* bn2; cons
 template <int ACT>
 struct WsProjectT {
   using Args = WsProjectArgs;
+  using Dim = DimProd;
   static constexpr int NTENS = 1;
-  static constexpr uint32_t STAGE = WS_ROWS_BYTES(1) + WS_NP * WS_WCONST;
+  static constexpr uint32_t STAGE = WS_ROWS_BYTES(1) + DimProd::NP * WS_WCONST;
   static constexpr uint32_t CF = 0;
   static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
     int slot, nc, mt;
@@ -440,30 +575,30 @@ struct WsProjectT {
       Db = A.D + (size_t)px.n[0] * A.P.MC * A.P.HWo + px.hw[0];
       ws_tile_images(mt * 128, A.P.Q, A.P.HWo, n0, nimg);
     }
-    __device__ __forceinline__ void issue(int c, unsigned char* st) const {
+    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t*) const {
 #pragma unroll
-      for (int i = 0; i < WS_RW; ++i) {
-        const int k = c * WS_KC + pw + i * WS_NP;
-        ws_ring_row(st + ((size_t)i * WS_NPT + ptid) * 16, A.D, Db, px, A.P.MC, coff + k, A.P.HWo, k < mc);
+      for (int i = 0; i < DimProd::RW; ++i) {
+        const int k = c * WS_KC + pw + i * DimProd::NP;
+        ws_ring_row(st + ((size_t)i * DimProd::NPT + ptid) * 16, A.D, Db, px, A.P.MC, coff + k, A.P.HWo, k < mc);
       }
       float* wc = (float*)(st + WS_ROWS_BYTES(1) + pw * WS_WCONST);
       if (lane < 8) {
-        const int k = c * WS_KC + pw + (lane & 3) * WS_NP;
-        const bool ok = k < mc;
+        const int i = lane & 3, k = c * WS_KC + pw + i * DimProd::NP;
+        const bool ok = i < DimProd::RW && k < mc;
         ws_cp4(wc + lane, A.bn2 + (lane < 4 ? 0 : A.P.MC) + coff + (ok ? k : 0), ok);
-      } else if (lane < 24 && se > 0 && nimg <= 4) {
+      } else if (lane < 8 + 4 * DimProd::RW && se > 0 && nimg <= 4) {
         const int i = (lane - 8) >> 2, m = (lane - 8) & 3;
-        const int k = c * WS_KC + pw + i * WS_NP;
+        const int k = c * WS_KC + pw + i * DimProd::NP;
         const bool ok = k < mc && m < nimg;
         ws_cp4(wc + lane, ok ? A.seg + (size_t)(n0 + m) * A.P.MCse + soff + k : A.seg, ok);
       }
     }
-    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile& t) const {
+    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimProd>& t) const {
       const float* wc = (const float*)(st + WS_ROWS_BYTES(1) + pw * WS_WCONST);
 #pragma unroll
-      for (int i = 0; i < WS_RW; ++i) {
-        const int k = c * WS_KC + pw + i * WS_NP;
-        const float4 a = *(const float4*)(st + ((size_t)i * WS_NPT + ptid) * 16);
+      for (int i = 0; i < DimProd::RW; ++i) {
+        const int k = c * WS_KC + pw + i * DimProd::NP;
+        const float4 a = *(const float4*)(st + ((size_t)i * DimProd::NPT + ptid) * 16);
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (k < mc) {
           const float mu = wc[i], r = wc[4 + i];
@@ -482,10 +617,68 @@ struct WsProjectT {
             }
           }
         }
-        ws_split(t, i, v);
+        ws_split<DimProd>(t, i, v);
       }
     }
   };
+  struct ProdB {
+    const Args& A; int ptid, pw, lane;
+    int nK, mc, coff, soff, se, n0, len1; size_t off0, off1;
+    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
+      int slot, nc, mt;
+      ws_decode(Sc, item, slot, nc, mt);
+      const Cand& cd = A.P.c[slot];
+      mc = cd.mc; coff = cd.coff; soff = cd.soff; se = cd.se;
+      nK = A.WA.s[slot].nK;
+      const WsSeg g = ws_seg(mt * 128, A.P.HWo);
+      n0 = g.n0; len1 = g.len1;
+      off0 = ((size_t)g.n0 * A.P.MC + coff) * A.P.HWo + g.hw0;
+      off1 = ((size_t)(g.n0 + 1) * A.P.MC + coff) * A.P.HWo;
+    }
+    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t* bar) const {
+      if (lane < 2 * DimProd::RW) {
+        const int kk = pw + (lane >> 1) * DimProd::NP, k = c * WS_KC + kk;
+        const size_t ro = (size_t)k * A.P.HWo;
+        ws_bulk_row(st + kk * 512, A.D + off0 + ro, A.D + off1 + ro, lane & 1, len1, k < mc, bar);
+      }
+      if (lane == 0) {
+        int nv = 0;
+#pragma unroll
+        for (int i = 0; i < DimProd::RW; ++i) nv += (c * WS_KC + pw + i * DimProd::NP < mc) ? 1 : 0;
+        mbar_expect_tx(bar, nv * 512);
+      }
+      // per-warp constants: [0..3] BN2 mean, [4..7] rstd, [8 + 4 i + m] SE gate of row i for image n0 + m (m = 0, 1)
+      float* wc = (float*)(st + WS_ROWS_BYTES(1) + pw * WS_WCONST);
+      if (lane < 8) {
+        const int i = lane & 3, k = c * WS_KC + pw + i * DimProd::NP;
+        const bool ok = i < DimProd::RW && k < mc;
+        ws_cp4(wc + lane, A.bn2 + (lane < 4 ? 0 : A.P.MC) + coff + (ok ? k : 0), ok);
+      } else if (lane < 8 + 4 * DimProd::RW && se > 0) {
+        const int i = (lane - 8) >> 2, m = (lane - 8) & 3;
+        const int k = c * WS_KC + pw + i * DimProd::NP;
+        const bool ok = k < mc && m < 2 && (m == 0 || len1 < 128);
+        ws_cp4(wc + lane, ok ? A.seg + (size_t)(n0 + m) * A.P.MCse + soff + k : A.seg, ok);
+      }
+    }
+    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimProd>& t) const {
+      const float* wc = (const float*)(st + WS_ROWS_BYTES(1) + pw * WS_WCONST);
+      const int img = lane * 4 >= len1 ? 1 : 0;       // the thread's 4 pixels lie in one image (HW % 4 == 0)
+#pragma unroll
+      for (int i = 0; i < DimProd::RW; ++i) {
+        const int kk = pw + i * DimProd::NP;
+        const bool ok = c * WS_KC + kk < mc;
+        const float4 a = *(const float4*)(st + kk * 512 + lane * 16);
+        const float mu = wc[i], r = wc[4 + i];
+        const float gt = se > 0 ? wc[8 + 4 * i + img] : 1.f;
+        const float d[4] = {a.x, a.y, a.z, a.w};
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = ok ? act_f<ACT>((d[e] - mu) * r) * gt : 0.f;   // rows past mc were not fetched
+        ws_split<DimProd>(t, i, v);
+      }
+    }
+  };
+  static constexpr bool WCONST = true;
   static __device__ __forceinline__ void epi_prep(const Args&, const WsSched&, int, float2*, int) {}
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2*,
                                                  int ew, int lane) {
@@ -493,7 +686,7 @@ struct WsProjectT {
     ws_decode(Sc, item, slot, nc, mt);
     const int Nc = A.WA.s[slot].Nc, oc = A.P.oc;
     const int ncol = min(Nc, oc - nc * Nc);
-    const WsEpi e = ws_epi(mt * 128, A.P.Q, A.P.HWo, Nc, ncol, acc, ew, lane);
+    const WsEpi e = ws_epi<DimProd>(mt * 128, A.P.Q, A.P.HWo, Nc, ncol, acc, ew, lane);
     const size_t HWo = (size_t)A.P.HWo;
     const int o0 = slot * oc + nc * Nc;                  // Z / BN3 channel of column 0
     float* zb = A.Zb + ((size_t)e.n * A.P.na * oc + o0) * HWo + e.hw;
@@ -537,8 +730,9 @@ struct WsDcArgs {
 template <int ACT>
 struct WsDcT {
   using Args = WsDcArgs;
+  using Dim = DimEpi;
   static constexpr int NTENS = 2;
-  static constexpr uint32_t STAGE = WS_ROWS_BYTES(2) + WS_NP * WS_WCONST;
+  static constexpr uint32_t STAGE = WS_ROWS_BYTES(2) + DimEpi::NP * WS_WCONST;
   static constexpr uint32_t CF = 2 * 256 * sizeof(float2);
   static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
     int slot, nc, mt;
@@ -559,45 +753,99 @@ struct WsDcT {
       Gb = A.G + (size_t)px.n[0] * A.P.oc * A.P.HWo + px.hw[0];
       Zbb = A.Zb + ((size_t)px.n[0] * A.P.na + slot) * A.P.oc * A.P.HWo + px.hw[0];
     }
-    __device__ __forceinline__ void issue(int c, unsigned char* st) const {
+    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t*) const {
 #pragma unroll
-      for (int i = 0; i < WS_RW; ++i) {
-        const int o = c * WS_KC + pw + i * WS_NP;
+      for (int i = 0; i < DimEpi::RW; ++i) {
+        const int o = c * WS_KC + pw + i * DimEpi::NP;
         const bool ok = o < A.P.oc;
-        ws_ring_row(st + ((size_t)i * WS_NPT + ptid) * 16, A.G, Gb, px, A.P.oc, o, A.P.HWo, ok);
+        ws_ring_row(st + ((size_t)i * DimEpi::NPT + ptid) * 16, A.G, Gb, px, A.P.oc, o, A.P.HWo, ok);
         // Zbb already points at this slot's first channel; the scalar path indexes the full [N][na*oc] tensor
-        if (px.vec) ws_cp16(st + ((size_t)(WS_RW + i) * WS_NPT + ptid) * 16, ok ? Zbb + (size_t)o * A.P.HWo : A.Zb, ok);
-        else ws_ring_row(st + ((size_t)(WS_RW + i) * WS_NPT + ptid) * 16, A.Zb, A.Zb, px, A.P.na * A.P.oc, slot * A.P.oc + o,
+        if (px.vec) ws_cp16(st + ((size_t)(DimEpi::RW + i) * DimEpi::NPT + ptid) * 16, ok ? Zbb + (size_t)o * A.P.HWo : A.Zb, ok);
+        else ws_ring_row(st + ((size_t)(DimEpi::RW + i) * DimEpi::NPT + ptid) * 16, A.Zb, A.Zb, px, A.P.na * A.P.oc, slot * A.P.oc + o,
                          A.P.HWo, ok);
       }
-      if (lane < WS_RW) {
-        const int o = c * WS_KC + pw + lane * WS_NP;
+      if (lane < DimEpi::RW) {
+        const int o = c * WS_KC + pw + lane * DimEpi::NP;
         const bool ok = o < A.P.oc;
         ws_cp16(st + WS_ROWS_BYTES(2) + pw * WS_WCONST + lane * 16, A.dzc2 + (ok ? slot * A.P.oc + o : 0), ok);
       }
     }
-    __device__ __forceinline__ void compute(int, const unsigned char* st, WsTile& t) const {
+    __device__ __forceinline__ void compute(int, const unsigned char* st, WsTile<DimEpi>& t) const {
       const float4* wc = (const float4*)(st + WS_ROWS_BYTES(2) + pw * WS_WCONST);
 #pragma unroll
-      for (int i = 0; i < WS_RW; ++i) {
+      for (int i = 0; i < DimEpi::RW; ++i) {
         const float4 cf = wc[i];                 // zero past oc
-        const float4 a = *(const float4*)(st + ((size_t)i * WS_NPT + ptid) * 16);
-        const float4 b = *(const float4*)(st + ((size_t)(WS_RW + i) * WS_NPT + ptid) * 16);
+        const float4 a = *(const float4*)(st + ((size_t)i * DimEpi::NPT + ptid) * 16);
+        const float4 b = *(const float4*)(st + ((size_t)(DimEpi::RW + i) * DimEpi::NPT + ptid) * 16);
         const float gg[4] = {a.x, a.y, a.z, a.w}, z[4] = {b.x, b.y, b.z, b.w};
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? fmaf(cf.x, gg[e], fmaf(cf.y, z[e], cf.z)) : 0.f;
-        ws_split(t, i, v);
+        ws_split<DimEpi>(t, i, v);
       }
     }
   };
+  struct ProdB {
+    const Args& A; int ptid, pw, lane;
+    int nK, slot, len1; size_t g0, g1, z0, z1;
+    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
+      int nc, mt;
+      ws_decode(Sc, item, slot, nc, mt);
+      nK = A.WA.s[slot].nK;
+      const WsSeg g = ws_seg(mt * 128, A.P.HWo);
+      len1 = g.len1;
+      const size_t HWo = A.P.HWo;
+      g0 = (size_t)g.n0 * A.P.oc * HWo + g.hw0;
+      g1 = (size_t)(g.n0 + 1) * A.P.oc * HWo;
+      z0 = ((size_t)g.n0 * A.P.na + slot) * A.P.oc * HWo + g.hw0;
+      z1 = ((size_t)(g.n0 + 1) * A.P.na + slot) * A.P.oc * HWo;
+    }
+    // ring stage: [G rows 16 KB | Z rows 16 KB | constants]
+    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t* bar) const {
+      if (lane < 4 * DimEpi::RW) {
+        const int tsel = lane / (2 * DimEpi::RW), r = lane % (2 * DimEpi::RW);
+        const int kk = pw + (r >> 1) * DimEpi::NP, o = c * WS_KC + kk;
+        const size_t ro = (size_t)o * A.P.HWo;
+        const float* T = tsel ? A.Zb : A.G;
+        ws_bulk_row(st + tsel * 16384 + kk * 512, T + (tsel ? z0 : g0) + ro, T + (tsel ? z1 : g1) + ro, r & 1, len1, o < A.P.oc, bar);
+      }
+      if (lane == 0) {
+        int nv = 0;
+#pragma unroll
+        for (int i = 0; i < DimEpi::RW; ++i) nv += (c * WS_KC + pw + i * DimEpi::NP < A.P.oc) ? 1 : 0;
+        mbar_expect_tx(bar, nv * 1024);
+      }
+      if (lane < DimEpi::RW) {
+        const int o = c * WS_KC + pw + lane * DimEpi::NP;
+        const bool ok = o < A.P.oc;
+        ws_cp16(st + WS_ROWS_BYTES(2) + pw * WS_WCONST + lane * 16, A.dzc2 + (ok ? slot * A.P.oc + o : 0), ok);
+      }
+    }
+    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimEpi>& t) const {
+      const float4* wc = (const float4*)(st + WS_ROWS_BYTES(2) + pw * WS_WCONST);
+#pragma unroll
+      for (int i = 0; i < DimEpi::RW; ++i) {
+        const int kk = pw + i * DimEpi::NP;
+        const bool ok = c * WS_KC + kk < A.P.oc;
+        const float4 cf = wc[i];
+        const float4 a = *(const float4*)(st + kk * 512 + lane * 16);
+        const float4 b = *(const float4*)(st + 16384 + kk * 512 + lane * 16);
+        const float gg[4] = {a.x, a.y, a.z, a.w}, z[4] = {b.x, b.y, b.z, b.w};
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = ok ? fmaf(cf.x, gg[e], fmaf(cf.y, z[e], cf.z)) : 0.f;
+        ws_split<DimEpi>(t, i, v);
+      }
+    }
+  };
+  static constexpr bool WCONST = true;
   static __device__ __forceinline__ void epi_prep(const Args& A, const WsSched& Sc, int item, float2* cf, int etid) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const Cand& cd = A.P.c[slot];
     const int Nc = A.WA.s[slot].Nc;
     const int ncol = min(Nc, cd.mc - nc * Nc), cst0 = cd.coff + nc * Nc;
-    for (int i = etid; i < ncol; i += WS_NE * 32) cf[i] = make_float2(A.bn2[cst0 + i], A.bn2[A.P.MC + cst0 + i]);
+    for (int i = etid; i < ncol; i += DimEpi::NE * 32) cf[i] = make_float2(A.bn2[cst0 + i], A.bn2[A.P.MC + cst0 + i]);
   }
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2* cft,
                                                  int ew, int lane) {
@@ -607,7 +855,7 @@ struct WsDcT {
     const Plan& P = A.P;
     const int Nc = A.WA.s[slot].Nc;
     const int ncol = min(Nc, cd.mc - nc * Nc), cst0 = cd.coff + nc * Nc;
-    const WsEpi e = ws_epi(mt * 128, P.Q, P.HWo, Nc, ncol, acc, ew, lane);
+    const WsEpi e = ws_epi<DimEpi>(mt * 128, P.Q, P.HWo, Nc, ncol, acc, ew, lane);
     const bool gated = cd.se > 0;
     // images covered by this warp's 32 consecutive pixels: at most two when HWo >= 32
     const int n_first = __shfl_sync(0xffffffffu, e.n, 0);
@@ -702,6 +950,7 @@ struct WsDxArgs { Plan P; UmW W; DxChunks CH; int ksplit; const float* DA; const
 template <int ACT>
 struct WsDxT {
   using Args = WsDxArgs;
+  using Dim = DimProd;
   static constexpr int NTENS = 2;
   static constexpr uint32_t STAGE = WS_ROWS_BYTES(2);
   static constexpr uint32_t CF = 0;
@@ -741,30 +990,30 @@ struct WsDxT {
       coff = A.P.c[slot].coff;
     }
     // ring stage: [DA rows | UH rows]
-    __device__ __forceinline__ void issue(int c, unsigned char* st) const {
+    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t*) const {
       int mc, coff, k0;
       locate(c, mc, coff, k0);
 #pragma unroll
-      for (int i = 0; i < WS_RW; ++i) {
-        const int k = k0 + pw + i * WS_NP;
+      for (int i = 0; i < DimProd::RW; ++i) {
+        const int k = k0 + pw + i * DimProd::NP;
         const bool ok = k < mc;
         const int cst = coff + k;
-        ws_ring_row(st + ((size_t)i * WS_NPT + ptid) * 16, A.DA, DAb, px, A.P.MC, cst, A.P.HW, ok);
-        ws_ring_row(st + ((size_t)(WS_RW + i) * WS_NPT + ptid) * 16, A.UH, UHb, px, A.P.MC, cst, A.P.HW, ok);
+        ws_ring_row(st + ((size_t)i * DimProd::NPT + ptid) * 16, A.DA, DAb, px, A.P.MC, cst, A.P.HW, ok);
+        ws_ring_row(st + ((size_t)(DimProd::RW + i) * DimProd::NPT + ptid) * 16, A.UH, UHb, px, A.P.MC, cst, A.P.HW, ok);
       }
     }
     // Rows past the candidate's width and invalid pixels are zero-filled in the ring, so du = 0 * act'(0) = 0 there.
     // BN1's rstd is folded into the prepped weights (umma_prep_bwd), the operand is plain du-hat.
-    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile& t) const {
+    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimProd>& t) const {
       int mc, coff, k0;
       locate(c, mc, coff, k0);
       float sacc[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) sacc[i] = 0.f;
 #pragma unroll
-      for (int i = 0; i < WS_RW; ++i) {
-        const float4 a = *(const float4*)(st + ((size_t)i * WS_NPT + ptid) * 16);
-        const float4 b = *(const float4*)(st + ((size_t)(WS_RW + i) * WS_NPT + ptid) * 16);
+      for (int i = 0; i < DimProd::RW; ++i) {
+        const float4 a = *(const float4*)(st + ((size_t)i * DimProd::NPT + ptid) * 16);
+        const float4 b = *(const float4*)(st + ((size_t)(DimProd::RW + i) * DimProd::NPT + ptid) * 16);
         const float da[4] = {a.x, a.y, a.z, a.w}, uh[4] = {b.x, b.y, b.z, b.w};
         float v[4];
 #pragma unroll
@@ -773,21 +1022,90 @@ struct WsDxT {
           sacc[2 * i] += v[e];
           sacc[2 * i + 1] += v[e] * uh[e];
         }
-        ws_split(t, i, v);
+        ws_split<DimProd>(t, i, v);
       }
-      // 2*WS_RW statistics (rows x {sum du, sum du*uh}) reduced together; lane l < 2*WS_RW ends up owning statistic l
-      static_assert(2 * WS_RW <= 16, "statistics must fit the 16-value warp reduction");
+      // 2*DimProd::RW statistics (rows x {sum du, sum du*uh}) reduced together; lane l < 2*DimProd::RW ends up owning statistic l
+      static_assert(2 * DimProd::RW <= 16, "statistics must fit the 16-value warp reduction");
       const float tot = warp_sum16(sacc);
-      const int k = k0 + pw + (lane >> 1) * WS_NP;
-      if (lane < 2 * WS_RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
+      const int k = k0 + pw + (lane >> 1) * DimProd::NP;
+      if (lane < 2 * DimProd::RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
     }
   };
+  struct ProdB {
+    const Args& A; int ptid, pw, lane;
+    int nK, ch0, len1; size_t off0, off1;
+    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
+      int mt, ch1;
+      part(A, Sc, item, mt, ch0, ch1);
+      nK = ch1 - ch0;
+      const WsSeg g = ws_seg(mt * 128, A.P.HW);
+      len1 = g.len1;
+      off0 = (size_t)g.n0 * A.P.MC * A.P.HW + g.hw0;
+      off1 = (size_t)(g.n0 + 1) * A.P.MC * A.P.HW;
+    }
+    __device__ __forceinline__ void locate(int c, int& mc, int& coff, int& k0) const {
+      const int g = ch0 + c;
+      int f0 = 0, slot = 0;
+#pragma unroll
+      for (int s = 1; s < TFNAS_MAX_OPS; ++s)
+        if (s < A.P.na && g >= A.CH.first[s]) { slot = s; f0 = A.CH.first[s]; }
+      k0 = (g - f0) * WS_KC;
+      mc = A.P.c[slot].mc;
+      coff = A.P.c[slot].coff;
+    }
+    // ring stage: [DA rows 16 KB | UH rows 16 KB]
+    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t* bar) const {
+      int mc, coff, k0;
+      locate(c, mc, coff, k0);
+      if (lane < 4 * DimProd::RW) {
+        const int tsel = lane / (2 * DimProd::RW), r = lane % (2 * DimProd::RW);
+        const int kk = pw + (r >> 1) * DimProd::NP, k = k0 + kk;
+        const size_t ro = (size_t)(coff + k) * A.P.HW;
+        const float* T = tsel ? A.UH : A.DA;
+        ws_bulk_row(st + tsel * 16384 + kk * 512, T + off0 + ro, T + off1 + ro, r & 1, len1, k < mc, bar);
+      }
+      if (lane == 0) {
+        int nv = 0;
+#pragma unroll
+        for (int i = 0; i < DimProd::RW; ++i) nv += (k0 + pw + i * DimProd::NP < mc) ? 1 : 0;
+        mbar_expect_tx(bar, nv * 1024);
+      }
+    }
+    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimProd>& t) const {
+      int mc, coff, k0;
+      locate(c, mc, coff, k0);
+      float sacc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sacc[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < DimProd::RW; ++i) {
+        const int kk = pw + i * DimProd::NP;
+        const bool ok = k0 + kk < mc;                 // rows past the candidate's width were not fetched
+        const float4 a = *(const float4*)(st + kk * 512 + lane * 16);
+        const float4 b = *(const float4*)(st + 16384 + kk * 512 + lane * 16);
+        const float da[4] = {a.x, a.y, a.z, a.w}, uh[4] = {b.x, b.y, b.z, b.w};
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float u = ok ? uh[e] : 0.f;
+          v[e] = ok ? da[e] * act_df<ACT>(u) : 0.f;
+          sacc[2 * i] += v[e];
+          sacc[2 * i + 1] += v[e] * u;
+        }
+        ws_split<DimProd>(t, i, v);
+      }
+      const float tot = warp_sum16(sacc);
+      const int k = k0 + pw + (lane >> 1) * DimProd::NP;
+      if (lane < 2 * DimProd::RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
+    }
+  };
+  static constexpr bool WCONST = false;
   static __device__ __forceinline__ void epi_prep(const Args&, const WsSched&, int, float2*, int) {}
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2*,
                                                  int ew, int lane) {
     int mt, ch0, ch1;
     part(A, Sc, item, mt, ch0, ch1);
-    const WsEpi e = ws_epi(mt * 128, A.P.P, A.P.HW, A.W.Nc, A.P.ic, acc, ew, lane);
+    const WsEpi e = ws_epi<DimProd>(mt * 128, A.P.P, A.P.HW, A.W.Nc, A.P.ic, acc, ew, lane);
     const size_t HW = (size_t)A.P.HW;
     float* ob = A.dx + (size_t)e.n * A.P.ic * HW + e.hw;
     for (int c0 = e.c_lo; c0 < e.c_hi; c0 += 16) {
@@ -810,25 +1128,39 @@ struct WsDxT {
 // -------------------------------------------------------------------------------------------------
 // kernels + host side
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WS_NT, 1) k_ws_expand(const __grid_constant__ WsExpandArgs A, const __grid_constant__ WsSched Sc,
-                                                        const __grid_constant__ WsCfg cfg) {
-  ws_run<WsExpandT>(A, Sc, cfg);
+template <bool BULK>
+__global__ void __launch_bounds__(DimEpi::NTHR, 1) k_ws_expand(const __grid_constant__ WsExpandArgs A, const __grid_constant__ WsSched Sc,
+                                                             const __grid_constant__ WsCfg cfg) {
+  ws_run<WsExpandT, BULK>(A, Sc, cfg);
 }
-template <int ACT>
-__global__ void __launch_bounds__(WS_NT, 1) k_ws_project(const __grid_constant__ WsProjectArgs A, const __grid_constant__ WsSched Sc,
+template <int ACT, bool BULK>
+__global__ void __launch_bounds__(DimProd::NTHR, 1) k_ws_project(const __grid_constant__ WsProjectArgs A, const __grid_constant__ WsSched Sc,
+                                                               const __grid_constant__ WsCfg cfg) {
+  ws_run<WsProjectT<ACT>, BULK>(A, Sc, cfg);
+}
+template <int ACT, bool BULK>
+__global__ void __launch_bounds__(DimEpi::NTHR, 1) k_ws_dc(const __grid_constant__ WsDcArgs A, const __grid_constant__ WsSched Sc,
                                                          const __grid_constant__ WsCfg cfg) {
-  ws_run<WsProjectT<ACT>>(A, Sc, cfg);
+  ws_run<WsDcT<ACT>, BULK>(A, Sc, cfg);
 }
-template <int ACT>
-__global__ void __launch_bounds__(WS_NT, 1) k_ws_dc(const __grid_constant__ WsDcArgs A, const __grid_constant__ WsSched Sc,
-                                                    const __grid_constant__ WsCfg cfg) {
-  ws_run<WsDcT<ACT>>(A, Sc, cfg);
+template <int ACT, bool BULK>
+__global__ void __launch_bounds__(DimProd::NTHR, 1) k_ws_dx(const __grid_constant__ WsDxArgs A, const __grid_constant__ WsSched Sc,
+                                                          const __grid_constant__ WsCfg cfg) {
+  ws_run<WsDxT<ACT>, BULK>(A, Sc, cfg);
 }
-template <int ACT>
-__global__ void __launch_bounds__(WS_NT, 1) k_ws_dx(const __grid_constant__ WsDxArgs A, const __grid_constant__ WsSched Sc,
-                                                    const __grid_constant__ WsCfg cfg) {
-  ws_run<WsDxT<ACT>>(A, Sc, cfg);
-}
+
+// launch helper: pick the activation / bulk instantiation
+#define WS_LAUNCH1(KERN, BULK_, NTHR_) do { \
+    if (BULK_) { ensure_smem(KERN<true>, smem); KERN<true><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
+    else { ensure_smem(KERN<false>, smem); KERN<false><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } } while (0)
+#define WS_LAUNCH2(KERN, RELU_, BULK_, NTHR_) do { \
+    if (RELU_) { \
+      if (BULK_) { ensure_smem(KERN<TFNAS_ACT_RELU, true>, smem); KERN<TFNAS_ACT_RELU, true><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
+      else { ensure_smem(KERN<TFNAS_ACT_RELU, false>, smem); KERN<TFNAS_ACT_RELU, false><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
+    } else { \
+      if (BULK_) { ensure_smem(KERN<TFNAS_ACT_SWISH, true>, smem); KERN<TFNAS_ACT_SWISH, true><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
+      else { ensure_smem(KERN<TFNAS_ACT_SWISH, false>, smem); KERN<TFNAS_ACT_SWISH, false><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
+    } } while (0)
 
 // TFNAS_WS: comma-separated subset of {expand,project,dc,dx} run by the persistent kernels; "0"/"none" disables, unset = all
 static int g_ws_mask = -1;
@@ -846,6 +1178,12 @@ int ws_enabled(int which) {
     }
   }
   return (g_ws_mask >> which) & 1;
+}
+
+// TFNAS_WS_BULK=0 forces the per-thread cp.async loads (A/B debugging)
+static bool ws_bulk_enabled() {
+  static const bool on = !(getenv("TFNAS_WS_BULK") && strcmp(getenv("TFNAS_WS_BULK"), "0") == 0);
+  return on;
 }
 
 // items of the per-slot GEMMs: slot major, then N chunk, then pixel tile
@@ -872,10 +1210,11 @@ bool ws_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1
   WsCfg cfg;
   if (maxNc > 256 || !ws_fit(maxNc, WsExpandT::STAGE, WsExpandT::CF, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
-  ensure_smem(k_ws_expand, smem);
   WsExpandArgs A{P, WA, x, bn1, UH};
   ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
-  k_ws_expand<<<min(Sc.n_items, sm_count()), WS_NT, smem, st>>>(A, Sc, cfg);
+  const int grid = min(Sc.n_items, sm_count());
+  const bool bulk = ws_bulk_enabled() && ws_bulk_ok(P.HW, P.P);
+  WS_LAUNCH1(k_ws_expand, bulk, DimEpi::NTHR);
   return true;
 }
 
@@ -893,13 +1232,8 @@ bool ws_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn
   ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
   const int grid = min(Sc.n_items, sm_count());
-  if (P.act == TFNAS_ACT_RELU) {
-    ensure_smem(k_ws_project<TFNAS_ACT_RELU>, smem);
-    k_ws_project<TFNAS_ACT_RELU><<<grid, WS_NT, smem, st>>>(A, Sc, cfg);
-  } else {
-    ensure_smem(k_ws_project<TFNAS_ACT_SWISH>, smem);
-    k_ws_project<TFNAS_ACT_SWISH><<<grid, WS_NT, smem, st>>>(A, Sc, cfg);
-  }
+  const bool bulk = ws_bulk_enabled() && ws_bulk_ok(P.HWo, P.Q);
+  WS_LAUNCH2(k_ws_project, P.act == TFNAS_ACT_RELU, bulk, DimProd::NTHR);
   return true;
 }
 
@@ -917,13 +1251,8 @@ bool ws_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, con
   ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
   const int grid = min(Sc.n_items, sm_count());
-  if (P.act == TFNAS_ACT_RELU) {
-    ensure_smem(k_ws_dc<TFNAS_ACT_RELU>, smem);
-    k_ws_dc<TFNAS_ACT_RELU><<<grid, WS_NT, smem, st>>>(A, Sc, cfg);
-  } else {
-    ensure_smem(k_ws_dc<TFNAS_ACT_SWISH>, smem);
-    k_ws_dc<TFNAS_ACT_SWISH><<<grid, WS_NT, smem, st>>>(A, Sc, cfg);
-  }
+  const bool bulk = ws_bulk_enabled() && ws_bulk_ok(P.HWo, P.Q);
+  WS_LAUNCH2(k_ws_dc, P.act == TFNAS_ACT_RELU, bulk, DimEpi::NTHR);
   return true;
 }
 
@@ -948,12 +1277,15 @@ bool ws_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, con
   WsDxArgs A{P, W, CH, ksplit, DA, UH, dx, sU};
   ProfScope ps("dx", 4.0 * P.P * (2.0 * P.MC + P.ic) + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   const int grid = min(Sc.n_items, sms);
-  if (P.act == TFNAS_ACT_RELU) {
-    ensure_smem(k_ws_dx<TFNAS_ACT_RELU>, smem);
-    k_ws_dx<TFNAS_ACT_RELU><<<grid, WS_NT, smem, st>>>(A, Sc, cfg);
-  } else {
-    ensure_smem(k_ws_dx<TFNAS_ACT_SWISH>, smem);
-    k_ws_dx<TFNAS_ACT_SWISH><<<grid, WS_NT, smem, st>>>(A, Sc, cfg);
-  }
+  const bool bulk = ws_bulk_enabled() && ws_bulk_ok(P.HW, P.P);
+  WS_LAUNCH2(k_ws_dx, P.act == TFNAS_ACT_RELU, bulk, DimProd::NTHR);
   return true;
+}
+
+// debug: enable / disable the phase trace of the persistent kernels (buf: device memory, n_ctas * WS_TRACE_SLOTS u64)
+extern "C" int tfnas_debug_ws_trace(void* buf, int n_ctas) {
+  unsigned long long* p = (unsigned long long*)buf;
+  if (cudaMemcpyToSymbol(g_ws_trace, &p, sizeof(p)) != cudaSuccess) return TFNAS_E_CUDA;
+  if (cudaMemcpyToSymbol(g_ws_trace_n, &n_ctas, sizeof(n_ctas)) != cudaSuccess) return TFNAS_E_CUDA;
+  return TFNAS_OK;
 }
