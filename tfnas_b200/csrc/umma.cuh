@@ -42,6 +42,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// same, but a thread that finds the phase incomplete is suspended by the hardware (up to `ns` nanoseconds per attempt)
+// instead of spinning: waiting warps then stay off the issue / fetch path of the warps that do the work
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+}
+
 // ---- proxies / fences -------------------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

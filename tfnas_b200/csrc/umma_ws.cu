@@ -6,18 +6,20 @@
 // have fixed roles that meet only through mbarriers, so no phase of one tile ever waits for another phase:
 //   NE warps      EPILOGUE   tcgen05.ld of the finished accumulator (lane quarter = warp & 3, column part = warp >> 2),
 //                            BN statistics / SE partial sums / coalesced per-channel stores
-//   NP warps      PRODUCERS  cp.async of the raw input rows (and their per-row constants) RS-1 K chunks ahead into a
-//                            thread-private ring; prologue math (BN / activation / SE gate / BN-backward on load),
-//                            tf32 hi/lo split, st.shared into one of S operand stages (MN-major, 128B swizzle)
-//   1 warp        MMA        one thread: waits operand stage + weight slot, issues the 12 kind::tf32 MMAs of the K chunk
-//                            (hi*hi + lo*hi + hi*lo per K=8 step), commits to the stage's / slot's "empty" barriers
-//   1 warp        WEIGHTS    one thread: bulk (TMA) copies of the pre-split, pre-swizzled weight blocks, NB-1 chunks ahead
-// (NE, NP) = (8, 16) for the prologue-bound kernels (project, dx), (16, 8) for the epilogue-bound ones (expand, dc):
-// the prologue / epilogue instruction streams are latency-bound per warp, so each side gets the warps it can use.
+//   NP warps      PRODUCERS  in G groups.  Group g owns every G-th K chunk (chunk j of the CTA's chunk stream goes to
+//                            group j % G and operand stage j % S): its warps load the raw input rows of their NEXT chunk
+//                            into registers right after handing over the current one, so the global-load latency hides
+//                            behind the wait for the operand stage; then prologue math (BN / activation / SE gate /
+//                            BN-backward on load), tf32 hi/lo split, st.shared into the stage (MN-major, 128B swizzle).
+//                            A producer iteration is a long dependent instruction stream (measured ~3k cycles), so G
+//                            chunks in flight are what keeps the tensor core fed.
+//   1 warp        MMA        waits operand stage + weight slot; one elected lane issues the 12 kind::tf32 MMAs of the K
+//                            chunk (hi*hi + lo*hi + hi*lo per K=8 step) and commits to the stage's / slot's "empty" barriers
+//   1 warp        WEIGHTS    bulk (TMA) copies of the pre-split, pre-swizzled weight blocks, NB-1 chunks ahead
 // The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile j overlaps the main loop of
 // tile j+1.  Per-CTA set-up (TMEM allocation, barrier init) is paid once per SM instead of once per tile.
 //
-// The numerics are those of umma_pw.cu (same operand split, same MMA order, same epilogue arithmetic).
+// The numerics are those of umma_pw.cu (same operand split, same MMA order within a tile, same epilogue arithmetic).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,22 +32,19 @@ using namespace umma;
 
 #define WS_KC 32
 #define WS_ACC_STRIDE 256                     // TMEM columns between the two accumulator buffers
-#define WS_ROWS_BYTES(ntens) ((ntens) * WS_KC * 128 * 4)      // one K chunk of raw rows: 32 rows x 128 pixels (16 KB) per tensor
-#define WS_WCONST 128                         // bytes of per-warp row constants in one ring stage
-// Warp split of a kernel: NE epilogue warps (multiple of 4: lane quarter = warp & 3, column part = warp >> 2),
-// NP producer warps (divides 32), then the MMA warp and the weight-copy warp.
-template <int NE_, int NP_>
+// Warp split of a kernel: NE epilogue warps (multiple of 4), NP producer warps in G groups, then the MMA warp and the
+// weight-copy warp.
+template <int NE_, int NP_, int G_>
 struct WsDim {
-  static constexpr int NE = NE_, NP = NP_;
-  static constexpr int RW = WS_KC / NP_;      // K rows per producer warp per chunk
-  static constexpr int NPT = NP_ * 32;
+  static constexpr int NE = NE_, NP = NP_, G = G_;
+  static constexpr int NPG = NP_ / G_;        // warps per producer group
+  static constexpr int RW = WS_KC / NPG;      // K rows per producer warp per chunk
   static constexpr int MMA_WARP = NE_ + NP_, TMA_WARP = NE_ + NP_ + 1;
   static constexpr int NTHR = 32 * (NE_ + NP_ + 2);
+  static_assert(NP_ % G_ == 0 && WS_KC % NPG == 0 && RW <= 8 && NE_ % 4 == 0, "bad warp split");
 };
-typedef WsDim<8, 16> DimProd;                 // prologue-bound kernels (project, dx)
-typedef WsDim<16, 8> DimEpi;                  // epilogue-bound kernels (expand, dc)
-#define WS_MAXS 4
-#define WS_MAXB 4
+#define WS_MAXS 8
+#define WS_MAXB 8
 #define WS_SMEM_LIMIT 232448                  // 227 KB opt-in maximum
 
 struct WsSched {
@@ -53,17 +52,16 @@ struct WsSched {
   float inv_tiles;
   int first[TFNAS_MAX_OPS + 1];               // first item of each slot (items of a slot: N chunk major, tile minor)
 };
-struct WsCfg { int S, NB, RS; uint32_t wslot, stage_bytes, cf_bytes; };
+struct WsCfg { int S, NB; uint32_t wslot, cf_bytes; };
 
 struct WsSmem {
-  unsigned char *a, *w, *ring;
+  unsigned char *a, *w;
   uint64_t *full, *empty, *wfull, *wempty, *accfull, *accempty;
-  uint64_t* rbar;          // bulk mode: [RS][NP] "rows landed" barriers, one per (ring stage, producer warp)
   uint32_t* tmem_slot;
   float2* cf;
 };
 
-// layout: [S operand stages x (hi 16K | lo 16K)] [NB weight slots] [barriers 1 KB] [cf tables] [ring]
+// layout: [S operand stages x (hi 16K | lo 16K)] [NB weight slots] [barriers 512 B] [cf tables]
 __device__ __forceinline__ void ws_carve(unsigned char* raw, const WsCfg& c, WsSmem& M) {
   unsigned char* sm = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   M.a = sm;
@@ -76,24 +74,24 @@ __device__ __forceinline__ void ws_carve(unsigned char* raw, const WsCfg& c, WsS
   M.accfull = M.wempty + WS_MAXB;
   M.accempty = M.accfull + 2;
   M.tmem_slot = (uint32_t*)(M.accempty + 2);
-  M.rbar = (uint64_t*)(tail + 256);           // 4 x 16 x 8 B
-  M.cf = (float2*)(tail + 1024);
-  M.ring = tail + 1024 + c.cf_bytes;
+  M.cf = (float2*)(tail + 512);
 }
 static size_t ws_smem_bytes(const WsCfg& c) {
-  return 1024 + (size_t)c.S * 32768 + (size_t)c.NB * c.wslot + 1024 + c.cf_bytes + (size_t)c.RS * c.stage_bytes;
+  return 1024 + (size_t)c.S * 32768 + (size_t)c.NB * c.wslot + 512 + c.cf_bytes;
 }
-// deepest pipeline that fits: operand stages S, weight slots NB, ring stages RS
-static bool ws_fit(int maxNc, uint32_t stage_bytes, uint32_t cf_bytes, WsCfg& c) {
-  static const int pref[][3] = {{3, 4, 4}, {3, 3, 4}, {3, 3, 3}, {2, 3, 3}, {2, 2, 3}, {2, 2, 2}, {2, 1, 2}};
+// deepest pipeline that fits: operand stages S = G * SM (SM <= max_sm), weight slots NB (<= max_nb)
+static bool ws_fit(int maxNc, int G, uint32_t cf_bytes, int max_sm, int max_nb, WsCfg& c) {
+  static const int nbs[] = {8, 6, 4, 3, 2};
   c.wslot = (uint32_t)2 * maxNc * 128;
-  c.stage_bytes = stage_bytes;
   c.cf_bytes = cf_bytes;
-  for (auto& p : pref) {
-    c.S = p[0]; c.NB = p[1]; c.RS = p[2];
-    if (ws_smem_bytes(c) <= WS_SMEM_LIMIT) return true;
-  }
-  return false;
+  for (int sm = max_sm; sm >= 1; --sm)
+    for (int nb : nbs) {
+      if (nb > max_nb) continue;
+      c.S = G * sm; c.NB = nb;
+      if (c.S <= WS_MAXS && ws_smem_bytes(c) <= WS_SMEM_LIMIT) return true;
+    }
+  c.S = G; c.NB = 1;
+  return ws_smem_bytes(c) <= WS_SMEM_LIMIT;
 }
 
 __device__ __forceinline__ void ws_decode(const WsSched& Sc, int item, int& slot, int& nc, int& mt) {
@@ -108,57 +106,34 @@ __device__ __forceinline__ void ws_decode(const WsSched& Sc, int item, int& slot
 }
 
 // ---- small helpers -------------------------------------------------------------------------------
-__device__ __forceinline__ void ws_cp16(void* dst, const void* src, bool valid) {
-  const uint32_t n = valid ? 16u : 0u;          // src-size 0: nothing is read, the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void ws_cp4(void* dst, const void* src, bool valid) {
-  const uint32_t n = valid ? 4u : 0u;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void ws_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void ws_cp_wait(int pending) {      // wait_group needs an immediate; pending is CTA-uniform
-  if (pending >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
-  else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-  else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-  else asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
 template <int NTHREADS>
 __device__ __forceinline__ void ws_bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
-
-// 4 pixels of row `ch` of an [N][C][HW] tensor -> this thread's 16 B ring slot (zero-filled when !rowok / invalid pixel)
-__device__ __forceinline__ void ws_ring_row(unsigned char* dst, const float* __restrict__ T, const float* __restrict__ Tb,
-                                            const Px4& px, int C, int ch, int HW, bool rowok) {
-  if (px.vec) {
-    ws_cp16(dst, rowok ? Tb + (size_t)ch * HW : T, rowok);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const bool ok = rowok && px.v[e];
-      ws_cp4(dst + 4 * e, ok ? T + ((size_t)px.n[e] * C + ch) * HW + px.hw[e] : T, ok);
-    }
-  }
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool ws_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
-template <class D>
-struct WsTile { float4 hi[D::RW], lo[D::RW]; };
-template <class D>
-__device__ __forceinline__ void ws_split(WsTile<D>& t, int i, const float (&v)[4]) {
+// load 4 consecutive pixels of plane `ch` as float4 (vector when aligned, else masked scalars); zero when !rowok
+__device__ __forceinline__ float4 ws_ld4(const float* __restrict__ T, const float* __restrict__ Tb, const Px4& px, int C, int ch,
+                                         int HW, bool rowok) {
+  if (!rowok) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (px.vec) return *(const float4*)(Tb + (size_t)ch * HW);
+  float d[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) d[e] = px.v[e] ? T[((size_t)px.n[e] * C + ch) * HW + px.hw[e]] : 0.f;
+  return make_float4(d[0], d[1], d[2], d[3]);
+}
+
+// split 4 values into tf32 hi / lo and store them as row kk of the operand stage (16 B chunk of pixels 4*lane..4*lane+3)
+__device__ __forceinline__ void ws_emit_row(unsigned char* a_hi, int kk, int lane, const float (&v)[4]) {
   float h[4], l[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
-  t.hi[i] = make_float4(h[0], h[1], h[2], h[3]);
-  t.lo[i] = make_float4(l[0], l[1], l[2], l[3]);
-}
-// row kk = pw + i * NP of the chunk, 16 B chunk of pixels 4*lane .. 4*lane+3
-template <class D>
-__device__ __forceinline__ void ws_store(const WsTile<D>& t, unsigned char* a_hi, int pw, int lane) {
-#pragma unroll
-  for (int i = 0; i < D::RW; ++i) {
-    const uint32_t off = mn_chunk_off(lane * 4, pw + i * D::NP, WS_KC * 128);
-    *(float4*)(a_hi + off) = t.hi[i];
-    *(float4*)(a_hi + 16384 + off) = t.lo[i];
-  }
+  const uint32_t off = mn_chunk_off(lane * 4, kk, WS_KC * 128);
+  *(float4*)(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+  *(float4*)(a_hi + 16384 + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
 // the 12 MMAs of one K chunk (one thread): operand stage at `a` (hi | lo), weights at `b` (hi block, lo block Nc*128 later)
@@ -194,18 +169,9 @@ __device__ __forceinline__ WsEpi ws_epi(int tile0, int total, int HW, int Nc, in
   return e;
 }
 
-// -------------------------------------------------------------------------------------------------
-// skeleton.  T supplies
-//   Args                                     kernel arguments (by value, __grid_constant__)
-//   NTENS                                    raw tensors staged per K chunk (ring stage = NTENS x 16 KB + constants)
-//   geom(A, Sc, item, nK, Nc, wb)            K chunks, MMA N and first prepped weight block of an item
-//   Prod{A, ptid, pw, lane}: bind(Sc, item), nK, issue(c, stage), compute(c, stage, tile)
-//   epi_prep(A, Sc, item, cf, etid)          fill the per-column coefficient table (epilogue warps, before the barrier)
-//   epi_run(A, Sc, item, acc, cf, ew, lane)  consume the accumulator
-// -------------------------------------------------------------------------------------------------
 // ---- optional phase trace (debug build -DUM_TRACE; tfnas_debug_ws_trace) ------------------------------------
-// Producer warp 0 / the MMA thread of each traced CTA accumulate clock64() deltas per phase.
-//   producer slots: [0] iterations [1] issue [2] wait data [3] compute [4] wait empty [5] store [6] fence [7] arrive
+// Producer warp 0 / the MMA warp of each traced CTA accumulate clock64() deltas per phase.
+//   producer slots: [0] iterations [1] advance + loads [2] - [3] - [4] wait empty [5] emit [6] fence [7] arrive
 //   MMA slots:      [8] chunks [9] wait weights [10] wait operands [11] issue + commits [12] wait accumulator
 #define WS_TRACE_SLOTS 16
 __device__ unsigned long long* g_ws_trace = nullptr;
@@ -237,7 +203,17 @@ struct WsTrace {
 };
 #endif
 
-template <class T, bool BULK>
+// -------------------------------------------------------------------------------------------------
+// skeleton.  T supplies
+//   Args, Dim                                kernel arguments (by value, __grid_constant__), warp split
+//   CF                                       bytes of per-column epilogue coefficient tables (0: none)
+//   geom(A, Sc, item, nK, Nc, wb)            K chunks, MMA N and first prepped weight block of an item
+//   Raw                                      registers holding one chunk of a warp's raw rows (+ its row constants)
+//   Prod{A, wi, lane}: bind(Sc, item), nK, load(c, raw), emit(c, raw, stage)
+//   epi_prep(A, Sc, item, cf, etid)          fill the per-column coefficient table (epilogue warps, before the barrier)
+//   epi_run(A, Sc, item, acc, cf, ew, lane)  consume the accumulator
+// -------------------------------------------------------------------------------------------------
+template <class T, bool VEC>
 __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched& Sc, const WsCfg& cfg) {
   using D = typename T::Dim;
   extern __shared__ __align__(1024) unsigned char ws_raw[];
@@ -245,10 +221,9 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
   ws_carve(ws_raw, cfg, M);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < WS_MAXS; ++s) { mbar_init(&M.full[s], D::NP); mbar_init(&M.empty[s], 1); }
+    for (int s = 0; s < WS_MAXS; ++s) { mbar_init(&M.full[s], D::NPG); mbar_init(&M.empty[s], 1); }
     for (int s = 0; s < WS_MAXB; ++s) { mbar_init(&M.wfull[s], 1); mbar_init(&M.wempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&M.accfull[s], 1); mbar_init(&M.accempty[s], D::NE); }
-    for (int s = 0; s < WS_MAXS * D::NP; ++s) mbar_init(&M.rbar[s], 1);
     fence_barrier_init();
   }
   if (warp == D::MMA_WARP) tmem_alloc(M.tmem_slot, 512);
@@ -267,7 +242,7 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
       float2* cf = M.cf + ab * 256;
       T::epi_prep(A, Sc, item, cf, tid);
       if (T::CF) ws_bar_epi<D::NE * 32>();
-      mbar_wait(&M.accfull[ab], au & 1);
+      mbar_wait_suspend(&M.accfull[ab], au & 1, 2000);
       tc_fence_after();
       T::epi_run(A, Sc, item, tmem + ab * WS_ACC_STRIDE, cf, warp, lane);
       tc_fence_before();
@@ -276,148 +251,127 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
     }
   } else if (warp < D::NE + D::NP) {
     // ------------------------------ producers ------------------------------
-    const int ptid = tid - D::NE * 32, pw = ptid >> 5;
-    typename std::conditional<BULK, typename T::ProdB, typename T::Prod>::type fi{A, ptid, pw, lane}, fc{A, ptid, pw, lane};
-    int item_i = item0, ci = 0;
-    bool vi = item_i < Sc.n_items;
-    if (vi) fi.bind(Sc, item_i);
-    // fetch the next chunk of this warp's rows into ring stage `stg`.  Generic mode: per-thread cp.async into private
-    // slots.  Bulk mode: a few lanes issue bulk (TMA) copies of whole 512 B rows, completion on the warp's own mbarrier.
-    auto issue_next = [&](int stg) {
-      if (vi) {
-        if (BULK) fi.issue(ci, M.ring + (size_t)stg * cfg.stage_bytes, &M.rbar[stg * D::NP + pw]);
-        else fi.issue(ci, M.ring + (size_t)stg * cfg.stage_bytes, nullptr);
-        if (++ci == fi.nK) {
-          ci = 0;
-          item_i += istep;
-          vi = item_i < Sc.n_items;
-          if (vi) fi.bind(Sc, item_i);
-        }
+    const int pw = warp - D::NE, gq = pw / D::NPG, wi = pw % D::NPG;
+    typename std::conditional<VEC, typename T::ProdV, typename T::Prod>::type f{A, wi, lane};
+    typename T::Raw raw;
+    int item = item0, c = 0;
+    bool valid = item < Sc.n_items;
+    if (valid) f.bind(Sc, item);
+    auto advance = [&]() {               // next chunk of the CTA's chunk stream
+      if (valid && ++c == f.nK) {
+        c = 0;
+        item += istep;
+        valid = item < Sc.n_items;
+        if (valid) f.bind(Sc, item);
       }
-      if (!BULK || T::WCONST) ws_cp_commit();  // one group per call (possibly empty) keeps the group count uniform
     };
-    const int RS = cfg.RS, S = cfg.S;
-    for (int k = 0; k < RS - 1; ++k) issue_next(k);
+#pragma unroll 1
+    for (int k = 0; k < gq; ++k) advance();
+    if (valid) f.load(c, raw);
+    const int SM = cfg.S / D::G;
+    int sm = 0;
+    uint32_t eph = 1;                    // parity to wait for on empty[s]: passes on the first use of each stage
     WsTrace tr;
     tr.begin(pw == 0 && lane == 0);
-    int rs = 0, rs_issue = RS - 1;             // ring stage of the chunk being emitted / being fetched
-    uint32_t rph = 0;                          // parity of the ring barriers of stage rs
-    int s = 0;
-    uint32_t eph = 1;                          // parity to wait for on empty[s]: passes on the first use of each stage
-    for (int item = item0; item < Sc.n_items; item += istep) {
-      fc.bind(Sc, item);
-      const int n = fc.nK;
-      for (int c = 0; c < n; ++c) {
-        __syncwarp();                          // every lane is done with the ring stage about to be refilled
-        tr.count();
-        tr.mark(7);
-        issue_next(rs_issue);
-        tr.mark(1);
-        if (!BULK || T::WCONST) ws_cp_wait(RS - 1);      // this thread's cp.async copies of the current chunk have landed
-        if (BULK) mbar_wait(&M.rbar[rs * D::NP + pw], rph);
-        __syncwarp();                          // ... and so have the warp-shared constants fetched by the other lanes
-        tr.mark(2);
-        WsTile<D> t;
-        fc.compute(c, M.ring + (size_t)rs * cfg.stage_bytes, t);
-        tr.mark(3);
-        mbar_wait(&M.empty[s], eph);           // the MMAs that read this operand stage have retired
-        tc_fence_after();
-        tr.mark(4);
-        ws_store<D>(t, M.a + (size_t)s * 32768, pw, lane);
-        tr.mark(5);
-        fence_proxy_async();
-        tr.mark(6);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&M.full[s]);
-        if (++rs == RS) { rs = 0; rph ^= 1; }
-        rs_issue = rs_issue + 1 == RS ? 0 : rs_issue + 1;
-        if (++s == S) { s = 0; eph ^= 1; }
-      }
+    while (valid) {
+      const int s = gq + D::G * sm;
+      tr.count();
+      mbar_wait_suspend(&M.empty[s], eph, 1000);       // the MMAs that read this operand stage have retired
+      tc_fence_after();
+      tr.mark(4);
+      f.emit(c, raw, M.a + (size_t)s * 32768);
+      tr.mark(5);
+      fence_proxy_async();
+      tr.mark(6);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&M.full[s]);
+      tr.mark(7);
+#pragma unroll
+      for (int k = 0; k < D::G; ++k) advance();
+      if (valid) f.load(c, raw);         // in flight across the wait for the stage
+      tr.mark(1);
+      if (++sm == SM) { sm = 0; eph ^= 1; }
     }
-    if (!BULK || T::WCONST) ws_cp_wait(0);
     tr.end(0);
   } else if (warp == D::MMA_WARP) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      int s = 0, b = 0, jj = 0;
-      uint32_t fph = 0, wph = 0;               // parities of full[s] / wfull[b]
-      const uint32_t a0 = smem_u32(M.a), w0 = smem_u32(M.w);
-      WsTrace tr;
-      tr.begin(true);
-      for (int item = item0; item < Sc.n_items; item += istep, ++jj) {
-        int nK, Nc;
-        const char* wb;
-        T::geom(A, Sc, item, nK, Nc, wb);
-        const int ab = jj & 1;
-        const uint32_t au = (uint32_t)jj >> 1;
-        tr.mark(3);
-        mbar_wait(&M.accempty[ab], (au & 1) ^ 1);     // the epilogue has drained this accumulator (passes for the first two)
+    // ------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues) ------------
+    int s = 0, b = 0, jj = 0;
+    uint32_t fph = 0, wph = 0;               // parities of full[s] / wfull[b]
+    const uint32_t a0 = smem_u32(M.a), w0 = smem_u32(M.w);
+    WsTrace tr;
+    tr.begin(lane == 0);
+    for (int item = item0; item < Sc.n_items; item += istep, ++jj) {
+      int nK, Nc;
+      const char* wb;
+      T::geom(A, Sc, item, nK, Nc, wb);
+      const int ab = jj & 1;
+      const uint32_t au = (uint32_t)jj >> 1;
+      tr.mark(3);
+      mbar_wait_suspend(&M.accempty[ab], (au & 1) ^ 1, 1000);     // the epilogue has drained this accumulator (passes for the first two)
+      tc_fence_after();
+      tr.mark(4);
+      const uint32_t idesc = idesc_tf32(128, Nc, 1, 0);
+      const uint32_t acc = tmem + ab * WS_ACC_STRIDE;
+      for (int c = 0; c < nK; ++c) {
+        tr.count();
+        mbar_wait_suspend(&M.wfull[b], wph, 1000);
+        tr.mark(1);
+        mbar_wait_suspend(&M.full[s], fph, 1000);
         tc_fence_after();
-        tr.mark(4);
-        const uint32_t idesc = idesc_tf32(128, Nc, 1, 0);
-        const uint32_t acc = tmem + ab * WS_ACC_STRIDE;
-        for (int c = 0; c < nK; ++c) {
-          tr.count();
-          mbar_wait(&M.wfull[b], wph);
-          tr.mark(1);
-          mbar_wait(&M.full[s], fph);
-          tc_fence_after();
-          tr.mark(2);
+        tr.mark(2);
+        if (ws_elect()) {
           ws_issue(a0 + s * 32768, w0 + b * cfg.wslot, Nc, acc, idesc, c == 0);
           mma_commit(&M.empty[s]);
           mma_commit(&M.wempty[b]);
-          tr.mark(3);
-          if (++s == cfg.S) { s = 0; fph ^= 1; }
-          if (++b == cfg.NB) { b = 0; wph ^= 1; }
         }
-        mma_commit(&M.accfull[ab]);
+        __syncwarp();
+        tr.mark(3);
+        if (++s == cfg.S) { s = 0; fph ^= 1; }
+        if (++b == cfg.NB) { b = 0; wph ^= 1; }
       }
-      tr.end(8);
+      if (ws_elect()) mma_commit(&M.accfull[ab]);
+      __syncwarp();
     }
-    __syncwarp();
+    tr.end(8);
   } else {
     // ------------------------------ weight copies ------------------------------
-    if (lane == 0) {
-      int b = 0;
-      uint32_t eph = 1;
-      for (int item = item0; item < Sc.n_items; item += istep) {
-        int nK, Nc;
-        const char* wb;
-        T::geom(A, Sc, item, nK, Nc, wb);
-        const uint32_t bytes = (uint32_t)2 * Nc * 128;
-        for (int c = 0; c < nK; ++c) {
-          mbar_wait(&M.wempty[b], eph);
+    int b = 0;
+    uint32_t eph = 1;
+    for (int item = item0; item < Sc.n_items; item += istep) {
+      int nK, Nc;
+      const char* wb;
+      T::geom(A, Sc, item, nK, Nc, wb);
+      const uint32_t bytes = (uint32_t)2 * Nc * 128;
+      for (int c = 0; c < nK; ++c) {
+        mbar_wait_suspend(&M.wempty[b], eph, 2000);
+        if (ws_elect()) {
           mbar_expect_tx(&M.wfull[b], bytes);
           bulk_g2s(M.w + (size_t)b * cfg.wslot, wb + (size_t)c * bytes, bytes, &M.wfull[b]);
-          if (++b == cfg.NB) { b = 0; eph ^= 1; }
         }
+        __syncwarp();
+        if (++b == cfg.NB) { b = 0; eph ^= 1; }
       }
     }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == D::MMA_WARP) tmem_dealloc(tmem, 512);
 }
 
-
-// Bulk mode (HW % 4 == 0, HW >= 128, pixel count a multiple of 128): a 128-pixel tile is one contiguous 512 B run per
-// channel row, or two runs when it straddles an image boundary (len1 pixels in image n0, the rest at the start of n0+1).
-struct WsSeg { int n0, hw0, len1; };
-__device__ __forceinline__ WsSeg ws_seg(int tile0, int HW) {
-  WsSeg g;
-  g.n0 = fast_div(tile0, HW, __frcp_rn((float)HW));
-  g.hw0 = tile0 - g.n0 * HW;
-  g.len1 = min(128, HW - g.hw0);
-  return g;
+// VEC mode (HW % 4 == 0, HW >= 128, pixel count a multiple of 128): every tile is full, a thread's 4 pixels lie in one
+// image and are 16 B aligned, and a tile spans at most two images.  The producers then run straight-line code: rows
+// past the K extent re-read the last valid row (clamped index) and are zeroed by a select.
+static bool ws_vec_ok(int HW, int total) { return (HW % 4) == 0 && HW >= 128 && (total % 128) == 0; }
+struct WsVecPx { int n, hw, img; };      // image / offset of the thread's first pixel; img = image index within the tile (0 / 1)
+__device__ __forceinline__ WsVecPx ws_vec_px(int tile0, int lane, int HW) {
+  const float r = __frcp_rn((float)HW);
+  WsVecPx v;
+  const int p = tile0 + lane * 4;
+  v.n = fast_div(p, HW, r);
+  v.hw = p - v.n * HW;
+  v.img = v.n - fast_div(tile0, HW, r);
+  return v;
 }
-// lane `l` of the issuing group copies run (l & 1) of row kk: src0 / src1 = start of the row's first / second run
-__device__ __forceinline__ void ws_bulk_row(unsigned char* row_dst, const float* src0, const float* src1, int seg, int len1,
-                                            bool rowok, uint64_t* bar) {
-  const int nbytes = seg ? (128 - len1) * 4 : len1 * 4;
-  if (rowok && nbytes > 0) bulk_g2s(row_dst + (seg ? len1 * 4 : 0), seg ? src1 : src0, (uint32_t)nbytes, bar);
-}
-static bool ws_bulk_ok(int HW, int total) { return (HW % 4) == 0 && HW >= 128 && (total % 128) == 0; }
 
 // images covered by a 128-pixel tile: first image and count
 __device__ __forceinline__ void ws_tile_images(int tile0, int total, int HW, int& n0, int& nimg) {
@@ -425,16 +379,19 @@ __device__ __forceinline__ void ws_tile_images(int tile0, int total, int HW, int
   n0 = fast_div(min(tile0, total - 1), HW, r);
   nimg = fast_div(min(tile0 + 127, total - 1), HW, r) - n0 + 1;
 }
+__device__ __forceinline__ float4 ws_shfl4(const float4& v, int src) {
+  return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src),
+                     __shfl_sync(0xffffffffu, v.w, src));
+}
 
 // -------------------------------------------------------------------------------------------------
 // F1a: expand      UH = BN1(W1 x)
 // -------------------------------------------------------------------------------------------------
 struct WsExpandArgs { Plan P; UmWAll WA; const float* x; const float* bn1; float* UH; };
+template <class Dim_>
 struct WsExpandT {
   using Args = WsExpandArgs;
-  using Dim = DimEpi;
-  static constexpr int NTENS = 1;
-  static constexpr uint32_t STAGE = WS_ROWS_BYTES(1);
+  using Dim = Dim_;
   static constexpr uint32_t CF = 2 * 256 * sizeof(float2);
   static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
     int slot, nc, mt;
@@ -443,8 +400,35 @@ struct WsExpandT {
     nK = W.nK; Nc = W.Nc;
     wb = (const char*)W.wp + (size_t)nc * W.nK * 2 * W.Nc * 128;
   }
+  struct Raw { float4 a[Dim::RW]; };
+  struct ProdV {
+    const Args& A; int wi, lane;
+    int nK; const float* xb;
+    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
+      int slot, nc, mt;
+      ws_decode(Sc, item, slot, nc, mt);
+      nK = A.WA.s[slot].nK;
+      const WsVecPx v = ws_vec_px(mt * 128, lane, A.P.HW);
+      xb = A.x + (size_t)v.n * A.P.ic * A.P.HW + v.hw;
+    }
+    __device__ __forceinline__ void load(int c, Raw& r) const {
+#pragma unroll
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int k = min(c * WS_KC + wi + i * Dim::NPG, A.P.ic - 1);
+        r.a[i] = *(const float4*)(xb + (uint32_t)(k * A.P.HW));
+      }
+    }
+    __device__ __forceinline__ void emit(int c, const Raw& r, unsigned char* a_hi) const {
+#pragma unroll
+      for (int i = 0; i < Dim::RW; ++i) {
+        const bool ok = c * WS_KC + wi + i * Dim::NPG < A.P.ic;
+        const float v[4] = {ok ? r.a[i].x : 0.f, ok ? r.a[i].y : 0.f, ok ? r.a[i].z : 0.f, ok ? r.a[i].w : 0.f};
+        ws_emit_row(a_hi, wi + i * Dim::NPG, lane, v);
+      }
+    }
+  };
   struct Prod {
-    const Args& A; int ptid, pw, lane;
+    const Args& A; int wi, lane;
     int nK; Px4 px; const float* xb;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int slot, nc, mt;
@@ -453,66 +437,28 @@ struct WsExpandT {
       px_decomp(px, mt * 128 + lane * 4, A.P.P, A.P.HW);
       xb = A.x + (size_t)px.n[0] * A.P.ic * A.P.HW + px.hw[0];
     }
-    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t*) const {
+    __device__ __forceinline__ void load(int c, Raw& r) const {
 #pragma unroll
-      for (int i = 0; i < DimEpi::RW; ++i) {
-        const int k = c * WS_KC + pw + i * DimEpi::NP;
-        ws_ring_row(st + ((size_t)i * DimEpi::NPT + ptid) * 16, A.x, xb, px, A.P.ic, k, A.P.HW, k < A.P.ic);
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int k = c * WS_KC + wi + i * Dim::NPG;
+        r.a[i] = ws_ld4(A.x, xb, px, A.P.ic, k, A.P.HW, k < A.P.ic);
       }
     }
-    __device__ __forceinline__ void compute(int, const unsigned char* st, WsTile<DimEpi>& t) const {
+    __device__ __forceinline__ void emit(int, const Raw& r, unsigned char* a_hi) const {
 #pragma unroll
-      for (int i = 0; i < DimEpi::RW; ++i) {
-        const float4 a = *(const float4*)(st + ((size_t)i * DimEpi::NPT + ptid) * 16);
-        const float v[4] = {a.x, a.y, a.z, a.w};
-        ws_split<DimEpi>(t, i, v);
+      for (int i = 0; i < Dim::RW; ++i) {
+        const float v[4] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w};
+        ws_emit_row(a_hi, wi + i * Dim::NPG, lane, v);
       }
     }
   };
-  struct ProdB {
-    const Args& A; int ptid, pw, lane;
-    int nK, len1; size_t off0, off1;
-    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
-      int slot, nc, mt;
-      ws_decode(Sc, item, slot, nc, mt);
-      nK = A.WA.s[slot].nK;
-      const WsSeg g = ws_seg(mt * 128, A.P.HW);
-      len1 = g.len1;
-      off0 = (size_t)g.n0 * A.P.ic * A.P.HW + g.hw0;
-      off1 = (size_t)(g.n0 + 1) * A.P.ic * A.P.HW;
-    }
-    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t* bar) const {
-      if (lane < 2 * DimEpi::RW) {
-        const int kk = pw + (lane >> 1) * DimEpi::NP, k = c * WS_KC + kk;
-        const size_t ro = (size_t)k * A.P.HW;
-        ws_bulk_row(st + kk * 512, A.x + off0 + ro, A.x + off1 + ro, lane & 1, len1, k < A.P.ic, bar);
-      }
-      if (lane == 0) {
-        int nv = 0;
-#pragma unroll
-        for (int i = 0; i < DimEpi::RW; ++i) nv += (c * WS_KC + pw + i * DimEpi::NP < A.P.ic) ? 1 : 0;
-        mbar_expect_tx(bar, nv * 512);
-      }
-    }
-    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimEpi>& t) const {
-#pragma unroll
-      for (int i = 0; i < DimEpi::RW; ++i) {
-        const int kk = pw + i * DimEpi::NP;
-        const float4 a = *(const float4*)(st + kk * 512 + lane * 16);
-        const bool ok = c * WS_KC + kk < A.P.ic;
-        const float v[4] = {ok ? a.x : 0.f, ok ? a.y : 0.f, ok ? a.z : 0.f, ok ? a.w : 0.f};
-        ws_split<DimEpi>(t, i, v);
-      }
-    }
-  };
-  static constexpr bool WCONST = false;
   static __device__ __forceinline__ void epi_prep(const Args& A, const WsSched& Sc, int item, float2* cf, int etid) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const Cand& cd = A.P.c[slot];
     const int Nc = A.WA.s[slot].Nc;
     const int ncol = min(Nc, cd.mc - nc * Nc), cst0 = cd.coff + nc * Nc;
-    for (int i = etid; i < ncol; i += DimEpi::NE * 32) cf[i] = make_float2(A.bn1[cst0 + i], A.bn1[A.P.MC + cst0 + i]);
+    for (int i = etid; i < ncol; i += Dim::NE * 32) cf[i] = make_float2(A.bn1[cst0 + i], A.bn1[A.P.MC + cst0 + i]);
   }
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2* cft,
                                                  int ew, int lane) {
@@ -521,7 +467,7 @@ struct WsExpandT {
     const Cand& cd = A.P.c[slot];
     const int Nc = A.WA.s[slot].Nc;
     const int ncol = min(Nc, cd.mc - nc * Nc), cst0 = cd.coff + nc * Nc;
-    const WsEpi e = ws_epi<DimEpi>(mt * 128, A.P.P, A.P.HW, Nc, ncol, acc, ew, lane);
+    const WsEpi e = ws_epi<Dim>(mt * 128, A.P.P, A.P.HW, Nc, ncol, acc, ew, lane);
     const size_t HW = (size_t)A.P.HW;
     float* ob = A.UH + ((size_t)e.n * A.P.MC + cst0) * HW + e.hw;
     for (int c0 = e.c_lo; c0 < e.c_hi; c0 += 16) {
@@ -546,12 +492,10 @@ struct WsExpandT {
 // F3: project      Z = W3 (act(BN2(D)) * gate), BN3 sums
 // -------------------------------------------------------------------------------------------------
 struct WsProjectArgs { Plan P; UmWAll WA; const float* D; const float* bn2; const float* seg; float* Zb; double* st3; };
-template <int ACT>
+template <int ACT, class Dim_>
 struct WsProjectT {
   using Args = WsProjectArgs;
-  using Dim = DimProd;
-  static constexpr int NTENS = 1;
-  static constexpr uint32_t STAGE = WS_ROWS_BYTES(1) + DimProd::NP * WS_WCONST;
+  using Dim = Dim_;
   static constexpr uint32_t CF = 0;
   static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
     int slot, nc, mt;
@@ -560,10 +504,54 @@ struct WsProjectT {
     nK = W.nK; Nc = W.Nc;
     wb = (const char*)W.wp + (size_t)nc * W.nK * 2 * W.Nc * 128;
   }
-  // per-warp constants of a ring stage (floats): [0..3] BN2 mean of rows 0..3, [4..7] rstd, [8 + 4 i + m] SE gate of
-  // row i for the m-th image of the tile (tiles spanning more than 4 images read the gate from global memory)
+  // cv: the row constants of the chunk, one per lane, handed out by shuffles: lanes 0..7 BN2 mean of rows 0..7,
+  // lanes 8..15 rstd, lanes 16 + 2 i + m the SE gate of row i for the m-th image of the tile (tiles spanning more than
+  // two images read the gate from global memory)
+  struct Raw { float4 a[Dim::RW]; float cv; };
+  struct ProdV {
+    const Args& A; int wi, lane;
+    int nK, mc, coff, soff, se, n0, img; const float* Db;
+    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
+      int slot, nc, mt;
+      ws_decode(Sc, item, slot, nc, mt);
+      const Cand& cd = A.P.c[slot];
+      mc = cd.mc; coff = cd.coff; soff = cd.soff; se = cd.se;
+      nK = A.WA.s[slot].nK;
+      const WsVecPx v = ws_vec_px(mt * 128, lane, A.P.HWo);
+      img = v.img;
+      n0 = v.n - v.img;
+      Db = A.D + ((size_t)v.n * A.P.MC + coff) * A.P.HWo + v.hw;
+    }
+    __device__ __forceinline__ void load(int c, Raw& r) const {
+#pragma unroll
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int k = min(c * WS_KC + wi + i * Dim::NPG, mc - 1);
+        r.a[i] = *(const float4*)(Db + (uint32_t)(k * A.P.HWo));
+      }
+      // one constant per lane (clamped, always-valid addresses; unused lanes are never read back)
+      const int i = lane < 16 ? (lane & 7) : ((lane - 16) >> 1);
+      const int k = min(c * WS_KC + wi + min(i, Dim::RW - 1) * Dim::NPG, mc - 1);
+      const float* src = lane < 16 ? A.bn2 + (lane < 8 ? 0 : A.P.MC) + coff + k
+                                   : A.seg + (size_t)min(n0 + (lane & 1), A.P.N - 1) * A.P.MCse + soff + k;
+      r.cv = (lane < 16 || se > 0) ? *src : 1.f;
+    }
+    __device__ __forceinline__ void emit(int c, const Raw& r, unsigned char* a_hi) const {
+#pragma unroll
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int kk = wi + i * Dim::NPG;
+        const bool ok = c * WS_KC + kk < mc;
+        const float mu = __shfl_sync(0xffffffffu, r.cv, i), rs = __shfl_sync(0xffffffffu, r.cv, 8 + i);
+        const float gt = __shfl_sync(0xffffffffu, r.cv, 16 + 2 * i + img);
+        const float d[4] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w};
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = ok ? act_f<ACT>((d[e] - mu) * rs) * gt : 0.f;
+        ws_emit_row(a_hi, kk, lane, v);
+      }
+    }
+  };
   struct Prod {
-    const Args& A; int ptid, pw, lane;
+    const Args& A; int wi, lane;
     int nK, mc, coff, soff, se, n0, nimg; Px4 px; const float* Db;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int slot, nc, mt;
@@ -575,110 +563,39 @@ struct WsProjectT {
       Db = A.D + (size_t)px.n[0] * A.P.MC * A.P.HWo + px.hw[0];
       ws_tile_images(mt * 128, A.P.Q, A.P.HWo, n0, nimg);
     }
-    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t*) const {
+    __device__ __forceinline__ void load(int c, Raw& r) const {
 #pragma unroll
-      for (int i = 0; i < DimProd::RW; ++i) {
-        const int k = c * WS_KC + pw + i * DimProd::NP;
-        ws_ring_row(st + ((size_t)i * DimProd::NPT + ptid) * 16, A.D, Db, px, A.P.MC, coff + k, A.P.HWo, k < mc);
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int k = c * WS_KC + wi + i * Dim::NPG;
+        r.a[i] = ws_ld4(A.D, Db, px, A.P.MC, coff + k, A.P.HWo, k < mc);
       }
-      float* wc = (float*)(st + WS_ROWS_BYTES(1) + pw * WS_WCONST);
-      if (lane < 8) {
-        const int i = lane & 3, k = c * WS_KC + pw + i * DimProd::NP;
-        const bool ok = i < DimProd::RW && k < mc;
-        ws_cp4(wc + lane, A.bn2 + (lane < 4 ? 0 : A.P.MC) + coff + (ok ? k : 0), ok);
-      } else if (lane < 8 + 4 * DimProd::RW && se > 0 && nimg <= 4) {
-        const int i = (lane - 8) >> 2, m = (lane - 8) & 3;
-        const int k = c * WS_KC + pw + i * DimProd::NP;
-        const bool ok = k < mc && m < nimg;
-        ws_cp4(wc + lane, ok ? A.seg + (size_t)(n0 + m) * A.P.MCse + soff + k : A.seg, ok);
+      if (lane < 16) {
+        const int i = lane & 7, k = c * WS_KC + wi + i * Dim::NPG;
+        r.cv = (i < Dim::RW && k < mc) ? A.bn2[(lane < 8 ? 0 : A.P.MC) + coff + k] : 0.f;
+      } else {
+        const int i = (lane - 16) >> 1, m = lane & 1, k = c * WS_KC + wi + i * Dim::NPG;
+        r.cv = (se > 0 && i < Dim::RW && k < mc && m < nimg) ? A.seg[(size_t)(n0 + m) * A.P.MCse + soff + k] : 1.f;
       }
     }
-    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimProd>& t) const {
-      const float* wc = (const float*)(st + WS_ROWS_BYTES(1) + pw * WS_WCONST);
+    __device__ __forceinline__ void emit(int c, const Raw& r, unsigned char* a_hi) const {
 #pragma unroll
-      for (int i = 0; i < DimProd::RW; ++i) {
-        const int k = c * WS_KC + pw + i * DimProd::NP;
-        const float4 a = *(const float4*)(st + ((size_t)i * DimProd::NPT + ptid) * 16);
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (k < mc) {
-          const float mu = wc[i], r = wc[4 + i];
-          const float d[4] = {a.x, a.y, a.z, a.w};
-          if (px.vec) {        // 4 valid pixels of one image
-            const float gt = se > 0 ? (nimg <= 4 ? wc[8 + 4 * i + (px.n[0] - n0)] : A.seg[(size_t)px.n[0] * A.P.MCse + soff + k]) : 1.f;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = act_f<ACT>((d[e] - mu) * r) * gt;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float b = act_f<ACT>((d[e] - mu) * r);
-              if (se > 0 && px.v[e])
-                b *= nimg <= 4 ? wc[8 + 4 * i + (px.n[e] - n0)] : A.seg[(size_t)px.n[e] * A.P.MCse + soff + k];
-              v[e] = px.v[e] ? b : 0.f;
-            }
-          }
-        }
-        ws_split<DimProd>(t, i, v);
-      }
-    }
-  };
-  struct ProdB {
-    const Args& A; int ptid, pw, lane;
-    int nK, mc, coff, soff, se, n0, len1; size_t off0, off1;
-    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
-      int slot, nc, mt;
-      ws_decode(Sc, item, slot, nc, mt);
-      const Cand& cd = A.P.c[slot];
-      mc = cd.mc; coff = cd.coff; soff = cd.soff; se = cd.se;
-      nK = A.WA.s[slot].nK;
-      const WsSeg g = ws_seg(mt * 128, A.P.HWo);
-      n0 = g.n0; len1 = g.len1;
-      off0 = ((size_t)g.n0 * A.P.MC + coff) * A.P.HWo + g.hw0;
-      off1 = ((size_t)(g.n0 + 1) * A.P.MC + coff) * A.P.HWo;
-    }
-    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t* bar) const {
-      if (lane < 2 * DimProd::RW) {
-        const int kk = pw + (lane >> 1) * DimProd::NP, k = c * WS_KC + kk;
-        const size_t ro = (size_t)k * A.P.HWo;
-        ws_bulk_row(st + kk * 512, A.D + off0 + ro, A.D + off1 + ro, lane & 1, len1, k < mc, bar);
-      }
-      if (lane == 0) {
-        int nv = 0;
-#pragma unroll
-        for (int i = 0; i < DimProd::RW; ++i) nv += (c * WS_KC + pw + i * DimProd::NP < mc) ? 1 : 0;
-        mbar_expect_tx(bar, nv * 512);
-      }
-      // per-warp constants: [0..3] BN2 mean, [4..7] rstd, [8 + 4 i + m] SE gate of row i for image n0 + m (m = 0, 1)
-      float* wc = (float*)(st + WS_ROWS_BYTES(1) + pw * WS_WCONST);
-      if (lane < 8) {
-        const int i = lane & 3, k = c * WS_KC + pw + i * DimProd::NP;
-        const bool ok = i < DimProd::RW && k < mc;
-        ws_cp4(wc + lane, A.bn2 + (lane < 4 ? 0 : A.P.MC) + coff + (ok ? k : 0), ok);
-      } else if (lane < 8 + 4 * DimProd::RW && se > 0) {
-        const int i = (lane - 8) >> 2, m = (lane - 8) & 3;
-        const int k = c * WS_KC + pw + i * DimProd::NP;
-        const bool ok = k < mc && m < 2 && (m == 0 || len1 < 128);
-        ws_cp4(wc + lane, ok ? A.seg + (size_t)(n0 + m) * A.P.MCse + soff + k : A.seg, ok);
-      }
-    }
-    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimProd>& t) const {
-      const float* wc = (const float*)(st + WS_ROWS_BYTES(1) + pw * WS_WCONST);
-      const int img = lane * 4 >= len1 ? 1 : 0;       // the thread's 4 pixels lie in one image (HW % 4 == 0)
-#pragma unroll
-      for (int i = 0; i < DimProd::RW; ++i) {
-        const int kk = pw + i * DimProd::NP;
-        const bool ok = c * WS_KC + kk < mc;
-        const float4 a = *(const float4*)(st + kk * 512 + lane * 16);
-        const float mu = wc[i], r = wc[4 + i];
-        const float gt = se > 0 ? wc[8 + 4 * i + img] : 1.f;
-        const float d[4] = {a.x, a.y, a.z, a.w};
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int kk = wi + i * Dim::NPG, k = c * WS_KC + kk;
+        const float mu = __shfl_sync(0xffffffffu, r.cv, i), rs = __shfl_sync(0xffffffffu, r.cv, 8 + i);
+        const float g0 = __shfl_sync(0xffffffffu, r.cv, 16 + 2 * i), g1 = __shfl_sync(0xffffffffu, r.cv, 17 + 2 * i);
+        const float d[4] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w};
         float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = ok ? act_f<ACT>((d[e] - mu) * r) * gt : 0.f;   // rows past mc were not fetched
-        ws_split<DimProd>(t, i, v);
+        for (int e = 0; e < 4; ++e) {
+          float b = act_f<ACT>((d[e] - mu) * rs);
+          if (se > 0) b *= nimg <= 2 ? (px.n[e] == n0 ? g0 : g1)
+                                     : (px.v[e] && k < mc ? A.seg[(size_t)px.n[e] * A.P.MCse + soff + k] : 0.f);
+          v[e] = (px.v[e] && k < mc) ? b : 0.f;
+        }
+        ws_emit_row(a_hi, kk, lane, v);
       }
     }
   };
-  static constexpr bool WCONST = true;
   static __device__ __forceinline__ void epi_prep(const Args&, const WsSched&, int, float2*, int) {}
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2*,
                                                  int ew, int lane) {
@@ -686,7 +603,7 @@ struct WsProjectT {
     ws_decode(Sc, item, slot, nc, mt);
     const int Nc = A.WA.s[slot].Nc, oc = A.P.oc;
     const int ncol = min(Nc, oc - nc * Nc);
-    const WsEpi e = ws_epi<DimProd>(mt * 128, A.P.Q, A.P.HWo, Nc, ncol, acc, ew, lane);
+    const WsEpi e = ws_epi<Dim>(mt * 128, A.P.Q, A.P.HWo, Nc, ncol, acc, ew, lane);
     const size_t HWo = (size_t)A.P.HWo;
     const int o0 = slot * oc + nc * Nc;                  // Z / BN3 channel of column 0
     float* zb = A.Zb + ((size_t)e.n * A.P.na * oc + o0) * HWo + e.hw;
@@ -727,12 +644,10 @@ struct WsDcArgs {
   Plan P; UmWAll WA; const float* G; const float* Zb; const float4* dzc2; const float* D; const float* bn2;
   float* DC; float* dg; double* sD;
 };
-template <int ACT>
+template <int ACT, class Dim_>
 struct WsDcT {
   using Args = WsDcArgs;
-  using Dim = DimEpi;
-  static constexpr int NTENS = 2;
-  static constexpr uint32_t STAGE = WS_ROWS_BYTES(2) + DimEpi::NP * WS_WCONST;
+  using Dim = Dim_;
   static constexpr uint32_t CF = 2 * 256 * sizeof(float2);
   static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
     int slot, nc, mt;
@@ -741,9 +656,12 @@ struct WsDcT {
     nK = W.nK; Nc = W.Nc;
     wb = (const char*)W.wp + (size_t)nc * W.nK * 2 * W.Nc * 128;
   }
-  // per-warp constants: float4 (A, B, C, -) of rows 0..3
+  // cf: lane i < RW holds (A, B, C, -) of row i
+  struct Raw { float4 a[Dim::RW], b[Dim::RW]; float4 cf; };
+  struct Prod;
+  typedef Prod ProdV;
   struct Prod {
-    const Args& A; int ptid, pw, lane;
+    const Args& A; int wi, lane;
     int nK, slot; Px4 px; const float* Gb; const float* Zbb;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int nc, mt;
@@ -751,101 +669,37 @@ struct WsDcT {
       nK = A.WA.s[slot].nK;
       px_decomp(px, mt * 128 + lane * 4, A.P.Q, A.P.HWo);
       Gb = A.G + (size_t)px.n[0] * A.P.oc * A.P.HWo + px.hw[0];
-      Zbb = A.Zb + ((size_t)px.n[0] * A.P.na + slot) * A.P.oc * A.P.HWo + px.hw[0];
+      Zbb = A.Zb + (size_t)px.n[0] * A.P.na * A.P.oc * A.P.HWo + px.hw[0];
     }
-    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t*) const {
+    __device__ __forceinline__ void load(int c, Raw& r) const {
 #pragma unroll
-      for (int i = 0; i < DimEpi::RW; ++i) {
-        const int o = c * WS_KC + pw + i * DimEpi::NP;
-        const bool ok = o < A.P.oc;
-        ws_ring_row(st + ((size_t)i * DimEpi::NPT + ptid) * 16, A.G, Gb, px, A.P.oc, o, A.P.HWo, ok);
-        // Zbb already points at this slot's first channel; the scalar path indexes the full [N][na*oc] tensor
-        if (px.vec) ws_cp16(st + ((size_t)(DimEpi::RW + i) * DimEpi::NPT + ptid) * 16, ok ? Zbb + (size_t)o * A.P.HWo : A.Zb, ok);
-        else ws_ring_row(st + ((size_t)(DimEpi::RW + i) * DimEpi::NPT + ptid) * 16, A.Zb, A.Zb, px, A.P.na * A.P.oc, slot * A.P.oc + o,
-                         A.P.HWo, ok);
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int o = c * WS_KC + wi + i * Dim::NPG;
+        r.a[i] = ws_ld4(A.G, Gb, px, A.P.oc, o, A.P.HWo, o < A.P.oc);
+        r.b[i] = ws_ld4(A.Zb, Zbb, px, A.P.na * A.P.oc, slot * A.P.oc + o, A.P.HWo, o < A.P.oc);
       }
-      if (lane < DimEpi::RW) {
-        const int o = c * WS_KC + pw + lane * DimEpi::NP;
-        const bool ok = o < A.P.oc;
-        ws_cp16(st + WS_ROWS_BYTES(2) + pw * WS_WCONST + lane * 16, A.dzc2 + (ok ? slot * A.P.oc + o : 0), ok);
-      }
+      const int o = c * WS_KC + wi + (lane & 7) * Dim::NPG;
+      r.cf = ((lane & 7) < Dim::RW && lane < 8 && o < A.P.oc) ? A.dzc2[slot * A.P.oc + o] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __device__ __forceinline__ void compute(int, const unsigned char* st, WsTile<DimEpi>& t) const {
-      const float4* wc = (const float4*)(st + WS_ROWS_BYTES(2) + pw * WS_WCONST);
+    __device__ __forceinline__ void emit(int, const Raw& r, unsigned char* a_hi) const {
 #pragma unroll
-      for (int i = 0; i < DimEpi::RW; ++i) {
-        const float4 cf = wc[i];                 // zero past oc
-        const float4 a = *(const float4*)(st + ((size_t)i * DimEpi::NPT + ptid) * 16);
-        const float4 b = *(const float4*)(st + ((size_t)(DimEpi::RW + i) * DimEpi::NPT + ptid) * 16);
-        const float gg[4] = {a.x, a.y, a.z, a.w}, z[4] = {b.x, b.y, b.z, b.w};
+      for (int i = 0; i < Dim::RW; ++i) {
+        const float4 cf = ws_shfl4(r.cf, i);              // zero past oc
+        const float gg[4] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w}, z[4] = {r.b[i].x, r.b[i].y, r.b[i].z, r.b[i].w};
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = px.v[e] ? fmaf(cf.x, gg[e], fmaf(cf.y, z[e], cf.z)) : 0.f;
-        ws_split<DimEpi>(t, i, v);
+        ws_emit_row(a_hi, wi + i * Dim::NPG, lane, v);
       }
     }
   };
-  struct ProdB {
-    const Args& A; int ptid, pw, lane;
-    int nK, slot, len1; size_t g0, g1, z0, z1;
-    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
-      int nc, mt;
-      ws_decode(Sc, item, slot, nc, mt);
-      nK = A.WA.s[slot].nK;
-      const WsSeg g = ws_seg(mt * 128, A.P.HWo);
-      len1 = g.len1;
-      const size_t HWo = A.P.HWo;
-      g0 = (size_t)g.n0 * A.P.oc * HWo + g.hw0;
-      g1 = (size_t)(g.n0 + 1) * A.P.oc * HWo;
-      z0 = ((size_t)g.n0 * A.P.na + slot) * A.P.oc * HWo + g.hw0;
-      z1 = ((size_t)(g.n0 + 1) * A.P.na + slot) * A.P.oc * HWo;
-    }
-    // ring stage: [G rows 16 KB | Z rows 16 KB | constants]
-    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t* bar) const {
-      if (lane < 4 * DimEpi::RW) {
-        const int tsel = lane / (2 * DimEpi::RW), r = lane % (2 * DimEpi::RW);
-        const int kk = pw + (r >> 1) * DimEpi::NP, o = c * WS_KC + kk;
-        const size_t ro = (size_t)o * A.P.HWo;
-        const float* T = tsel ? A.Zb : A.G;
-        ws_bulk_row(st + tsel * 16384 + kk * 512, T + (tsel ? z0 : g0) + ro, T + (tsel ? z1 : g1) + ro, r & 1, len1, o < A.P.oc, bar);
-      }
-      if (lane == 0) {
-        int nv = 0;
-#pragma unroll
-        for (int i = 0; i < DimEpi::RW; ++i) nv += (c * WS_KC + pw + i * DimEpi::NP < A.P.oc) ? 1 : 0;
-        mbar_expect_tx(bar, nv * 1024);
-      }
-      if (lane < DimEpi::RW) {
-        const int o = c * WS_KC + pw + lane * DimEpi::NP;
-        const bool ok = o < A.P.oc;
-        ws_cp16(st + WS_ROWS_BYTES(2) + pw * WS_WCONST + lane * 16, A.dzc2 + (ok ? slot * A.P.oc + o : 0), ok);
-      }
-    }
-    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimEpi>& t) const {
-      const float4* wc = (const float4*)(st + WS_ROWS_BYTES(2) + pw * WS_WCONST);
-#pragma unroll
-      for (int i = 0; i < DimEpi::RW; ++i) {
-        const int kk = pw + i * DimEpi::NP;
-        const bool ok = c * WS_KC + kk < A.P.oc;
-        const float4 cf = wc[i];
-        const float4 a = *(const float4*)(st + kk * 512 + lane * 16);
-        const float4 b = *(const float4*)(st + 16384 + kk * 512 + lane * 16);
-        const float gg[4] = {a.x, a.y, a.z, a.w}, z[4] = {b.x, b.y, b.z, b.w};
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = ok ? fmaf(cf.x, gg[e], fmaf(cf.y, z[e], cf.z)) : 0.f;
-        ws_split<DimEpi>(t, i, v);
-      }
-    }
-  };
-  static constexpr bool WCONST = true;
   static __device__ __forceinline__ void epi_prep(const Args& A, const WsSched& Sc, int item, float2* cf, int etid) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const Cand& cd = A.P.c[slot];
     const int Nc = A.WA.s[slot].Nc;
     const int ncol = min(Nc, cd.mc - nc * Nc), cst0 = cd.coff + nc * Nc;
-    for (int i = etid; i < ncol; i += DimEpi::NE * 32) cf[i] = make_float2(A.bn2[cst0 + i], A.bn2[A.P.MC + cst0 + i]);
+    for (int i = etid; i < ncol; i += Dim::NE * 32) cf[i] = make_float2(A.bn2[cst0 + i], A.bn2[A.P.MC + cst0 + i]);
   }
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2* cft,
                                                  int ew, int lane) {
@@ -855,7 +709,7 @@ struct WsDcT {
     const Plan& P = A.P;
     const int Nc = A.WA.s[slot].Nc;
     const int ncol = min(Nc, cd.mc - nc * Nc), cst0 = cd.coff + nc * Nc;
-    const WsEpi e = ws_epi<DimEpi>(mt * 128, P.Q, P.HWo, Nc, ncol, acc, ew, lane);
+    const WsEpi e = ws_epi<Dim>(mt * 128, P.Q, P.HWo, Nc, ncol, acc, ew, lane);
     const bool gated = cd.se > 0;
     // images covered by this warp's 32 consecutive pixels: at most two when HWo >= 32
     const int n_first = __shfl_sync(0xffffffffu, e.n, 0);
@@ -947,12 +801,10 @@ struct WsDcT {
 // B3b: dx_main = sum_i W1_i^T (r1 * du-hat), K = stacked mid channels (per-candidate chunks of 32), split over items
 // -------------------------------------------------------------------------------------------------
 struct WsDxArgs { Plan P; UmW W; DxChunks CH; int ksplit; const float* DA; const float* UH; float* dx; double* sU; };
-template <int ACT>
+template <int ACT, class Dim_>
 struct WsDxT {
   using Args = WsDxArgs;
-  using Dim = DimProd;
-  static constexpr int NTENS = 2;
-  static constexpr uint32_t STAGE = WS_ROWS_BYTES(2);
+  using Dim = Dim_;
   static constexpr uint32_t CF = 0;
   // item = tile + tiles_m * ksplit part
   static __device__ __forceinline__ void part(const Args& A, const WsSched& Sc, int item, int& mt, int& ch0, int& ch1) {
@@ -967,8 +819,65 @@ struct WsDxT {
     nK = ch1 - ch0; Nc = A.W.Nc;
     wb = (const char*)A.W.wp + (size_t)ch0 * 2 * A.W.Nc * 128;
   }
+  struct Raw { float4 a[Dim::RW], b[Dim::RW]; };
+  struct ProdV {
+    const Args& A; int wi, lane;
+    int nK, ch0; const float* DAb; ptrdiff_t uh_minus_da;
+    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
+      int mt, ch1;
+      part(A, Sc, item, mt, ch0, ch1);
+      nK = ch1 - ch0;
+      const WsVecPx v = ws_vec_px(mt * 128, lane, A.P.HW);
+      DAb = A.DA + (size_t)v.n * A.P.MC * A.P.HW + v.hw;
+      uh_minus_da = A.UH - A.DA;
+    }
+    __device__ __forceinline__ void locate(int c, int& mc, int& coff, int& k0) const {
+      const int g = ch0 + c;
+      int f0 = 0, slot = 0;
+#pragma unroll
+      for (int s = 1; s < TFNAS_MAX_OPS; ++s)
+        if (s < A.P.na && g >= A.CH.first[s]) { slot = s; f0 = A.CH.first[s]; }
+      k0 = (g - f0) * WS_KC;
+      mc = A.P.c[slot].mc;
+      coff = A.P.c[slot].coff;
+    }
+    __device__ __forceinline__ void load(int c, Raw& r) const {
+      int mc, coff, k0;
+      locate(c, mc, coff, k0);
+#pragma unroll
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int k = coff + min(k0 + wi + i * Dim::NPG, mc - 1);
+        const float* p = DAb + (uint32_t)(k * A.P.HW);
+        r.a[i] = *(const float4*)p;
+        r.b[i] = *(const float4*)(p + uh_minus_da);
+      }
+    }
+    __device__ __forceinline__ void emit(int c, const Raw& r, unsigned char* a_hi) const {
+      int mc, coff, k0;
+      locate(c, mc, coff, k0);
+      float sacc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sacc[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < Dim::RW; ++i) {
+        const bool ok = k0 + wi + i * Dim::NPG < mc;
+        const float da[4] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w}, uh[4] = {r.b[i].x, r.b[i].y, r.b[i].z, r.b[i].w};
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[e] = ok ? da[e] * act_df<ACT>(uh[e]) : 0.f;
+          sacc[2 * i] += v[e];
+          sacc[2 * i + 1] += v[e] * uh[e];
+        }
+        ws_emit_row(a_hi, wi + i * Dim::NPG, lane, v);
+      }
+      const float tot = warp_sum16(sacc);
+      const int k = k0 + wi + (lane >> 1) * Dim::NPG;
+      if (lane < 2 * Dim::RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
+    }
+  };
   struct Prod {
-    const Args& A; int ptid, pw, lane;
+    const Args& A; int wi, lane;
     int nK, ch0; Px4 px; const float* DAb; const float* UHb;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int mt, ch1;
@@ -989,32 +898,27 @@ struct WsDxT {
       mc = A.P.c[slot].mc;
       coff = A.P.c[slot].coff;
     }
-    // ring stage: [DA rows | UH rows]
-    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t*) const {
+    __device__ __forceinline__ void load(int c, Raw& r) const {
       int mc, coff, k0;
       locate(c, mc, coff, k0);
 #pragma unroll
-      for (int i = 0; i < DimProd::RW; ++i) {
-        const int k = k0 + pw + i * DimProd::NP;
-        const bool ok = k < mc;
-        const int cst = coff + k;
-        ws_ring_row(st + ((size_t)i * DimProd::NPT + ptid) * 16, A.DA, DAb, px, A.P.MC, cst, A.P.HW, ok);
-        ws_ring_row(st + ((size_t)(DimProd::RW + i) * DimProd::NPT + ptid) * 16, A.UH, UHb, px, A.P.MC, cst, A.P.HW, ok);
+      for (int i = 0; i < Dim::RW; ++i) {
+        const int k = k0 + wi + i * Dim::NPG;
+        r.a[i] = ws_ld4(A.DA, DAb, px, A.P.MC, coff + k, A.P.HW, k < mc);
+        r.b[i] = ws_ld4(A.UH, UHb, px, A.P.MC, coff + k, A.P.HW, k < mc);
       }
     }
-    // Rows past the candidate's width and invalid pixels are zero-filled in the ring, so du = 0 * act'(0) = 0 there.
+    // Rows past the candidate's width and invalid pixels are loaded as zeros, so du = 0 * act'(0) = 0 there.
     // BN1's rstd is folded into the prepped weights (umma_prep_bwd), the operand is plain du-hat.
-    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimProd>& t) const {
+    __device__ __forceinline__ void emit(int c, const Raw& r, unsigned char* a_hi) const {
       int mc, coff, k0;
       locate(c, mc, coff, k0);
       float sacc[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) sacc[i] = 0.f;
 #pragma unroll
-      for (int i = 0; i < DimProd::RW; ++i) {
-        const float4 a = *(const float4*)(st + ((size_t)i * DimProd::NPT + ptid) * 16);
-        const float4 b = *(const float4*)(st + ((size_t)(DimProd::RW + i) * DimProd::NPT + ptid) * 16);
-        const float da[4] = {a.x, a.y, a.z, a.w}, uh[4] = {b.x, b.y, b.z, b.w};
+      for (int i = 0; i < Dim::RW; ++i) {
+        const float da[4] = {r.a[i].x, r.a[i].y, r.a[i].z, r.a[i].w}, uh[4] = {r.b[i].x, r.b[i].y, r.b[i].z, r.b[i].w};
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -1022,90 +926,21 @@ struct WsDxT {
           sacc[2 * i] += v[e];
           sacc[2 * i + 1] += v[e] * uh[e];
         }
-        ws_split<DimProd>(t, i, v);
+        ws_emit_row(a_hi, wi + i * Dim::NPG, lane, v);
       }
-      // 2*DimProd::RW statistics (rows x {sum du, sum du*uh}) reduced together; lane l < 2*DimProd::RW ends up owning statistic l
-      static_assert(2 * DimProd::RW <= 16, "statistics must fit the 16-value warp reduction");
+      // 2*RW statistics (rows x {sum du, sum du*uh}) reduced together; lane l < 2*RW ends up owning statistic l
+      static_assert(2 * Dim::RW <= 16, "statistics must fit the 16-value warp reduction");
       const float tot = warp_sum16(sacc);
-      const int k = k0 + pw + (lane >> 1) * DimProd::NP;
-      if (lane < 2 * DimProd::RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
+      const int k = k0 + wi + (lane >> 1) * Dim::NPG;
+      if (lane < 2 * Dim::RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
     }
   };
-  struct ProdB {
-    const Args& A; int ptid, pw, lane;
-    int nK, ch0, len1; size_t off0, off1;
-    __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
-      int mt, ch1;
-      part(A, Sc, item, mt, ch0, ch1);
-      nK = ch1 - ch0;
-      const WsSeg g = ws_seg(mt * 128, A.P.HW);
-      len1 = g.len1;
-      off0 = (size_t)g.n0 * A.P.MC * A.P.HW + g.hw0;
-      off1 = (size_t)(g.n0 + 1) * A.P.MC * A.P.HW;
-    }
-    __device__ __forceinline__ void locate(int c, int& mc, int& coff, int& k0) const {
-      const int g = ch0 + c;
-      int f0 = 0, slot = 0;
-#pragma unroll
-      for (int s = 1; s < TFNAS_MAX_OPS; ++s)
-        if (s < A.P.na && g >= A.CH.first[s]) { slot = s; f0 = A.CH.first[s]; }
-      k0 = (g - f0) * WS_KC;
-      mc = A.P.c[slot].mc;
-      coff = A.P.c[slot].coff;
-    }
-    // ring stage: [DA rows 16 KB | UH rows 16 KB]
-    __device__ __forceinline__ void issue(int c, unsigned char* st, uint64_t* bar) const {
-      int mc, coff, k0;
-      locate(c, mc, coff, k0);
-      if (lane < 4 * DimProd::RW) {
-        const int tsel = lane / (2 * DimProd::RW), r = lane % (2 * DimProd::RW);
-        const int kk = pw + (r >> 1) * DimProd::NP, k = k0 + kk;
-        const size_t ro = (size_t)(coff + k) * A.P.HW;
-        const float* T = tsel ? A.UH : A.DA;
-        ws_bulk_row(st + tsel * 16384 + kk * 512, T + off0 + ro, T + off1 + ro, r & 1, len1, k < mc, bar);
-      }
-      if (lane == 0) {
-        int nv = 0;
-#pragma unroll
-        for (int i = 0; i < DimProd::RW; ++i) nv += (k0 + pw + i * DimProd::NP < mc) ? 1 : 0;
-        mbar_expect_tx(bar, nv * 1024);
-      }
-    }
-    __device__ __forceinline__ void compute(int c, const unsigned char* st, WsTile<DimProd>& t) const {
-      int mc, coff, k0;
-      locate(c, mc, coff, k0);
-      float sacc[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) sacc[i] = 0.f;
-#pragma unroll
-      for (int i = 0; i < DimProd::RW; ++i) {
-        const int kk = pw + i * DimProd::NP;
-        const bool ok = k0 + kk < mc;                 // rows past the candidate's width were not fetched
-        const float4 a = *(const float4*)(st + kk * 512 + lane * 16);
-        const float4 b = *(const float4*)(st + 16384 + kk * 512 + lane * 16);
-        const float da[4] = {a.x, a.y, a.z, a.w}, uh[4] = {b.x, b.y, b.z, b.w};
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float u = ok ? uh[e] : 0.f;
-          v[e] = ok ? da[e] * act_df<ACT>(u) : 0.f;
-          sacc[2 * i] += v[e];
-          sacc[2 * i + 1] += v[e] * u;
-        }
-        ws_split<DimProd>(t, i, v);
-      }
-      const float tot = warp_sum16(sacc);
-      const int k = k0 + pw + (lane >> 1) * DimProd::NP;
-      if (lane < 2 * DimProd::RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
-    }
-  };
-  static constexpr bool WCONST = false;
   static __device__ __forceinline__ void epi_prep(const Args&, const WsSched&, int, float2*, int) {}
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2*,
                                                  int ew, int lane) {
     int mt, ch0, ch1;
     part(A, Sc, item, mt, ch0, ch1);
-    const WsEpi e = ws_epi<DimProd>(mt * 128, A.P.P, A.P.HW, A.W.Nc, A.P.ic, acc, ew, lane);
+    const WsEpi e = ws_epi<Dim>(mt * 128, A.P.P, A.P.HW, A.W.Nc, A.P.ic, acc, ew, lane);
     const size_t HW = (size_t)A.P.HW;
     float* ob = A.dx + (size_t)e.n * A.P.ic * HW + e.hw;
     for (int c0 = e.c_lo; c0 < e.c_hi; c0 += 16) {
@@ -1128,46 +963,47 @@ struct WsDxT {
 // -------------------------------------------------------------------------------------------------
 // kernels + host side
 // -------------------------------------------------------------------------------------------------
-template <bool BULK>
-__global__ void __launch_bounds__(DimEpi::NTHR, 1) k_ws_expand(const __grid_constant__ WsExpandArgs A, const __grid_constant__ WsSched Sc,
-                                                             const __grid_constant__ WsCfg cfg) {
-  ws_run<WsExpandT, BULK>(A, Sc, cfg);
+typedef WsDim<16, 8, 2> DimExpand;            // epilogue-bound (stores N = mc columns), K = ic is 1..6 chunks
+typedef WsDim<4, 16, 4> DimProject;           // prologue-bound: 4 chunks in flight, 8 rows per warp
+typedef WsDim<16, 8, 1> DimDc;                // epilogue-bound (loads D, stores DC); two tensors per chunk
+typedef WsDim<4, 16, 2> DimDx;                // prologue-bound, two tensors per chunk: 2 chunks in flight, 4 rows per warp
+
+template <bool VEC>
+__global__ void __launch_bounds__(DimExpand::NTHR, 1) k_ws_expand(const __grid_constant__ WsExpandArgs A, const __grid_constant__ WsSched Sc,
+                                                                const __grid_constant__ WsCfg cfg) {
+  ws_run<WsExpandT<DimExpand>, VEC>(A, Sc, cfg);
 }
-template <int ACT, bool BULK>
-__global__ void __launch_bounds__(DimProd::NTHR, 1) k_ws_project(const __grid_constant__ WsProjectArgs A, const __grid_constant__ WsSched Sc,
-                                                               const __grid_constant__ WsCfg cfg) {
-  ws_run<WsProjectT<ACT>, BULK>(A, Sc, cfg);
+template <int ACT, bool VEC>
+__global__ void __launch_bounds__(DimProject::NTHR, 1) k_ws_project(const __grid_constant__ WsProjectArgs A, const __grid_constant__ WsSched Sc,
+                                                                  const __grid_constant__ WsCfg cfg) {
+  ws_run<WsProjectT<ACT, DimProject>, VEC>(A, Sc, cfg);
 }
-template <int ACT, bool BULK>
-__global__ void __launch_bounds__(DimEpi::NTHR, 1) k_ws_dc(const __grid_constant__ WsDcArgs A, const __grid_constant__ WsSched Sc,
-                                                         const __grid_constant__ WsCfg cfg) {
-  ws_run<WsDcT<ACT>, BULK>(A, Sc, cfg);
+template <int ACT, bool VEC>
+__global__ void __launch_bounds__(DimDc::NTHR, 1) k_ws_dc(const __grid_constant__ WsDcArgs A, const __grid_constant__ WsSched Sc,
+                                                        const __grid_constant__ WsCfg cfg) {
+  ws_run<WsDcT<ACT, DimDc>, VEC>(A, Sc, cfg);
 }
-template <int ACT, bool BULK>
-__global__ void __launch_bounds__(DimProd::NTHR, 1) k_ws_dx(const __grid_constant__ WsDxArgs A, const __grid_constant__ WsSched Sc,
-                                                          const __grid_constant__ WsCfg cfg) {
-  ws_run<WsDxT<ACT>, BULK>(A, Sc, cfg);
+template <int ACT, bool VEC>
+__global__ void __launch_bounds__(DimDx::NTHR, 1) k_ws_dx(const __grid_constant__ WsDxArgs A, const __grid_constant__ WsSched Sc,
+                                                        const __grid_constant__ WsCfg cfg) {
+  ws_run<WsDxT<ACT, DimDx>, VEC>(A, Sc, cfg);
 }
 
-// launch helper: pick the activation / bulk instantiation
-#define WS_LAUNCH1(KERN, BULK_, NTHR_) do { \
-    if (BULK_) { ensure_smem(KERN<true>, smem); KERN<true><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
-    else { ensure_smem(KERN<false>, smem); KERN<false><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } } while (0)
-#define WS_LAUNCH2(KERN, RELU_, BULK_, NTHR_) do { \
-    if (RELU_) { \
-      if (BULK_) { ensure_smem(KERN<TFNAS_ACT_RELU, true>, smem); KERN<TFNAS_ACT_RELU, true><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
-      else { ensure_smem(KERN<TFNAS_ACT_RELU, false>, smem); KERN<TFNAS_ACT_RELU, false><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
-    } else { \
-      if (BULK_) { ensure_smem(KERN<TFNAS_ACT_SWISH, true>, smem); KERN<TFNAS_ACT_SWISH, true><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
-      else { ensure_smem(KERN<TFNAS_ACT_SWISH, false>, smem); KERN<TFNAS_ACT_SWISH, false><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
-    } } while (0)
+#define WS_LAUNCH_V(KERN, ACT_, NTHR_) do { \
+    if (vec) { ensure_smem(KERN<ACT_, true>, smem); KERN<ACT_, true><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } \
+    else { ensure_smem(KERN<ACT_, false>, smem); KERN<ACT_, false><<<grid, NTHR_, smem, st>>>(A, Sc, cfg); } } while (0)
+#define WS_LAUNCH(KERN, NTHR_) do { \
+    if (P.act == TFNAS_ACT_RELU) WS_LAUNCH_V(KERN, TFNAS_ACT_RELU, NTHR_); \
+    else WS_LAUNCH_V(KERN, TFNAS_ACT_SWISH, NTHR_); } while (0)
 
-// TFNAS_WS: comma-separated subset of {expand,project,dc,dx} run by the persistent kernels; "0"/"none" disables, unset = all
+// TFNAS_WS: comma-separated subset of {expand,project,dc,dx} run by the persistent kernels ("none" disables, "all" = all
+// four).  Default: expand, project, dx -- dc is bound by its epilogue (D loads, DC stores, statistics), which the
+// many-CTA kernel of umma_pw.cu overlaps better.
 static int g_ws_mask = -1;
 int ws_enabled(int which) {
   if (g_ws_mask < 0) {
     const char* e = getenv("TFNAS_WS");
-    if (!e) g_ws_mask = 15;
+    if (!e) g_ws_mask = 1 | 2 | 8;
     else {
       g_ws_mask = 0;
       if (strstr(e, "expand")) g_ws_mask |= 1;
@@ -1178,12 +1014,6 @@ int ws_enabled(int which) {
     }
   }
   return (g_ws_mask >> which) & 1;
-}
-
-// TFNAS_WS_BULK=0 forces the per-thread cp.async loads (A/B debugging)
-static bool ws_bulk_enabled() {
-  static const bool on = !(getenv("TFNAS_WS_BULK") && strcmp(getenv("TFNAS_WS_BULK"), "0") == 0);
-  return on;
 }
 
 // items of the per-slot GEMMs: slot major, then N chunk, then pixel tile
@@ -1208,13 +1038,13 @@ bool ws_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1
   if ((long long)tiles * TFNAS_MAX_OPS * 64 >= (1 << 23)) return false;
   ws_sched_slots(P, WA, tiles, Sc, maxNc);
   WsCfg cfg;
-  if (maxNc > 256 || !ws_fit(maxNc, WsExpandT::STAGE, WsExpandT::CF, cfg)) return false;
+  if (maxNc > 256 || !ws_fit(maxNc, DimExpand::G, WsExpandT<DimExpand>::CF, 2, 4, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
   WsExpandArgs A{P, WA, x, bn1, UH};
   ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   const int grid = min(Sc.n_items, sm_count());
-  const bool bulk = ws_bulk_enabled() && ws_bulk_ok(P.HW, P.P);
-  WS_LAUNCH1(k_ws_expand, bulk, DimEpi::NTHR);
+  if (ws_vec_ok(P.HW, P.P)) { ensure_smem(k_ws_expand<true>, smem); k_ws_expand<true><<<grid, DimExpand::NTHR, smem, st>>>(A, Sc, cfg); }
+  else { ensure_smem(k_ws_expand<false>, smem); k_ws_expand<false><<<grid, DimExpand::NTHR, smem, st>>>(A, Sc, cfg); }
   return true;
 }
 
@@ -1226,14 +1056,14 @@ bool ws_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn
   if ((long long)tiles * TFNAS_MAX_OPS * 64 >= (1 << 23)) return false;
   ws_sched_slots(P, WA, tiles, Sc, maxNc);
   WsCfg cfg;
-  if (maxNc > 256 || !ws_fit(maxNc, WsProjectT<0>::STAGE, WsProjectT<0>::CF, cfg)) return false;
+  if (maxNc > 256 || !ws_fit(maxNc, DimProject::G, 0, 1, 4, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
   WsProjectArgs A{P, WA, D, bn2, seg, Zb, st3};
   ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
   const int grid = min(Sc.n_items, sm_count());
-  const bool bulk = ws_bulk_enabled() && ws_bulk_ok(P.HWo, P.Q);
-  WS_LAUNCH2(k_ws_project, P.act == TFNAS_ACT_RELU, bulk, DimProd::NTHR);
+  const bool vec = ws_vec_ok(P.HWo, P.Q);
+  WS_LAUNCH(k_ws_project, DimProject::NTHR);
   return true;
 }
 
@@ -1245,14 +1075,14 @@ bool ws_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, con
   if ((long long)tiles * TFNAS_MAX_OPS * 64 >= (1 << 23)) return false;
   ws_sched_slots(P, WA, tiles, Sc, maxNc);
   WsCfg cfg;
-  if (maxNc > 256 || !ws_fit(maxNc, WsDcT<0>::STAGE, WsDcT<0>::CF, cfg)) return false;
+  if (maxNc > 256 || !ws_fit(maxNc, DimDc::G, 2 * 256 * sizeof(float2), 2, 4, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
   WsDcArgs A{P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD};
   ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
   const int grid = min(Sc.n_items, sm_count());
-  const bool bulk = ws_bulk_enabled() && ws_bulk_ok(P.HWo, P.Q);
-  WS_LAUNCH2(k_ws_dc, P.act == TFNAS_ACT_RELU, bulk, DimEpi::NTHR);
+  const bool vec = false;
+  WS_LAUNCH(k_ws_dc, DimDc::NTHR);
   return true;
 }
 
@@ -1265,7 +1095,7 @@ bool ws_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, con
   if (tiles < 3 * sms) ksplit = max(1, min(max(1, CH.total / 4), (3 * sms) / tiles));
   if ((long long)tiles * ksplit >= (1 << 23)) return false;
   WsCfg cfg;
-  if (W.Nc > 256 || !ws_fit(W.Nc, WsDxT<0>::STAGE, WsDxT<0>::CF, cfg)) return false;
+  if (W.Nc > 256 || !ws_fit(W.Nc, DimDx::G, 0, 2, 4, cfg)) return false;
   WsSched Sc;
   memset(&Sc, 0, sizeof(Sc));
   Sc.tiles_m = tiles;
@@ -1277,8 +1107,8 @@ bool ws_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, con
   WsDxArgs A{P, W, CH, ksplit, DA, UH, dx, sU};
   ProfScope ps("dx", 4.0 * P.P * (2.0 * P.MC + P.ic) + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   const int grid = min(Sc.n_items, sms);
-  const bool bulk = ws_bulk_enabled() && ws_bulk_ok(P.HW, P.P);
-  WS_LAUNCH2(k_ws_dx, P.act == TFNAS_ACT_RELU, bulk, DimProd::NTHR);
+  const bool vec = ws_vec_ok(P.HW, P.P);
+  WS_LAUNCH(k_ws_dx, DimDx::NTHR);
   return true;
 }
 

@@ -16,7 +16,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 SLOTS = 16
-PN = ['iters', 'issue', 'wait_data', 'compute', 'wait_empty', 'store', 'fence', 'arrive+sync']
+PN = ['iters', 'advance+loads', '-', '-', 'wait_empty', 'emit', 'fence', 'arrive']
 MN = ['chunks', 'wait_w', 'wait_operands', 'issue+commit', 'wait_acc']
 
 
