@@ -75,3 +75,36 @@ def test_bisampled_wstep_matches_reference_golden():
     assert H.rel_l2(npar['first_stem.conv.weight'].grad, torch.from_numpy(z['g_first_stem'])) < 5e-3
     assert H.rel_l2(npar['classifier.linear.weight'].grad, torch.from_numpy(z['g_classifier'])) < TOL
     assert all(all(m.switches) for m in net.modules() if hasattr(m, 'switches'))
+
+
+def test_two_stream_wstep_equals_single_stream():
+    """search_loop.w_step with the two sampled passes on two CUDA streams gives the same loss, sampled paths and weight
+    update as the sequential single-stream step."""
+    import torch.nn as nn
+    from tfnas_b200 import model_search
+    from tfnas_b200.search_loop import make_optimizers, w_step
+
+    class Wrap(nn.Module):          # the loops address the network as model.module (nn.DataParallel in the reference)
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+        def forward(self, *a, **k):
+            return self.module(*a, **k)
+
+    res = []
+    for overlap in (False, True):
+        net, x, tgt = _net()
+        model = Wrap(net)
+        opt_w, _ = make_optimizers(net)
+        random.seed(7)
+        model_search.seed_noise(13)
+        loss, logits = w_step(model, x, tgt, nn.CrossEntropyLoss().cuda(), opt_w, 5.0, None, bisample=True, overlap=overlap)
+        torch.cuda.synchronize()
+        flat = torch.cat([p.detach().reshape(-1) for p in net.weight_parameters()])
+        res.append((float(loss), logits.detach().clone(), flat.clone()))
+    model_search.seed_noise(None)
+    (l0, g0, w0), (l1, g1, w1) = res
+    e = dict(loss=abs(l0 - l1), logits=H.rel_l2(g1, g0), weights=H.rel_l2(w1, w0))
+    print('two-stream vs single-stream w-step', e)
+    assert e['loss'] < 1e-4 and e['logits'] < 1e-4 and e['weights'] < 1e-5

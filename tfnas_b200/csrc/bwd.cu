@@ -897,6 +897,37 @@ static void launch_dxfin(const Plan& P, OcTile T, const float* x, const float* M
   k_dxfin<TK><<<cdiv(P.P, PW_TPX), NT, 0, st>>>(P, T, x, Mm, cvec2, G, dx);
 }
 
+// ---- side stream for the weight-gradient GEMMs ---------------------------------------------------------------------
+// dW3 / dW1 only feed the caller (nothing on the dgrad chain reads them), and a sampled single-candidate pass leaves most
+// SMs idle, so they are forked onto a library-owned stream per caller stream and joined before the call's last kernels:
+// every launch of the call is still ordered before whatever the caller enqueues next on ITS stream.
+// Opt-in (TFNAS_SIDE_STREAM=1): with the two sampled passes of a w-step already on two streams (search_loop.w_step) the
+// extra stream measured no gain on B200 (1843 vs 1907 images/s), so by default everything stays on the caller's stream.
+#include <map>
+#include <mutex>
+struct SideStream { cudaStream_t s; cudaEvent_t fork1, fork2, join; };
+static SideStream* side_stream_for(cudaStream_t main) {
+  static const bool on = getenv("TFNAS_SIDE_STREAM") && strcmp(getenv("TFNAS_SIDE_STREAM"), "1") == 0;
+  if (!on) return nullptr;
+  static std::map<std::pair<int, cudaStream_t>, SideStream> streams;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_pair(dev, main);
+  auto it = streams.find(key);
+  if (it == streams.end()) {
+    if (streams.size() >= 64) return nullptr;
+    SideStream sd;
+    if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaEventCreateWithFlags(&sd.fork1, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sd.fork2, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming);
+    it = streams.insert({key, sd}).first;
+  }
+  return &it->second;
+}
+
 void launch_backward(const Plan& P, const float* x, const float* dout, const float* dlat, float T,
                      int alpha_mode, const char* saved, const SavedLayout& L, const BwdScratch& S,
                      float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st) {
@@ -946,13 +977,16 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     if (maxmc > 64) launch_dc<16>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
     else launch_dc<8>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
   }
-  if (dweights) {   // dW3 = sum_p dz c^T
+  SideStream* side = (dweights && umma_enabled()) ? side_stream_for(st) : nullptr;
+  const cudaStream_t wst = side ? side->s : st;      // stream of the weight-gradient GEMMs
+  if (dweights) {   // dW3 = sum_p dz c^T  (reads D, dout, Z, bn2, seg, dzc2: none of them is written again in this call)
+    if (side) { cudaEventRecord(side->fork1, st); cudaStreamWaitEvent(wst, side->fork1, 0); }
     for (int s = 0; s < P.na; ++s) {
       const Cand& cd = P.c[s];
       float* gw3 = dweights[cd.id].w3;
-      cudaMemsetAsync(gw3, 0, (size_t)oc * cd.mc * sizeof(float), st);
+      cudaMemsetAsync(gw3, 0, (size_t)oc * cd.mc * sizeof(float), umma_enabled() ? wst : st);
       if (umma_enabled()) {
-        umma_wgrad(P, s, 0, D, nullptr, dout, Zb, bn2, seg, bn3, S.dzc2, gw3, st);
+        umma_wgrad(P, s, 0, D, nullptr, dout, Zb, bn2, seg, bn3, S.dzc2, gw3, wst);
       } else {
         int nsplit = max(1, min(cdiv(P.Q, 2048), cdiv(6 * sm_count(), cdiv(oc, WG_T) * cdiv(cd.mc, WG_T))));
         dim3 grid(cdiv(oc, WG_T), cdiv(cd.mc, WG_T), nsplit);
@@ -1009,6 +1043,17 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     launch_dw_bwd<3, 2>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
     launch_dw_bwd<5, 2>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
   }
+  if (side) {
+    // Smat = sum_p du-hat x^T reads DA / UH / x, final since the transposed depthwise: forked alongside the dx GEMM
+    cudaEventRecord(side->fork2, st);
+    cudaStreamWaitEvent(wst, side->fork2, 0);
+    for (int s = 0; s < P.na; ++s) {
+      const Cand& cd = P.c[s];
+      float* Sm = S.Smat + (size_t)cd.coff * ic;
+      cudaMemsetAsync(Sm, 0, (size_t)cd.mc * ic * sizeof(float), wst);
+      umma_wgrad(P, s, 1, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, nullptr, Sm, wst);
+    }
+  }
   // B3b
   OcTile Tx = oc_tile(ic, 24);
   if (umma_enabled()) {
@@ -1028,12 +1073,18 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     }
   }
   if (dweights) {   // dW1 via Smat
+    if (side) {       // Smat was accumulated on the side stream (forked before the dx GEMM); join before the finishing kernels
+      cudaEventRecord(side->join, wst);
+      cudaStreamWaitEvent(st, side->join, 0);
+    }
     for (int s = 0; s < P.na; ++s) {
       const Cand& cd = P.c[s];
       float* Sm = S.Smat + (size_t)cd.coff * ic;
-      cudaMemsetAsync(Sm, 0, (size_t)cd.mc * ic * sizeof(float), st);
+      if (!side) cudaMemsetAsync(Sm, 0, (size_t)cd.mc * ic * sizeof(float), st);
       const int smat_t = umma_enabled();     // tensor-core path writes Smat transposed [ic][mc]
-      if (smat_t) {
+      if (side) {
+        // already accumulated on the side stream
+      } else if (smat_t) {
         umma_wgrad(P, s, 1, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, nullptr, Sm, st);
       } else {
         int nsplit = max(1, min(cdiv(P.P, 2048), cdiv(6 * sm_count(), cdiv(cd.mc, WG_T) * cdiv(ic, WG_T))));

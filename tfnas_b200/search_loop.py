@@ -46,17 +46,57 @@ def _set_requires_grad(net, weights, arch):
         p.requires_grad = arch
 
 
-def w_step(model, x_w, target_w, criterion, optimizer_w, grad_clip, sync=None, bisample=True):
-    """One weight step (train_search.py:370-385): loss = CE(gumbel path) [+ CE(random other path)]."""
+_SIDE_STREAMS = {}
+# the two passes of a bi-sampled step accumulate into the shared stem / head parameters from two streams on purpose
+if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+
+
+def _side_streams(device):
+    """Two side streams per device for the bi-sampled w-step (created once)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=key), torch.cuda.Stream(device=key))
+    return _SIDE_STREAMS[key]
+
+
+def w_step(model, x_w, target_w, criterion, optimizer_w, grad_clip, sync=None, bisample=True, overlap=True):
+    """One weight step (train_search.py:370-385): loss = CE(gumbel path) [+ CE(random other path)].
+
+    The two sampled sub-networks of a bi-sampled step are independent until their losses are added, and a single
+    sampled path leaves most SMs idle in the late stages (49 pixel tiles at 7x7), so with ``overlap`` the two passes are
+    enqueued on two CUDA streams (forward and, through autograd's stream tracking, backward).  The host-side order of
+    the sampling decisions (gumbel path first, then a random OTHER path) is unchanged."""
     net = model.module
     _set_requires_grad(net, True, False)
-    logits_g, _ = model(x_w, sampling=True, mode='gumbel')
-    loss = criterion(logits_g, target_w)
-    if bisample:
-        logits_r, _ = model(x_w, sampling=True, mode='random')
-        loss = loss + criterion(logits_r, target_w)
+    if bisample and overlap and x_w.is_cuda:
+        cur = torch.cuda.current_stream(x_w.device)
+        s1, s2 = _side_streams(x_w.device)
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            logits_g, _ = model(x_w, sampling=True, mode='gumbel')
+            loss_g = criterion(logits_g, target_w)
+        with torch.cuda.stream(s2):
+            logits_r, _ = model(x_w, sampling=True, mode='random')
+            loss_r = criterion(logits_r, target_w)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+        for t in (x_w, target_w):
+            t.record_stream(s1)
+            t.record_stream(s2)
+        for t in (logits_g, loss_g):
+            t.record_stream(cur)
+        loss_r.record_stream(cur)
+        loss = loss_g + loss_r
     else:
-        net.reset_switches()
+        logits_g, _ = model(x_w, sampling=True, mode='gumbel')
+        loss = criterion(logits_g, target_w)
+        if bisample:
+            logits_r, _ = model(x_w, sampling=True, mode='random')
+            loss = loss + criterion(logits_r, target_w)
+        else:
+            net.reset_switches()
     optimizer_w.zero_grad()
     loss.backward()
     if sync is not None:

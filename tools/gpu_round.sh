@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, bench line, ncu launch list, per-shape kernel timings, one full ncu capture.
 # usage (from the repo root, under gpurun):  bash tools/gpu_round.sh [tag] [stages]
-#   stages: any of t(ests) b(ench) l(aunch list) k(ernel timings) n(cu full), default "tblkn"
+#   stages: any of t(ests) b(ench) l(aunch list) k(ernel timings) n(cu full) d(ram traffic per kernel), default "tblkn"
 tag=${1:-r1}
 stages=${2:-tblkn}
 out=gpurun_out/$tag
@@ -32,7 +32,7 @@ fi
 if [[ $stages == *n* ]]; then
   # full-set capture of the GEMM + depthwise kernels of ONE alpha-mode MixedOP fwd+bwd (second pass; the first is warm-up)
   for blk in ${NCU_BLOCKS:-1 10}; do
-    timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_um_(expand|project|dc|dx)|k_dw_' \
+    timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_ws_|k_um_(expand|project|dc|dx)|k_dw' \
       --launch-skip 8 --launch-count 8 -o $out/mixedop_blk${blk} -f \
       python tools/time_mixedops.py --mode alpha --only $blk --reps 1 --out $out/ncu_dummy.json > $out/ncu_full_blk${blk}.log 2>&1
     echo "ncu full blk $blk exit $?"
@@ -41,5 +41,13 @@ if [[ $stages == *n* ]]; then
     sz=$(stat -c %s $out/mixedop_blk${blk}.ncu-rep 2>/dev/null || echo 0)
     if [ "$sz" -gt 12000000 ]; then rm -f $out/mixedop_blk${blk}.ncu-rep; echo "dropped ncu-rep ($sz bytes)"; fi
   done
+fi
+if [[ $stages == *d* ]]; then
+  # DRAM bytes per launch of the GEMM / depthwise kernels over one search unit (two metrics: a single ncu pass per kernel)
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $out/dram.csv \
+    -k 'regex:k_ws_|k_um_|k_dw|k_dxfin|k_b2b' python bench.py --profile-only --steps 1 --warmup 1 --no-cpu-baseline > $out/dram.log 2>&1
+  echo "ncu dram exit $?"
+  python tools/ncu_traffic.py $out/dram.csv > $out/ncu_traffic.json 2>> $out/dram.log
+  head -c 600 $out/ncu_traffic.json
 fi
 du -sh gpurun_out; ls -la $out
