@@ -295,15 +295,16 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
     tr.end(0);
   } else if (warp == D::MMA_WARP) {
     // ------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues) ------------
-    int s = 0, b = 0, jj = 0;
-    uint32_t fph = 0, wph = 0;               // parities of full[s] / wfull[b]
+    int s = 0, rot = 0, jj = 0;
+    uint32_t fph = 0, wpar = 0;              // parity of full[s]; bit b of wpar = parity of wfull[b]
     const uint32_t a0 = smem_u32(M.a), w0 = smem_u32(M.w);
     WsTrace tr;
     tr.begin(lane == 0);
     for (int item = item0; item < Sc.n_items; item += istep, ++jj) {
-      int nK, Nc;
+      int nK, Nc, key;
       const char* wb;
-      T::geom(A, Sc, item, nK, Nc, wb);
+      T::geom(A, Sc, item, nK, Nc, wb, key);
+      const bool resident = nK <= cfg.NB;    // every chunk of the item has its own weight slot (see the weight warp)
       const int ab = jj & 1;
       const uint32_t au = (uint32_t)jj >> 1;
       tr.mark(3);
@@ -314,7 +315,10 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
       const uint32_t acc = tmem + ab * WS_ACC_STRIDE;
       for (int c = 0; c < nK; ++c) {
         tr.count();
-        mbar_wait_suspend(&M.wfull[b], wph, 1000);
+        int b = c;
+        if (!resident) { b = rot; rot = rot + 1 == cfg.NB ? 0 : rot + 1; }
+        mbar_wait_suspend(&M.wfull[b], (wpar >> b) & 1, 1000);
+        wpar ^= 1u << b;
         tr.mark(1);
         mbar_wait_suspend(&M.full[s], fph, 1000);
         tc_fence_after();
@@ -327,7 +331,6 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
         __syncwarp();
         tr.mark(3);
         if (++s == cfg.S) { s = 0; fph ^= 1; }
-        if (++b == cfg.NB) { b = 0; wph ^= 1; }
       }
       if (ws_elect()) mma_commit(&M.accfull[ab]);
       __syncwarp();
@@ -335,22 +338,34 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
     tr.end(8);
   } else {
     // ------------------------------ weight copies ------------------------------
-    int b = 0;
-    uint32_t eph = 1;
+    // Items whose K chunks all fit the NB weight slots keep chunk c in slot c; consecutive items of a CTA nearly always
+    // share (candidate, N chunk), and then the slots already hold the right blocks: no copy, just the hand-shake.
+    // Longer items rotate through the slots as a ring.
+    int rot = 0, cur_key = -1;
+    uint32_t epar = 0;                         // bit b = number of uses of slot b so far, mod 2
     for (int item = item0; item < Sc.n_items; item += istep) {
-      int nK, Nc;
+      int nK, Nc, key;
       const char* wb;
-      T::geom(A, Sc, item, nK, Nc, wb);
+      T::geom(A, Sc, item, nK, Nc, wb, key);
       const uint32_t bytes = (uint32_t)2 * Nc * 128;
+      const bool resident = nK <= cfg.NB;
+      const bool hit = resident && key == cur_key;
       for (int c = 0; c < nK; ++c) {
-        mbar_wait_suspend(&M.wempty[b], eph, 2000);
+        int b = c;
+        if (!resident) { b = rot; rot = rot + 1 == cfg.NB ? 0 : rot + 1; }
+        mbar_wait_suspend(&M.wempty[b], ((epar >> b) & 1) ^ 1, 2000);     // passes on the first use of each slot
+        epar ^= 1u << b;
         if (ws_elect()) {
-          mbar_expect_tx(&M.wfull[b], bytes);
-          bulk_g2s(M.w + (size_t)b * cfg.wslot, wb + (size_t)c * bytes, bytes, &M.wfull[b]);
+          if (hit) {
+            mbar_arrive(&M.wfull[b]);
+          } else {
+            mbar_expect_tx(&M.wfull[b], bytes);
+            bulk_g2s(M.w + (size_t)b * cfg.wslot, wb + (size_t)c * bytes, bytes, &M.wfull[b]);
+          }
         }
         __syncwarp();
-        if (++b == cfg.NB) { b = 0; eph ^= 1; }
       }
+      cur_key = resident ? key : -1;
     }
   }
   tc_fence_before();
@@ -393,12 +408,13 @@ struct WsExpandT {
   using Args = WsExpandArgs;
   using Dim = Dim_;
   static constexpr uint32_t CF = 2 * 256 * sizeof(float2);
-  static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
+  static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb, int& key) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const UmW& W = A.WA.s[slot];
     nK = W.nK; Nc = W.Nc;
     wb = (const char*)W.wp + (size_t)nc * W.nK * 2 * W.Nc * 128;
+    key = slot * 64 + nc;
   }
   struct Raw { float4 a[Dim::RW]; };
   struct ProdV {
@@ -497,12 +513,13 @@ struct WsProjectT {
   using Args = WsProjectArgs;
   using Dim = Dim_;
   static constexpr uint32_t CF = 0;
-  static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
+  static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb, int& key) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const UmW& W = A.WA.s[slot];
     nK = W.nK; Nc = W.Nc;
     wb = (const char*)W.wp + (size_t)nc * W.nK * 2 * W.Nc * 128;
+    key = slot * 64 + nc;
   }
   // cv: the row constants of the chunk, one per lane, handed out by shuffles: lanes 0..7 BN2 mean of rows 0..7,
   // lanes 8..15 rstd, lanes 16 + 2 i + m the SE gate of row i for the m-th image of the tile (tiles spanning more than
@@ -649,12 +666,13 @@ struct WsDcT {
   using Args = WsDcArgs;
   using Dim = Dim_;
   static constexpr uint32_t CF = 2 * 256 * sizeof(float2);
-  static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
+  static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb, int& key) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const UmW& W = A.WA.s[slot];
     nK = W.nK; Nc = W.Nc;
     wb = (const char*)W.wp + (size_t)nc * W.nK * 2 * W.Nc * 128;
+    key = slot * 64 + nc;
   }
   // cf: lane i < RW holds (A, B, C, -) of row i
   struct Raw { float4 a[Dim::RW], b[Dim::RW]; float4 cf; };
@@ -813,11 +831,12 @@ struct WsDxT {
     ch0 = (int)((long long)A.CH.total * ks / A.ksplit);
     ch1 = (int)((long long)A.CH.total * (ks + 1) / A.ksplit);
   }
-  static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb) {
+  static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb, int& key) {
     int mt, ch0, ch1;
     part(A, Sc, item, mt, ch0, ch1);
     nK = ch1 - ch0; Nc = A.W.Nc;
     wb = (const char*)A.W.wp + (size_t)ch0 * 2 * A.W.Nc * 128;
+    key = ch0;
   }
   struct Raw { float4 a[Dim::RW], b[Dim::RW]; };
   struct ProdV {
@@ -1038,7 +1057,7 @@ bool ws_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1
   if ((long long)tiles * TFNAS_MAX_OPS * 64 >= (1 << 23)) return false;
   ws_sched_slots(P, WA, tiles, Sc, maxNc);
   WsCfg cfg;
-  if (maxNc > 256 || !ws_fit(maxNc, DimExpand::G, WsExpandT<DimExpand>::CF, 2, 4, cfg)) return false;
+  if (maxNc > 256 || !ws_fit(maxNc, DimExpand::G, WsExpandT<DimExpand>::CF, 2, 6, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
   WsExpandArgs A{P, WA, x, bn1, UH};
   ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
