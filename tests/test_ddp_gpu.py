@@ -64,12 +64,26 @@ def _worker(rank, world, port, q):
         rerun = max(float((again[n] - mine[n]).norm() / (mine[n].norm() + 1e-20)) for n in mine)
         for n, p in net.named_parameters():
             p.grad = mine.get(n)
+        # reference for the collective: gather what every rank computed for ITS shard and average
+        names = sorted(mine)
+        flat_mine = torch.cat([mine[n].reshape(-1) for n in names])
+        gathered = [torch.empty_like(flat_mine) for _ in range(world)]
+        dist.all_gather(gathered, flat_mine)
+        ref_flat = sum(gathered) / world
         nbytes = GradSync()(net.weight_parameters())
-        worst = 0.0
-        for n, p in net.named_parameters():
-            if n in per[0]:
-                ref = sum(per[s][n] for s in range(world)) / world
-                worst = max(worst, float((p.grad - ref).norm() / (ref.norm() + 1e-20)))
+        npar = dict(net.named_parameters())
+        got_flat = torch.cat([npar[n].grad.reshape(-1) for n in names])
+        worst = float((got_flat - ref_flat).norm() / (ref_flat.norm() + 1e-20))
+        # cross-rank reproducibility: the other shards recomputed HERE vs what their owners computed (atomics-order noise)
+        cross = 0.0
+        off = 0
+        for n in names:
+            k = mine[n].numel()
+            for s_ in range(world):
+                other = gathered[s_][off:off + k].view_as(mine[n])
+                cross = max(cross, float((per[s_][n] - other).norm() / (other.norm() + 1e-20)))
+            off += k
+        rerun = max(rerun, cross)
         same_keys = all(set(per[0]) == set(per[s]) for s in range(world))
         # one real optimiser step through the public loop, then compare weights across ranks
         model_search.seed_noise(3)
