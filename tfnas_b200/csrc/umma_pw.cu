@@ -627,6 +627,10 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const flo
   for (int i = threadIdx.x; i < ncol; i += UM_NT) S.cf[i] = make_float2(bn2[cst0 + i], bn2[P.MC + cst0 + i]);
   float4* cft = (float4*)S.ring;                        // [oc] BN3-backward coefficients of this slot
   for (int i = threadIdx.x; i < P.oc; i += UM_NT) cft[i] = dzc2[slot * P.oc + i];
+  // BN2-backward sums of the CTA's four lane quarters meet in shared memory first: one global fp64 atomic per column
+  // and CTA instead of four (same-address atomics serialise at ~9 ns each)
+  double* sacc = (double*)(S.ring + (((size_t)P.oc * sizeof(float4) + 15) & ~(size_t)15));
+  for (int i = threadIdx.x; i < 2 * W.Nc; i += UM_NT) sacc[i] = 0.0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   DcF f{P, W, G, Zb, G, Zb, cft, Px4(), nc, slot, lane, warp};
   px_decomp(f.px, blockIdx.x * 128 + lane * 4, P.Q, P.HWo);
@@ -742,10 +746,14 @@ __global__ void __launch_bounds__(UM_NT, 2) k_um_dc(Plan P, UmWAll WA, const flo
     } else {
       const float s1 = warp_sum16(v), s2 = warp_sum16(d);
       if (lane < 16 && col < c_hi) {
-        atomicAdd(&sD[2 * (cst0 + col)], (double)s1);
-        atomicAdd(&sD[2 * (cst0 + col) + 1], (double)s2);
+        atomicAdd(&sacc[2 * col], (double)s1);
+        atomicAdd(&sacc[2 * col + 1], (double)s2);
       }
     }
+  }
+  if (!gated) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * ncol; i += UM_NT) atomicAdd(&sD[2 * cst0 + i], sacc[i]);
   }
   um_teardown(tmem, W.Nc);
 }
@@ -1042,7 +1050,7 @@ void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, c
   if (ws_enabled(2) && ws_dc(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD, st)) return;
   int maxN, maxNc;
   um_max(P, WA, maxN, maxNc);
-  size_t smem = um_smem_bytes(maxNc, (size_t)P.oc * sizeof(float4));     // + the per-row coefficient table
+  size_t smem = um_smem_bytes(maxNc, (size_t)P.oc * sizeof(float4) + 16 + (size_t)2 * maxNc * sizeof(double));     // + coefficient table + sums
   dim3 grid(cdiv(P.Q, 128), maxN, P.na);
   ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);

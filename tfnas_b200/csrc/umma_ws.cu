@@ -52,16 +52,23 @@ struct WsSched {
   float inv_tiles;
   int first[TFNAS_MAX_OPS + 1];               // first item of each slot (items of a slot: N chunk major, tile minor)
 };
-struct WsCfg { int S, NB; uint32_t wslot, cf_bytes; };
+struct WsCfg { int S, NB; uint32_t wslot, cf_bytes, acc_bytes; };
 
 struct WsSmem {
   unsigned char *a, *w;
   uint64_t *full, *empty, *wfull, *wempty, *accfull, *accempty;
   uint32_t* tmem_slot;
   float2* cf;
+  double* acc;             // per-CTA statistic accumulators (see "statistics" below)
 };
 
-// layout: [S operand stages x (hi 16K | lo 16K)] [NB weight slots] [barriers 512 B] [cf tables]
+// layout: [S operand stages x (hi 16K | lo 16K)] [NB weight slots] [barriers 512 B] [cf tables] [statistic accumulators]
+//
+// Statistics: the BN sums these kernels produce (BN3 in project, BN2-backward in dc, BN1-backward in dx) end in fp64
+// global atomics on a handful of addresses.  Issued per tile they serialise at ~9 ns per same-address atomic (measured:
+// project at 56x56 took 1.35 ms with them, 0.43 ms without), so a persistent CTA first accumulates in shared-memory
+// doubles and flushes once per (candidate, N chunk) it visits: a few hundred global atomics per address instead of
+// tens of thousands.
 __device__ __forceinline__ void ws_carve(unsigned char* raw, const WsCfg& c, WsSmem& M) {
   unsigned char* sm = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   M.a = sm;
@@ -75,15 +82,17 @@ __device__ __forceinline__ void ws_carve(unsigned char* raw, const WsCfg& c, WsS
   M.accempty = M.accfull + 2;
   M.tmem_slot = (uint32_t*)(M.accempty + 2);
   M.cf = (float2*)(tail + 512);
+  M.acc = (double*)(tail + 512 + c.cf_bytes);
 }
 static size_t ws_smem_bytes(const WsCfg& c) {
-  return 1024 + (size_t)c.S * 32768 + (size_t)c.NB * c.wslot + 512 + c.cf_bytes;
+  return 1024 + (size_t)c.S * 32768 + (size_t)c.NB * c.wslot + 512 + c.cf_bytes + c.acc_bytes;
 }
 // deepest pipeline that fits: operand stages S = G * SM (SM <= max_sm), weight slots NB (<= max_nb)
-static bool ws_fit(int maxNc, int G, uint32_t cf_bytes, int max_sm, int max_nb, WsCfg& c) {
+static bool ws_fit(int maxNc, int G, uint32_t cf_bytes, uint32_t acc_bytes, int max_sm, int max_nb, WsCfg& c) {
   static const int nbs[] = {8, 6, 4, 3, 2};
   c.wslot = (uint32_t)2 * maxNc * 128;
   c.cf_bytes = cf_bytes;
+  c.acc_bytes = acc_bytes;
   for (int sm = max_sm; sm >= 1; --sm)
     for (int nb : nbs) {
       if (nb > max_nb) continue;
@@ -227,6 +236,7 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
     fence_barrier_init();
   }
   if (warp == D::MMA_WARP) tmem_alloc(M.tmem_slot, 512);
+  for (uint32_t i = tid; i < cfg.acc_bytes / 8; i += D::NTHR) M.acc[i] = 0.0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -235,24 +245,31 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
 
   if (warp < D::NE) {
     // ------------------------------ epilogue ------------------------------
-    int jj = 0;
+    int jj = 0, prev_item = -1, prev_key = -1;
     for (int item = item0; item < Sc.n_items; item += istep, ++jj) {
       const int ab = jj & 1;
       const uint32_t au = (uint32_t)jj >> 1;
       float2* cf = M.cf + ab * 256;
+      if (T::EPI_ACC) {                     // statistics of the previous (candidate, N chunk) go out when the key changes
+        const int key = T::epi_key(A, Sc, item);
+        if (prev_item >= 0 && key != prev_key) T::epi_flush(A, Sc, prev_item, M.acc, tid);
+        prev_item = item;
+        prev_key = key;
+      }
       T::epi_prep(A, Sc, item, cf, tid);
       if (T::CF) ws_bar_epi<D::NE * 32>();
       mbar_wait_suspend(&M.accfull[ab], au & 1, 2000);
       tc_fence_after();
-      T::epi_run(A, Sc, item, tmem + ab * WS_ACC_STRIDE, cf, warp, lane);
+      T::epi_run(A, Sc, item, tmem + ab * WS_ACC_STRIDE, cf, M.acc, warp, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&M.accempty[ab]);
     }
+    if (T::EPI_ACC && prev_item >= 0) T::epi_flush(A, Sc, prev_item, M.acc, tid);
   } else if (warp < D::NE + D::NP) {
     // ------------------------------ producers ------------------------------
     const int pw = warp - D::NE, gq = pw / D::NPG, wi = pw % D::NPG;
-    typename std::conditional<VEC, typename T::ProdV, typename T::Prod>::type f{A, wi, lane};
+    typename std::conditional<VEC, typename T::ProdV, typename T::Prod>::type f{A, wi, lane, M.acc};
     typename T::Raw raw;
     int item = item0, c = 0;
     bool valid = item < Sc.n_items;
@@ -370,6 +387,7 @@ __device__ __forceinline__ void ws_run(const typename T::Args& A, const WsSched&
   }
   tc_fence_before();
   __syncthreads();
+  T::final_flush(A, M.acc, tid);           // producer-side accumulators (dx)
   if (warp == D::MMA_WARP) tmem_dealloc(tmem, 512);
 }
 
@@ -407,6 +425,10 @@ template <class Dim_>
 struct WsExpandT {
   using Args = WsExpandArgs;
   using Dim = Dim_;
+  static constexpr bool EPI_ACC = false;
+  static __device__ __forceinline__ int epi_key(const Args&, const WsSched&, int) { return 0; }
+  static __device__ __forceinline__ void epi_flush(const Args&, const WsSched&, int, double*, int) {}
+  static __device__ __forceinline__ void final_flush(const Args&, double*, int) {}
   static constexpr uint32_t CF = 2 * 256 * sizeof(float2);
   static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb, int& key) {
     int slot, nc, mt;
@@ -418,7 +440,7 @@ struct WsExpandT {
   }
   struct Raw { float4 a[Dim::RW]; };
   struct ProdV {
-    const Args& A; int wi, lane;
+    const Args& A; int wi, lane; double* cta_acc;
     int nK; const float* xb;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int slot, nc, mt;
@@ -444,7 +466,7 @@ struct WsExpandT {
     }
   };
   struct Prod {
-    const Args& A; int wi, lane;
+    const Args& A; int wi, lane; double* cta_acc;
     int nK; Px4 px; const float* xb;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int slot, nc, mt;
@@ -477,7 +499,7 @@ struct WsExpandT {
     for (int i = etid; i < ncol; i += Dim::NE * 32) cf[i] = make_float2(A.bn1[cst0 + i], A.bn1[A.P.MC + cst0 + i]);
   }
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2* cft,
-                                                 int ew, int lane) {
+                                                 double* sacc, int ew, int lane) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const Cand& cd = A.P.c[slot];
@@ -507,11 +529,33 @@ struct WsExpandT {
 // -------------------------------------------------------------------------------------------------
 // F3: project      Z = W3 (act(BN2(D)) * gate), BN3 sums
 // -------------------------------------------------------------------------------------------------
-struct WsProjectArgs { Plan P; UmWAll WA; const float* D; const float* bn2; const float* seg; float* Zb; double* st3; };
+struct WsProjectArgs { Plan P; UmWAll WA; const float* D; const float* bn2; const float* seg; float* Zb; double* st3; int nostats; };
 template <int ACT, class Dim_>
 struct WsProjectT {
   using Args = WsProjectArgs;
   using Dim = Dim_;
+  static constexpr bool EPI_ACC = true;       // BN3 sums: shared-memory doubles [2 * Nc], flushed per (candidate, N chunk)
+  static constexpr uint32_t ACC_BYTES = 2 * 256 * sizeof(double);
+  static __device__ __forceinline__ int epi_key(const Args& A, const WsSched& Sc, int item) {
+    int slot, nc, mt;
+    ws_decode(Sc, item, slot, nc, mt);
+    return slot * 64 + nc;
+  }
+  static __device__ __forceinline__ void epi_flush(const Args& A, const WsSched& Sc, int item, double* sacc, int tid) {
+    int slot, nc, mt;
+    ws_decode(Sc, item, slot, nc, mt);
+    const int Nc = A.WA.s[slot].Nc, oc = A.P.oc;
+    const int ncol = min(Nc, oc - nc * Nc);
+    double* dst = A.st3 + 2 * (slot * oc + nc * Nc);
+    ws_bar_epi<Dim::NE * 32>();                 // every epilogue warp has added its sums of the finished tiles
+    for (int i = tid; i < 2 * ncol; i += Dim::NE * 32) {
+      const double v = sacc[i];
+      sacc[i] = 0.0;
+      atomicAdd(&dst[i], v);
+    }
+    ws_bar_epi<Dim::NE * 32>();                 // zeroed before the next key's sums arrive
+  }
+  static __device__ __forceinline__ void final_flush(const Args&, double*, int) {}
   static constexpr uint32_t CF = 0;
   static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb, int& key) {
     int slot, nc, mt;
@@ -526,7 +570,7 @@ struct WsProjectT {
   // two images read the gate from global memory)
   struct Raw { float4 a[Dim::RW]; float cv; };
   struct ProdV {
-    const Args& A; int wi, lane;
+    const Args& A; int wi, lane; double* cta_acc;
     int nK, mc, coff, soff, se, n0, img; const float* Db;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int slot, nc, mt;
@@ -568,7 +612,7 @@ struct WsProjectT {
     }
   };
   struct Prod {
-    const Args& A; int wi, lane;
+    const Args& A; int wi, lane; double* cta_acc;
     int nK, mc, coff, soff, se, n0, nimg; Px4 px; const float* Db;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int slot, nc, mt;
@@ -615,7 +659,7 @@ struct WsProjectT {
   };
   static __device__ __forceinline__ void epi_prep(const Args&, const WsSched&, int, float2*, int) {}
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2*,
-                                                 int ew, int lane) {
+                                                 double* sacc, int ew, int lane) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const int Nc = A.WA.s[slot].Nc, oc = A.P.oc;
@@ -646,9 +690,9 @@ struct WsProjectT {
       for (int j = 0; j < 16; ++j) q[j] = v[j] * v[j];
       const float s1 = warp_sum16(v), s2 = warp_sum16(q);
       const int col = c0 + (lane & 15);
-      if (lane < 16 && col < e.c_hi) {
-        atomicAdd(&A.st3[2 * (o0 + col)], (double)s1);
-        atomicAdd(&A.st3[2 * (o0 + col) + 1], (double)s2);
+      if (lane < 16 && col < e.c_hi && !A.nostats) {
+        atomicAdd(&sacc[2 * col], (double)s1);
+        atomicAdd(&sacc[2 * col + 1], (double)s2);
       }
     }
   }
@@ -665,6 +709,31 @@ template <int ACT, class Dim_>
 struct WsDcT {
   using Args = WsDcArgs;
   using Dim = Dim_;
+  static constexpr bool EPI_ACC = true;       // BN2-backward sums: shared-memory doubles [2 * Nc], flushed per (candidate, N chunk)
+  static constexpr uint32_t ACC_BYTES = 2 * 256 * sizeof(double);
+  static __device__ __forceinline__ int epi_key(const Args& A, const WsSched& Sc, int item) {
+    int slot, nc, mt;
+    ws_decode(Sc, item, slot, nc, mt);
+    return slot * 64 + nc;
+  }
+  static __device__ __forceinline__ void epi_flush(const Args& A, const WsSched& Sc, int item, double* sacc, int tid) {
+    int slot, nc, mt;
+    ws_decode(Sc, item, slot, nc, mt);
+    const Cand& cd = A.P.c[slot];
+    const int Nc = A.WA.s[slot].Nc;
+    const int ncol = min(Nc, cd.mc - nc * Nc);
+    double* dst = A.sD + 2 * (cd.coff + nc * Nc);
+    ws_bar_epi<Dim::NE * 32>();
+    if (cd.se == 0) {                            // gated candidates send their sums to dg instead
+      for (int i = tid; i < 2 * ncol; i += Dim::NE * 32) {
+        const double v = sacc[i];
+        sacc[i] = 0.0;
+        atomicAdd(&dst[i], v);
+      }
+    }
+    ws_bar_epi<Dim::NE * 32>();
+  }
+  static __device__ __forceinline__ void final_flush(const Args&, double*, int) {}
   static constexpr uint32_t CF = 2 * 256 * sizeof(float2);
   static __device__ __forceinline__ void geom(const Args& A, const WsSched& Sc, int item, int& nK, int& Nc, const char*& wb, int& key) {
     int slot, nc, mt;
@@ -679,7 +748,7 @@ struct WsDcT {
   struct Prod;
   typedef Prod ProdV;
   struct Prod {
-    const Args& A; int wi, lane;
+    const Args& A; int wi, lane; double* cta_acc;
     int nK, slot; Px4 px; const float* Gb; const float* Zbb;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int nc, mt;
@@ -720,7 +789,7 @@ struct WsDcT {
     for (int i = etid; i < ncol; i += Dim::NE * 32) cf[i] = make_float2(A.bn2[cst0 + i], A.bn2[A.P.MC + cst0 + i]);
   }
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2* cft,
-                                                 int ew, int lane) {
+                                                 double* sacc, int ew, int lane) {
     int slot, nc, mt;
     ws_decode(Sc, item, slot, nc, mt);
     const Cand& cd = A.P.c[slot];
@@ -807,8 +876,8 @@ struct WsDcT {
       } else {
         const float s1 = warp_sum16(v), s2 = warp_sum16(d);
         if (lane < 16 && col < e.c_hi) {
-          atomicAdd(&A.sD[2 * (cst0 + col)], (double)s1);
-          atomicAdd(&A.sD[2 * (cst0 + col) + 1], (double)s2);
+          atomicAdd(&sacc[2 * col], (double)s1);
+          atomicAdd(&sacc[2 * col + 1], (double)s2);
         }
       }
     }
@@ -818,11 +887,23 @@ struct WsDcT {
 // -------------------------------------------------------------------------------------------------
 // B3b: dx_main = sum_i W1_i^T (r1 * du-hat), K = stacked mid channels (per-candidate chunks of 32), split over items
 // -------------------------------------------------------------------------------------------------
-struct WsDxArgs { Plan P; UmW W; DxChunks CH; int ksplit; const float* DA; const float* UH; float* dx; double* sU; };
+struct WsDxArgs { Plan P; UmW W; DxChunks CH; int ksplit; const float* DA; const float* UH; float* dx; double* sU; int acc_rows; };
 template <int ACT, class Dim_>
 struct WsDxT {
   using Args = WsDxArgs;
   using Dim = Dim_;
+  static constexpr bool EPI_ACC = false;
+  static __device__ __forceinline__ int epi_key(const Args&, const WsSched&, int) { return 0; }
+  static __device__ __forceinline__ void epi_flush(const Args&, const WsSched&, int, double*, int) {}
+  // BN1-backward sums are produced by the PRODUCERS (one pair per mid channel and tile).  Without a K split every item
+  // covers all ΣMC rows, so the CTA accumulates them in shared-memory doubles [2 * MC] and flushes once at the end
+  // (A.acc_rows = MC when that fits, 0 = straight global atomics: the split shapes have few tiles per channel anyway).
+  static __device__ __forceinline__ void final_flush(const Args& A, double* sacc, int tid) {
+    for (int i = tid; i < 2 * A.acc_rows; i += Dim::NTHR) {
+      const double v = sacc[i];
+      if (v != 0.0) atomicAdd(&A.sU[i], v);
+    }
+  }
   static constexpr uint32_t CF = 0;
   // item = tile + tiles_m * ksplit part
   static __device__ __forceinline__ void part(const Args& A, const WsSched& Sc, int item, int& mt, int& ch0, int& ch1) {
@@ -840,7 +921,7 @@ struct WsDxT {
   }
   struct Raw { float4 a[Dim::RW], b[Dim::RW]; };
   struct ProdV {
-    const Args& A; int wi, lane;
+    const Args& A; int wi, lane; double* cta_acc;
     int nK, ch0; const float* DAb; ptrdiff_t uh_minus_da;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int mt, ch1;
@@ -892,11 +973,14 @@ struct WsDxT {
       }
       const float tot = warp_sum16(sacc);
       const int k = k0 + wi + (lane >> 1) * Dim::NPG;
-      if (lane < 2 * Dim::RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
+      if (lane < 2 * Dim::RW && k < mc) {
+        if (A.acc_rows) atomicAdd(&cta_acc[2 * (coff + k) + (lane & 1)], (double)tot);
+        else atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
+      }
     }
   };
   struct Prod {
-    const Args& A; int wi, lane;
+    const Args& A; int wi, lane; double* cta_acc;
     int nK, ch0; Px4 px; const float* DAb; const float* UHb;
     __device__ __forceinline__ void bind(const WsSched& Sc, int item) {
       int mt, ch1;
@@ -951,12 +1035,15 @@ struct WsDxT {
       static_assert(2 * Dim::RW <= 16, "statistics must fit the 16-value warp reduction");
       const float tot = warp_sum16(sacc);
       const int k = k0 + wi + (lane >> 1) * Dim::NPG;
-      if (lane < 2 * Dim::RW && k < mc) atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
+      if (lane < 2 * Dim::RW && k < mc) {
+        if (A.acc_rows) atomicAdd(&cta_acc[2 * (coff + k) + (lane & 1)], (double)tot);
+        else atomicAdd(&A.sU[2 * (coff + k) + (lane & 1)], (double)tot);
+      }
     }
   };
   static __device__ __forceinline__ void epi_prep(const Args&, const WsSched&, int, float2*, int) {}
   static __device__ __forceinline__ void epi_run(const Args& A, const WsSched& Sc, int item, uint32_t acc, const float2*,
-                                                 int ew, int lane) {
+                                                 double* sacc, int ew, int lane) {
     int mt, ch0, ch1;
     part(A, Sc, item, mt, ch0, ch1);
     const WsEpi e = ws_epi<Dim>(mt * 128, A.P.P, A.P.HW, A.W.Nc, A.P.ic, acc, ew, lane);
@@ -1057,7 +1144,7 @@ bool ws_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1
   if ((long long)tiles * TFNAS_MAX_OPS * 64 >= (1 << 23)) return false;
   ws_sched_slots(P, WA, tiles, Sc, maxNc);
   WsCfg cfg;
-  if (maxNc > 256 || !ws_fit(maxNc, DimExpand::G, WsExpandT<DimExpand>::CF, 2, 6, cfg)) return false;
+  if (maxNc > 256 || !ws_fit(maxNc, DimExpand::G, WsExpandT<DimExpand>::CF, 0, 2, 6, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
   WsExpandArgs A{P, WA, x, bn1, UH};
   ProfScope ps("expand", 4.0 * P.P * P.ic + 4.0 * P.P * P.MC + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
@@ -1075,9 +1162,10 @@ bool ws_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn
   if ((long long)tiles * TFNAS_MAX_OPS * 64 >= (1 << 23)) return false;
   ws_sched_slots(P, WA, tiles, Sc, maxNc);
   WsCfg cfg;
-  if (maxNc > 256 || !ws_fit(maxNc, DimProject::G, 0, 1, 4, cfg)) return false;
+  if (maxNc > 256 || !ws_fit(maxNc, DimProject::G, 0, 2 * 256 * sizeof(double), 1, 4, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
-  WsProjectArgs A{P, WA, D, bn2, seg, Zb, st3};
+  static const int nostats = getenv("TFNAS_DEBUG_NOSTATS") ? 1 : 0;     // timing experiment only: results are wrong
+  WsProjectArgs A{P, WA, D, bn2, seg, Zb, st3, nostats};
   ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);
   const int grid = min(Sc.n_items, sm_count());
@@ -1094,7 +1182,7 @@ bool ws_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, con
   if ((long long)tiles * TFNAS_MAX_OPS * 64 >= (1 << 23)) return false;
   ws_sched_slots(P, WA, tiles, Sc, maxNc);
   WsCfg cfg;
-  if (maxNc > 256 || !ws_fit(maxNc, DimDc::G, 2 * 256 * sizeof(float2), 2, 4, cfg)) return false;
+  if (maxNc > 256 || !ws_fit(maxNc, DimDc::G, 2 * 256 * sizeof(float2), 2 * 256 * sizeof(double), 2, 4, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
   WsDcArgs A{P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD};
   ProfScope ps("dc", 4.0 * P.Q * ((double)P.oc * (1 + P.na) + 2.0 * P.MC) + 4.0 * P.MC * P.oc,
@@ -1114,7 +1202,16 @@ bool ws_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, con
   if (tiles < 3 * sms) ksplit = max(1, min(max(1, CH.total / 4), (3 * sms) / tiles));
   if ((long long)tiles * ksplit >= (1 << 23)) return false;
   WsCfg cfg;
-  if (W.Nc > 256 || !ws_fit(W.Nc, DimDx::G, 0, 2, 4, cfg)) return false;
+  // per-CTA accumulation of the BN1-backward sums when the K axis is not split and 2 * MC doubles fit next to the pipeline
+  // (off by default: measured 5-18 % slower on B200 -- shared-memory fp64 adds are CAS loops, and with 2 * MC distinct
+  //  addresses the global atomics of this kernel do not serialise the way the BN3 / BN2-backward sums did)
+  static const bool dx_acc = getenv("TFNAS_DX_ACC") && strcmp(getenv("TFNAS_DX_ACC"), "1") == 0;
+  int acc_rows = (dx_acc && ksplit == 1 && P.MC <= 2048) ? P.MC : 0;
+  if (W.Nc > 256) return false;
+  if (!acc_rows || !ws_fit(W.Nc, DimDx::G, 0, (uint32_t)(2 * acc_rows * sizeof(double)), 2, 4, cfg) || cfg.NB < 2) {
+    acc_rows = 0;
+    if (!ws_fit(W.Nc, DimDx::G, 0, 0, 2, 4, cfg)) return false;
+  }
   WsSched Sc;
   memset(&Sc, 0, sizeof(Sc));
   Sc.tiles_m = tiles;
@@ -1123,7 +1220,7 @@ bool ws_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, con
   Sc.n_items = tiles * ksplit;
   if (ksplit > 1) cudaMemsetAsync(dx, 0, (size_t)P.P * P.ic * sizeof(float), st);
   const size_t smem = ws_smem_bytes(cfg);
-  WsDxArgs A{P, W, CH, ksplit, DA, UH, dx, sU};
+  WsDxArgs A{P, W, CH, ksplit, DA, UH, dx, sU, acc_rows};
   ProfScope ps("dx", 4.0 * P.P * (2.0 * P.MC + P.ic) + 4.0 * P.MC * P.ic, 2.0 * P.P * (double)P.MC * P.ic, st);
   const int grid = min(Sc.n_items, sms);
   const bool vec = ws_vec_ok(P.HW, P.P);
