@@ -209,13 +209,17 @@ def run_b200(args, rank, local, world, emit=print):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(from_host, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
+        h0 = time.perf_counter()
         for i in range(steps):
             unit(i, from_host)
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps     # host time to ENQUEUE a unit (no sync inside)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -235,6 +239,7 @@ def run_b200(args, rank, local, world, emit=print):
     sampler = ClockSampler(local)
     sampler.start()
     ms, launches = timed(False, args.steps)
+    host_enqueue = host_ms[0]
     sampler.stop()
     unit(0, True)                                           # warm the H2D path
     ms_e2e, _ = timed(True, args.steps)
@@ -276,7 +281,8 @@ def run_b200(args, rank, local, world, emit=print):
             'dtype': 'f32', 'data': 'synthetic', 'config': base_config(world),
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * 4,
                     'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline}
+            'gpu_launches': launches, 'host_enqueue_ms_per_step': host_enqueue, 'clocks': sampler.summary(),
+            'roofline': roofline}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_sample()
     emit(json.dumps(line))

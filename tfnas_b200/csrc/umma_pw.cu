@@ -1352,7 +1352,9 @@ void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float*
   um_tile(nb, g.Nc, g.nN);
   const int total = mode == 0 ? P.Q : P.P;
   const int mt = cdiv(cd.mc, 128);
-  int nsplit = max(1, min(cdiv(total, 1024), cdiv(3 * sm_count(), mt * g.nN)));
+  // K splits over the pixel axis: enough CTAs for ~3 per SM, each at least 256 pixels long (the 14x14 / 7x7 stages have
+  // only 25k / 6k pixels: with 1024-pixel splits a 1152-wide candidate ran on 54 CTAs)
+  int nsplit = max(1, min(cdiv(total, 256), cdiv(3 * sm_count(), mt * g.nN)));
   size_t smem = 1024 + 32768 + (size_t)2 * g.Nc * 128 + 64;
   dim3 grid(mt, g.nN, nsplit);
   const bool relu = P.act == TFNAS_ACT_RELU;

@@ -24,7 +24,7 @@ if [[ $stages == *k* ]]; then
 fi
 if [[ $stages == *l* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches.csv \
-    python bench.py --profile-only --steps 1 --warmup 1 --no-cpu-baseline > $out/launches.log 2>&1
+    python bench.py --profile-only --steps 1 --warmup ${NCU_WARMUP:-1} --no-cpu-baseline > $out/launches.log 2>&1
   echo "ncu launch list exit $?"
   python tools/summarize_ncu.py $out/launches.csv > $out/launches_summary.csv 2>> $out/launches.log
   head -30 $out/launches_summary.csv
@@ -45,7 +45,7 @@ fi
 if [[ $stages == *d* ]]; then
   # DRAM bytes per launch of the GEMM / depthwise kernels over one search unit (two metrics: a single ncu pass per kernel)
   timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $out/dram.csv \
-    -k 'regex:k_ws_|k_um_|k_dw|k_dxfin|k_b2b' python bench.py --profile-only --steps 1 --warmup 1 --no-cpu-baseline > $out/dram.log 2>&1
+    -k 'regex:k_ws_|k_um_|k_dw|k_dxfin|k_b2b' python bench.py --profile-only --steps 1 --warmup ${NCU_WARMUP:-1} --no-cpu-baseline > $out/dram.log 2>&1
   echo "ncu dram exit $?"
   python tools/ncu_traffic.py $out/dram.csv > $out/ncu_traffic.json 2>> $out/dram.log
   head -c 600 $out/ncu_traffic.json
