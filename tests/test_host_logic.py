@@ -111,3 +111,43 @@ def test_parameter_list_cache_matches_reference_filters():
     net.extra = torch.nn.Linear(2, 2)
     net.invalidate_param_cache()
     assert len(net.weight_parameters()) == 732
+
+
+def test_refresh_host_alphas_batches_and_tracks_updates():
+    """Network.refresh_host_alphas mirrors every MixedOP's log_alphas on the host in one copy, follows in-place updates
+    and `.data = ...` re-assignments (train_search.py:421-422), and gives _sample_index the values it would fetch itself."""
+    import torch
+    import torch.nn.functional as F
+    from tfnas_b200 import config, model_search
+    from tfnas_b200.model_search import MixedOP, Network
+    from tests import golden_inputs as gi
+    net = Network(10, config.get_mc_num_dddict(config.mc_mask_dddict), gi.load_lut())
+    ops = [m for m in net.modules() if isinstance(m, MixedOP)]
+    assert len(ops) == 18
+    g = torch.Generator().manual_seed(0)
+    for m in ops:
+        m.log_alphas.data = F.log_softmax(torch.randn(8, generator=g), dim=-1)
+    net.refresh_host_alphas()
+    for m in ops:
+        assert torch.equal(m._host_alpha[1], m.log_alphas.detach()) and m._host_alpha[1].dtype == torch.float32
+        assert m._alphas_on_host() is m._host_alpha[1]                     # the per-module path sees a fresh mirror
+    held = [m._host_alpha[1] for m in ops]
+    net.refresh_host_alphas()                                              # nothing stale: nothing replaced
+    assert all(a is m._host_alpha[1] for a, m in zip(held, ops))
+    with torch.no_grad():
+        ops[3].log_alphas.add_(0.25)                                       # in-place update bumps the version
+    ops[7].log_alphas.data = F.log_softmax(torch.randn(8, generator=g), dim=-1)   # re-assignment changes the storage
+    net.refresh_host_alphas()
+    for m in ops:
+        assert torch.equal(m._host_alpha[1], m.log_alphas.detach())
+    # same sampled indices as the lazy per-module mirrors
+    model_search.seed_noise(5)
+    a = [m._sample_index('gumbel') for m in ops]
+    net.reset_switches()
+    for m in ops:
+        m._host_alpha = None
+    model_search.seed_noise(5)
+    b = [m._sample_index('gumbel') for m in ops]
+    net.reset_switches()
+    model_search.seed_noise(None)
+    assert a == b

@@ -347,6 +347,8 @@ class Network(nn.Module):
 
     def forward(self, x, sampling, mode='max'):
         out_lat = self.lat_lookup['base'] if not sampling else 0.0
+        if sampling and mode in ('gumbel', 'gumbel_2', 'min_alphas', 'max_alphas'):
+            self.refresh_host_alphas()         # one device->host copy for all 18 MixedOPs instead of one each
         # stems / head run on cuDNN; keep them in true fp32 so the 1e-3 parity bar holds
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             x = self.first_stem(x)
@@ -365,6 +367,27 @@ class Network(nn.Module):
         for m in self.modules():
             if isinstance(m, MixedOP):
                 m.set_temperature(T)
+
+    def refresh_host_alphas(self):
+        """Bring the host mirrors of every MixedOP's log_alphas up to date with ONE device->host copy.
+
+        The 'gumbel' index is drawn on the host (MixedOP._sample_index), so after an alpha update every MixedOP needs its
+        new log_alphas on the host.  Fetched lazily per MixedOP that is 18 synchronising copies per pass, each of which
+        drains the stream (57 ms of a 124 ms search unit in profiles/host_profile_r1.txt); stacked, it is one."""
+        stale = []
+        for m in self._param_lists()[4]:
+            h = m._host_alpha
+            if h is None or h[0] != m.log_alphas._version or h[2] != m.log_alphas.data_ptr():
+                stale.append(m)
+        if not stale:
+            return
+        if len(set(m.log_alphas.numel() for m in stale)) == 1 and len(set(m.log_alphas.device for m in stale)) == 1:
+            flat = torch.stack([m.log_alphas.detach().float().reshape(-1) for m in stale]).cpu()
+            for m, row in zip(stale, flat):
+                m._host_alpha = (m.log_alphas._version, row.clone(), m.log_alphas.data_ptr())
+        else:                                   # mixed widths / devices: per-module copies
+            for m in stale:
+                m._alphas_on_host()
 
     # The reference filters named_parameters() by suffix on every call (models/model_search.py:306-350); walking the
     # 1282-module tree costs ~2.7 ms of host time and the search loop asks a dozen times per step, so the four lists are
