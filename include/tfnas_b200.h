@@ -143,6 +143,12 @@ int tfnas_dwconv_fwd(int N, int C, int H, int W, int K, int stride, const float*
 int tfnas_dwconv_bwd(int N, int C, int H, int W, int K, int stride, const float* x, const float* w, const float* dy,
                      float* dx, float* dw, void* stream);
 
+/* Test helper (host only): pipeline configuration of the persistent tcgen05 GEMM `which` (0 expand, 1 project, 2 dc,
+ * 3 dx; tfnas_b200/csrc/umma_ws.cu) for an N chunk of max_nc columns:
+ * out5 = {operand stages, weight slots, dynamic shared-memory bytes, producer groups, threads per CTA}.
+ * TFNAS_E_UNSUPPORTED: nothing fits, the call would use the per-tile kernel. */
+int tfnas_debug_ws_config(int which, int max_nc, uint32_t* out5);
+
 /* Test helper: byte offsets of the backward workspace regions
  * {sG, sGY, sD, sU, cvec2, Mm, dg, DC, DA, total} (10 entries). */
 int tfnas_debug_bwd_layout(const TfnasMixedOpDesc* d, uint32_t cand_mask, int want_wgrad, size_t* out10);

@@ -62,3 +62,25 @@ def test_sizes_and_validation_without_gpu():
     assert rc == -1
     with pytest.raises(_lib.TfnasError):
         _lib.check(rc)
+
+
+def test_persistent_gemm_configs_fit_the_sm():
+    """Host-side check of the pipeline configurations the persistent tcgen05 GEMMs pick (umma_ws.cu::ws_fit) for every N
+    chunk width the supernet produces and for the extremes: at most 227 KB of shared memory, operand stages a multiple of
+    the producer groups, at least two weight slots up to 176 columns, at most 1024 threads."""
+    import ctypes
+    from tfnas_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_uint32 * 5)()
+    widths = sorted(set([16, 32, 48, 80, 112, 128, 144, 160, 176, 192, 208, 256]))
+    for which in range(4):
+        for nc in widths:
+            rc = lib.tfnas_debug_ws_config(which, nc, out)
+            if rc != 0:
+                assert nc > 192, (which, nc)          # only chunks wider than any prep cap may be refused
+                continue
+            S, NB, smem, G, nthr = list(out)
+            assert smem <= 232448 and S >= G and S % G == 0 and S <= 8 and 1 <= NB <= 8 and nthr <= 1024, (which, nc, list(out))
+            if nc <= 176:        # (project at 192 columns runs with a single weight slot: 4 stages + 48 KB slots + sums)
+                assert NB >= 2, (which, nc, list(out))
+    assert lib.tfnas_debug_ws_config(7, 32, out) != 0 and lib.tfnas_debug_ws_config(1, 24, out) != 0

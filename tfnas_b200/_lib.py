@@ -41,7 +41,7 @@ EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
            'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout', 'tfnas_debug_bwd_layout',
            'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd',
-           'tfnas_dwconv_fwd', 'tfnas_dwconv_bwd']
+           'tfnas_dwconv_fwd', 'tfnas_dwconv_bwd', 'tfnas_debug_ws_config']
 
 _lib = None
 
@@ -80,6 +80,8 @@ def load():
                                          vp, sz, vp]
     lib.tfnas_debug_saved_layout.restype = i32
     lib.tfnas_debug_saved_layout.argtypes = [dp, u32, ctypes.POINTER(sz)]
+    lib.tfnas_debug_ws_config.restype = i32
+    lib.tfnas_debug_ws_config.argtypes = [i32, i32, ctypes.POINTER(u32)]
     lib.tfnas_debug_bwd_layout.restype = i32
     lib.tfnas_debug_bwd_layout.argtypes = [dp, u32, i32, ctypes.POINTER(sz)]
     lib.tfnas_bn_act_fwd.restype = i32

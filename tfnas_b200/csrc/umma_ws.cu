@@ -1235,3 +1235,24 @@ extern "C" int tfnas_debug_ws_trace(void* buf, int n_ctas) {
   if (cudaMemcpyToSymbol(g_ws_trace_n, &n_ctas, sizeof(n_ctas)) != cudaSuccess) return TFNAS_E_CUDA;
   return TFNAS_OK;
 }
+
+// test helper (host only, no device needed): the pipeline configuration the persistent kernel `which` (0 expand, 1 project,
+// 2 dc, 3 dx) would run an N chunk of `max_nc` columns with -> out5 = {operand stages S, weight slots NB, dynamic shared
+// memory bytes, producer groups G, threads per CTA}; returns TFNAS_E_UNSUPPORTED when nothing fits (the caller would fall
+// back to the per-tile kernels)
+extern "C" int tfnas_debug_ws_config(int which, int max_nc, uint32_t* out5) {
+  if (!out5 || max_nc < 16 || (max_nc & 15)) return TFNAS_E_INVALID;
+  WsCfg c;
+  bool ok = false;
+  int G = 0, nthr = 0;
+  switch (which) {
+    case 0: G = DimExpand::G; nthr = DimExpand::NTHR; ok = ws_fit(max_nc, G, WsExpandT<DimExpand>::CF, 0, 2, 6, c); break;
+    case 1: G = DimProject::G; nthr = DimProject::NTHR; ok = ws_fit(max_nc, G, 0, 2 * 256 * sizeof(double), 1, 4, c); break;
+    case 2: G = DimDc::G; nthr = DimDc::NTHR; ok = ws_fit(max_nc, G, 2 * 256 * sizeof(float2), 2 * 256 * sizeof(double), 2, 4, c); break;
+    case 3: G = DimDx::G; nthr = DimDx::NTHR; ok = ws_fit(max_nc, G, 0, 0, 2, 4, c); break;
+    default: return TFNAS_E_INVALID;
+  }
+  if (!ok || max_nc > 256) return TFNAS_E_UNSUPPORTED;
+  out5[0] = (uint32_t)c.S; out5[1] = (uint32_t)c.NB; out5[2] = (uint32_t)ws_smem_bytes(c); out5[3] = (uint32_t)G; out5[4] = (uint32_t)nthr;
+  return TFNAS_OK;
+}
