@@ -25,12 +25,6 @@ def test_fullsize_parity_and_properties(ic, oc, s, act, size):
     _fullsize(ic, oc, s, act, size, H.default_mcs(ic))
 
 
-def test_fullsize_ragged_widths():
-    """Widths after the elastic search are arbitrary integers (train_search.py:293-305): odd mid widths at BASELINE size
-    go through the straight-line (VEC) producers with clamped row indices and unaligned channel offsets."""
-    _fullsize(40, 40, 1, 'swish', 28, H.default_mcs(40, ragged=True))
-
-
 def _fullsize(ic, oc, s, act, size, mcs):
     N = 128
     P, x, gum, lats = H.make_problem(ic, oc, s, size, N, mcs, seed=size)
