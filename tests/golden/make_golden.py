@@ -6,7 +6,8 @@ Runs only in the build container.  Outputs (committed):
   lut_gpu.npz            the latency LUT (reference latency_pkl/latency_gpu.pkl) as flat arrays
   mixedop_cfg1.npz       BASELINE config 1: stage2.block1 MixedOP, bs=2, 32x32, alpha mode fwd+bwd
   network_alpha.npz      full supernet alpha-step (bs=2, 224x224): logits, lat, alpha/beta grads
-  network_wstep.npz      bi-sampled w-step (gumbel + random path): logits, indices, grad norms
+  network_wstep.npz      bi-sampled w-step (gumbel + random path): logits, indices, grad norms and four seeded random
+                         projections of every live weight gradient
 Inputs are regenerated in the tests from the recorded seeds with the same seeded generators.
 """
 import os
@@ -97,8 +98,12 @@ def network_steps(lut):
     wn = [n for n, _ in net.named_parameters() if not (n.endswith('log_alphas') or n.endswith('betas'))]
     gnorm = np.array([float(npar[n].grad.norm()) if npar[n].grad is not None else -1.0 for n in wn], dtype=np.float64)
     sel = ['first_stem.conv.weight', 'classifier.linear.weight']
+    # element-level pin of EVERY live gradient without committing 35 MB: four seeded random projections per tensor
+    # (a permuted, transposed or sign-flipped dW changes them by O(|g|))
+    gproj = np.stack([gi.grad_projections(npar[n].grad, j) if npar[n].grad is not None else np.zeros(gi.NPROJ)
+                      for j, n in enumerate(wn)])
     np.savez_compressed(os.path.join(HERE, 'network_wstep.npz'), logits_g=lg.detach().numpy(), logits_r=lr.detach().numpy(),
-                        idx_g=np.array(idx_g), loss=np.float32(loss_w.item()), gnorm=gnorm, wnames=np.array(wn),
+                        idx_g=np.array(idx_g), loss=np.float32(loss_w.item()), gnorm=gnorm, gproj=gproj, wnames=np.array(wn),
                         g_first_stem=npar[sel[0]].grad.numpy(), g_classifier=npar[sel[1]].grad.numpy())
     print('w step loss', float(loss_w), 'live grads', int((gnorm >= 0).sum()))
 

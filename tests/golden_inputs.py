@@ -54,3 +54,13 @@ def network_inputs():
     x = torch.randn(NET['N'], 3, NET['size'], NET['size'], generator=g)
     tgt = torch.randint(0, 100, (NET['N'],), generator=g)
     return P, x, tgt
+
+
+NPROJ = 4
+
+
+def grad_projections(g, j):
+    """<g, r_k> for NPROJ seeded N(0,1) tensors r_k (seed derived from the tensor's index j in the weight list); fp64."""
+    gen = torch.Generator().manual_seed(100003 + int(j))
+    r = torch.randn(NPROJ, g.numel(), generator=gen, dtype=torch.float64)
+    return (r @ g.detach().double().cpu().reshape(-1)).numpy()

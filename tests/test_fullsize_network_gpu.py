@@ -1,0 +1,109 @@
+"""Full supernet at BASELINE size (bs 128, 3x224x224; configs 2 and 3): the drop-in Network on the CUDA kernels against
+the oracle port evaluated ON THE SAME GPU in fp32 (cuDNN / cuBLAS with TF32 off) -- alpha-step logits, latency, every
+d(log alpha) and d(beta); bi-sampled w-step logits and EVERY live weight gradient element-wise.  Covers all 18 MixedOPs at
+full size, including the stride-2 swish shapes (24->40 @56, 40->80 @28, 112->192 @14) that no single-MixedOP test reaches."""
+import random
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import port
+from tests import golden_inputs as gi
+from tests import helpers as H
+from tfnas_b200 import config
+from tfnas_b200.model_search import MixedOP, Network, NoisePlan, injected
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+BS = 128
+
+
+def _setup(seed):
+    mcs = config.get_mc_num_dddict(config.mc_mask_dddict)
+    lut = gi.load_lut()
+    P, _x, _t = gi.network_inputs()                       # seed-2 init, perturbed log_alphas / betas
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(BS, 3, 224, 224, generator=g)
+    tgt = torch.randint(0, 100, (BS,), generator=g)
+    noise = [port.draw_gumbel(generator=g) for _ in range(18)]
+    net = Network(100, mcs, lut)
+    net.load_state_dict(P)
+    net.set_temperature(5.0)
+    return mcs, lut, P, x.cuda(), tgt.cuda(), noise, net.cuda().train()
+
+
+def test_alpha_step_bs128_matches_port_on_gpu():
+    assert not torch.backends.cudnn.allow_tf32 and not torch.backends.cuda.matmul.allow_tf32
+    mcs, lut, P, x, tgt, noise, net = _setup(31)
+    # --- oracle on the GPU --------------------------------------------------------------------------------------------
+    Pg = {k: v.cuda().requires_grad_(port.is_arch_key(k)) for k, v in P.items()}
+    lo, lat = port.network_forward(x, Pg, mcs, lut, False, 5.0, noise=[n.cuda() for n in noise])
+    loss, _, _ = port.arch_loss(lo, lat, tgt, 15.0, 0.1)
+    loss.backward()
+    ref = dict(logits=lo.detach().cpu(), lat=float(lat), loss=float(loss),
+               da=torch.stack([Pg[k].grad for k in Pg if k.endswith('log_alphas')]).cpu(),
+               db=torch.cat([Pg[k].grad for k in Pg if k.endswith('betas')]).cpu())
+    del Pg, lo, lat, loss
+    torch.cuda.empty_cache()
+    # --- CUDA path ----------------------------------------------------------------------------------------------------
+    for p in net.weight_parameters():
+        p.requires_grad_(False)
+    with injected(NoisePlan(noise=noise)):
+        logits, lat = net(x, sampling=False)
+    loss = F.cross_entropy(logits, tgt) + torch.abs(lat / 15.0 - 1.) * 0.1
+    loss.backward()
+    npar = dict(net.named_parameters())
+    da = torch.stack([npar[k].grad for k in npar if k.endswith('log_alphas')])
+    db = torch.cat([npar[k].grad for k in npar if k.endswith('betas')])
+    e = dict(logits=H.rel_l2(logits, ref['logits']), logits_max=H.rel_max(logits, ref['logits']),
+             lat=abs(float(lat) - ref['lat']), loss=abs(float(loss) - ref['loss']),
+             dalpha=H.rel_l2(da, ref['da']), dalpha_max=H.rel_max(da, ref['da']), dbeta=H.rel_l2(db, ref['db']))
+    print('bs128 alpha-step vs port on GPU', e)
+    assert e['logits'] < TOL and e['logits_max'] < TOL and e['lat'] < 1e-4 and e['loss'] < 1e-4
+    assert e['dalpha'] < TOL and e['dalpha_max'] < TOL and e['dbeta'] < TOL
+
+
+def test_bisampled_wstep_bs128_matches_port_on_gpu():
+    mcs, lut, P, x, tgt, noise, net = _setup(32)
+    for p in net.arch_parameters():
+        p.requires_grad_(False)
+    random.seed(9)
+    sampled = []
+    orig = MixedOP._sample_index
+
+    def spy(self, mode):
+        i = orig(self, mode)
+        sampled.append(i)
+        return i
+    MixedOP._sample_index = spy
+    try:
+        with injected(NoisePlan(noise=noise)):
+            lg, _ = net(x, sampling=True, mode='gumbel')
+        lr, _ = net(x, sampling=True, mode='random')
+    finally:
+        MixedOP._sample_index = orig
+    idx_g, idx_r = sampled[:18], sampled[18:]
+    assert all(a != b for a, b in zip(idx_g, idx_r))         # the random path excludes the gumbel path's candidates
+    (F.cross_entropy(lg, tgt) + F.cross_entropy(lr, tgt)).backward()
+    got = {k: p.grad.detach().cpu() for k, p in net.named_parameters() if p.grad is not None}
+    lg, lr = lg.detach().cpu(), lr.detach().cpu()
+    del net
+    torch.cuda.empty_cache()
+    Pg = {k: v.cuda().requires_grad_(not port.is_arch_key(k)) for k, v in P.items()}
+    rg, _ = port.network_forward(x, Pg, mcs, lut, True, indices=idx_g)
+    rr, _ = port.network_forward(x, Pg, mcs, lut, True, indices=idx_r)
+    (F.cross_entropy(rg, tgt) + F.cross_entropy(rr, tgt)).backward()
+    ref = {k: v.grad.cpu() for k, v in Pg.items() if v.grad is not None}
+    assert set(ref) == set(got)
+    assert H.rel_l2(lg, rg) < TOL and H.rel_l2(lr, rr) < TOL
+    gmax = max(float(v.norm()) for v in ref.values())
+    worst, worst_name = 0.0, None
+    for k, v in ref.items():
+        # tensors whose whole gradient is below fp32 noise of the step (e.g. a bias feeding a BatchNorm) are compared
+        # on the scale of the largest gradient instead of their own norm
+        e = float((got[k].double() - v.double()).norm() / max(float(v.double().norm()), 1e-6 * gmax))
+        if e > worst:
+            worst, worst_name = e, k
+    print('bs128 bi-sampled w-step: %d live tensors, worst element-wise rel-l2 %.2e (%s)' % (len(ref), worst, worst_name))
+    assert worst < TOL

@@ -83,12 +83,14 @@ def test_network_wstep_matches_golden():
     (F.cross_entropy(lg, tgt) + F.cross_entropy(lr, tgt)).backward()
     assert H.rel_max(lg.detach(), torch.from_numpy(z['logits_g'])) < TOL
     assert H.rel_max(lr.detach(), torch.from_numpy(z['logits_r'])) < TOL
-    for n, gn in zip(z['wnames'], z['gnorm']):
+    for j, (n, gn) in enumerate(zip(z['wnames'], z['gnorm'])):
         g = Pg[str(n)].grad
         if gn < 0:
             assert g is None or float(g.abs().max()) == 0.0
         else:
             assert abs(float(g.norm()) - gn) <= 1e-3 * gn + 1e-7, n
+            # element-level pin: seeded random projections of the reference's gradient (scale of <g, r> is |g|)
+            assert np.abs(gi.grad_projections(g, j) - z['gproj'][j]).max() <= 1e-4 * gn + 1e-9, n
     assert H.rel_max(Pg['first_stem.conv.weight'].grad, torch.from_numpy(z['g_first_stem'])) < 1e-3
 
 

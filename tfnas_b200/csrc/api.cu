@@ -187,6 +187,9 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
   return o;
 }
 
+// the float4 / bulk-copy paths of the kernels assume what the header states: 16-byte aligned boundary tensors
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
 static int check_cuda(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TFNAS_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -225,6 +228,8 @@ int tfnas_mixedop_fwd(const TfnasMixedOpDesc* d, uint32_t cand_mask, const float
   int rc = build_plan(d, cand_mask, weights, P);
   if (rc != TFNAS_OK) return rc;
   if (!x || !out || !saved || !workspace) return fail(TFNAS_E_INVALID, "null tensor pointer");
+  if (!aligned16(x) || !aligned16(out) || !aligned16(saved) || !aligned16(workspace))
+    return fail(TFNAS_E_INVALID, "x / out / saved / workspace must be 16-byte aligned");
   const uint32_t full = (1u << d->num_ops) - 1u;
   const int alpha_mode = (cand_mask & full) == full && d->num_ops > 1 ? 1 : 0;
   if (alpha_mode) {
@@ -253,6 +258,8 @@ int tfnas_mixedop_bwd(const TfnasMixedOpDesc* d, uint32_t cand_mask, const float
   int rc = build_plan(d, cand_mask, weights, P);
   if (rc != TFNAS_OK) return rc;
   if (!x || !dout || !saved || !workspace) return fail(TFNAS_E_INVALID, "null tensor pointer");
+  if (!aligned16(x) || !aligned16(dout) || !aligned16(dx) || !aligned16(saved) || !aligned16(workspace))
+    return fail(TFNAS_E_INVALID, "x / dout / dx / saved / workspace must be 16-byte aligned");
   if (!dx && dweights) return fail(TFNAS_E_INVALID, "weight gradients need dx");
   const uint32_t full = (1u << d->num_ops) - 1u;
   const int alpha_mode = (cand_mask & full) == full && d->num_ops > 1 ? 1 : 0;
@@ -389,6 +396,9 @@ int tfnas_stage_sink_fwd(int K, size_t numel, const float* const* res, const flo
                          float* out, float* out_lat, void* stream) {
   if (K < 1 || K > 4) return fail(TFNAS_E_INVALID, "sink K=%d not in 1..4", K);
   if (!res || !betas || !out) return fail(TFNAS_E_INVALID, "null pointer");
+  if (!aligned16(out)) return fail(TFNAS_E_INVALID, "sink: out must be 16-byte aligned");
+  for (int j = 0; j < K; ++j)
+    if (!res[j] || !aligned16(res[j])) return fail(TFNAS_E_INVALID, "sink: res[%d] null or not 16-byte aligned", j);
   cudaGetLastError();
   launch_sink_fwd(K, numel, res, betas, cumlat, out, out_lat, (cudaStream_t)stream);
   return check_cuda("tfnas_stage_sink_fwd");

@@ -1164,7 +1164,11 @@ bool ws_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn
   WsCfg cfg;
   if (maxNc > 256 || !ws_fit(maxNc, DimProject::G, 0, 2 * 256 * sizeof(double), 1, 4, cfg)) return false;
   const size_t smem = ws_smem_bytes(cfg);
+#ifdef UM_TRACE      // debug (trace) build only: the product library has no switch that changes results
   static const int nostats = getenv("TFNAS_DEBUG_NOSTATS") ? 1 : 0;     // timing experiment only: results are wrong
+#else
+  const int nostats = 0;
+#endif
   WsProjectArgs A{P, WA, D, bn2, seg, Zb, st3, nostats};
   ProfScope ps("project", 4.0 * P.Q * ((double)P.MC + (double)P.na * P.oc) + 4.0 * P.MC * P.oc,
                2.0 * P.Q * (double)P.MC * P.oc, st);

@@ -104,6 +104,9 @@ class MixedOpFn(torch.autograd.Function):
         lib = _lib.load()
         call = ctx.call
         d = call.desc
+        if ctx.saved_buf is None:
+            raise _lib.TfnasError('MixedOP backward ran twice: the buffers kept from forward are released after the '
+                                  'first backward (retain_graph / double backward are not supported)')
         x = ctx.saved_tensors[0]
         weights = ctx.saved_tensors[1:]
         need_dx = ctx.needs_input_grad[0]

@@ -28,7 +28,17 @@ class DeviceMeter(object):
 
     @property
     def avg(self):
-        return float(self.sum) / max(self.cnt, 1) if self.sum is not None else 0.0
+        """Mean over everything seen so far, over ALL ranks when torch.distributed is initialised (every rank reads its
+        meters at the same steps, so the all-reduce is collective-safe)."""
+        if self.sum is None:
+            return 0.0
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            t = torch.stack([self.sum.reshape(()).double(), torch.tensor(float(self.cnt), dtype=torch.float64,
+                                                                         device=self.sum.device)])
+            dist.all_reduce(t)
+            return float(t[0]) / max(float(t[1]), 1.0)
+        return float(self.sum) / max(self.cnt, 1)
 
 
 def accuracy(output, target, topk=(1,)):

@@ -109,6 +109,10 @@ def make_queues(args, rank, world):
 def main(argv=None):
     args = build_parser().parse_args(argv)
     rank, local, world = parallel.init_from_env()
+    # the kernels index pixels (N*H*W of the 112x112 first-stem plane at 224x224) with 23-bit fast division
+    if args.batch_size * ((args.image_size + 1) // 2) ** 2 >= 1 << 23:
+        raise SystemExit('--batch_size %d too large for one GPU at image size %d: N*H*W of the first-stem plane must stay '
+                         'below 2^23 pixels (bs <= 668 at 224x224); use more ranks' % (args.batch_size, args.image_size))
     if not torch.cuda.is_available():
         logging.info('No GPU device available')
         sys.exit(1)
@@ -156,6 +160,10 @@ def main(argv=None):
         optimizer_w, optimizer_a = search_loop.make_optimizers(net, lr_list[epoch], args.w_mom, args.w_wd, args.a_lr,
                                                                 args.a_beta1, args.a_beta2, args.a_wd)
         logging.info('Epoch: %d lr: %e T: %e', epoch, lr_list[epoch], args.T)
+        for q in (train_queue, val_queue):      # distributed samplers reshuffle / repartition per epoch
+            smp = getattr(q, 'sampler', None)
+            if smp is not None and hasattr(smp, 'set_epoch'):
+                smp.set_epoch(epoch)
         t0 = time.time()
         if epoch < args.warm_epochs:
             train_acc = search_loop.train_wo_arch(train_queue, model, criterion, optimizer_w, args, sync)
