@@ -179,7 +179,8 @@ def run_b200(args, rank, local, world, emit=print):
     net = Network(100, mcs, lut)
     net.set_temperature(5.0)
     model = SearchParallel(net).to(dev).train()
-    criterion = nn.CrossEntropyLoss().to(dev)
+    from tfnas_b200.step import FusedCrossEntropy
+    criterion = FusedCrossEntropy().to(dev)
     opt_w, opt_a = make_optimizers(net)
     sync = GradSync()
     g = torch.Generator().manual_seed(2 + rank)

@@ -176,6 +176,89 @@ int tfnas_prof_collect(TfnasProfEntry* out, int max_entries);
 int tfnas_umma_selftest(int M, int N, int K, const float* A, const float* B, float* C, float* wp_scratch,
                         size_t wp_bytes, int variant, void* stream);
 
+
+/* =====================================================================================================================
+ * Supernet body: the six MixedStages of Network.forward (reference models/model_search.py:291-296; per stage
+ * MixedStage.forward :157-206) executed in ONE call per direction over one caller-provided arena -- the MixedOPs in
+ * forward order, each stage closed by its sink-connecting sum (start_res == 1: the sink sums the outputs of all blocks
+ * of the stage, as for every stage of the reference Network).  Replaces the per-MixedOP / per-sink calls above when the
+ * whole body runs (same kernels, same arithmetic); the launch sequence depends only on (descriptor, masks, pointers), so a
+ * call can be captured in a CUDA graph.
+ * ===================================================================================================================== */
+#define TFNAS_MAX_BLOCKS 32
+#define TFNAS_MAX_STAGES 8
+typedef struct TfnasBodyDesc {
+  int32_t num_stages;                      /* <= TFNAS_MAX_STAGES */
+  int32_t num_blocks;                      /* total MixedOPs = sum(stage_blocks) <= TFNAS_MAX_BLOCKS */
+  int32_t stage_blocks[TFNAS_MAX_STAGES];  /* MixedOPs per stage, 1..4 */
+  TfnasMixedOpDesc op[TFNAS_MAX_BLOCKS];   /* in forward order; op[i+1] input shape == op[i] output shape */
+} TfnasBodyDesc;
+
+/* Bytes of the arena for one forward(+backward) pass with these candidate masks (0 on an invalid descriptor).  The
+ * arena keeps every MixedOP's output and saved buffer from forward to backward; size it with the want_wgrad the backward
+ * will use.  256-byte aligned device memory. */
+size_t tfnas_body_arena_bytes(const TfnasBodyDesc* d, const uint32_t* cand_masks, int want_wgrad);
+
+/*
+ * Forward.  cand_masks[i]: all candidates (alpha mode) or one-hot (sampled) per MixedOP, as for tfnas_mixedop_fwd.
+ * weights: host array [num_blocks][TFNAS_MAX_OPS]; log_alphas: host array of num_blocks device pointers (alpha mode);
+ * betas: host array of num_stages device pointers; gumbel, lat: device [num_blocks][TFNAS_MAX_OPS] (alpha mode).
+ * out: [N, oc_last, Ho, Wo]; out_lat: device scalar = sum over stages of sum_j softmax(betas)_j * cumlat_j (the caller
+ * adds lut['base'], models/model_search.py:282), may be NULL when no MixedOP is in alpha mode.
+ */
+int tfnas_body_fwd(const TfnasBodyDesc* d, const uint32_t* cand_masks, const float* x, const TfnasCandPtrs* weights,
+                   const float* const* log_alphas, const float* const* betas, const float* gumbel, const float* lat,
+                   float T, float* out, float* out_lat, void* arena, size_t arena_bytes, void* stream);
+/*
+ * Backward of the same pass (same descriptor, masks, x, weights, betas, arena).
+ * dout: dL/dout; dlat: device scalar dL/dout_lat or NULL.  dx: dL/dx or NULL
+ * (then the first MixedOP only produces its d log_alpha).  dlog_alphas: host array of num_blocks device pointers [num_ops]
+ * or NULL; dbetas: host array of num_stages device pointers or NULL; dweights: host array [num_blocks][TFNAS_MAX_OPS] of
+ * the active candidates' gradient tensors (written, not accumulated) or NULL.
+ */
+int tfnas_body_bwd(const TfnasBodyDesc* d, const uint32_t* cand_masks, const float* x, const TfnasCandPtrs* weights,
+                   const float* const* betas, const float* dout, const float* dlat, float T, float* dx,
+                   float* const* dlog_alphas, float* const* dbetas, const TfnasCandPtrs* dweights, void* arena,
+                   size_t arena_bytes, void* stream);
+
+/* =====================================================================================================================
+ * Step glue of train_w_arch (reference train_search.py:381-385 and :414-422): global-norm gradient clipping fused with
+ * the optimiser update over a table of the LIVE tensors (parameters whose gradient exists this step -- the reference's
+ * torch.optim skips tensors with grad None), and the loss of train_search.py:121.
+ * ===================================================================================================================== */
+typedef struct TfnasSgdTensor {
+  float* p;        /* parameter (updated in place) */
+  float* g;        /* gradient (scaled in place by grad_scale * clip coefficient, like clip_grad_norm_) */
+  float* buf;      /* momentum buffer (zero-initialised by the caller the first time the tensor is live) */
+  int64_t numel;
+} TfnasSgdTensor;
+/*
+ * nn.utils.clip_grad_norm_(max_norm) + torch.optim.SGD(momentum, weight_decay, dampening 0, no nesterov):
+ *   g *= grad_scale (1/world after a SUM all-reduce); coef = min(1, max_norm / (||g||_2 + 1e-6)) (max_norm <= 0: no clip);
+ *   d = coef*g + wd*p; buf = momentum*buf + d; p -= lr*buf.
+ * t: host array of n entries.  workspace: >= 16 bytes of device memory.  total_norm_out: device float or NULL.
+ */
+int tfnas_sgd_step(int n, const TfnasSgdTensor* t, float lr, float momentum, float weight_decay, float max_norm,
+                   float grad_scale, float* total_norm_out, void* workspace, size_t ws_bytes, void* stream);
+
+typedef struct TfnasAdamTensor {
+  float* p; float* g; float* m; float* v;   /* parameter, gradient, exp_avg, exp_avg_sq (zero-initialised) */
+  int32_t numel;                            /* <= 64 (architecture parameters: 8 log_alphas / <= 4 betas per tensor) */
+  int32_t renorm;                           /* 1: p = log_softmax(p) after the update (train_search.py:421-422) */
+} TfnasAdamTensor;
+/*
+ * clip_grad_norm_ + torch.optim.Adam(betas, eps, weight_decay; not amsgrad) + the log_softmax renormalisation of every
+ * architecture parameter, in one launch.  n <= 64 tensors.  step: 1-based update count (bias correction).
+ */
+int tfnas_adam_step(int n, const TfnasAdamTensor* t, int step, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float max_norm, float grad_scale, void* stream);
+
+/*
+ * nn.CrossEntropyLoss (mean reduction) forward + gradient in one launch: loss = mean_i (logsumexp(logits_i) -
+ * logits_i[target_i]); dlogits = (softmax(logits) - onehot(target)) / N.  logits, dlogits: [N, C] fp32; targets: int64.
+ */
+int tfnas_softmax_ce(int N, int C, const float* logits, const int64_t* targets, float* loss, float* dlogits, void* stream);
+
 /* Number of kernel launches issued through this library since load (bench "gpu_launches"). */
 uint64_t tfnas_launch_count(void);
 

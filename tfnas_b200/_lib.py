@@ -35,13 +35,36 @@ class ProfEntry(ctypes.Structure):
                 ('flops', ctypes.c_double), ('launches', ctypes.c_int64)]
 
 
+MAX_BLOCKS, MAX_STAGES = 32, 8
+
+
+class BodyDesc(ctypes.Structure):
+    _fields_ = [('num_stages', ctypes.c_int32), ('num_blocks', ctypes.c_int32),
+                ('stage_blocks', ctypes.c_int32 * MAX_STAGES), ('op', MixedOpDesc * MAX_BLOCKS)]
+
+
+class SgdTensor(ctypes.Structure):
+    _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('buf', ctypes.c_void_p), ('numel', ctypes.c_int64)]
+
+
+class AdamTensor(ctypes.Structure):
+    _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p),
+                ('numel', ctypes.c_int32), ('renorm', ctypes.c_int32)]
+
+
 CandArray = CandPtrs * MAX_OPS
+BodyCandArray = CandPtrs * (MAX_OPS * MAX_BLOCKS)
+BodyMasks = ctypes.c_uint32 * MAX_BLOCKS
+BlockPtrs = ctypes.c_void_p * MAX_BLOCKS
+StagePtrs = ctypes.c_void_p * MAX_STAGES
 EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
            'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout', 'tfnas_debug_bwd_layout',
            'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd',
-           'tfnas_dwconv_fwd', 'tfnas_dwconv_bwd', 'tfnas_debug_ws_config']
+           'tfnas_dwconv_fwd', 'tfnas_dwconv_bwd', 'tfnas_debug_ws_config',
+           'tfnas_body_arena_bytes', 'tfnas_body_fwd', 'tfnas_body_bwd',
+           'tfnas_sgd_step', 'tfnas_adam_step', 'tfnas_softmax_ce']
 
 _lib = None
 
@@ -98,6 +121,21 @@ def load():
     lib.tfnas_prof_collect.argtypes = [ctypes.POINTER(ProfEntry), i32]
     lib.tfnas_umma_selftest.restype = i32
     lib.tfnas_umma_selftest.argtypes = [i32, i32, i32, vp, vp, vp, vp, sz, i32, vp]
+    bp = ctypes.POINTER(BodyDesc)
+    mp = ctypes.POINTER(u32)
+    pp = ctypes.POINTER(vp)
+    lib.tfnas_body_arena_bytes.restype = sz
+    lib.tfnas_body_arena_bytes.argtypes = [bp, mp, i32]
+    lib.tfnas_body_fwd.restype = i32
+    lib.tfnas_body_fwd.argtypes = [bp, mp, vp, cp, pp, pp, vp, vp, f32, vp, vp, vp, sz, vp]
+    lib.tfnas_body_bwd.restype = i32
+    lib.tfnas_body_bwd.argtypes = [bp, mp, vp, cp, pp, vp, vp, f32, vp, pp, pp, cp, vp, sz, vp]
+    lib.tfnas_sgd_step.restype = i32
+    lib.tfnas_sgd_step.argtypes = [i32, ctypes.POINTER(SgdTensor), f32, f32, f32, f32, f32, vp, vp, sz, vp]
+    lib.tfnas_adam_step.restype = i32
+    lib.tfnas_adam_step.argtypes = [i32, ctypes.POINTER(AdamTensor), i32, f32, f32, f32, f32, f32, f32, f32, vp]
+    lib.tfnas_softmax_ce.restype = i32
+    lib.tfnas_softmax_ce.argtypes = [i32, i32, vp, vp, vp, vp, vp]
     if lib.tfnas_version() != 1:
         raise TfnasError('ABI version mismatch: %d' % lib.tfnas_version())
     _lib = lib

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 #include "kernels.h"
+#include "api_internal.h"
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
@@ -56,7 +57,7 @@ void ensure_smem_impl(const void* kern, size_t smem) {
   }
 }
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -64,7 +65,7 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-static int build_plan(const TfnasMixedOpDesc* d, uint32_t mask, const TfnasCandPtrs* w, Plan& P) {
+int build_plan(const TfnasMixedOpDesc* d, uint32_t mask, const TfnasCandPtrs* w, Plan& P) {
   if (!d) return fail(TFNAS_E_INVALID, "null descriptor");
   if (d->num_ops < 1 || d->num_ops > TFNAS_MAX_OPS) return fail(TFNAS_E_INVALID, "num_ops=%d out of range", d->num_ops);
   if (d->N < 1 || d->ic < 1 || d->oc < 1 || d->H < 1 || d->W < 1) return fail(TFNAS_E_INVALID, "non-positive shape");
@@ -109,7 +110,7 @@ static int build_plan(const TfnasMixedOpDesc* d, uint32_t mask, const TfnasCandP
   return TFNAS_OK;
 }
 
-static void saved_layout(const Plan& P, SavedLayout& L) {
+void saved_layout(const Plan& P, SavedLayout& L) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   L.xmom = take((size_t)(P.ic + P.ic * P.ic) * sizeof(double));
@@ -127,7 +128,7 @@ static void saved_layout(const Plan& P, SavedLayout& L) {
   L.total = o;
 }
 
-static size_t fwd_scratch(const Plan& P, char* base, FwdScratch& S) {
+size_t fwd_scratch(const Plan& P, char* base, FwdScratch& S) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   // the four double accumulators must be CONTIGUOUS (one memset): take them as one block
@@ -146,7 +147,7 @@ static size_t fwd_scratch(const Plan& P, char* base, FwdScratch& S) {
   return o;
 }
 
-static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch& S) {
+size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch& S) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   // [sG | sGY | sD | sU] contiguous doubles (one memset)
@@ -187,10 +188,7 @@ static size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch&
   return o;
 }
 
-// the float4 / bulk-copy paths of the kernels assume what the header states: 16-byte aligned boundary tensors
-static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
-
-static int check_cuda(const char* what) {
+int check_cuda(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TFNAS_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return TFNAS_OK;

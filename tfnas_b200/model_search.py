@@ -14,6 +14,8 @@ Differences that are deliberate and documented in DESIGN.md:
   * The 'gumbel' sampling index is computed from a host mirror of log_alphas (one D2H copy per
     arch-parameter version instead of one ``.item()`` sync per MixedOP per pass).
 """
+import ctypes
+import os
 import random
 from collections import OrderedDict
 
@@ -21,8 +23,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .config import CAND_SPEC, PRIMITIVES, lut_key
-from .ops import MixedOpCall, MixedOpFn, StageSinkFn, bn_act, dwconv
+from .ops import ArenaPool, BodyCall, BodyFn, MixedOpCall, MixedOpFn, StageSinkFn, bn_act, dwconv
 
 __all__ = ['PRIMITIVES', 'OPS', 'MixedOP', 'MixedStage', 'Network', 'MBInvertedResBlock', 'ConvLayer',
            'LinearLayer', 'NoisePlan', 'injected', 'seed_noise', 'draw_gumbel']
@@ -87,6 +90,11 @@ OPS = {
     'MBI_k5_e3_se': lambda ic, mc, oc, s, aff, act: MBInvertedResBlock(ic, mc, ic, oc, 5, s, affine=aff, act_func=act),
     'MBI_k5_e6_se': lambda ic, mc, oc, s, aff, act: MBInvertedResBlock(ic, mc, ic * 2, oc, 5, s, affine=aff, act_func=act),
 }
+
+
+def ctypes_copy(dst, src):
+    """memberwise copy of a ctypes Structure (dst may be an element of an array inside another Structure)."""
+    ctypes.memmove(ctypes.byref(dst), ctypes.byref(src), ctypes.sizeof(src))
 
 
 class NoisePlan(object):
@@ -343,25 +351,109 @@ class Network(nn.Module):
         self.feature_mix_layer = ConvLayer(320, 1280, kernel_size=1, stride=1, affine=False, act_func='swish')
         self.global_avg_pooling = nn.AdaptiveAvgPool2d(1)
         self.classifier = LinearLayer(1280, num_classes)
+        # TFNAS_BODY=0: evaluate the stages through the per-MixedOP autograd Functions (MixedStage.forward) instead of the
+        # C++ body executor -- same kernels, same results; kept for A/B tests
+        self.use_body = os.environ.get('TFNAS_BODY', '1') != '0'
         self._initialization()
 
     def forward(self, x, sampling, mode='max'):
         out_lat = self.lat_lookup['base'] if not sampling else 0.0
         if sampling and mode in ('gumbel', 'gumbel_2', 'min_alphas', 'max_alphas'):
             self.refresh_host_alphas()         # one device->host copy for all 18 MixedOPs instead of one each
-        # stems / head run on cuDNN; keep them in true fp32 so the 1e-3 parity bar holds
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            x = self.first_stem(x)
-            x = self.second_stem(x)
-        for s in range(1, 7):
-            x, lat = getattr(self, 'stage%d' % s)(x, sampling, mode)
+        # stems / head run on cuDNN / cuBLAS in true fp32 (TF32 is switched off package-wide, tfnas_b200/__init__.py)
+        x = self.first_stem(x)
+        x = self.second_stem(x)
+        if self.use_body:
+            x, lat = self._body(x, sampling, mode)
             out_lat = out_lat + lat
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            x = self.feature_mix_layer(x)
+        else:
+            for s in range(1, 7):
+                x, lat = getattr(self, 'stage%d' % s)(x, sampling, mode)
+                out_lat = out_lat + lat
+        x = self.feature_mix_layer(x)
         x = self.global_avg_pooling(x)
         x = x.view(x.size(0), -1)
         x = self.classifier(x)
         return x, out_lat
+
+    # --- the six MixedStages in one library call per direction (csrc/body.cu) ----------------------------------------
+    def _stages(self):
+        return [getattr(self, 'stage%d' % s) for s in range(1, 7)]
+
+    def _body_desc(self, x):
+        key = (tuple(x.shape), x.device)
+        c = self.__dict__.setdefault('_body_cache', {})
+        if key not in c:
+            d = _lib.BodyDesc()
+            stages = self._stages()
+            d.num_stages = len(stages)
+            N, _c, H, W = x.shape
+            bi = 0
+            lat_rows = []
+            for si, st in enumerate(stages):
+                if st.start_res != 1:
+                    raise _lib.TfnasError('the body executor sums the outputs of all blocks of a stage (start_res == 1)')
+                d.stage_blocks[si] = st.nblocks
+                for j in range(st.nblocks):
+                    m = getattr(st, 'block%d' % (j + 1))
+                    call = m._call(torch.empty((N, m.in_channels, H, W), device='meta'), (1 << m.num_ops) - 1)
+                    ctypes_copy(d.op[bi], call.desc)
+                    lat_rows.append(m.get_lookup_latency(H) + [0.0] * (_lib.MAX_OPS - m.num_ops))
+                    _n, _oc, H, W = call.out_shape()
+                    bi += 1
+            d.num_blocks = bi
+            out_shape = (N, d.op[bi - 1].oc, H, W)
+            lat = torch.tensor(lat_rows, dtype=torch.float32, device=x.device)
+            lib = _lib.load()
+            full = _lib.BodyMasks(*[(1 << d.op[i].num_ops) - 1 for i in range(bi)])
+            # the largest candidate of every MixedOP (k5, e6, SE: the last primitive) bounds the arena of any sampled pass
+            big = _lib.BodyMasks(*[1 << (d.op[i].num_ops - 1) for i in range(bi)])
+            sizes = dict(alpha=lib.tfnas_body_arena_bytes(ctypes.byref(d), full, 0),
+                         sampled=lib.tfnas_body_arena_bytes(ctypes.byref(d), big, 1))
+            if not sizes['alpha'] or not sizes['sampled']:
+                _lib.check(-1)
+            c[key] = (d, bi, out_shape, lat, sizes)
+        return c[key]
+
+    def _body(self, x, sampling, mode):
+        d, nb, out_shape, lat, sizes = self._body_desc(x)
+        mops = self._param_lists()[4]
+        pool = self.__dict__.setdefault('_arena_pool', ArenaPool())
+        betas = [st.betas for st in self._stages()]
+        T = getattr(mops[0], 'T', 1.0)
+        if sampling:
+            idx = [m._sample_index(mode) for m in mops]
+            tensors = []
+            n_per = []
+            for m, i in zip(mops, idx):
+                wl = m.m_ops[i].weight_list()
+                tensors += wl
+                n_per.append([len(wl)])
+            masks = [1 << i for i in idx]
+            need = sizes['sampled']
+            if any(m.m_ops[i].mid_channels > m.m_ops[-1].mid_channels for m, i in zip(mops, idx)):   # elastic widths
+                need = max(need, _lib.load().tfnas_body_arena_bytes(ctypes.byref(d), _lib.BodyMasks(*masks), 1))
+            call = BodyCall(d, nb, len(betas), masks, False, T, None, None, [[i] for i in idx], n_per, pool, need, out_shape)
+            out, _ = BodyFn.apply(x, call, *(tensors + betas))
+            return out, 0.0
+        plan = _ACTIVE_PLAN[0]
+        noise = []
+        for m in mops:
+            g = plan.next()[0] if plan is not None else None
+            noise.append(g if g is not None else draw_gumbel(m.num_ops))
+        gd = torch.stack([F.pad(g.float(), (0, _lib.MAX_OPS - g.numel())) for g in noise]).to(x.device, non_blocking=True)
+        tensors, n_per, active = [], [], []
+        for m in mops:
+            per = []
+            for op in m.m_ops:
+                wl = op.weight_list()
+                tensors += wl
+                per.append(len(wl))
+            n_per.append(per)
+            active.append(list(range(m.num_ops)))
+        masks = [(1 << m.num_ops) - 1 for m in mops]
+        call = BodyCall(d, nb, len(betas), masks, True, T, gd, lat, active, n_per, pool, sizes['alpha'], out_shape)
+        return BodyFn.apply(x, call, *(tensors + [m.log_alphas for m in mops] + betas))
 
     def set_temperature(self, T):
         for m in self.modules():

@@ -242,3 +242,149 @@ class DwConvFn(torch.autograd.Function):
 
 def dwconv(x, weight):
     return DwConvFn.apply(x, weight)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Supernet body: all MixedStages of Network.forward in one C-ABI call per direction (csrc/body.cu)
+# ------------------------------------------------------------------------------------------------------------------
+class ArenaPool(object):
+    """Device buffers for tfnas_body_fwd/_bwd, kept across steps (no allocation in the steady state).  A buffer is leased
+    for one forward pass and handed back when the pass's autograd context dies (after backward, or right away under
+    no_grad); best-fit reuse keeps one large (alpha-step) and two small (bi-sampled w-step) buffers alive."""
+
+    def __init__(self):
+        self.free = []
+
+    def lease(self, nbytes, device):
+        best = None
+        for i, b in enumerate(self.free):
+            if b.numel() >= nbytes and b.device == device and (best is None or b.numel() < self.free[best].numel()):
+                best = i
+        buf = self.free.pop(best) if best is not None else torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return _Lease(self, buf)
+
+    def clear(self):
+        self.free = []
+
+
+class _Lease(object):
+    __slots__ = ('pool', 'buf')
+
+    def __init__(self, pool, buf):
+        self.pool, self.buf = pool, buf
+
+    def release(self):
+        if self.buf is not None:
+            self.pool.free.append(self.buf)
+            self.buf = None
+
+    def __del__(self):
+        self.release()
+
+
+class BodyCall(object):
+    """One pass through the body: static shapes (BodyDesc), this pass's candidate masks and the flat tensor layout
+    [live weights in (block, candidate, slot) order | log_alphas per block (alpha mode) | betas per stage]."""
+
+    def __init__(self, desc, nblocks, nstages, masks, alpha_mode, T, gumbel, lat, active, n_per, pool, arena_bytes, out_shape):
+        self.desc, self.nblocks, self.nstages = desc, nblocks, nstages
+        self.masks = _lib.BodyMasks(*masks)
+        self.alpha_mode, self.T, self.gumbel, self.lat = alpha_mode, float(T), gumbel, lat
+        self.active = active          # per block: list of active candidate ids
+        self.n_per = n_per            # per block: tensors per active candidate (3 or 7)
+        self.nweights = sum(sum(n) for n in n_per)
+        self.pool, self.arena_bytes, self.out_shape = pool, arena_bytes, out_shape
+
+    def cand_array(self, tensors):
+        arr = _lib.BodyCandArray()
+        pos = 0
+        for b in range(self.nblocks):
+            base = b * _lib.MAX_OPS
+            for i, n in zip(self.active[b], self.n_per[b]):
+                c = arr[base + i]
+                for name, t in zip(_SLOTS[:n], tensors[pos:pos + n]):
+                    setattr(c, name, t.data_ptr())
+                pos += n
+        return arr
+
+
+def _ptr_array(cls, tensors):
+    return cls(*[t.data_ptr() for t in tensors])
+
+
+class BodyFn(torch.autograd.Function):
+    """forward(x, call, *tensors) -> (out, out_lat)."""
+
+    @staticmethod
+    def forward(ctx, x, call, *tensors):
+        lib = _lib.load()
+        _require_cuda_f32(x, 'x')
+        x = x.contiguous()
+        for t in tensors:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise _lib.TfnasError('body parameters must be contiguous CUDA float32 tensors')
+        nw = call.nweights
+        weights = tensors[:nw]
+        la = tensors[nw:nw + call.nblocks] if call.alpha_mode else ()
+        betas = tensors[nw + len(la):]
+        lease = call.pool.lease(call.arena_bytes, x.device)
+        out = torch.empty(call.out_shape, dtype=torch.float32, device=x.device)
+        out_lat = torch.zeros((), dtype=torch.float32, device=x.device)
+        warr = call.cand_array(weights)
+        check(lib.tfnas_body_fwd(ctypes.byref(call.desc), call.masks, _ptr(x), warr,
+                                 _ptr_array(_lib.BlockPtrs, la) if call.alpha_mode else None,
+                                 _ptr_array(_lib.StagePtrs, betas),
+                                 _ptr(call.gumbel) if call.alpha_mode else None, _ptr(call.lat) if call.alpha_mode else None,
+                                 call.T, _ptr(out), _ptr(out_lat), _ptr(lease.buf), lease.buf.numel(), _stream()))
+        ctx.call = call
+        ctx.lease = lease
+        ctx.warr = warr
+        ctx.save_for_backward(x, *tensors)
+        return out, out_lat
+
+    @staticmethod
+    def backward(ctx, gout, glat):
+        lib = _lib.load()
+        call = ctx.call
+        lease = ctx.lease
+        if lease is None or lease.buf is None:
+            raise _lib.TfnasError('body backward ran twice: the arena of the pass is released after the first backward')
+        x = ctx.saved_tensors[0]
+        tensors = ctx.saved_tensors[1:]
+        nw, nb = call.nweights, call.nblocks
+        la = tensors[nw:nw + nb] if call.alpha_mode else ()
+        betas = tensors[nw + len(la):]
+        nig = ctx.needs_input_grad
+        need_dw = any(nig[2:2 + nw])
+        need_da = call.alpha_mode and any(nig[2 + nw:2 + nw + nb])
+        need_db = any(nig[2 + nw + len(la):])
+        need_dx = nig[0] or need_dw
+        dev = x.device
+        gout = gout.contiguous()
+        dx = torch.empty_like(x) if need_dx else None
+        grads, garr = (), None
+        if need_dw:
+            flat = torch.empty(sum(t.numel() for t in tensors[:nw]), dtype=torch.float32, device=dev)
+            grads = tuple(g.view(t.shape) for g, t in zip(flat.split([t.numel() for t in tensors[:nw]]), tensors[:nw]))
+            garr = call.cand_array(grads)
+        dla = dla_rows = None
+        if need_da:
+            dla = torch.zeros((nb, _lib.MAX_OPS), dtype=torch.float32, device=dev)
+            dla_rows = [dla[i, :la[i].numel()] for i in range(nb)]
+        dbe = None
+        if need_db:
+            dbe = [torch.zeros_like(b) for b in betas]
+        gl = glat.contiguous() if (glat is not None and call.alpha_mode) else None
+        check(lib.tfnas_body_bwd(ctypes.byref(call.desc), call.masks, _ptr(x), ctx.warr, _ptr_array(_lib.StagePtrs, betas),
+                                 _ptr(gout), _ptr(gl), call.T, _ptr(dx),
+                                 _ptr_array(_lib.BlockPtrs, dla_rows) if need_da else None,
+                                 _ptr_array(_lib.StagePtrs, dbe) if need_db else None, garr,
+                                 _ptr(lease.buf), lease.buf.numel(), _stream()))
+        lease.release()
+        ctx.lease = None
+        out = [dx if nig[0] else None, None]
+        out += list(grads) if need_dw else [None] * nw
+        if call.alpha_mode:
+            out += dla_rows if need_da else [None] * nb
+        out += dbe if need_db else [None] * len(betas)
+        return tuple(out)

@@ -48,24 +48,68 @@ def world_size():
 
 
 class GradSync(object):
-    """Average the live gradients of ``params`` over ranks with one flat all-reduce."""
+    """Sum (or average) the live gradients of ``params`` over ranks.
+
+    Gradients that are adjacent views of one storage -- the body executor writes all weight gradients of a sampled pass
+    into ONE flat buffer (ops.BodyFn.backward) -- are all-reduced in place as one range: no ``cat`` and no copy back.  What is
+    left (the dozen stem / head tensors) goes through one small packed bucket."""
+
+    SMALL = 1 << 18      # ranges below 1 MB are packed together
 
     def __init__(self):
         self.bytes_last = 0
+        self.calls_last = 0
 
-    def __call__(self, params):
+    def __call__(self, params, average=True):
         if world_size() == 1:
             return 0
         grads = [p.grad for p in params if p.grad is not None]
         if not grads:
             return 0
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(world_size())
-        outs = flat.split([g.numel() for g in grads])
-        torch._foreach_copy_(grads, [o.view_as(g) for o, g in zip(outs, grads)])
-        self.bytes_last = flat.numel() * 4
-        return self.bytes_last
+        w = world_size()
+        # coalesce adjacent views of the same storage
+        by_store = {}
+        for g in grads:
+            if not g.is_contiguous():
+                raise RuntimeError('GradSync needs contiguous gradients')
+            by_store.setdefault(g.untyped_storage().data_ptr(), []).append(g)
+        big, small = [], []
+        for gs in by_store.values():
+            gs.sort(key=lambda t: t.storage_offset())
+            start, end, first = gs[0].storage_offset(), gs[0].storage_offset() + gs[0].numel(), gs[0]
+            members = [gs[0]]
+            runs = []
+            for g in gs[1:]:
+                if g.storage_offset() == end:
+                    end += g.numel()
+                    members.append(g)
+                else:
+                    runs.append((first, start, end, members))
+                    start, end, first, members = g.storage_offset(), g.storage_offset() + g.numel(), g, [g]
+            runs.append((first, start, end, members))
+            for first, start, end, members in runs:
+                if end - start >= self.SMALL:
+                    big.append(first.new_empty(0).set_(first.untyped_storage(), start, (end - start,), (1,)))
+                else:
+                    small += members
+        nbytes = 0
+        calls = 0
+        for flat in big:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if average:
+                flat.div_(w)
+            nbytes += flat.numel() * 4
+            calls += 1
+        if small:
+            flat = torch.cat([g.reshape(-1) for g in small])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if average:
+                flat.div_(w)
+            torch._foreach_copy_(small, [o.view_as(g) for o, g in zip(flat.split([g.numel() for g in small]), small)])
+            nbytes += flat.numel() * 4
+            calls += 1
+        self.bytes_last, self.calls_last = nbytes, calls
+        return nbytes
 
 
 def assert_in_sync(values):

@@ -11,7 +11,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .parallel import GradSync
+from .parallel import GradSync, world_size
+from .step import FusedArchAdam, FusedCrossEntropy, FusedSGD
 
 
 class DeviceMeter(object):
@@ -109,12 +110,25 @@ def w_step(model, x_w, target_w, criterion, optimizer_w, grad_clip, sync=None, b
             net.reset_switches()
     optimizer_w.zero_grad()
     loss.backward()
-    if sync is not None:
-        sync(net.weight_parameters())
-    if grad_clip > 0:
-        nn.utils.clip_grad_norm_(net.weight_parameters(), grad_clip)
-    optimizer_w.step()
+    _apply_update(optimizer_w, net.weight_parameters(), grad_clip, sync)
     return loss, logits_g
+
+
+def _apply_update(optimizer, params, grad_clip, sync):
+    """all-reduce (data parallel) -> global-norm clip -> optimiser step.  With the fused optimisers the three are two
+    library launches over a table of the live tensors (the 1/world of the gradient mean rides in the same kernels)."""
+    if isinstance(optimizer, (FusedSGD, FusedArchAdam)):
+        scale = 1.0
+        if sync is not None and world_size() > 1:
+            sync(params, average=False)
+            scale = 1.0 / world_size()
+        optimizer.step(max_norm=grad_clip, grad_scale=scale)
+        return
+    if sync is not None:
+        sync(params)
+    if grad_clip > 0:
+        nn.utils.clip_grad_norm_(params, grad_clip)
+    optimizer.step()
 
 
 def alpha_step(model, x_a, target_a, criterion, optimizer_a, target_lat, lambda_lat, grad_clip, sync=None):
@@ -127,13 +141,10 @@ def alpha_step(model, x_a, target_a, criterion, optimizer_a, target_lat, lambda_
     loss = loss_a + loss_l
     optimizer_a.zero_grad()
     loss.backward()
-    if sync is not None:
-        sync(net.arch_parameters())
-    if grad_clip > 0:
-        nn.utils.clip_grad_norm_(net.arch_parameters(), grad_clip)
-    optimizer_a.step()
-    for p in net.arch_parameters():      # applies to betas too (quirk Q4)
-        p.data = F.log_softmax(p.detach().data, dim=-1)
+    _apply_update(optimizer_a, net.arch_parameters(), grad_clip, sync)
+    if not isinstance(optimizer_a, FusedArchAdam):      # the fused kernel renormalises in the same launch
+        for p in net.arch_parameters():      # applies to betas too (quirk Q4)
+            p.data = F.log_softmax(p.detach().data, dim=-1)
     return loss_a, loss_l
 
 
@@ -209,8 +220,15 @@ def validate(val_queue, model, criterion, args):
     return top1.avg
 
 
-def make_optimizers(net, w_lr=0.025, w_mom=0.9, w_wd=1e-5, a_lr=0.01, a_beta1=0.5, a_beta2=0.999, a_wd=5e-4):
-    """train_search.py:196-206."""
+def make_optimizers(net, w_lr=0.025, w_mom=0.9, w_wd=1e-5, a_lr=0.01, a_beta1=0.5, a_beta2=0.999, a_wd=5e-4, fused=None):
+    """train_search.py:196-206.  ``fused`` (default: on for CUDA parameters, TFNAS_FUSED_OPT=0 turns it off) selects the
+    library's fused clip + update kernels (tfnas_b200/step.py) instead of torch.optim; same update rules."""
+    if fused is None:
+        import os
+        fused = os.environ.get('TFNAS_FUSED_OPT', '1') != '0' and next(net.parameters()).is_cuda
+    if fused:
+        return (FusedSGD(net.weight_parameters(), lr=w_lr, momentum=w_mom, weight_decay=w_wd),
+                FusedArchAdam(net.arch_parameters(), lr=a_lr, betas=(a_beta1, a_beta2), weight_decay=a_wd))
     optimizer_w = torch.optim.SGD(net.weight_parameters(), lr=w_lr, momentum=w_mom, weight_decay=w_wd)
     optimizer_a = torch.optim.Adam(net.arch_parameters(), lr=a_lr, betas=(a_beta1, a_beta2), weight_decay=a_wd)
     return optimizer_w, optimizer_a

@@ -29,7 +29,8 @@ def main():
     net = Network(100, config.get_mc_num_dddict(config.mc_mask_dddict), gi.load_lut())
     net.set_temperature(5.0)
     model = SearchParallel(net).to(dev).train()
-    crit = nn.CrossEntropyLoss().to(dev)
+    from tfnas_b200.step import FusedCrossEntropy
+    crit = FusedCrossEntropy().to(dev)
     opt_w, opt_a = make_optimizers(net)
     sync = GradSync()
     g = torch.Generator().manual_seed(2)

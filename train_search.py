@@ -147,7 +147,8 @@ def main(argv=None):
         torch.save({'state_dict': state_dict, 'mc_mask_dddict': mc_mask_dddict}, path(0))
     lr_list = cosine_lr_list(args.w_lr, args.epochs)
     del model
-    criterion = nn.CrossEntropyLoss().cuda()
+    from tfnas_b200.step import FusedCrossEntropy
+    criterion = FusedCrossEntropy().cuda()        # nn.CrossEntropyLoss() (reference :121) with its gradient in one launch
     train_queue, val_queue = make_queues(args, rank, world)
     sync = parallel.GradSync()
 
