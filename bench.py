@@ -16,10 +16,16 @@ T=5, lambda_lat=0.1, target_lat=15, the reference's latency_gpu LUT.  images/sec
   roofline     the kernel with the largest share of the step, timed with CUDA events on its stream
                (library event profiler) over the same K units: algorithmic bytes / time vs the
                measured HBM peak
-  cpu_baseline the oracle port (torch CPU, all host threads) on a bounded sample (bs 8)
+  mixedop_roofline  SURVEY 8(d)'s micro-benchmark: alpha-mode fwd+bwd of the 18 MixedOPs (one supernet's worth, body
+               executor) timed with CUDA events; ALGORITHMIC GB/s (1.694 GB) and TFLOP/s (1.27 TF) and the fraction of the
+               binding bound (tf32x3 tensor floor)
+  cpu_baseline the oracle port (torch CPU, all host threads) on a bounded sample (search units at bs 32, the
+               reference's default batch; bs 128 does not fit host memory -- config.ref_batch states it)
+  gpu_baseline the same oracle port (= the reference's own PyTorch code path: cuDNN / cuBLAS / ATen) on THIS GPU at
+               bs 128, with TF32 off (true fp32, what parity requires) and on (PyTorch's cuDNN default)
 
 --impl reference times that same CPU oracle port (the reference is pure Python/PyTorch and does
-not travel to the GPU box) for the same metric/config, one search unit per step.
+not travel to the GPU box) for the same metric/config, one search unit (at bs 32) per step.
 """
 import argparse
 import json
@@ -34,7 +40,7 @@ sys.path.insert(0, ROOT)
 sys.dont_write_bytecode = True
 
 BS = 128
-REF_BS = 8
+REF_BS = 32        # CPU arm: the reference's default --batch_size (train_search.py:44); bs 128 needs ~70 GB of host RAM
 METRIC = 'supernet_search_step_images_per_sec'
 UNIT = 'images/s'
 
@@ -42,11 +48,18 @@ UNIT = 'images/s'
 EXTRA_WARMUP = 2      # untimed units after the requested warm-up (allocator / optimiser state settle)
 
 
+def target_lat_for(world):
+    """BASELINE.json: target_lat 15.0 for the single-GPU configs (2, 3), 18.0 for the 8-GPU search (config 4)."""
+    return 18.0 if world >= 8 else 15.0
+
+
 def base_config(world):
+    tl = target_lat_for(world)
     return {'workload': 'full supernet (Network) search unit = 2 bi-sampled w-steps + 1 alpha-step, '
-                        'synthetic 3x224x224 fp32, bs %d per GPU, target_lat 15.0, latency_gpu LUT' % BS,
+                        'synthetic 3x224x224 fp32, bs %d per GPU, target_lat %.1f, latency_gpu LUT' % (BS, tl),
             'per_gpu_batch': BS, 'global_batch': BS * world, 'image': '3x224x224', 'num_classes': 100,
-            'T': 5.0, 'lambda_lat': 0.1, 'target_lat': 15.0, 'parallelism': 'dp%d' % world,
+            'T': 5.0, 'lambda_lat': 0.1, 'target_lat': tl, 'parallelism': 'dp%d' % world,
+            'ref_batch': REF_BS,      # batch of the CPU arms (--impl reference, cpu_baseline): per-image throughput is reported
             'l2_policy': 'per-step working set (>20 GB of activations) far exceeds the 126 MB L2; no flush needed'}
 
 
@@ -114,12 +127,14 @@ def run_reference(args, rank, world, emit=print):
     g = torch.Generator().manual_seed(2)
     batches = [(torch.randn(REF_BS, 3, 224, 224, generator=g), torch.randint(0, 100, (REF_BS,), generator=g))
                for _ in range(2)]
+    tl = target_lat_for(max(world, 1))
+    state = {}
     for _ in range(args.warmup):
-        port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1)
+        port.search_unit_cpu(P, mcs, lut, batches, 5.0, tl, 0.1, state=state)
     t0 = time.time()
     n_img = 0
     for _ in range(args.steps):
-        n_img += port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1)
+        n_img += port.search_unit_cpu(P, mcs, lut, batches, 5.0, tl, 0.1, state=state)
     dt = time.time() - t0
     val = n_img / dt
     sample = 'search unit at bs %d on CPU (%d threads), fp32, same supernet / LUT / losses' % (REF_BS, torch.get_num_threads())
@@ -146,14 +161,101 @@ def cpu_baseline_sample():
     g = torch.Generator().manual_seed(2)
     batches = [(torch.randn(REF_BS, 3, 224, 224, generator=g), torch.randint(0, 100, (REF_BS,), generator=g))
                for _ in range(2)]
-    port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1)       # warm-up
+    state = {}
+    port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1, state=state)       # warm-up
     t0 = time.time()
     n = 0
     for _ in range(2):
-        n += port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1)
+        n += port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1, state=state)
     dt = time.time() - t0
     return {'value': n / dt, 'unit': UNIT, 'cores': nthr, 'kind': 'port',
             'sample': '2 search units at bs %d (oracle/port.py, torch CPU fp32, %d threads), %.1f s' % (REF_BS, nthr, dt)}
+
+
+def gpu_baseline_sample(dev):
+    """The reference's own code path (oracle port = the same PyTorch ops: cuDNN convs, ATen BN / elementwise, torch.autograd)
+    on this GPU at bs 128: search units with TF32 off (true fp32) and on (PyTorch's cuDNN default).  SURVEY 8(d) last row."""
+    import torch
+    from oracle import port
+    from tests import golden_inputs as gi
+    from tfnas_b200 import config
+    lut = gi.load_lut()
+    mcs = config.get_mc_num_dddict(config.mc_mask_dddict)
+    g = torch.Generator().manual_seed(2)
+    batches = [(torch.randn(BS, 3, 224, 224, generator=g).to(dev), torch.randint(0, 100, (BS,), generator=g).to(dev))
+               for _ in range(2)]
+    out = {'unit': UNIT, 'kind': 'port on cuda (stock PyTorch ops)', 'batch': BS, 'units_timed': 2}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, tf32 in (('tf32_off', False), ('tf32_on', True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            P = {k: v.to(dev) for k, v in port.init_params(mcs, seed=2).items()}
+            state = {}
+            port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1, state=state)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            n = 0
+            for _ in range(2):
+                n += port.search_unit_cpu(P, mcs, lut, batches, 5.0, 15.0, 0.1, state=state)
+            torch.cuda.synchronize()
+            out[name] = n / (time.time() - t0)
+            del P, state
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return out
+
+
+# SURVEY.md 8(d), N = 128, fp32, initial widths, sums over the 18 MixedOPs
+ALG = dict(bytes_fwd=685.0e6, bytes_bwd=1009.3e6, gf_1x1=570.86, gf_dw=60.56, gf_se=3.52, gf_elem=47.30)
+
+
+def mixedop_roofline(net, dev, reps, peak_gbs):
+    """alpha-mode fwd+bwd of all 18 MixedOPs (+ the 6 sinks) at bs 128 through the body executor, CUDA events."""
+    import torch
+    from tfnas_b200.model_search import NoisePlan, injected
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(BS, 16, 112, 112, generator=g).to(dev).requires_grad_(True) for _ in range(2)]
+    G = torch.randn(BS, 320, 7, 7, generator=g).to(dev)
+    for p in net.weight_parameters():
+        p.requires_grad = False
+    for p in net.arch_parameters():
+        p.requires_grad = True
+
+    def once(x):
+        out, lat = net._body(x, False, 'max')
+        torch.autograd.backward([out, lat], [G, torch.ones_like(lat)])
+        x.grad = None
+    for i in range(2):
+        once(xs[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        once(xs[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    for p in net.arch_parameters():
+        p.grad = None
+    nbytes = ALG['bytes_fwd'] + ALG['bytes_bwd']
+    flops = 2.0 * (ALG['gf_1x1'] + ALG['gf_dw'] + ALG['gf_se']) * 1e9
+    pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+    bf16 = float(pk.get('bf16_tflops', 1617.8))
+    floor_bytes = nbytes / (peak_gbs * 1e9) * 1e3
+    floor_tensor = 2.0 * ALG['gf_1x1'] * 1e9 * 3.0 / (0.5 * bf16 * 1e12) * 1e3      # tf32 = 1/2 bf16 rate, 3-term split
+    floor_fp32 = 2.0 * (ALG['gf_dw'] + ALG['gf_se'] + ALG['gf_elem']) * 1e9 / 74e12 * 1e3
+    floor = max(floor_bytes, floor_tensor, floor_fp32)
+    tp = os.path.join(ROOT, 'profiles', 'ncu_tensor_pipe.json')
+    return {'what': 'alpha-mode fwd+bwd of the 18 MixedOPs at bs 128 (SURVEY 8d micro-benchmark unit, dx of the first MixedOP included)',
+            'ms': ms, 'algorithmic_bytes': nbytes, 'algorithmic_flops': flops,
+            'achieved_GBps': nbytes / ms / 1e6, 'hbm_frac_algorithmic': nbytes / ms / 1e6 / peak_gbs,
+            'achieved_TFLOPs': flops / ms / 1e9,
+            'floors_ms': {'bytes': floor_bytes, 'tensor_tf32x3': floor_tensor, 'fp32_pipe': floor_fp32},
+            'binding_bound': 'tensor (tf32 x3 split the 1e-3 parity bar requires)' if floor == floor_tensor else 'other',
+            'binding_bound_frac': floor / ms,
+            'tensor_pipe_pct_ncu': json.load(open(tp)) if os.path.exists(tp) else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -202,7 +304,7 @@ def run_b200(args, rank, local, world, emit=print):
                 xa, ta = src[(2 * i + it + 1) % npool]
                 if from_host:
                     xa, ta = xa.to(dev, non_blocking=True), ta.to(dev, non_blocking=True)
-                la, ll = alpha_step(model, xa, ta, criterion, opt_a, 15.0, 0.1, 5.0, sync)
+                la, ll = alpha_step(model, xa, ta, criterion, opt_a, target_lat_for(world), 0.1, 5.0, sync)
                 losses += [la, ll]
         if from_host:
             return [float(v) for v in torch.stack([v.detach().float() for v in losses]).cpu()]
@@ -275,8 +377,13 @@ def run_b200(args, rank, local, world, emit=print):
     tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(top['name'])
+    mop = mixedop_roofline(net, dev, 6, peak) if rank == 0 else None
+    for p_ in net.parameters():
+        p_.grad = None
     roofline = {'kernel': top['name'], 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'bytes_model': 'materialised tensors this kernel reads + writes (DESIGN.md section 5), not SURVEY 8(d) compulsory bytes',
+                'algorithmic_frac': mop['hbm_frac_algorithmic'] if mop else None,
                 'share_of_step': top['ms'] / tot_ms, 'launches_per_step': top['launches'] / args.steps,
                 'avg_launch_ms': per_launch_ms, 'achieved_tflops': top['flops'] / top['launches'] / per_launch_ms / 1e9,
                 'kernel_ms_per_step': tot_ms / args.steps,
@@ -293,7 +400,11 @@ def run_b200(args, rank, local, world, emit=print):
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'host_enqueue_ms_per_step': host_enqueue, 'extra_untimed_warmup': EXTRA_WARMUP, 'clocks': sampler.summary(),
             'roofline': roofline}
+    line['mixedop_roofline'] = mop
     if world == 1 and not args.no_cpu_baseline:
+        del model, net, opt_w, opt_a, pool
+        torch.cuda.empty_cache()
+        line['gpu_baseline'] = gpu_baseline_sample(dev)
         line['cpu_baseline'] = cpu_baseline_sample()
     emit(json.dumps(line))
 

@@ -167,6 +167,13 @@ typedef struct TfnasProfEntry {
 } TfnasProfEntry;
 int tfnas_prof_enable(int on);
 int tfnas_prof_collect(TfnasProfEntry* out, int max_entries);
+/* The same records un-aggregated, in launch order: start / end in ms relative to the first recorded launch. */
+typedef struct TfnasProfLaunch {
+  char name[32];
+  uint64_t stream;
+  double start_ms, end_ms;
+} TfnasProfLaunch;
+int tfnas_prof_timeline(TfnasProfLaunch* out, int max_entries);
 
 /*
  * Test helper for the tcgen05 building blocks: C[n][p] = sum_k B[n][k] * A[k][p] (A: [K][M], B: [N][K],
@@ -220,6 +227,37 @@ int tfnas_body_bwd(const TfnasBodyDesc* d, const uint32_t* cand_masks, const flo
                    const float* const* betas, const float* dout, const float* dlat, float T, float* dx,
                    float* const* dlog_alphas, float* const* dbetas, const TfnasCandPtrs* dweights, void* arena,
                    size_t arena_bytes, void* stream);
+
+
+/* =====================================================================================================================
+ * The two stems of Network.forward (reference models/model_search.py:219-220, :283-284): first_stem = ConvLayer(3, 32,
+ * k3, s2, BN, ReLU) (models/layers.py:190-256), second_stem = MBInvertedResBlock(32, 32, se 8, 16, k3, s1, relu) without an
+ * expand conv (models/layers.py:479-482).  One call per direction over a caller-provided arena; BN = batch statistics,
+ * biased variance, eps 1e-5, no affine.  The image needs no gradient.
+ * ===================================================================================================================== */
+typedef struct TfnasStemDesc {
+  int32_t N, H, W;    /* image batch [N, c_in, H, W] */
+  int32_t c_in;       /* 3 */
+  int32_t c_mid;      /* 32: first-stem output = second-stem mid width */
+  int32_t se;         /* 8: squeeze-excite hidden width of the second stem */
+  int32_t c_out;      /* 16: second-stem output channels */
+} TfnasStemDesc;
+typedef struct TfnasStemPtrs {
+  float* conv_w;      /* first_stem.conv.weight                         [c_mid, c_in, 3, 3] */
+  float* dw;          /* second_stem.depth_conv.conv.weight             [c_mid, 1, 3, 3]    */
+  float* se_rw;       /* second_stem.squeeze_excite.conv_reduce.weight  [se, c_mid]          */
+  float* se_rb;       /*                            conv_reduce.bias    [se]                 */
+  float* se_ew;       /*                            conv_expand.weight  [c_mid, se]          */
+  float* se_eb;       /*                            conv_expand.bias    [c_mid]              */
+  float* pw;          /* second_stem.point_linear.conv.weight           [c_out, c_mid]       */
+} TfnasStemPtrs;
+size_t tfnas_stem_arena_bytes(const TfnasStemDesc* d, int want_wgrad);
+/* out: [N, c_out, H/2, W/2] (the input of the first MixedOP).  The arena keeps what the backward needs. */
+int tfnas_stem_fwd(const TfnasStemDesc* d, const float* img, const TfnasStemPtrs* w, float* out, void* arena,
+                   size_t arena_bytes, void* stream);
+/* dw: gradient tensors of the seven parameters (written, not accumulated). */
+int tfnas_stem_bwd(const TfnasStemDesc* d, const float* img, const TfnasStemPtrs* w, const float* dout,
+                   const TfnasStemPtrs* dw, void* arena, size_t arena_bytes, void* stream);
 
 /* =====================================================================================================================
  * Step glue of train_w_arch (reference train_search.py:381-385 and :414-422): global-norm gradient clipping fused with

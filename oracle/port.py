@@ -223,11 +223,18 @@ def is_arch_key(k):
     return k.endswith('log_alphas') or k.endswith('betas')
 
 
-def search_unit_cpu(P, mcs, lut, batches, T, target_lat, lambda_lat, seed=2):
-    """One 'search unit' = 2 iterations of train_w_arch (train_search.py:366-426) WITHOUT the
-    optimiser updates' side effects mattering for timing: 2 bi-sampled w-steps + 1 alpha-step,
-    forward + backward + clip + SGD/Adam step on CPU.  Used only as the timed CPU baseline.
+def search_unit_cpu(P, mcs, lut, batches, T, target_lat, lambda_lat, seed=2, state=None):
+    """One 'search unit' = 2 iterations of train_w_arch (train_search.py:366-426): 2 bi-sampled w-steps + 1 alpha-step,
+    each forward + backward + global-norm clip (5.0) + optimiser step -- SGD(lr .025, momentum .9, wd 1e-5) on the live
+    weights (tensors without a gradient are skipped, as torch.optim does), Adam(lr .01, betas (.5, .999), wd 5e-4) on the
+    architecture parameters followed by the log_softmax renormalisation (:421-422).  ``state`` (a dict kept by the caller)
+    carries the momentum buffers / Adam moments between units.  Runs on whatever device P and the batches live on (the
+    timed CPU baseline of bench.py, and its same-box GPU baseline).
     """
+    state = state if state is not None else {}
+    mom = state.setdefault('mom', {})
+    adam = state.setdefault('adam', {})
+    dev = next(iter(P.values())).device
     gen = torch.Generator().manual_seed(seed)
     rnd = _pyrandom.Random(seed)
     wkeys = [k for k in P if not is_arch_key(k)]
@@ -241,7 +248,8 @@ def search_unit_cpu(P, mcs, lut, batches, T, target_lat, lambda_lat, seed=2):
         for k in akeys:
             P[k].requires_grad_(False)
         noise = [draw_gumbel(generator=gen) for _ in range(18)]
-        idx_g = [sample_gumbel_index(P[n + 'log_alphas'], noise[i]) for i, n in enumerate(names)]
+        la_host = torch.stack([P[n + 'log_alphas'].detach() for n in names]).cpu()
+        idx_g = [sample_gumbel_index(la_host[i], noise[i]) for i in range(len(names))]
         idx_r = []
         for ig in idx_g:
             rest = [j for j in range(NUM_OPS) if j != ig]
@@ -250,12 +258,16 @@ def search_unit_cpu(P, mcs, lut, batches, T, target_lat, lambda_lat, seed=2):
         lr, _ = network_forward(x_w, P, mcs, lut, True, T, indices=idx_r)
         loss = F.cross_entropy(lg, t_w) + F.cross_entropy(lr, t_w)
         grads = torch.autograd.grad(loss, [P[k] for k in wkeys], allow_unused=True)
-        live = [(P[k], g) for k, g in zip(wkeys, grads) if g is not None]
-        tot = torch.sqrt(sum((g.double() ** 2).sum() for _, g in live)).float()
+        live = [(k, P[k], g) for k, g in zip(wkeys, grads) if g is not None]
+        tot = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for _, _, g in live]))
         coef = torch.clamp(5.0 / (tot + 1e-6), max=1.0)
         with torch.no_grad():
-            for p, g in live:
-                p.add_(g * coef + 1e-5 * p, alpha=-0.025)
+            for k, p, g in live:
+                d = g * coef + 1e-5 * p
+                b = mom.get(k)
+                b = d.clone() if b is None else b.mul_(0.9).add_(d)
+                mom[k] = b
+                p.add_(b, alpha=-0.025)
         n_img += x_w.shape[0]
         if it % 2 == 0:
             x_a, t_a = batches[(it + 1) % len(batches)]
@@ -263,13 +275,23 @@ def search_unit_cpu(P, mcs, lut, batches, T, target_lat, lambda_lat, seed=2):
                 P[k].requires_grad_(False)
             for k in akeys:
                 P[k].requires_grad_(True)
-            noise = [draw_gumbel(generator=gen) for _ in range(18)]
+            noise = [draw_gumbel(generator=gen).to(dev) for _ in range(18)]
             la, lat = network_forward(x_a, P, mcs, lut, False, T, noise=noise)
             loss, _, _ = arch_loss(la, lat, t_a, target_lat, lambda_lat)
             grads = torch.autograd.grad(loss, [P[k] for k in akeys])
+            tot = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in grads]))
+            coef = torch.clamp(5.0 / (tot + 1e-6), max=1.0)
+            state['t'] = t = state.get('t', 0) + 1
             with torch.no_grad():
                 for k, g in zip(akeys, grads):
-                    P[k].copy_(F.log_softmax(P[k] - 0.01 * g, dim=-1))
+                    p = P[k]
+                    g = g * coef + 5e-4 * p
+                    m, v = adam.get(k, (torch.zeros_like(p), torch.zeros_like(p)))
+                    m = m.lerp(g, 0.5)
+                    v = v.mul(0.999).addcmul(g, g, value=0.001)
+                    adam[k] = (m, v)
+                    denom = v.sqrt() / (1 - 0.999 ** t) ** 0.5 + 1e-8
+                    p.copy_(F.log_softmax(p - (0.01 / (1 - 0.5 ** t)) * m / denom, dim=-1))
     for k in P:
         P[k].requires_grad_(False)
     return n_img

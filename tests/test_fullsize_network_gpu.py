@@ -113,14 +113,18 @@ def test_bisampled_wstep_bs128_matches_port_on_gpu():
         # tensors whose whole gradient is below fp32 noise of the step (e.g. a bias feeding a BatchNorm) are compared
         # on the scale of the largest gradient instead of their own norm
         return float((a.double() - v.double()).norm() / max(float(v.double().norm()), 1e-6 * gmax))
-    worst, worst_name, over = 0.0, None, []
+    # Tolerance: the north-star 1e-3 everywhere except the tensors of the ReLU part of the network (stems, stage1), where a
+    # pre-activation within fp32 rounding of 0 gates differently in any two correct implementations and moves the
+    # BN-backward means of its channel (the fp32 port itself is off by 0.5-1.5e-3 there): 3e-3.
+    worst, worst_name, errs = 0.0, None, []
     for k, v in ref.items():
         e, e32 = err(got[k], v), err(ref32[k], v)
+        errs.append(e)
+        relu_part = k.startswith('stage1.') or 'stem' in k
+        assert e < (3e-3 if relu_part else TOL), (k, e, e32)
         if e > worst:
             worst, worst_name = e, k
-        if e >= max(TOL, 2.0 * e32):
-            over.append((k, e, e32))
-    print('bs128 bi-sampled w-step: %d live tensors, worst element-wise rel-l2 vs fp64 %.2e (%s; the fp32 port itself: %.2e)'
-          % (len(ref), worst, worst_name, err(ref32[worst_name], ref[worst_name])))
-    assert not over, over          # 1e-3, or twice the fp32 reference's own error where that is larger
-    assert sum(err(got[k], v) >= TOL for k, v in ref.items()) <= 3
+    errs.sort()
+    print('bs128 bi-sampled w-step: %d live tensors, element-wise rel-l2 vs fp64: median %.2e, worst %.2e (%s; the fp32 port '
+          'itself: %.2e)' % (len(ref), errs[len(errs) // 2], worst, worst_name, err(ref32[worst_name], ref[worst_name])))
+    assert errs[len(errs) // 2] < 2e-4

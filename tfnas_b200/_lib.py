@@ -43,6 +43,16 @@ class BodyDesc(ctypes.Structure):
                 ('stage_blocks', ctypes.c_int32 * MAX_STAGES), ('op', MixedOpDesc * MAX_BLOCKS)]
 
 
+class StemDesc(ctypes.Structure):
+    _fields_ = [('N', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('c_in', ctypes.c_int32),
+                ('c_mid', ctypes.c_int32), ('se', ctypes.c_int32), ('c_out', ctypes.c_int32)]
+
+
+class StemPtrs(ctypes.Structure):
+    _fields_ = [('conv_w', ctypes.c_void_p), ('dw', ctypes.c_void_p), ('se_rw', ctypes.c_void_p),
+                ('se_rb', ctypes.c_void_p), ('se_ew', ctypes.c_void_p), ('se_eb', ctypes.c_void_p), ('pw', ctypes.c_void_p)]
+
+
 class SgdTensor(ctypes.Structure):
     _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('buf', ctypes.c_void_p), ('numel', ctypes.c_int64)]
 
@@ -50,6 +60,11 @@ class SgdTensor(ctypes.Structure):
 class AdamTensor(ctypes.Structure):
     _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p),
                 ('numel', ctypes.c_int32), ('renorm', ctypes.c_int32)]
+
+
+class ProfLaunch(ctypes.Structure):
+    _fields_ = [('name', ctypes.c_char * 32), ('stream', ctypes.c_uint64), ('start_ms', ctypes.c_double),
+                ('end_ms', ctypes.c_double)]
 
 
 CandArray = CandPtrs * MAX_OPS
@@ -61,9 +76,10 @@ EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
            'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout', 'tfnas_debug_bwd_layout',
-           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd',
+           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_prof_timeline', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd',
            'tfnas_dwconv_fwd', 'tfnas_dwconv_bwd', 'tfnas_debug_ws_config',
            'tfnas_body_arena_bytes', 'tfnas_body_fwd', 'tfnas_body_bwd',
+           'tfnas_stem_arena_bytes', 'tfnas_stem_fwd', 'tfnas_stem_bwd',
            'tfnas_sgd_step', 'tfnas_adam_step', 'tfnas_softmax_ce']
 
 _lib = None
@@ -119,6 +135,8 @@ def load():
     lib.tfnas_prof_enable.argtypes = [i32]
     lib.tfnas_prof_collect.restype = i32
     lib.tfnas_prof_collect.argtypes = [ctypes.POINTER(ProfEntry), i32]
+    lib.tfnas_prof_timeline.restype = i32
+    lib.tfnas_prof_timeline.argtypes = [ctypes.POINTER(ProfLaunch), i32]
     lib.tfnas_umma_selftest.restype = i32
     lib.tfnas_umma_selftest.argtypes = [i32, i32, i32, vp, vp, vp, vp, sz, i32, vp]
     bp = ctypes.POINTER(BodyDesc)
@@ -130,6 +148,13 @@ def load():
     lib.tfnas_body_fwd.argtypes = [bp, mp, vp, cp, pp, pp, vp, vp, f32, vp, vp, vp, sz, vp]
     lib.tfnas_body_bwd.restype = i32
     lib.tfnas_body_bwd.argtypes = [bp, mp, vp, cp, pp, vp, vp, f32, vp, pp, pp, cp, vp, sz, vp]
+    sdp, spp = ctypes.POINTER(StemDesc), ctypes.POINTER(StemPtrs)
+    lib.tfnas_stem_arena_bytes.restype = sz
+    lib.tfnas_stem_arena_bytes.argtypes = [sdp, i32]
+    lib.tfnas_stem_fwd.restype = i32
+    lib.tfnas_stem_fwd.argtypes = [sdp, vp, spp, vp, vp, sz, vp]
+    lib.tfnas_stem_bwd.restype = i32
+    lib.tfnas_stem_bwd.argtypes = [sdp, vp, spp, vp, spp, vp, sz, vp]
     lib.tfnas_sgd_step.restype = i32
     lib.tfnas_sgd_step.argtypes = [i32, ctypes.POINTER(SgdTensor), f32, f32, f32, f32, f32, vp, vp, sz, vp]
     lib.tfnas_adam_step.restype = i32
@@ -163,3 +188,12 @@ def prof_collect(max_entries=64):
         check(n)
     return [dict(name=buf[i].name.decode(), ms=buf[i].ms, bytes=buf[i].bytes, flops=buf[i].flops,
                  launches=int(buf[i].launches)) for i in range(n)]
+
+
+def prof_timeline(max_entries=20000):
+    """-> list of (name, stream, start_ms, end_ms) per recorded launch, in launch order."""
+    buf = (ProfLaunch * max_entries)()
+    n = load().tfnas_prof_timeline(buf, max_entries)
+    if n < 0:
+        check(n)
+    return [(buf[i].name.decode(), int(buf[i].stream), buf[i].start_ms, buf[i].end_ms) for i in range(n)]

@@ -16,7 +16,7 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 // ---- optional per-launch profiling (CUDA events on the launching stream) -----------------------
-struct ProfRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; };
+struct ProfRec { const char* name; double bytes, flops; cudaEvent_t e0, e1; cudaStream_t st; };
 static bool g_prof = false;
 static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_pool;
@@ -33,7 +33,7 @@ ProfScope::ProfScope(const char* name, double bytes, double flops, cudaStream_t 
   count_launch(1);
   if (!g_prof) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  ProfRec* r = new ProfRec{name, bytes, flops, get_event(), get_event()};
+  ProfRec* r = new ProfRec{name, bytes, flops, get_event(), get_event(), st};
   cudaEventRecord(r->e0, st);
   rec_ = r;
 }
@@ -359,6 +359,29 @@ int tfnas_prof_collect(TfnasProfEntry* out, int max_entries) {
   for (auto& k : order) {
     if (n >= max_entries) break;
     out[n++] = agg[k];
+  }
+  return n;
+}
+
+/* Raw launch timeline of the profiled region: per recorded launch its name, stream and start / end time in ms relative to
+ * the first recorded launch's start (events on the launching streams; tools/timeline.py turns it into per-stream gaps). */
+int tfnas_prof_timeline(TfnasProfLaunch* out, int max_entries) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_recs.empty()) return 0;
+  int n = 0;
+  cudaEvent_t base = g_recs[0].e0;
+  for (auto& r : g_recs) {
+    if (n >= max_entries) break;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return fail(TFNAS_E_CUDA, "prof: event sync failed");
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, base, r.e0);
+    cudaEventElapsedTime(&b, base, r.e1);
+    memset(&out[n], 0, sizeof(out[n]));
+    strncpy(out[n].name, r.name, sizeof(out[n].name) - 1);
+    out[n].stream = (uint64_t)(uintptr_t)r.st;
+    out[n].start_ms = a;
+    out[n].end_ms = b;
+    ++n;
   }
   return n;
 }

@@ -606,6 +606,7 @@ __global__ void __launch_bounds__(NT) k_dxfin(Plan P, OcTile T, const float* __r
   __shared__ __align__(16) float ws[PW_KC * (8 * TK + 4)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ic = P.ic;
+  const int o0 = blockIdx.y * T.occ;          // output-channel chunk of this CTA (small planes: several CTAs per pixel tile)
   Px4 px;
   px_decomp(px, blockIdx.x * PW_TPX + lane * 4, P.P, P.HW);
   float acc[TK][4];
@@ -623,15 +624,15 @@ __global__ void __launch_bounds__(NT) k_dxfin(Plan P, OcTile T, const float* __r
       if (kk < nk) load4(d, x, px, ic, k0 + kk, P.HW);
       *(float4*)(ins + kk * PW_LDP + lane * 4) = make_float4(d[0], d[1], d[2], d[3]);
     }
-    stage_w_t<TK>(ws, Mm, ic, 0, ic, k0, nk);
+    stage_w_t<TK>(ws, Mm, ic, o0, min(T.occ, ic - o0), k0, nk);
     __syncthreads();
     if (warp < T.ng) pw_mma<TK>(acc, ins, ws, lane, warp);
   }
   if (warp < T.ng) {
 #pragma unroll
     for (int j = 0; j < TK; ++j) {
-      const int k = warp * TK + j;
-      if (k < ic) {
+      const int k = o0 + warp * TK + j;
+      if (k < ic && warp * TK + j < T.occ) {
         float m[4], o[4], g[4] = {0.f, 0.f, 0.f, 0.f};
         load4(m, dx, px, ic, k, P.HW);
         if (P.residual) load4(g, G, px, ic, k, P.HW);   // residual => oc == ic, HWo == HW
@@ -894,7 +895,7 @@ template <int TK>
 static void launch_dxfin(const Plan& P, OcTile T, const float* x, const float* Mm, const float* cvec2, const float* G,
                          float* dx, cudaStream_t st) {
   ProfScope ps("dxfin", 4.0 * P.P * P.ic * (3.0 + (P.residual ? 1 : 0)), 2.0 * P.P * (double)P.ic * P.ic, st);
-  k_dxfin<TK><<<cdiv(P.P, PW_TPX), NT, 0, st>>>(P, T, x, Mm, cvec2, G, dx);
+  k_dxfin<TK><<<dim3(cdiv(P.P, PW_TPX), T.nchunk), NT, 0, st>>>(P, T, x, Mm, cvec2, G, dx);
 }
 
 // ---- side stream for the weight-gradient GEMMs ---------------------------------------------------------------------
@@ -930,7 +931,7 @@ static SideStream* side_stream_for(cudaStream_t main) {
 
 void launch_backward(const Plan& P, const float* x, const float* dout, const float* dlat, float T,
                      int alpha_mode, const char* saved, const SavedLayout& L, const BwdScratch& S,
-                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st) {
+                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st, int stop_at_da) {
   const double* xmom = (const double*)(saved + L.xmom);
   const float* bn1 = (const float*)(saved + L.bn1);
   const float* bn2 = (const float*)(saved + L.bn2);
@@ -957,7 +958,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       k_b2prep<<<1, 256, 0, st>>>(P, mixw, bn3, S.sG, S.sGY, S.dzc, S.dzc2, S.dmix); }
   }
   const float4* dzc = S.dzc;
-  if (!dx) {   // input needs no gradient (first MixedOP of the alpha step): only dL/dlog_alpha
+  if (!dx && !stop_at_da) {   // input needs no gradient (first MixedOP of the alpha step): only dL/dlog_alpha
     if (alpha_mode && dlog_alphas) {
       ProfScope ps("alpha_grad", 128, 0, st);
       k_alpha_grad<<<1, 32, 0, st>>>(P.num_ops, mixw, latsave, S.dmix, dlat, T, dlog_alphas);
@@ -969,7 +970,9 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   UmW WX;
   DxChunks CHX;
   if (umma_enabled()) {
-    umma_prep_bwd(P, bn1, S.umprep, WD, WX, CHX, st);
+    // stop_at_da (second stem: no expand conv in front of the depthwise stage): only the dc weights exist
+    if (stop_at_da) umma_prep_dc(P, S.umprep, WD, st);
+    else umma_prep_bwd(P, bn1, S.umprep, WD, WX, CHX, st);
     umma_dc(P, WD, dout, Zb, S.dzc2, D, bn2, S.DC, S.dg, S.sD, st);
   } else {
     int maxmc = 0;
@@ -977,7 +980,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     if (maxmc > 64) launch_dc<16>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
     else launch_dc<8>(P, maxmc, dout, Zb, bn3, dzc, D, bn2, S.DC, S.dg, S.sD, st);
   }
-  SideStream* side = (dweights && umma_enabled()) ? side_stream_for(st) : nullptr;
+  SideStream* side = (dweights && umma_enabled() && !stop_at_da) ? side_stream_for(st) : nullptr;
   const cudaStream_t wst = side ? side->s : st;      // stream of the weight-gradient GEMMs
   if (dweights) {   // dW3 = sum_p dz c^T  (reads D, dout, Z, bn2, seg, dzc2: none of them is written again in this call)
     if (side) { cudaEventRecord(side->fork1, st); cudaStreamWaitEvent(wst, side->fork1, 0); }
@@ -1043,6 +1046,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     launch_dw_bwd<3, 2>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
     launch_dw_bwd<5, 2>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
   }
+  if (stop_at_da) return;      // S.DA = dL/d act(UH); the caller finishes (first-stem BN backward + conv weight gradient)
   if (side) {
     // Smat = sum_p du-hat x^T reads DA / UH / x, final since the transposed depthwise: forked alongside the dx GEMM
     cudaEventRecord(side->fork2, st);
@@ -1111,12 +1115,20 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       count_launch(1); }
     { ProfScope ps("b4fin", 4.0 * ic * ic, 2.0 * ic * ic, st);
       k_b4fin<<<cdiv(ic, 64), 64, 0, st>>>(ic, S.Mm, xmom, S.cvec2); }
-    switch (Tx.TC) {
-      case 4: launch_dxfin<4>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
-      case 8: launch_dxfin<8>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
-      case 12: launch_dxfin<12>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
-      case 16: launch_dxfin<16>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
-      default: launch_dxfin<24>(P, Tx, x, S.Mm, S.cvec2, dout, dx, st); break;
+    // few pixel tiles (14x14 / 7x7 planes): split the output channels over several CTAs per tile so the grid covers the SMs
+    OcTile Tf = Tx;
+    {
+      const int tiles = cdiv(P.P, PW_TPX);
+      const int tcs[4] = {16, 12, 8, 4};
+      for (int t = 0; t < 4 && tiles * Tf.nchunk < 2 * sm_count(); ++t)
+        if (tcs[t] < Tf.TC) Tf = oc_tile(ic, tcs[t]);
+    }
+    switch (Tf.TC) {
+      case 4: launch_dxfin<4>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
+      case 8: launch_dxfin<8>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
+      case 12: launch_dxfin<12>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
+      case 16: launch_dxfin<16>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
+      default: launch_dxfin<24>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
     }
   }
   if (alpha_mode && dlog_alphas) {

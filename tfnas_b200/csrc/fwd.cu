@@ -154,6 +154,124 @@ __global__ void __launch_bounds__(NT) k_xcov(Plan P, const float* __restrict__ x
   }
 }
 
+// ONE pass over x for both input moments: S1[k] = sum_p x_k and S2[k][l] = sum_p x_k x_l (uncentred; centred in fp64 by
+// k_xfin_raw, like the BN2 / BN3 statistics).  A CTA walks tiles of TP pixels: the tile is staged in shared memory with a row
+// of ones appended (the Gram matrix's last column is then S1), threads own 4x4 blocks of the upper triangle (several pixel
+// slices per block when there are fewer blocks than threads, several blocks per thread when there are more) and keep their
+// partial sums in registers across tiles; one fp64 atomic per entry and CTA at the end.
+// XM_MAXB = blocks per thread: ic <= 192 -> 49 x 50 / 2 = 1225 blocks / 256 threads = 5; the narrow instantiations (1 block
+// for ic <= 87, 2 for ic <= 123) keep the register count low enough for 3-4 CTAs per SM
+template <int XM_MAXB>
+__global__ void __launch_bounds__(NT) k_xmom(Plan P, const float* __restrict__ x, int TP, int tp_shift,
+                                              double* __restrict__ xsum, double* __restrict__ xx) {
+  extern __shared__ float xs[];        // [icp][LD], LD = TP + 1 (odd: rows fall into different banks)
+  const int ic = P.ic, nb = (ic + 1 + 3) >> 2, icp = nb * 4, nut = nb * (nb + 1) / 2, LD = TP + 1;
+  const int tid = threadIdx.x;
+  const int nsplit = nut >= NT ? 1 : NT / nut;
+  const int sp = nut >= NT ? 0 : tid / nut;
+  const bool active = nut >= NT ? true : tid < nut * nsplit;
+  int bi[XM_MAXB], bj[XM_MAXB];
+#pragma unroll
+  for (int l = 0; l < XM_MAXB; ++l) {
+    int q = (nut >= NT ? tid : tid % nut) + l * NT;
+    bi[l] = -1; bj[l] = 0;
+    if (active && q < nut && (l == 0 || nut > NT)) {
+      int r = 0, rowlen = nb;
+      while (q >= rowlen) { q -= rowlen; ++r; --rowlen; }
+      bi[l] = r; bj[l] = r + q;
+    }
+  }
+  float acc[XM_MAXB][16];
+#pragma unroll
+  for (int l = 0; l < XM_MAXB; ++l)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[l][e] = 0.f;
+  const int ntiles = (P.P + TP - 1) >> tp_shift;
+  const float inv_hw = 1.f / (float)P.HW;
+  const bool vec = (P.HW & 3) == 0 && ((((uintptr_t)x) & 15) == 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile << tp_shift;
+    __syncthreads();
+    if (vec) {
+      const int q4 = TP >> 2;
+      for (int i = tid; i < icp * q4; i += NT) {
+        const int k = i / q4, pp = (i - k * q4) << 2, p = p0 + pp;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < P.P) {               // P.P % 4 == 0 here, so the four pixels are valid and in the same image
+          if (k < ic) {
+            const int n = fast_div(p, P.HW, inv_hw), hw = p - n * P.HW;
+            v = *(const float4*)(x + ((size_t)n * ic + k) * P.HW + hw);
+          } else if (k == ic) v = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        float* d = xs + k * LD + pp;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      for (int i = tid; i < icp * TP; i += NT) {
+        const int k = i >> tp_shift, pp = i & (TP - 1), p = p0 + pp;
+        float v = 0.f;
+        if (p < P.P) {
+          if (k < ic) {
+            const int n = fast_div(p, P.HW, inv_hw), hw = p - n * P.HW;
+            v = x[((size_t)n * ic + k) * P.HW + hw];
+          } else if (k == ic) v = 1.f;
+        }
+        xs[k * LD + pp] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < XM_MAXB; ++l) {
+      if (bi[l] < 0) continue;
+      const float* ra = xs + (bi[l] * 4) * LD;
+      const float* rb = xs + (bj[l] * 4) * LD;
+      for (int pp = sp; pp < TP; pp += nsplit) {
+        float a[4], b[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { a[e] = ra[e * LD + pp]; b[e] = rb[e * LD + pp]; }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[l][e] += a[e >> 2] * b[e & 3];
+      }
+    }
+  }
+  // entry (r, c) of block (bi, bj): rows / columns < ic are second moments, column ic (the ones row) holds the sums
+  auto emit = [&](int r, int c, double v, bool offdiag) {
+    if (r < ic && c < ic) {
+      atomicAdd(&xx[r * ic + c], v);
+      if (offdiag) atomicAdd(&xx[c * ic + r], v);
+    } else if (r < ic && c == ic) {
+      atomicAdd(&xsum[r], v);
+    }
+  };
+  if (nsplit > 1) {
+    __syncthreads();
+    float* red = xs;                 // [nsplit][nut][16] <= 256 * 16 floats
+    if (active)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) red[(sp * nut + (tid % nut)) * 16 + e] = acc[0][e];
+    __syncthreads();
+    for (int i = tid; i < nut * 16; i += NT) {
+      float t = 0.f;
+      for (int s2 = 0; s2 < nsplit; ++s2) t += red[s2 * nut * 16 + i];
+      int q = i >> 4, e = i & 15, r = 0, rowlen = nb;
+      while (q >= rowlen) { q -= rowlen; ++r; --rowlen; }
+      const int cb = r + q;
+      if (cb == r && (e >> 2) > (e & 3)) continue;          // diagonal block: upper triangle only
+      emit(r * 4 + (e >> 2), cb * 4 + (e & 3), (double)t, !(cb == r && (e >> 2) == (e & 3)));
+    }
+  } else {
+#pragma unroll
+    for (int l = 0; l < XM_MAXB; ++l) {
+      if (bi[l] < 0) continue;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if (bi[l] == bj[l] && (e >> 2) > (e & 3)) continue;
+        emit(bi[l] * 4 + (e >> 2), bj[l] * 4 + (e & 3), (double)acc[l][e], !(bi[l] == bj[l] && (e >> 2) == (e & 3)));
+      }
+    }
+  }
+}
+
 // normalise the accumulators into mean / biased covariance (double, kept in `saved`)
 __global__ void k_xfin(int ic, int Pn, const double* __restrict__ xsum, const double* __restrict__ xcov,
                        double* __restrict__ xmom) {
@@ -637,7 +755,24 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
   size_t zbytes = (size_t)(ic + ic * ic + 2 * P.MC + 2 * P.na * P.oc) * sizeof(double);
   cudaMemsetAsync(S.xsum, 0, zbytes, st);
   // F0
-  if (umma_enabled()) {
+  static const bool xmom_gemm = getenv("TFNAS_XMOM") && strcmp(getenv("TFNAS_XMOM"), "gemm") == 0;   // A/B: the two-pass tensor-core moments
+  if (umma_enabled() && !xmom_gemm) {
+    // one-pass moments: tile width by channel count so the staged tile stays under 52 KB (4 CTAs per SM)
+    const int icp = ((ic + 1 + 3) >> 2) << 2;
+    const int tp_shift = icp >= 96 ? 6 : icp >= 48 ? 7 : icp >= 24 ? 8 : 9, TP = 1 << tp_shift;
+    const size_t smem = (size_t)icp * (TP + 1) * 4;
+    const int tiles = cdiv(P.P, TP);
+    const int nb4 = icp >> 2, nut = nb4 * (nb4 + 1) / 2, maxb = cdiv(nut, NT);
+    { ProfScope ps("xmom", xbytes, 1.0 * P.P * ic * ic, st);
+      const int grid = max(1, min(tiles, 4 * sm_count()));
+      if (maxb <= 1) { ensure_smem(k_xmom<1>, smem); k_xmom<1><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xsum, S.xcov); }
+      else if (maxb <= 2) { ensure_smem(k_xmom<2>, smem); k_xmom<2><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xsum, S.xcov); }
+      else { ensure_smem(k_xmom<5>, smem); k_xmom<5><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xsum, S.xcov); } }
+    { ProfScope ps("xfin", 16.0 * ic * ic, 0, st);
+      k_xfin_raw<<<cdiv(ic * ic, 256), 256, 0, st>>>(ic, P.P, S.xsum, S.xcov, xmom); }
+    { ProfScope ps("bn1", 4.0 * P.MC * ic + 8.0 * ic * ic, 2.0 * P.MC * ic * ic, st);
+      k_bn1<<<cdiv(P.MC, BN1_CH), NT, (size_t)BN1_CH * ic * 4, st>>>(P, xmom, bn1); }
+  } else if (umma_enabled()) {
     int split = max(1, min(P.N, 4 * sm_count() / max(ic, 1)));
     { ProfScope ps("xsum", xbytes, 1.0 * P.P * ic, st);
       k_xsum<<<dim3(ic, split), NT, 0, st>>>(P, x, S.xsum); }
@@ -678,6 +813,26 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
       k_expand<8><<<grid, NT, 0, st>>>(P, x, bn1, UH);
     }
   }
+  launch_forward_tail(P, umma_enabled() ? &WP : nullptr, x, log_alphas, gumbel, lat8, T, alpha_mode, out, out_lat, saved, L, S, st);
+}
+
+// F1b .. F4 from a given UH = BN1-normalised pre-activation input of the depthwise stage (saved + L.UH) and bn1 (saved + L.bn1).
+// The second stem of the supernet (an MBConv without expand conv, models/model_search.py:220) enters here with UH = the
+// normalised first-stem convolution.  WP: project weights already prepped (tcgen05 path), nullptr on the SIMT path.
+// The BN2 / BN3 accumulators S.st2 / S.st3 must have been zeroed by the caller.
+void launch_forward_tail(const Plan& P, const UmWAll* WPp, const float* x, const float* log_alphas, const float* gumbel,
+                         const float* lat8, float T, int alpha_mode, float* out, float* out_lat, char* saved,
+                         const SavedLayout& L, const FwdScratch& S, cudaStream_t st) {
+  float* bn2 = (float*)(saved + L.bn2);
+  float* bn3 = (float*)(saved + L.bn3);
+  float* mixw = (float*)(saved + L.mixw);
+  float* latsave = (float*)(saved + L.lat);
+  float* sep = (float*)(saved + L.sep);
+  float* set = (float*)(saved + L.set);
+  float* seg = (float*)(saved + L.seg);
+  float* UH = (float*)(saved + L.UH);
+  float* D = (float*)(saved + L.D);
+  float* Zb = (float*)(saved + L.Z);
   // F1b
   static const bool dw_tile = getenv("TFNAS_DW") && strcmp(getenv("TFNAS_DW"), "tile") == 0;
   if (!dw_tile && dws_supported(P)) {
@@ -713,7 +868,7 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
   }
   // F3
   if (umma_enabled()) {
-    umma_project(P, WP, D, bn2, seg, Zb, S.st3, st);
+    umma_project(P, *WPp, D, bn2, seg, Zb, S.st3, st);
   } else {
     OcTile T3 = oc_tile(P.oc, 16);
     switch (T3.TC) {

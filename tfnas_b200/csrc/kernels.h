@@ -105,9 +105,17 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
                     const float* lat8, float T, int alpha_mode, float* out, float* out_lat,
                     char* saved, const SavedLayout& L, const FwdScratch& S, cudaStream_t st);
 
+void launch_forward_tail(const Plan& P, const UmWAll* WPp, const float* x, const float* log_alphas, const float* gumbel,
+                         const float* lat8, float T, int alpha_mode, float* out, float* out_lat, char* saved,
+                         const SavedLayout& L, const FwdScratch& S, cudaStream_t st);
+// project weights only (the second stem has no expand conv)
+void umma_prep_project(const Plan& P, float* prep_buf, UmWAll& WP, cudaStream_t st);
+// dc weights only
+void umma_prep_dc(const Plan& P, float* prep_buf, UmWAll& WD, cudaStream_t st);
+
 void launch_backward(const Plan& P, const float* x, const float* dout, const float* dlat, float T,
                      int alpha_mode, const char* saved, const SavedLayout& L, const BwdScratch& S,
-                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st);
+                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st, int stop_at_da = 0);
 
 void launch_sink_fwd(int K, size_t numel, const float* const* res, const float* betas,
                      const float* cumlat, float* out, float* out_lat, cudaStream_t st);

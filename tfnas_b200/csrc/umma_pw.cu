@@ -911,11 +911,14 @@ size_t umma_bwd_prep_bytes(const Plan& P) {
 struct PrepJob { const float* src; const float* kscale; float* dst; int ld_r, ld_k, nrows, K, Nc, nN, nK; };   // kscale: optional per-k factor
 struct PrepJobs { int n; PrepJob j[2 * TFNAS_MAX_OPS]; };
 
-// grid (max nK, max nN, jobs): all candidates' weights of one GEMM in ONE launch
+// grid (max nK, max nN, jobs): all candidates' weights of one GEMM in ONE launch.  A CTA converts one (K chunk, N chunk) tile:
+// coalesced loads along whichever index is contiguous in the source into a shared-memory tile, then one 16-byte chunk (4
+// consecutive k of a row) per thread: tf32 hi / lo split and two vector stores into the swizzled K-major layout.
 __global__ void __launch_bounds__(256) k_umma_prep_all(PrepJobs J) {
   const PrepJob& q = J.j[blockIdx.z];
   const int kc = blockIdx.x, nc = blockIdx.y;
   if (kc >= q.nK || nc >= q.nN) return;
+  __shared__ float tile[UM_KC][256 + 1];
   char* base = (char*)q.dst + ((size_t)nc * q.nK + kc) * 2 * q.Nc * 128;
   for (int i = threadIdx.x; i < q.Nc * UM_KC; i += blockDim.x) {
     int r, kk;
@@ -924,10 +927,18 @@ __global__ void __launch_bounds__(256) k_umma_prep_all(PrepJobs J) {
     const int gr = nc * q.Nc + r, k = kc * UM_KC + kk;
     float x = (gr < q.nrows && k < q.K) ? q.src[(size_t)gr * q.ld_r + (size_t)k * q.ld_k] : 0.f;
     if (q.kscale && k < q.K) x *= q.kscale[k];
-    float hi, lo;
-    split_tf32(x, hi, lo);
-    *(float*)(base + k_elem_off(r, kk)) = hi;
-    *(float*)(base + (size_t)q.Nc * 128 + k_elem_off(r, kk)) = lo;
+    tile[kk][r] = x;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < q.Nc * (UM_KC / 4); i += blockDim.x) {
+    const int r = i / (UM_KC / 4), kk = (i - r * (UM_KC / 4)) * 4;
+    float4 hi, lo;
+    split_tf32(tile[kk][r], hi.x, lo.x);
+    split_tf32(tile[kk + 1][r], hi.y, lo.y);
+    split_tf32(tile[kk + 2][r], hi.z, lo.z);
+    split_tf32(tile[kk + 3][r], hi.w, lo.w);
+    *(float4*)(base + k_elem_off(r, kk)) = hi;
+    *(float4*)(base + (size_t)q.Nc * 128 + k_elem_off(r, kk)) = lo;
   }
 }
 
@@ -956,6 +967,22 @@ void umma_prep_fwd(const Plan& P, float* prep_buf, UmWAll& WE, UmWAll& WP, cudaS
   float* cur = prep_buf;
   for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w1, P.ic, 1, P.c[s].mc, P.ic, WE.s[s], cur, UM_EXPAND_NCAP);
   for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w3, P.c[s].mc, 1, P.oc, P.c[s].mc, WP.s[s], cur);
+  prep_launch(J, st);
+}
+
+void umma_prep_project(const Plan& P, float* prep_buf, UmWAll& WP, cudaStream_t st) {
+  PrepJobs J;
+  J.n = 0;
+  float* cur = prep_buf;
+  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w3, P.c[s].mc, 1, P.oc, P.c[s].mc, WP.s[s], cur);
+  prep_launch(J, st);
+}
+
+void umma_prep_dc(const Plan& P, float* prep_buf, UmWAll& WD, cudaStream_t st) {
+  PrepJobs J;
+  J.n = 0;
+  float* cur = prep_buf;
+  for (int s = 0; s < P.na; ++s) prep(J, P.c[s].w3, 1, P.c[s].mc, P.c[s].mc, P.oc, WD.s[s], cur, UM_DC_NCAP);
   prep_launch(J, st);
 }
 

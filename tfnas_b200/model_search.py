@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .config import CAND_SPEC, PRIMITIVES, lut_key
-from .ops import ArenaPool, BodyCall, BodyFn, MixedOpCall, MixedOpFn, StageSinkFn, bn_act, dwconv
+from .ops import ArenaPool, BodyCall, BodyFn, StemFn, MixedOpCall, MixedOpFn, StageSinkFn, bn_act, dwconv
 
 __all__ = ['PRIMITIVES', 'OPS', 'MixedOP', 'MixedStage', 'Network', 'MBInvertedResBlock', 'ConvLayer',
            'LinearLayer', 'NoisePlan', 'injected', 'seed_noise', 'draw_gumbel']
@@ -361,8 +361,15 @@ class Network(nn.Module):
         if sampling and mode in ('gumbel', 'gumbel_2', 'min_alphas', 'max_alphas'):
             self.refresh_host_alphas()         # one device->host copy for all 18 MixedOPs instead of one each
         # stems / head run on cuDNN / cuBLAS in true fp32 (TF32 is switched off package-wide, tfnas_b200/__init__.py)
-        x = self.first_stem(x)
-        x = self.second_stem(x)
+        if self.use_body:
+            ss = self.second_stem
+            x = StemFn.apply(x, self.__dict__.setdefault('_arena_pool', ArenaPool()), self.first_stem.conv.weight,
+                             ss.depth_conv.conv.weight, ss.squeeze_excite.conv_reduce.weight,
+                             ss.squeeze_excite.conv_reduce.bias, ss.squeeze_excite.conv_expand.weight,
+                             ss.squeeze_excite.conv_expand.bias, ss.point_linear.conv.weight)
+        else:
+            x = self.first_stem(x)
+            x = self.second_stem(x)
         if self.use_body:
             x, lat = self._body(x, sampling, mode)
             out_lat = out_lat + lat

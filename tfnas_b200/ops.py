@@ -388,3 +388,62 @@ class BodyFn(torch.autograd.Function):
             out += dla_rows if need_da else [None] * nb
         out += dbe if need_db else [None] * len(betas)
         return tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Stems: first_stem (conv 3x3/2 + BN + ReLU) and second_stem (MBConv without expand) in one call per direction
+# ------------------------------------------------------------------------------------------------------------------
+_STEM_SLOTS = ('conv_w', 'dw', 'se_rw', 'se_rb', 'se_ew', 'se_eb', 'pw')
+
+
+def _stem_ptrs(tensors):
+    p = _lib.StemPtrs()
+    for name, t in zip(_STEM_SLOTS, tensors):
+        setattr(p, name, t.data_ptr())
+    return p
+
+
+class StemFn(torch.autograd.Function):
+    """forward(img, pool, conv_w, dw, se_rw, se_rb, se_ew, se_eb, pw) -> x0 [N, c_out, H/2, W/2]."""
+
+    @staticmethod
+    def forward(ctx, img, pool, *weights):
+        lib = _lib.load()
+        _require_cuda_f32(img, 'img')
+        img = img.contiguous()
+        for w in weights:
+            if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
+                raise _lib.TfnasError('stem parameters must be contiguous CUDA float32 tensors')
+        d = _lib.StemDesc()
+        d.N, d.c_in, d.H, d.W = img.shape
+        d.c_mid, d.se, d.c_out = weights[0].shape[0], weights[2].shape[0], weights[6].shape[0]
+        need_grad = any(ctx.needs_input_grad[2:])
+        nbytes = lib.tfnas_stem_arena_bytes(ctypes.byref(d), 1 if need_grad else 0)
+        if not nbytes:
+            check(-1)
+        lease = pool.lease(nbytes, img.device)
+        out = torch.empty((d.N, d.c_out, (d.H - 1) // 2 + 1, (d.W - 1) // 2 + 1), dtype=torch.float32, device=img.device)
+        wp = _stem_ptrs(weights)
+        check(lib.tfnas_stem_fwd(ctypes.byref(d), _ptr(img), ctypes.byref(wp), _ptr(out), _ptr(lease.buf), lease.buf.numel(),
+                                 _stream()))
+        ctx.desc, ctx.lease, ctx.wp = d, lease, wp
+        ctx.save_for_backward(img, *weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        lease = ctx.lease
+        if lease is None or lease.buf is None:
+            raise _lib.TfnasError('stem backward ran twice: the arena of the pass is released after the first backward')
+        img = ctx.saved_tensors[0]
+        weights = ctx.saved_tensors[1:]
+        gout = gout.contiguous()
+        flat = torch.empty(sum(w.numel() for w in weights), dtype=torch.float32, device=img.device)
+        grads = tuple(g.view(w.shape) for g, w in zip(flat.split([w.numel() for w in weights]), weights))
+        gp = _stem_ptrs(grads)
+        check(lib.tfnas_stem_bwd(ctypes.byref(ctx.desc), _ptr(img), ctypes.byref(ctx.wp), _ptr(gout), ctypes.byref(gp),
+                                 _ptr(lease.buf), lease.buf.numel(), _stream()))
+        lease.release()
+        ctx.lease = None
+        return (None, None) + grads
