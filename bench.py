@@ -267,7 +267,7 @@ def run_b200(args, rank, local, world, emit=print):
     from tfnas_b200 import _lib, config, model_search
     from tfnas_b200.model_search import Network
     from tfnas_b200.parallel import GradSync, SearchParallel
-    from tfnas_b200.search_loop import alpha_step, make_optimizers, w_step
+    from tfnas_b200.search_loop import DevicePrefetcher, alpha_step, make_optimizers, w_step
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback')
@@ -291,22 +291,26 @@ def run_b200(args, rank, local, world, emit=print):
             for _ in range(npool)]
     pool = [(x.to(dev), t.to(dev)) for x, t in host]
 
-    def unit(i, from_host):
+    def host_batches(steps):
+        """the pinned host batches of `steps` units in the order the units consume them"""
+        for i in range(steps):
+            for it in range(2):
+                yield host[(2 * i + it) % npool]
+                if it % 2 == 0:
+                    yield host[(2 * i + it + 1) % npool]
+
+    def unit(i, feed=None):
+        """feed: iterator of device batches copied from pinned host memory (e2e); None: batches resident in HBM"""
         losses = []
         for it in range(2):
-            src = host if from_host else pool
-            x, t = src[(2 * i + it) % npool]
-            if from_host:
-                x, t = x.to(dev, non_blocking=True), t.to(dev, non_blocking=True)
+            x, t = next(feed) if feed is not None else pool[(2 * i + it) % npool]
             lw, _ = w_step(model, x, t, criterion, opt_w, 5.0, sync, bisample=True)
             losses.append(lw)
             if it % 2 == 0:
-                xa, ta = src[(2 * i + it + 1) % npool]
-                if from_host:
-                    xa, ta = xa.to(dev, non_blocking=True), ta.to(dev, non_blocking=True)
+                xa, ta = next(feed) if feed is not None else pool[(2 * i + it + 1) % npool]
                 la, ll = alpha_step(model, xa, ta, criterion, opt_a, target_lat_for(world), 0.1, 5.0, sync)
                 losses += [la, ll]
-        if from_host:
+        if feed is not None:
             return [float(v) for v in torch.stack([v.detach().float() for v in losses]).cpu()]
         return losses
 
@@ -315,7 +319,7 @@ def run_b200(args, rank, local, world, emit=print):
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_ms = [0.0]
+    host_ms = [0.0, 0.0]
 
     def timed(from_host, steps):
         barrier()
@@ -323,9 +327,15 @@ def run_b200(args, rank, local, world, emit=print):
         l0 = _lib.launch_count()
         e0.record()
         h0 = time.perf_counter()
+        # e2e: every batch comes from pinned host memory inside the timed region (H2D on a copy stream, one batch ahead of
+        # the compute: search_loop.DevicePrefetcher, what train_search.py's loops use) and the losses are read back per unit
+        feed = iter(DevicePrefetcher(host_batches(steps), dev)) if from_host else None
+        b0 = net.__dict__.get('host_blocked_s', 0.0)
         for i in range(steps):
-            unit(i, from_host)
-        host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps     # host time to ENQUEUE a unit (no sync inside)
+            unit(i, feed)
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps     # host wall time to enqueue a unit ...
+        host_ms[1] = (net.__dict__.get('host_blocked_s', 0.0) - b0) * 1e3 / steps   # ... of which blocked in the one D2H read
+        # per unit (the new log_alphas the 'gumbel' sampling of the next w-step needs: it waits for the alpha update)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -336,30 +346,30 @@ def run_b200(args, rank, local, world, emit=print):
         return ms, _lib.launch_count() - l0
 
     for i in range(args.warmup):
-        unit(i, False)
+        unit(i)
     if not args.profile_only:
         # two more untimed units: every step samples new candidates, so the caching allocator (workspace sizes) and the
         # optimiser (momentum buffers of first-seen candidates) keep growing for a few units; a cudaMalloc inside the timed
         # region showed up once as a 15 % outlier of `value` next to an unaffected `e2e`
         for i in range(EXTRA_WARMUP):
-            unit(args.warmup + i, False)
+            unit(args.warmup + i)
     if args.profile_only:      # under ncu: just run K more units and leave (numbers under a profiler are not bench values)
         for i in range(args.steps):
-            unit(i, False)
+            unit(i)
         torch.cuda.synchronize()
         return
     sampler = ClockSampler(local)
     sampler.start()
     ms, launches = timed(False, args.steps)
-    host_enqueue = host_ms[0]
+    host_enqueue, host_blocked = host_ms[0], host_ms[1]
     sampler.stop()
-    unit(0, True)                                           # warm the H2D path
+    unit(0, iter(DevicePrefetcher(host_batches(1), dev)))     # warm the H2D path
     ms_e2e, _ = timed(True, args.steps)
     # per-kernel attribution over the same K units (CUDA events on the launching stream)
     _lib.prof_enable(True)
     barrier()
     for i in range(args.steps):
-        unit(i, False)
+        unit(i)
     torch.cuda.synchronize()
     recs = _lib.prof_collect()
     _lib.prof_enable(False)
@@ -398,7 +408,9 @@ def run_b200(args, rank, local, world, emit=print):
             'dtype': 'f32', 'data': 'synthetic', 'config': base_config(world),
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * 4,
                     'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches, 'host_enqueue_ms_per_step': host_enqueue, 'extra_untimed_warmup': EXTRA_WARMUP, 'clocks': sampler.summary(),
+            'gpu_launches': launches, 'launches_per_step': launches / args.steps,
+            'host_enqueue_ms_per_step': host_enqueue, 'host_blocked_on_gpu_ms_per_step': host_blocked,
+            'host_busy_ms_per_step': host_enqueue - host_blocked, 'extra_untimed_warmup': EXTRA_WARMUP, 'clocks': sampler.summary(),
             'roofline': roofline}
     line['mixedop_roofline'] = mop
     if world == 1 and not args.no_cpu_baseline:

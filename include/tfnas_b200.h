@@ -8,7 +8,9 @@
  *   - returns 0 on success, a negative TFNAS_E_* code otherwise (message via
  *     tfnas_last_error()), never throws across the ABI;
  *   - never allocates or frees caller memory, never synchronises the device;
- *   - launches only on the cudaStream_t it is given (passed as void*).
+ *   - orders all its work on the cudaStream_t it is given (passed as void*): the weight-gradient GEMMs of a backward
+ *     call may run on a library-owned side stream that is forked from and joined back into the caller's stream by
+ *     events INSIDE the call (TFNAS_SIDE_STREAM=0 keeps everything on the caller's stream).
  * All tensors are fp32, contiguous NCHW, device memory, 16-byte aligned.
  *
  * Reference interfaces replaced (paths relative to the reference tree):

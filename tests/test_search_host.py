@@ -120,3 +120,36 @@ def test_master_copy_round_trip_and_channel_reselection():
     assert torch.equal(master[key][:, off], before[key][:, off])        # masked-out channels untouched
     op_w, depth_w = parsing.get_op_and_depth_weights(narrow)
     assert len(op_w) == 18 and len(depth_w) == 6 and abs(float(op_w[0].sum()) - 1.0 * np.exp(1.0) * 1.0) >= 0
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference not mounted')
+def test_checkpoint_is_consumed_by_the_reference_parser_and_model(tmp_path):
+    """A checkpoint written the way train_search.py writes it (max-width state_dict under 'module.' + channel masks) goes
+    through the REFERENCE's own parsing_model.get_op_and_depth_weights / parse_architecture / get_mc_num_dddict and loads
+    (strict) into the reference's own search Network."""
+    import torch.nn.functional as F
+    ms, _cfg, pm = ref_shim._import()
+    lut = gi.load_lut()
+    mx = config.get_mc_num_dddict(config.mc_mask_dddict, is_max=True)
+    model = SearchParallel(Network(100, mx, lut))
+    g = torch.Generator().manual_seed(0)
+    sd = model.state_dict()
+    for k in sd:
+        if k.endswith('log_alphas'):
+            sd[k] = F.log_softmax(torch.randn(8, generator=g), -1)
+        elif k.endswith('betas'):
+            sd[k] = torch.randn(sd[k].shape, generator=g)
+    masks = config.make_mc_mask_dddict()
+    masks['stage3']['block2'][1][-17:] = 0
+    path = str(tmp_path / 'searched_model_03.pth.tar')
+    torch.save({'state_dict': sd, 'mc_mask_dddict': masks}, path)
+    op_w, depth_w = pm.get_op_and_depth_weights(path)
+    ours_op, ours_depth = parsing.get_op_and_depth_weights(path)
+    assert len(op_w) == 18 and len(depth_w) == 6
+    assert all(np.array_equal(a, b) for a, b in zip(op_w, ours_op)) and all(np.array_equal(a, b) for a, b in zip(depth_w, ours_depth))
+    assert pm.parse_architecture(op_w, depth_w) == parsing.parse_architecture(ours_op, ours_depth)
+    ref_masks = torch.load(path, weights_only=False)['mc_mask_dddict']
+    assert pm.get_mc_num_dddict(ref_masks) == config.get_mc_num_dddict(masks)
+    ref_net = ms.Network(100, mx, lut)
+    missing = ref_net.load_state_dict({k[len('module.'):]: v for k, v in sd.items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys

@@ -902,13 +902,14 @@ static void launch_dxfin(const Plan& P, OcTile T, const float* x, const float* M
 // dW3 / dW1 only feed the caller (nothing on the dgrad chain reads them), and a sampled single-candidate pass leaves most
 // SMs idle, so they are forked onto a library-owned stream per caller stream and joined before the call's last kernels:
 // every launch of the call is still ordered before whatever the caller enqueues next on ITS stream.
-// Opt-in (TFNAS_SIDE_STREAM=1): with the two sampled passes of a w-step already on two streams (search_loop.w_step) the
-// extra stream measured no gain on B200 (1843 vs 1907 images/s), so by default everything stays on the caller's stream.
+// On by default since round 2 (TFNAS_SIDE_STREAM=0 disables): with the launch sequence issued from C++ (body executor) the
+// weight-gradient GEMMs of a sampled pass overlap the dx chain instead of sitting on its critical path: 2288 -> 2322
+// images/s (profiles/bench_r2*.json).  Round 1, with Python issuing every launch, had measured no gain (1843 vs 1907).
 #include <map>
 #include <mutex>
 struct SideStream { cudaStream_t s; cudaEvent_t fork1, fork2, join; };
 static SideStream* side_stream_for(cudaStream_t main) {
-  static const bool on = getenv("TFNAS_SIDE_STREAM") && strcmp(getenv("TFNAS_SIDE_STREAM"), "1") == 0;
+  static const bool on = !(getenv("TFNAS_SIDE_STREAM") && strcmp(getenv("TFNAS_SIDE_STREAM"), "0") == 0);
   if (!on) return nullptr;
   static std::map<std::pair<int, cudaStream_t>, SideStream> streams;
   static std::mutex mu;

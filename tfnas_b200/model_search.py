@@ -17,6 +17,7 @@ Differences that are deliberate and documented in DESIGN.md:
 import ctypes
 import os
 import random
+import time
 from collections import OrderedDict
 
 import torch
@@ -357,19 +358,26 @@ class Network(nn.Module):
         self._initialization()
 
     def forward(self, x, sampling, mode='max'):
+        return self.forward_from_stem(self.forward_stems(x), sampling, mode)
+
+    def forward_stems(self, x):
+        """first_stem + second_stem (models/model_search.py:283-284).  Split out so a bi-sampled w-step can evaluate the
+        stems ONCE for its two sampled sub-networks: both see the same batch and the same stem weights, so the stem output
+        (and, by linearity, one backward over the summed gradient) is shared -- identical to two full forwards."""
+        if self.use_body:
+            ss = self.second_stem
+            return StemFn.apply(x, self.__dict__.setdefault('_arena_pool', ArenaPool()), self.first_stem.conv.weight,
+                                ss.depth_conv.conv.weight, ss.squeeze_excite.conv_reduce.weight,
+                                ss.squeeze_excite.conv_reduce.bias, ss.squeeze_excite.conv_expand.weight,
+                                ss.squeeze_excite.conv_expand.bias, ss.point_linear.conv.weight)
+        # stems / head on cuDNN / cuBLAS run in true fp32 (TF32 is switched off package-wide, tfnas_b200/__init__.py)
+        return self.second_stem(self.first_stem(x))
+
+    def forward_from_stem(self, x, sampling, mode='max'):
+        """stage1..6, feature mix, pooling, classifier (models/model_search.py:285-304) from the stem output."""
         out_lat = self.lat_lookup['base'] if not sampling else 0.0
         if sampling and mode in ('gumbel', 'gumbel_2', 'min_alphas', 'max_alphas'):
             self.refresh_host_alphas()         # one device->host copy for all 18 MixedOPs instead of one each
-        # stems / head run on cuDNN / cuBLAS in true fp32 (TF32 is switched off package-wide, tfnas_b200/__init__.py)
-        if self.use_body:
-            ss = self.second_stem
-            x = StemFn.apply(x, self.__dict__.setdefault('_arena_pool', ArenaPool()), self.first_stem.conv.weight,
-                             ss.depth_conv.conv.weight, ss.squeeze_excite.conv_reduce.weight,
-                             ss.squeeze_excite.conv_reduce.bias, ss.squeeze_excite.conv_expand.weight,
-                             ss.squeeze_excite.conv_expand.bias, ss.point_linear.conv.weight)
-        else:
-            x = self.first_stem(x)
-            x = self.second_stem(x)
         if self.use_body:
             x, lat = self._body(x, sampling, mode)
             out_lat = out_lat + lat
@@ -481,7 +489,11 @@ class Network(nn.Module):
         if not stale:
             return
         if len(set(m.log_alphas.numel() for m in stale)) == 1 and len(set(m.log_alphas.device for m in stale)) == 1:
+            t0 = time.perf_counter()
             flat = torch.stack([m.log_alphas.detach().float().reshape(-1) for m in stale]).cpu()
+            # the copy drains the stream (it waits for the alpha update it reads): host time spent BLOCKED here is GPU time,
+            # not host work -- bench.py subtracts it from the enqueue time it reports
+            self.__dict__['host_blocked_s'] = self.__dict__.get('host_blocked_s', 0.0) + (time.perf_counter() - t0)
             for m, row in zip(stale, flat):
                 m._host_alpha = (m.log_alphas._version, row.clone(), m.log_alphas.data_ptr())
         else:                                   # mixed widths / devices: per-module copies

@@ -42,6 +42,49 @@ class DeviceMeter(object):
         return float(self.sum) / max(self.cnt, 1)
 
 
+class DevicePrefetcher(object):
+    """Iterate a queue of (pinned) host batches with the host->device copy of batch i+1 running on a side stream while step i
+    computes (the reference copies on the compute stream right before use, train_search.py:367-368).  Yields device
+    tensors that are safe to use on the current stream."""
+
+    _STREAMS = {}
+
+    def __init__(self, queue, device=None):
+        self.queue = queue
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def __len__(self):
+        return len(self.queue)
+
+    def _load(self, batch):
+        key = self.device.index
+        if key not in DevicePrefetcher._STREAMS:
+            DevicePrefetcher._STREAMS[key] = torch.cuda.Stream(device=self.device)
+        cs = DevicePrefetcher._STREAMS[key]
+        with torch.cuda.stream(cs):
+            dev = tuple(t.to(self.device, non_blocking=True) for t in batch)
+            ev = cs.record_event()
+        return dev, ev
+
+    def __iter__(self):
+        it = iter(self.queue)
+        try:
+            nxt = self._load(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            batch, ev = nxt
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for t in batch:
+                t.record_stream(cur)
+            try:
+                nxt = self._load(next(it))
+            except StopIteration:
+                nxt = None
+            yield batch
+
+
 def accuracy(output, target, topk=(1,)):
     """tools/utils.py:61-74, returning device tensors (no host sync)."""
     maxk = max(topk)
@@ -83,17 +126,21 @@ def w_step(model, x_w, target_w, criterion, optimizer_w, grad_clip, sync=None, b
     if bisample and overlap and x_w.is_cuda:
         cur = torch.cuda.current_stream(x_w.device)
         s1, s2 = _side_streams(x_w.device)
+        # the stems see the same batch and the same weights in both sampled sub-networks: evaluate them once (and, in
+        # backward, once over the sum of the two gradients) -- same result as two full forwards
+        shared = hasattr(net, 'forward_stems')
+        x0 = net.forward_stems(x_w) if shared else None
         s1.wait_stream(cur)
         s2.wait_stream(cur)
         with torch.cuda.stream(s1):
-            logits_g, _ = model(x_w, sampling=True, mode='gumbel')
+            logits_g, _ = net.forward_from_stem(x0, True, 'gumbel') if shared else model(x_w, sampling=True, mode='gumbel')
             loss_g = criterion(logits_g, target_w)
         with torch.cuda.stream(s2):
-            logits_r, _ = model(x_w, sampling=True, mode='random')
+            logits_r, _ = net.forward_from_stem(x0, True, 'random') if shared else model(x_w, sampling=True, mode='random')
             loss_r = criterion(logits_r, target_w)
         cur.wait_stream(s1)
         cur.wait_stream(s2)
-        for t in (x_w, target_w):
+        for t in (x_w, target_w) + ((x0,) if shared else ()):
             t.record_stream(s1)
             t.record_stream(s2)
         for t in (logits_g, loss_g):
@@ -152,9 +199,7 @@ def train_wo_arch(train_queue, model, criterion, optimizer_w, args, sync=None):
     objs_w, top1, top5 = DeviceMeter(), DeviceMeter(), DeviceMeter()
     model.train()
     sync = sync if sync is not None else GradSync()
-    for step, (x_w, target_w) in enumerate(train_queue):
-        x_w = x_w.cuda(non_blocking=True)
-        target_w = target_w.cuda(non_blocking=True)
+    for step, (x_w, target_w) in enumerate(DevicePrefetcher(train_queue)):
         loss, logits = w_step(model, x_w, target_w, criterion, optimizer_w, args.grad_clip, sync, bisample=False)
         prec1, prec5 = accuracy(logits, target_w, topk=(1, 5))
         n = x_w.size(0)
@@ -172,9 +217,7 @@ def train_w_arch(train_queue, val_queue, model, criterion, optimizer_w, optimize
     model.train()
     sync = sync if sync is not None else GradSync()
     val_queue_iter = None
-    for step, (x_w, target_w) in enumerate(train_queue):
-        x_w = x_w.cuda(non_blocking=True)
-        target_w = target_w.cuda(non_blocking=True)
+    for step, (x_w, target_w) in enumerate(DevicePrefetcher(train_queue)):
         loss_w, logits = w_step(model, x_w, target_w, criterion, optimizer_w, args.grad_clip, sync, bisample=True)
         prec1, prec5 = accuracy(logits, target_w, topk=(1, 5))
         n = x_w.size(0)
@@ -185,10 +228,8 @@ def train_w_arch(train_queue, val_queue, model, criterion, optimizer_w, optimize
             try:
                 x_a, target_a = next(val_queue_iter)
             except (StopIteration, TypeError):
-                val_queue_iter = iter(val_queue)
+                val_queue_iter = iter(DevicePrefetcher(val_queue))
                 x_a, target_a = next(val_queue_iter)
-            x_a = x_a.cuda(non_blocking=True)
-            target_a = target_a.cuda(non_blocking=True)
             loss_a, loss_l = alpha_step(model, x_a, target_a, criterion, optimizer_a, args.target_lat,
                                         args.lambda_lat, args.grad_clip, sync)
             n = x_a.size(0)
@@ -203,9 +244,7 @@ def train_w_arch(train_queue, val_queue, model, criterion, optimizer_w, optimize
 def validate(val_queue, model, criterion, args):
     objs, top1, top5 = DeviceMeter(), DeviceMeter(), DeviceMeter()
     model.train()    # batch statistics on purpose: no running stats exist (quirk Q7)
-    for step, (x, target) in enumerate(val_queue):
-        x = x.cuda(non_blocking=True)
-        target = target.cuda(non_blocking=True)
+    for step, (x, target) in enumerate(DevicePrefetcher(val_queue)):
         with torch.no_grad():
             logits, _ = model(x, sampling=True, mode='gumbel')
             loss = criterion(logits, target)

@@ -123,6 +123,7 @@ def main(argv=None):
     fmt = '%(asctime)s %(message)s'
     logging.basicConfig(stream=sys.stdout, level=logging.INFO if rank == 0 else logging.WARNING, format=fmt,
                         datefmt='%m/%d %I:%M:%S %p')
+    logging.getLogger().setLevel(logging.INFO if rank == 0 else logging.WARNING)     # basicConfig is a no-op under a host app
     if rank == 0:
         fh = logging.FileHandler(os.path.join(args.save, 'log.txt'))
         fh.setFormatter(logging.Formatter(fmt))
