@@ -28,6 +28,17 @@ def _worker(rank, world, port_no, q):
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world)
     try:
+        _worker_body(rank, world, q)
+    except BaseException as e:          # a failing rank must not leave its peer waiting in a collective until the timeout
+        import traceback
+        q.put((rank, 'error', traceback.format_exc()))
+        os._exit(1)
+    finally:
+        dist.destroy_process_group()
+
+
+def _worker_body(rank, world, q):
+    if True:
         import random
         import torch.nn.functional as F
         from oracle import port
@@ -98,8 +109,6 @@ def _worker(rank, world, port_no, q):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         q.put((rank, worst, same_keys and same_idx, nbytes, bool((lo == hi).all().item())))
-    finally:
-        dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
@@ -110,10 +119,19 @@ def test_two_gpu_nccl_grad_mean_and_weight_sync():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in procs)
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    res = []
+    try:
+        for _ in procs:
+            r = q.get(timeout=300)
+            assert r[1] != 'error', r[2]
+            res.append(r)
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
+    res.sort()
+    assert all(p.exitcode == 0 for p in procs)
     for rank, worst, same_keys, nbytes, synced in res:
         print('rank', rank, 'worst element-wise rel-l2 of the all-reduced grads vs the mean of per-shard ORACLE grads', worst,
               'bucket bytes', nbytes)

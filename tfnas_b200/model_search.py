@@ -404,7 +404,7 @@ class Network(nn.Module):
             d.num_stages = len(stages)
             N, _c, H, W = x.shape
             bi = 0
-            lat_rows = []
+            sizes_in = []
             for si, st in enumerate(stages):
                 if st.start_res != 1:
                     raise _lib.TfnasError('the body executor sums the outputs of all blocks of a stage (start_res == 1)')
@@ -413,12 +413,11 @@ class Network(nn.Module):
                     m = getattr(st, 'block%d' % (j + 1))
                     call = m._call(torch.empty((N, m.in_channels, H, W), device='meta'), (1 << m.num_ops) - 1)
                     ctypes_copy(d.op[bi], call.desc)
-                    lat_rows.append(m.get_lookup_latency(H) + [0.0] * (_lib.MAX_OPS - m.num_ops))
+                    sizes_in.append(H)
                     _n, _oc, H, W = call.out_shape()
                     bi += 1
             d.num_blocks = bi
             out_shape = (N, d.op[bi - 1].oc, H, W)
-            lat = torch.tensor(lat_rows, dtype=torch.float32, device=x.device)
             lib = _lib.load()
             full = _lib.BodyMasks(*[(1 << d.op[i].num_ops) - 1 for i in range(bi)])
             # the largest candidate of every MixedOP (k5, e6, SE: the last primitive) bounds the arena of any sampled pass
@@ -427,11 +426,21 @@ class Network(nn.Module):
                          sampled=lib.tfnas_body_arena_bytes(ctypes.byref(d), big, 1))
             if not sizes['alpha'] or not sizes['sampled']:
                 _lib.check(-1)
-            c[key] = (d, bi, out_shape, lat, sizes)
+            c[key] = [d, bi, out_shape, None, sizes, sizes_in]
         return c[key]
 
+    def _body_lat_table(self, entry, device):
+        """[num_blocks, 8] LUT latencies of every candidate at this input size (alpha mode only: the sampled passes never
+        touch the LUT, models/model_search.py:84-85, so an image size the LUT does not cover is fine there)."""
+        if entry[3] is None:
+            mops = self._param_lists()[4]
+            rows = [m.get_lookup_latency(h) + [0.0] * (_lib.MAX_OPS - m.num_ops) for m, h in zip(mops, entry[5])]
+            entry[3] = torch.tensor(rows, dtype=torch.float32, device=device)
+        return entry[3]
+
     def _body(self, x, sampling, mode):
-        d, nb, out_shape, lat, sizes = self._body_desc(x)
+        entry = self._body_desc(x)
+        d, nb, out_shape, _lat, sizes = entry[:5]
         mops = self._param_lists()[4]
         pool = self.__dict__.setdefault('_arena_pool', ArenaPool())
         betas = [st.betas for st in self._stages()]
@@ -467,6 +476,7 @@ class Network(nn.Module):
             n_per.append(per)
             active.append(list(range(m.num_ops)))
         masks = [(1 << m.num_ops) - 1 for m in mops]
+        lat = self._body_lat_table(entry, x.device)
         call = BodyCall(d, nb, len(betas), masks, True, T, gd, lat, active, n_per, pool, sizes['alpha'], out_shape)
         return BodyFn.apply(x, call, *(tensors + [m.log_alphas for m in mops] + betas))
 
