@@ -261,6 +261,29 @@ int tfnas_stem_fwd(const TfnasStemDesc* d, const float* img, const TfnasStemPtrs
 int tfnas_stem_bwd(const TfnasStemDesc* d, const float* img, const TfnasStemPtrs* w, const float* dout,
                    const TfnasStemPtrs* dw, void* arena, size_t arena_bytes, void* stream);
 
+
+/* =====================================================================================================================
+ * The head of Network.forward (reference models/model_search.py:275-277, :299-302): feature_mix_layer = ConvLayer(320,
+ * 1280, k1, BN, Swish), AdaptiveAvgPool2d(1), LinearLayer(1280, num_classes).  BN = batch statistics, no affine.
+ * ===================================================================================================================== */
+typedef struct TfnasHeadDesc {
+  int32_t N, H, W;        /* input [N, c_in, H, W] (the last stage's output) */
+  int32_t c_in;           /* 320 */
+  int32_t c_mid;          /* 1280 */
+  int32_t num_classes;
+} TfnasHeadDesc;
+typedef struct TfnasHeadPtrs {
+  float* fm_w;            /* feature_mix_layer.conv.weight  [c_mid, c_in]        */
+  float* fc_w;            /* classifier.linear.weight       [num_classes, c_mid] */
+  float* fc_b;            /* classifier.linear.bias         [num_classes]        */
+} TfnasHeadPtrs;
+size_t tfnas_head_arena_bytes(const TfnasHeadDesc* d);
+int tfnas_head_fwd(const TfnasHeadDesc* d, const float* x, const TfnasHeadPtrs* w, float* logits, void* arena,
+                   size_t arena_bytes, void* stream);
+/* dx: dL/dx (written).  dw: gradients of the three parameters (written) or NULL (alpha step: weights frozen). */
+int tfnas_head_bwd(const TfnasHeadDesc* d, const float* x, const TfnasHeadPtrs* w, const float* dlogits, float* dx,
+                   const TfnasHeadPtrs* dw, void* arena, size_t arena_bytes, void* stream);
+
 /* =====================================================================================================================
  * Step glue of train_w_arch (reference train_search.py:381-385 and :414-422): global-norm gradient clipping fused with
  * the optimiser update over a table of the LIVE tensors (parameters whose gradient exists this step -- the reference's

@@ -53,3 +53,40 @@ def test_stem_no_grad_forward():
         out = StemFn.apply(img, ArenaPool(), *w)
     ref, _ = _ref(img, w, torch.float64)
     assert H.rel_l2(out, ref) < 1e-4
+
+
+def _head_ref(x, fm_w, fc_w, fc_b, dtype):
+    ws = [t.detach().to(dtype).requires_grad_(True) for t in (fm_w, fc_w, fc_b)]
+    xr = x.detach().to(dtype).requires_grad_(True)
+    y = F.batch_norm(F.conv2d(xr, ws[0]), None, None, None, None, True, 0.0, 1e-5)
+    y = y * torch.sigmoid(y)
+    p = F.adaptive_avg_pool2d(y, 1).flatten(1)
+    return F.linear(p, ws[1], ws[2]), xr, ws
+
+
+@pytest.mark.parametrize('N,hw,cin,cmid,ncls', [(4, 7, 320, 1280, 100), (128, 7, 320, 1280, 100), (3, 5, 72, 200, 10)])
+def test_head_matches_torch_fp64(N, hw, cin, cmid, ncls):
+    """tfnas_head_fwd/_bwd (feature-mix 1x1 conv on the tcgen05 project / dc / weight-gradient kernels with the identity
+    activation, BN + Swish + pooling, classifier) against torch fp64: logits, dx and the three weight gradients."""
+    from tfnas_b200.ops import HeadFn
+    g = torch.Generator().manual_seed(N + hw)
+    x = torch.randn(N, cin, hw, hw, generator=g).cuda().requires_grad_(True)
+    fm_w = (torch.randn(cmid, cin, 1, 1, generator=g) / cin ** 0.5).cuda().requires_grad_(True)
+    fc_w = (torch.randn(ncls, cmid, generator=g) / cmid ** 0.5).cuda().requires_grad_(True)
+    fc_b = (torch.randn(ncls, generator=g) * 0.1).cuda().requires_grad_(True)
+    G = torch.randn(N, ncls, generator=g).cuda()
+    pool = ArenaPool()
+    logits = HeadFn.apply(x, pool, fm_w, fc_w, fc_b)
+    (logits * G).sum().backward()
+    ref, xr, ws = _head_ref(x, fm_w, fc_w, fc_b, torch.float64)
+    (ref * G.double()).sum().backward()
+    e = dict(logits=H.rel_l2(logits, ref), dx=H.rel_l2(x.grad, xr.grad), fm_w=H.rel_l2(fm_w.grad, ws[0].grad),
+             fc_w=H.rel_l2(fc_w.grad, ws[1].grad), fc_b=H.rel_l2(fc_b.grad, ws[2].grad))
+    print('head N=%d %dx%d %d->%d->%d errors' % (N, hw, hw, cin, cmid, ncls), {k: '%.1e' % v for k, v in e.items()})
+    assert all(v < 1e-3 for v in e.values()), e
+    assert len(pool.free) == 1
+    # weights frozen (alpha step): dx only
+    x2 = x.detach().clone().requires_grad_(True)
+    l2 = HeadFn.apply(x2, pool, fm_w.detach(), fc_w.detach(), fc_b.detach())
+    (l2 * G).sum().backward()
+    assert H.rel_l2(x2.grad, xr.grad) < 1e-3

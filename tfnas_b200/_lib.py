@@ -53,6 +53,15 @@ class StemPtrs(ctypes.Structure):
                 ('se_rb', ctypes.c_void_p), ('se_ew', ctypes.c_void_p), ('se_eb', ctypes.c_void_p), ('pw', ctypes.c_void_p)]
 
 
+class HeadDesc(ctypes.Structure):
+    _fields_ = [('N', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('c_in', ctypes.c_int32),
+                ('c_mid', ctypes.c_int32), ('num_classes', ctypes.c_int32)]
+
+
+class HeadPtrs(ctypes.Structure):
+    _fields_ = [('fm_w', ctypes.c_void_p), ('fc_w', ctypes.c_void_p), ('fc_b', ctypes.c_void_p)]
+
+
 class SgdTensor(ctypes.Structure):
     _fields_ = [('p', ctypes.c_void_p), ('g', ctypes.c_void_p), ('buf', ctypes.c_void_p), ('numel', ctypes.c_int64)]
 
@@ -80,6 +89,7 @@ EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_dwconv_fwd', 'tfnas_dwconv_bwd', 'tfnas_debug_ws_config',
            'tfnas_body_arena_bytes', 'tfnas_body_fwd', 'tfnas_body_bwd',
            'tfnas_stem_arena_bytes', 'tfnas_stem_fwd', 'tfnas_stem_bwd',
+           'tfnas_head_arena_bytes', 'tfnas_head_fwd', 'tfnas_head_bwd',
            'tfnas_sgd_step', 'tfnas_adam_step', 'tfnas_softmax_ce']
 
 _lib = None
@@ -155,6 +165,13 @@ def load():
     lib.tfnas_stem_fwd.argtypes = [sdp, vp, spp, vp, vp, sz, vp]
     lib.tfnas_stem_bwd.restype = i32
     lib.tfnas_stem_bwd.argtypes = [sdp, vp, spp, vp, spp, vp, sz, vp]
+    hdp, hpp = ctypes.POINTER(HeadDesc), ctypes.POINTER(HeadPtrs)
+    lib.tfnas_head_arena_bytes.restype = sz
+    lib.tfnas_head_arena_bytes.argtypes = [hdp]
+    lib.tfnas_head_fwd.restype = i32
+    lib.tfnas_head_fwd.argtypes = [hdp, vp, hpp, vp, vp, sz, vp]
+    lib.tfnas_head_bwd.restype = i32
+    lib.tfnas_head_bwd.argtypes = [hdp, vp, hpp, vp, vp, hpp, vp, sz, vp]
     lib.tfnas_sgd_step.restype = i32
     lib.tfnas_sgd_step.argtypes = [i32, ctypes.POINTER(SgdTensor), f32, f32, f32, f32, f32, vp, vp, sz, vp]
     lib.tfnas_adam_step.restype = i32

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libtfnas_b200.so')
-SOURCES = ['api.cu', 'body.cu', 'stem.cu', 'optim.cu', 'fwd.cu', 'bwd.cu', 'stage.cu', 'umma_selftest.cu', 'umma_pw.cu', 'umma_ws.cu', 'dws.cu']
+SOURCES = ['api.cu', 'body.cu', 'stem.cu', 'head.cu', 'optim.cu', 'fwd.cu', 'bwd.cu', 'stage.cu', 'umma_selftest.cu', 'umma_pw.cu', 'umma_ws.cu', 'dws.cu']
 HEADERS = ['common.cuh', 'kernels.h', 'api_internal.h', 'pw.cuh', 'umma.cuh', os.path.join('..', '..', 'include', 'tfnas_b200.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-DTFNAS_NO_FAST_MATH',

@@ -1000,6 +1000,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       }
     }
   }
+  if (stop_at_da == 2) return;     // head (feature-mix conv): S.DC = dL/d(input), dW3 written; no depthwise stage behind it
   // SE backward + B2b
   if (P.MCse > 0) {
     int maxmc = 0, maxse = 0;

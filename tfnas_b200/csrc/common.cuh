@@ -50,12 +50,14 @@ __device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.f + ex2_f
 template <int ACT>
 __device__ __forceinline__ float act_f(float x) {
   if (ACT == TFNAS_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == TFNAS_ACT_NONE) return x;          // the head's feature-mix conv reads the sink output as is
   return x * sigmoid_f(x);
 }
 // derivative of the activation at pre-activation x
 template <int ACT>
 __device__ __forceinline__ float act_df(float x) {
   if (ACT == TFNAS_ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  if (ACT == TFNAS_ACT_NONE) return 1.f;
   const float s = sigmoid_f(x);
   return s * (1.f + x * (1.f - s));
 }

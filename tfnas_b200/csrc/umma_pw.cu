@@ -1042,6 +1042,7 @@ void umma_project(const Plan& P, const UmWAll& WA, const float* D, const float* 
   const bool relu = P.act == TFNAS_ACT_RELU;
 #define UM_PROJ(RS_) \
   (relu ? launch_um_project<TFNAS_ACT_RELU, RS_>(P, WA, grid, smem, nb, D, bn2, seg, Zb, st3, st) \
+        : P.act == TFNAS_ACT_NONE ? launch_um_project<TFNAS_ACT_NONE, RS_>(P, WA, grid, smem, nb, D, bn2, seg, Zb, st3, st) \
         : launch_um_project<TFNAS_ACT_SWISH, RS_>(P, WA, grid, smem, nb, D, bn2, seg, Zb, st3, st))
   if (RS == 3) UM_PROJ(3);
   else if (RS == 2) UM_PROJ(2);
@@ -1084,6 +1085,9 @@ void umma_dc(const Plan& P, const UmWAll& WA, const float* G, const float* Zb, c
   if (P.act == TFNAS_ACT_RELU) {
     ensure_smem(k_um_dc<TFNAS_ACT_RELU>, (size_t)(smem));
     k_um_dc<TFNAS_ACT_RELU><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD);
+  } else if (P.act == TFNAS_ACT_NONE) {
+    ensure_smem(k_um_dc<TFNAS_ACT_NONE>, (size_t)(smem));
+    k_um_dc<TFNAS_ACT_NONE><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD);
   } else {
     ensure_smem(k_um_dc<TFNAS_ACT_SWISH>, (size_t)(smem));
     k_um_dc<TFNAS_ACT_SWISH><<<grid, UM_NT, smem, st>>>(P, WA, G, Zb, dzc2, D, bn2, DC, dg, sD);
@@ -1389,6 +1393,7 @@ void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float*
   if (mode == 0) {
     ProfScope ps("wgrad_w3", 4.0 * P.Q * (2.0 * P.oc + cd.mc), 2.0 * P.Q * (double)P.oc * cd.mc, st);
     if (relu) launch_um_wgrad<0, TFNAS_ACT_RELU>(nbr, grid, smem, P, slot, g, st);
+    else if (P.act == TFNAS_ACT_NONE) launch_um_wgrad<0, TFNAS_ACT_NONE>(nbr, grid, smem, P, slot, g, st);
     else launch_um_wgrad<0, TFNAS_ACT_SWISH>(nbr, grid, smem, P, slot, g, st);
   } else {
     ProfScope ps("wgrad_w1", 4.0 * P.P * (2.0 * cd.mc + P.ic), 2.0 * P.P * (double)P.ic * cd.mc, st);

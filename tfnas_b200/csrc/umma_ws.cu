@@ -1101,6 +1101,10 @@ __global__ void __launch_bounds__(DimDx::NTHR, 1) k_ws_dx(const __grid_constant_
 #define WS_LAUNCH(KERN, NTHR_) do { \
     if (P.act == TFNAS_ACT_RELU) WS_LAUNCH_V(KERN, TFNAS_ACT_RELU, NTHR_); \
     else WS_LAUNCH_V(KERN, TFNAS_ACT_SWISH, NTHR_); } while (0)
+// + the identity activation (head: feature-mix conv on the project kernel)
+#define WS_LAUNCH3(KERN, NTHR_) do { \
+    if (P.act == TFNAS_ACT_NONE) WS_LAUNCH_V(KERN, TFNAS_ACT_NONE, NTHR_); \
+    else WS_LAUNCH(KERN, NTHR_); } while (0)
 
 // TFNAS_WS: comma-separated subset of {expand,project,dc,dx} run by the persistent kernels ("none" disables, "all" = all
 // four).  Default: expand, project, dx -- dc is bound by its epilogue (D loads, DC stores, statistics), which the
@@ -1174,7 +1178,7 @@ bool ws_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn
                2.0 * P.Q * (double)P.MC * P.oc, st);
   const int grid = min(Sc.n_items, sm_count());
   const bool vec = ws_vec_ok(P.HWo, P.Q);
-  WS_LAUNCH(k_ws_project, DimProject::NTHR);
+  WS_LAUNCH3(k_ws_project, DimProject::NTHR);
   return true;
 }
 

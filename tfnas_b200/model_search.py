@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .config import CAND_SPEC, PRIMITIVES, lut_key
-from .ops import ArenaPool, BodyCall, BodyFn, StemFn, MixedOpCall, MixedOpFn, StageSinkFn, bn_act, dwconv
+from .ops import ArenaPool, BodyCall, BodyFn, HeadFn, StemFn, MixedOpCall, MixedOpFn, StageSinkFn, bn_act, dwconv
 
 __all__ = ['PRIMITIVES', 'OPS', 'MixedOP', 'MixedStage', 'Network', 'MBInvertedResBlock', 'ConvLayer',
            'LinearLayer', 'NoisePlan', 'injected', 'seed_noise', 'draw_gumbel']
@@ -385,6 +385,10 @@ class Network(nn.Module):
             for s in range(1, 7):
                 x, lat = getattr(self, 'stage%d' % s)(x, sampling, mode)
                 out_lat = out_lat + lat
+        if self.use_body:
+            x = HeadFn.apply(x, self.__dict__.setdefault('_arena_pool', ArenaPool()), self.feature_mix_layer.conv.weight,
+                             self.classifier.linear.weight, self.classifier.linear.bias)
+            return x, out_lat
         x = self.feature_mix_layer(x)
         x = self.global_avg_pooling(x)
         x = x.view(x.size(0), -1)

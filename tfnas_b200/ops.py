@@ -447,3 +447,51 @@ class StemFn(torch.autograd.Function):
         lease.release()
         ctx.lease = None
         return (None, None) + grads
+
+
+class HeadFn(torch.autograd.Function):
+    """forward(x, pool, fm_w, fc_w, fc_b) -> logits: feature-mix 1x1 conv + BN + Swish + global average pooling + classifier."""
+
+    @staticmethod
+    def forward(ctx, x, pool, fm_w, fc_w, fc_b):
+        lib = _lib.load()
+        _require_cuda_f32(x, 'x')
+        x = x.contiguous()
+        for w in (fm_w, fc_w, fc_b):
+            if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
+                raise _lib.TfnasError('head parameters must be contiguous CUDA float32 tensors')
+        d = _lib.HeadDesc()
+        d.N, d.c_in, d.H, d.W = x.shape
+        d.c_mid, d.num_classes = fm_w.shape[0], fc_w.shape[0]
+        nbytes = lib.tfnas_head_arena_bytes(ctypes.byref(d))
+        if not nbytes:
+            check(-1)
+        lease = pool.lease(nbytes, x.device)
+        logits = torch.empty((d.N, d.num_classes), dtype=torch.float32, device=x.device)
+        wp = _lib.HeadPtrs(fm_w.data_ptr(), fc_w.data_ptr(), fc_b.data_ptr())
+        check(lib.tfnas_head_fwd(ctypes.byref(d), _ptr(x), ctypes.byref(wp), _ptr(logits), _ptr(lease.buf), lease.buf.numel(),
+                                 _stream()))
+        ctx.desc, ctx.lease, ctx.wp = d, lease, wp
+        ctx.save_for_backward(x, fm_w, fc_w, fc_b)
+        return logits
+
+    @staticmethod
+    def backward(ctx, glogits):
+        lib = _lib.load()
+        lease = ctx.lease
+        if lease is None or lease.buf is None:
+            raise _lib.TfnasError('head backward ran twice: the arena of the pass is released after the first backward')
+        x, fm_w, fc_w, fc_b = ctx.saved_tensors
+        glogits = glogits.contiguous()
+        dx = torch.empty_like(x)
+        grads = (None, None, None)
+        gp = None
+        if any(ctx.needs_input_grad[2:]):
+            grads = (torch.empty_like(fm_w), torch.empty_like(fc_w), torch.empty_like(fc_b))
+            gpv = _lib.HeadPtrs(grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr())
+            gp = ctypes.byref(gpv)
+        check(lib.tfnas_head_bwd(ctypes.byref(ctx.desc), _ptr(x), ctypes.byref(ctx.wp), _ptr(glogits), _ptr(dx), gp,
+                                 _ptr(lease.buf), lease.buf.numel(), _stream()))
+        lease.release()
+        ctx.lease = None
+        return (dx if ctx.needs_input_grad[0] else None, None) + grads
