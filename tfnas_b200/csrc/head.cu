@@ -93,11 +93,14 @@ __global__ void __launch_bounds__(NT) k_head_dpool(int N, int C, int HW, const f
   for (int i = lane; i < HW; i += 32) o[i] = g * act_df<TFNAS_ACT_SWISH>((z[i] - mu) * r);
 }
 
-// logits[n][o] = sum_c p[n][c] W[o][c] + b[o]
+// logits[n][o] = sum_c p[n][c] W[o][c] + b[o]; split over c (blockIdx.z) into zeroed logits, the bias rides with split 0
+#define HEAD_FC_SPLIT 16
 __global__ void __launch_bounds__(NT) k_head_fc(int N, int C, int K, const float* __restrict__ p, const float* __restrict__ W,
                                                  const float* __restrict__ b, float* __restrict__ logits) {
+  const int per = (C + gridDim.z - 1) / gridDim.z, k0 = blockIdx.z * per, k1 = min(C, k0 + per);
+  const bool first = blockIdx.z == 0;
   fc_tile<false>(N, K, C, W, [&](int n, int c) { return p[(size_t)n * C + c]; },
-                 [&](int n, int o, float v) { logits[(size_t)n * K + o] = v + b[o]; });
+                 [&](int n, int o, float v) { atomicAdd(&logits[(size_t)n * K + o], first ? v + b[o] : v); }, k0, k1);
 }
 // dp[n][c] = sum_o dl[n][o] W[o][c]
 __global__ void __launch_bounds__(NT) k_head_fc_dp(int N, int C, int K, const float* __restrict__ dl, const float* __restrict__ W,
@@ -163,8 +166,9 @@ int tfnas_head_fwd(const TfnasHeadDesc* d, const float* x, const TfnasHeadPtrs* 
     k_head_bnfin<<<cdiv(C, 256), 256, 0, st>>>(C, 1.0 / (double)P.Q, S.st3, bn3); }
   { ProfScope ps("head_pool", 4.0 * P.Q * C, 6.0 * P.Q * C, st);
     k_head_pool<<<cdiv((long long)P.N * C * 32, NT), NT, 0, st>>>(P.N, C, P.HW, Zb, bn3, pooled); }
+  cudaMemsetAsync(logits, 0, (size_t)P.N * K * sizeof(float), st);
   { ProfScope ps("head_fc", 4.0 * (P.N * C + K * C), 2.0 * P.N * C * K, st);
-    k_head_fc<<<dim3(cdiv(P.N, FC_TN), cdiv(K, FC_TO)), NT, 0, st>>>(P.N, C, K, pooled, w->fc_w, w->fc_b, logits); }
+    k_head_fc<<<dim3(cdiv(P.N, FC_TN), cdiv(K, FC_TO), HEAD_FC_SPLIT), NT, 0, st>>>(P.N, C, K, pooled, w->fc_w, w->fc_b, logits); }
   return check_cuda("tfnas_head_fwd");
 }
 

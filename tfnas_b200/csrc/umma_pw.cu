@@ -1386,6 +1386,9 @@ void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float*
   // K splits over the pixel axis: enough CTAs for ~3 per SM, each at least 256 pixels long (the 14x14 / 7x7 stages have
   // only 25k / 6k pixels: with 1024-pixel splits a 1152-wide candidate ran on 54 CTAs)
   int nsplit = max(1, min(cdiv(total, 256), cdiv(3 * sm_count(), mt * g.nN)));
+  // every split adds its partial tile with float atomics: keep (output elements x splits) bounded -- the head's
+  // 1280 x 320 feature-mix gradient at 25 splits spent its time in 10 M atomics
+  nsplit = max(1, min(nsplit, (int)(3000000LL / ((long long)cd.mc * nb))));
   size_t smem = 1024 + 32768 + (size_t)2 * g.Nc * 128 + 64;
   dim3 grid(mt, g.nN, nsplit);
   const bool relu = P.act == TFNAS_ACT_RELU;
