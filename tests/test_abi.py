@@ -46,7 +46,11 @@ def test_sizes_and_validation_without_gpu():
     # D + UH + Z dominate: N*MC*(HW + HWo)*4 + N*8*oc*HWo*4
     assert full >= 2 * 384 * (64 + 16) * 4 + 2 * 8 * 24 * 16 * 4
     assert lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), 0xFF, 0) > 0
-    assert lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), 0x02, 1) > lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), 0x02, 0)
+    # max(forward scratch, backward scratch): the weight-gradient regions can only grow it
+    assert lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), 0x02, 1) >= lib.tfnas_mixedop_workspace_bytes(ctypes.byref(d), 0x02, 0)
+    o0, o1 = (ctypes.c_size_t * 10)(), (ctypes.c_size_t * 10)()
+    assert lib.tfnas_debug_bwd_layout(ctypes.byref(d), 0x02, 0, o0) == 0 and lib.tfnas_debug_bwd_layout(ctypes.byref(d), 0x02, 1, o1) == 0
+    assert o1[9] > o0[9]
     bad = _desc(stride=3)
     assert lib.tfnas_mixedop_saved_bytes(ctypes.byref(bad), 0xFF) == 0
     assert b'stride' in lib.tfnas_last_error()

@@ -136,8 +136,11 @@ size_t fwd_scratch(const Plan& P, char* base, FwdScratch& S) {
   size_t acc = take(nd * sizeof(double));
   size_t coef = take((size_t)(P.na * P.oc + P.oc) * 4);
   size_t umprep = take(umma_fwd_prep_bytes(P));
+  const size_t nb4 = ((size_t)P.ic + 1 + 3) / 4;
+  size_t xpart = take((size_t)XM_MAXCTA * (nb4 * (nb4 + 1) / 2) * 16 * sizeof(float));
   if (base) {
     S.umprep = (float*)(base + umprep);
+    S.xpart = (float*)(base + xpart);
     S.xsum = (double*)(base + acc);
     S.xcov = S.xsum + P.ic;
     S.st2 = S.xcov + (size_t)P.ic * P.ic;

@@ -17,6 +17,7 @@ struct OpSlot {
   Plan P;
   SavedLayout L;
   size_t out, saved, lat, dlat;   // byte offsets in the arena (lat / dlat: one float each)
+  size_t prep_f, prep_b;          // pre-split / pre-swizzled tcgen05 weights of the forward / backward GEMMs
   size_t out_numel, in_numel;
 };
 struct StageSlot {
@@ -74,6 +75,8 @@ static int body_layout(const TfnasBodyDesc* d, const uint32_t* masks, const Tfna
       O.saved = take(O.L.total);
       O.lat = take(4);
       O.dlat = take(4);
+      O.prep_f = take(umma_fwd_prep_bytes(O.P));
+      O.prep_b = take(umma_bwd_prep_bytes(O.P));
       FwdScratch F;
       BwdScratch Bs;
       wsb = max(wsb, max(fwd_scratch(O.P, nullptr, F), bwd_scratch(O.P, want_wgrad, nullptr, Bs)));
@@ -245,6 +248,14 @@ int tfnas_body_fwd(const TfnasBodyDesc* d, const uint32_t* cand_masks, const flo
   char* A = (char*)arena;
   cudaStream_t st = (cudaStream_t)stream;
   cudaGetLastError();
+  // every weight of the pass is known up front: convert them all for the tcgen05 GEMMs in a few launches
+  static thread_local PreppedFwd PF[TFNAS_MAX_BLOCKS];
+  const bool pre = umma_enabled() != 0;
+  if (pre) {
+    umma_prep_batch_begin();
+    for (int i = 0; i < B.nb; ++i) umma_prep_fwd(B.op[i].P, (float*)(A + B.op[i].prep_f), PF[i].WE, PF[i].WP, st);
+    umma_prep_batch_flush(st);
+  }
   const float* cur = x;
   LatPtrs LP;
   memset(&LP, 0, sizeof(LP));
@@ -264,7 +275,7 @@ int tfnas_body_fwd(const TfnasBodyDesc* d, const uint32_t* cand_masks, const flo
       float* l = (float*)(A + O.lat);
       if (!am) cudaMemsetAsync(l, 0, 4, st);
       launch_forward(O.P, cur, am ? log_alphas[i] : nullptr, am ? gumbel + (size_t)i * TFNAS_MAX_OPS : nullptr,
-                     am ? lat + (size_t)i * TFNAS_MAX_OPS : nullptr, T, am, o, l, A + O.saved, O.L, F, st);
+                     am ? lat + (size_t)i * TFNAS_MAX_OPS : nullptr, T, am, o, l, A + O.saved, O.L, F, st, pre ? &PF[i] : nullptr);
       res[j] = o;
       lats[j] = l;
       cur = o;
@@ -319,6 +330,15 @@ int tfnas_body_bwd(const TfnasBodyDesc* d, const uint32_t* cand_masks, const flo
   char* A = (char*)arena;
   cudaStream_t st = (cudaStream_t)stream;
   cudaGetLastError();
+  static thread_local PreppedBwd PB[TFNAS_MAX_BLOCKS];
+  const bool pre = umma_enabled() != 0;
+  if (pre) {      // the backward GEMMs' weights (dc: W3^T; dx: W1^T scaled by the forward's BN1 rstd) of all MixedOPs at once
+    umma_prep_batch_begin();
+    for (int i = (dx ? 0 : 1); i < B.nb; ++i)
+      umma_prep_bwd(B.op[i].P, (const float*)(A + B.op[i].saved + B.op[i].L.bn1), (float*)(A + B.op[i].prep_b), PB[i].WD, PB[i].WX,
+                    PB[i].CH, st);
+    umma_prep_batch_flush(st);
+  }
   const float* gstage = dout;          // gradient w.r.t. the current stage's (sink) output
   int gs_idx = 0;
   for (int s = B.ns - 1; s >= 0; --s) {
@@ -361,7 +381,8 @@ int tfnas_body_bwd(const TfnasBodyDesc* d, const uint32_t* cand_masks, const flo
       BwdScratch Bs;
       bwd_scratch(O.P, dweights != nullptr, A + B.ws, Bs);
       launch_backward(O.P, xin, gcur, am ? (const float*)(A + O.dlat) : nullptr, T, am, A + O.saved, O.L, Bs, dxo,
-                      (am && dlog_alphas) ? dlog_alphas[i] : nullptr, dweights ? dweights + (size_t)i * TFNAS_MAX_OPS : nullptr, st);
+                      (am && dlog_alphas) ? dlog_alphas[i] : nullptr, dweights ? dweights + (size_t)i * TFNAS_MAX_OPS : nullptr, st, 0,
+                      (pre && (dxo || i > 0)) ? &PB[i] : nullptr);
       if (j > 0) {
         // gradient of block j-1's output: dx of block j plus its share beta_{j-1} * gstage of the sink
         int blocks = (int)min((size_t)(4 * sm_count()), (S.numel / 4 + NT - 1) / NT);

@@ -932,7 +932,8 @@ static SideStream* side_stream_for(cudaStream_t main) {
 
 void launch_backward(const Plan& P, const float* x, const float* dout, const float* dlat, float T,
                      int alpha_mode, const char* saved, const SavedLayout& L, const BwdScratch& S,
-                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st, int stop_at_da) {
+                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st, int stop_at_da,
+                     const PreppedBwd* pre) {
   const double* xmom = (const double*)(saved + L.xmom);
   const float* bn1 = (const float*)(saved + L.bn1);
   const float* bn2 = (const float*)(saved + L.bn2);
@@ -972,7 +973,8 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   DxChunks CHX;
   if (umma_enabled()) {
     // stop_at_da (second stem: no expand conv in front of the depthwise stage): only the dc weights exist
-    if (stop_at_da) umma_prep_dc(P, S.umprep, WD, st);
+    if (pre) { WD = pre->WD; WX = pre->WX; CHX = pre->CH; }
+    else if (stop_at_da) umma_prep_dc(P, S.umprep, WD, st);
     else umma_prep_bwd(P, bn1, S.umprep, WD, WX, CHX, st);
     umma_dc(P, WD, dout, Zb, S.dzc2, D, bn2, S.DC, S.dg, S.sD, st);
   } else {

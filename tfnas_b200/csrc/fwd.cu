@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT) k_xcov(Plan P, const float* __restrict__ x
 // for ic <= 87, 2 for ic <= 123) keep the register count low enough for 3-4 CTAs per SM
 template <int XM_MAXB>
 __global__ void __launch_bounds__(NT) k_xmom(Plan P, const float* __restrict__ x, int TP, int tp_shift,
-                                              double* __restrict__ xsum, double* __restrict__ xx) {
+                                              float* __restrict__ xpart) {
   extern __shared__ float xs[];        // [icp][LD], LD = TP + 2 (even: pixel pairs load as float2; rows 2 banks apart)
   const int ic = P.ic, nb = (ic + 1 + 3) >> 2, icp = nb * 4, nut = nb * (nb + 1) / 2, LD = TP + 2;
   const int tid = threadIdx.x;
@@ -193,15 +193,16 @@ __global__ void __launch_bounds__(NT) k_xmom(Plan P, const float* __restrict__ x
     const int p0 = tile << tp_shift;
     __syncthreads();
     if (vec) {
-      const int q4 = TP >> 2;
-      for (int i = tid; i < icp * q4; i += NT) {
-        const int k = i / q4, pp = (i - k * q4) << 2, p = p0 + pp;
+      // TP / 4 <= NT: a thread keeps its 4 pixels for the whole tile and walks the channel rows (no per-element division)
+      const int q4s = tp_shift - 2, pp = (tid & ((1 << q4s) - 1)) << 2, p = p0 + pp;
+      const bool pv = p < P.P;           // P.P % 4 == 0 here, so the four pixels are valid and in the same image
+      const int n = pv ? fast_div(p, P.HW, inv_hw) : 0, hw = p - n * P.HW;
+      const float* src = x + (size_t)n * ic * P.HW + hw;
+      for (int k = tid >> q4s; k < icp; k += NT >> q4s) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < P.P) {               // P.P % 4 == 0 here, so the four pixels are valid and in the same image
-          if (k < ic) {
-            const int n = fast_div(p, P.HW, inv_hw), hw = p - n * P.HW;
-            v = *(const float4*)(x + ((size_t)n * ic + k) * P.HW + hw);
-          } else if (k == ic) v = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (pv) {
+          if (k < ic) v = *(const float4*)(src + (size_t)k * P.HW);
+          else if (k == ic) v = make_float4(1.f, 1.f, 1.f, 1.f);
         }
         float* d = xs + k * LD + pp;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
@@ -234,15 +235,9 @@ __global__ void __launch_bounds__(NT) k_xmom(Plan P, const float* __restrict__ x
       }
     }
   }
-  // entry (r, c) of block (bi, bj): rows / columns < ic are second moments, column ic (the ones row) holds the sums
-  auto emit = [&](int r, int c, double v, bool offdiag) {
-    if (r < ic && c < ic) {
-      atomicAdd(&xx[r * ic + c], v);
-      if (offdiag) atomicAdd(&xx[c * ic + r], v);
-    } else if (r < ic && c == ic) {
-      atomicAdd(&xsum[r], v);
-    }
-  };
+  // the CTA's partial Gram blocks go to its slice of xpart ([cta][block][16], plain stores): k_xred sums the slices in
+  // fp64.  (One fp64 atomic per entry and CTA measured 40-60 us per launch: 2-3 M atomics at ic >= 112.)
+  float* mine = xpart + (size_t)blockIdx.x * nut * 16;
   if (nsplit > 1) {
     __syncthreads();
     float* red = xs;                 // [nsplit][nut][16] <= 256 * 16 floats
@@ -253,22 +248,44 @@ __global__ void __launch_bounds__(NT) k_xmom(Plan P, const float* __restrict__ x
     for (int i = tid; i < nut * 16; i += NT) {
       float t = 0.f;
       for (int s2 = 0; s2 < nsplit; ++s2) t += red[s2 * nut * 16 + i];
-      int q = i >> 4, e = i & 15, r = 0, rowlen = nb;
-      while (q >= rowlen) { q -= rowlen; ++r; --rowlen; }
-      const int cb = r + q;
-      if (cb == r && (e >> 2) > (e & 3)) continue;          // diagonal block: upper triangle only
-      emit(r * 4 + (e >> 2), cb * 4 + (e & 3), (double)t, !(cb == r && (e >> 2) == (e & 3)));
+      mine[i] = t;
     }
   } else {
 #pragma unroll
     for (int l = 0; l < XM_MAXB; ++l) {
       if (bi[l] < 0) continue;
+      const int q = tid + l * NT;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        if (bi[l] == bj[l] && (e >> 2) > (e & 3)) continue;
-        emit(bi[l] * 4 + (e >> 2), bj[l] * 4 + (e & 3), (double)acc[l][e], !(bi[l] == bj[l] && (e >> 2) == (e & 3)));
-      }
+      for (int e4 = 0; e4 < 4; ++e4)
+        *(float4*)(mine + (size_t)q * 16 + e4 * 4) = make_float4(acc[l][e4 * 4], acc[l][e4 * 4 + 1], acc[l][e4 * 4 + 2], acc[l][e4 * 4 + 3]);
     }
+  }
+}
+
+// sum the per-CTA partial blocks (fp64) and scatter them into S1[k] (the ones column) and the full symmetric S2[k][l].
+// Eight threads per entry walk the CTA slices with stride 8 (a single thread per entry spent 27 us in ~300 dependent loads).
+__global__ void __launch_bounds__(NT) k_xred(int ic, int nctas, const float* __restrict__ xpart, double* __restrict__ xsum,
+                                              double* __restrict__ xx) {
+  const int nb = (ic + 1 + 3) >> 2, nut = nb * (nb + 1) / 2;
+  const int i = (blockIdx.x * NT + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+  const bool ok = i < nut * 16;
+  double t = 0.0;
+  if (ok)
+    for (int c = sub; c < nctas; c += 8) t += (double)xpart[(size_t)c * nut * 16 + i];
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 4);
+  if (!ok || sub != 0) return;
+  int q = i >> 4, e = i & 15, rb = 0, rowlen = nb;
+  while (q >= rowlen) { q -= rowlen; ++rb; --rowlen; }
+  const int cb = rb + q;
+  const int r = rb * 4 + (e >> 2), c = cb * 4 + (e & 3);
+  if (cb == rb && (e >> 2) > (e & 3)) return;          // diagonal block: upper triangle only
+  if (r < ic && c < ic) {
+    xx[r * ic + c] = t;
+    if (r != c) xx[c * ic + r] = t;
+  } else if (r < ic && c == ic) {
+    xsum[r] = t;
   }
 }
 
@@ -736,7 +753,7 @@ static void launch_project(const Plan& P, OcTile T, const float* D, const float*
 
 void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
                     const float* lat8, float T, int alpha_mode, float* out, float* out_lat,
-                    char* saved, const SavedLayout& L, const FwdScratch& S, cudaStream_t st) {
+                    char* saved, const SavedLayout& L, const FwdScratch& S, cudaStream_t st, const PreppedFwd* pre) {
   double* xmom = (double*)(saved + L.xmom);
   float* bn1 = (float*)(saved + L.bn1);
   float* bn2 = (float*)(saved + L.bn2);
@@ -764,10 +781,12 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
     const int tiles = cdiv(P.P, TP);
     const int nb4 = icp >> 2, nut = nb4 * (nb4 + 1) / 2, maxb = cdiv(nut, NT);
     { ProfScope ps("xmom", xbytes, 1.0 * P.P * ic * ic, st);
-      const int grid = max(1, min(tiles, 4 * sm_count()));
-      if (maxb <= 1) { ensure_smem(k_xmom<1>, smem); k_xmom<1><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xsum, S.xcov); }
-      else if (maxb <= 2) { ensure_smem(k_xmom<2>, smem); k_xmom<2><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xsum, S.xcov); }
-      else { ensure_smem(k_xmom<5>, smem); k_xmom<5><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xsum, S.xcov); } }
+      const int grid = max(1, min(tiles, min(2 * sm_count(), XM_MAXCTA)));
+      if (maxb <= 1) { ensure_smem(k_xmom<1>, smem); k_xmom<1><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
+      else if (maxb <= 2) { ensure_smem(k_xmom<2>, smem); k_xmom<2><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
+      else { ensure_smem(k_xmom<5>, smem); k_xmom<5><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
+      count_launch(1);
+      k_xred<<<cdiv(nut * 16 * 8, NT), NT, 0, st>>>(ic, grid, S.xpart, S.xsum, S.xcov); }
     { ProfScope ps("xfin", 16.0 * ic * ic, 0, st);
       k_xfin_raw<<<cdiv(ic * ic, 256), 256, 0, st>>>(ic, P.P, S.xsum, S.xcov, xmom); }
     { ProfScope ps("bn1", 4.0 * P.MC * ic + 8.0 * ic * ic, 2.0 * P.MC * ic * ic, st);
@@ -799,7 +818,8 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
   // F1a
   UmWAll WE, WP;
   if (umma_enabled()) {
-    umma_prep_fwd(P, S.umprep, WE, WP, st);
+    if (pre) { WE = pre->WE; WP = pre->WP; }
+    else umma_prep_fwd(P, S.umprep, WE, WP, st);
     umma_expand(P, WE, x, bn1, UH, st);
   } else {
     int maxmc = 0;

@@ -26,7 +26,9 @@ struct FwdScratch {   // all device pointers into the workspace
   double* st3;    // [2*na*oc]
   float* coef;    // [na*oc + oc]
   float* umprep;  // pre-split / pre-swizzled weights for the tcgen05 GEMMs (expand, project)
+  float* xpart;   // [XM_MAXCTA][upper-triangular 4x4 blocks of the (ic+1)^2 Gram matrix][16]: per-CTA partial input moments
 };
+#define XM_MAXCTA 320
 
 struct BwdScratch {
   float* DC;      // [N*MC*HWo]  dL/dc, then dL/dd-hat in place
@@ -70,6 +72,12 @@ struct DxChunks {            // chunk c of the stacked K axis -> (slot, first lo
 };
 
 void umma_prep_fwd(const Plan& P, float* prep_buf, UmWAll& WE, UmWAll& WP, cudaStream_t st);
+// deferred prep (see umma_pw.cu): queue the jobs of several MixedOPs, convert them in a few launches
+void umma_prep_batch_begin();
+void umma_prep_batch_flush(cudaStream_t st);
+// geometry of weights prepped ahead of the call (body executor); nullptr = the call preps its own into its workspace
+struct PreppedFwd { UmWAll WE, WP; };
+struct PreppedBwd { UmWAll WD; UmW WX; DxChunks CH; };
 void umma_prep_bwd(const Plan& P, const float* bn1, float* prep_buf, UmWAll& WD, UmW& WX, DxChunks& CH, cudaStream_t st);
 void umma_expand(const Plan& P, const UmWAll& WA, const float* x, const float* bn1, float* UH, cudaStream_t st);
 void umma_project(const Plan& P, const UmWAll& WA, const float* D, const float* bn2, const float* seg, float* Zb,
@@ -103,7 +111,7 @@ void launch_dws_bwd(const Plan& P, const float* DC, const float* D, const float*
 
 void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
                     const float* lat8, float T, int alpha_mode, float* out, float* out_lat,
-                    char* saved, const SavedLayout& L, const FwdScratch& S, cudaStream_t st);
+                    char* saved, const SavedLayout& L, const FwdScratch& S, cudaStream_t st, const PreppedFwd* pre = nullptr);
 
 void launch_forward_tail(const Plan& P, const UmWAll* WPp, const float* x, const float* log_alphas, const float* gumbel,
                          const float* lat8, float T, int alpha_mode, float* out, float* out_lat, char* saved,
@@ -115,7 +123,8 @@ void umma_prep_dc(const Plan& P, float* prep_buf, UmWAll& WD, cudaStream_t st);
 
 void launch_backward(const Plan& P, const float* x, const float* dout, const float* dlat, float T,
                      int alpha_mode, const char* saved, const SavedLayout& L, const BwdScratch& S,
-                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st, int stop_at_da = 0);
+                     float* dx, float* dlog_alphas, const TfnasCandPtrs* dweights, cudaStream_t st, int stop_at_da = 0,
+                     const PreppedBwd* pre = nullptr);
 
 void launch_sink_fwd(int K, size_t numel, const float* const* res, const float* betas,
                      const float* cumlat, float* out, float* out_lat, cudaStream_t st);

@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 #include "kernels.h"
 #include "pw.cuh"
 #include "umma.cuh"
@@ -909,7 +910,8 @@ size_t umma_bwd_prep_bytes(const Plan& P) {
 }
 
 struct PrepJob { const float* src; const float* kscale; float* dst; int ld_r, ld_k, nrows, K, Nc, nN, nK; };   // kscale: optional per-k factor
-struct PrepJobs { int n; PrepJob j[2 * TFNAS_MAX_OPS]; };
+#define PREP_MAXJ 64          // jobs per launch: 64 x 56 B of kernel parameters
+struct PrepJobs { int n; PrepJob j[PREP_MAXJ]; };
 
 // grid (max nK, max nN, jobs): all candidates' weights of one GEMM in ONE launch.  A CTA converts one (K chunk, N chunk) tile:
 // coalesced loads along whichever index is contiguous in the source into a shared-memory tile, then one 16-byte chunk (4
@@ -920,7 +922,8 @@ __global__ void __launch_bounds__(256) k_umma_prep_all(PrepJobs J) {
   if (kc >= q.nK || nc >= q.nN) return;
   __shared__ float tile[UM_KC][256 + 1];
   char* base = (char*)q.dst + ((size_t)nc * q.nK + kc) * 2 * q.Nc * 128;
-  for (int i = threadIdx.x; i < q.Nc * UM_KC; i += blockDim.x) {
+#pragma unroll 4
+  for (int i = threadIdx.x; i < q.Nc * UM_KC; i += blockDim.x) {      // unrolled: four independent loads in flight
     int r, kk;
     if (q.ld_k == 1) { r = i / UM_KC; kk = i - r * UM_KC; }
     else { kk = i / q.Nc; r = i - kk * q.Nc; }
@@ -952,7 +955,33 @@ static void prep(PrepJobs& J, const float* src, int ld_r, int ld_k, int nrows, i
   q.src = src; q.kscale = kscale; q.dst = cursor; q.ld_r = ld_r; q.ld_k = ld_k; q.nrows = nrows; q.K = K; q.Nc = W.Nc; q.nN = W.nN; q.nK = W.nK;
   cursor += (size_t)W.nN * W.nK * 2 * W.Nc * 32;
 }
+// Deferred prep: between umma_prep_batch_begin() and umma_prep_batch_flush() the per-MixedOP prep calls only compute their
+// geometry and queue their jobs; the flush converts the weights of ALL queued MixedOPs in a few launches (the body executor
+// knows every weight of a pass up front: 2 launches per sampled pass instead of 36 on its critical chain).
+static thread_local std::vector<PrepJob>* g_prep_batch = nullptr;
+static void prep_launch(const PrepJobs& J, cudaStream_t st);
+void umma_prep_batch_begin() {
+  static thread_local std::vector<PrepJob> batch;
+  batch.clear();
+  g_prep_batch = &batch;
+}
+void umma_prep_batch_flush(cudaStream_t st) {
+  std::vector<PrepJob>* b = g_prep_batch;
+  g_prep_batch = nullptr;
+  if (!b) return;
+  for (size_t i0 = 0; i0 < b->size(); i0 += PREP_MAXJ) {
+    PrepJobs J;
+    J.n = (int)min((size_t)PREP_MAXJ, b->size() - i0);
+    for (int i = 0; i < J.n; ++i) J.j[i] = (*b)[i0 + i];
+    prep_launch(J, st);
+  }
+  b->clear();
+}
 static void prep_launch(const PrepJobs& J, cudaStream_t st) {
+  if (g_prep_batch) {
+    for (int i = 0; i < J.n; ++i) g_prep_batch->push_back(J.j[i]);
+    return;
+  }
   int mk = 0, mn = 0;
   double bytes = 0;
   for (int i = 0; i < J.n; ++i) { mk = max(mk, J.j[i].nK); mn = max(mn, J.j[i].nN); bytes += 12.0 * J.j[i].nrows * J.j[i].K; }
