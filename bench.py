@@ -64,36 +64,51 @@ def base_config(world):
 
 
 # ------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe), sampled through NVML in-process:
-    a few light driver queries every 250 ms (spawning nvidia-smi from a thread, or running `nvidia-smi -lms` beside
-    the bench, was measured to slow the launching thread by 10-17 %)."""
+_SAMPLER_SRC = r"""
+import os, sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print('max %f' % float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), flush=True)
+while True:
+    print('%f %d' % (float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))), flush=True)
+    time.sleep(0.2)
+"""
+
+
+class ClockSampler(object):
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe), sampled through NVML every 200 ms by a
+    CHILD PROCESS: a sampling thread inside the bench process competes with the launching thread for the interpreter lock
+    (measured: value leg 4 % slower than the same units without it), and nvidia-smi in a loop is heavier still."""
 
     def __init__(self, index):
-        super(ClockSampler, self).__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.max_mhz = index, [], False, None
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        ids = [int(v) for v in vis.split(',') if v.strip().isdigit()]       # NVML enumerates physical devices
+        self.phys = ids[index] if index < len(ids) else index
+        self.proc, self.rows, self.max_mhz = None, [], None
 
-    def run(self):
+    def start(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
-            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
-            ids = [int(v) for v in vis.split(',') if v.strip().isdigit()]
-            phys = ids[self.index] if self.index < len(ids) else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            while not self.stop_flag:
-                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                self.rows.append((sm, reasons))
-                time.sleep(0.25)
+            self.proc = subprocess.Popen([sys.executable, '-c', _SAMPLER_SRC, str(self.phys)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline()          # wait until the child is sampling
+            if first.startswith('max'):
+                self.max_mhz = float(first.split()[1])
         except Exception:
-            pass
+            self.proc = None
 
     def stop(self):
-        self.stop_flag = True
-        self.join(timeout=2)
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+            for line in out.splitlines():
+                a = line.split()
+                if len(a) == 2:
+                    self.rows.append((float(a[0]), int(a[1])))
+        except Exception:
+            pass
 
     def summary(self):
         sm = sorted(r[0] for r in self.rows)
@@ -299,12 +314,12 @@ def run_b200(args, rank, local, world, emit=print):
                 if it % 2 == 0:
                     yield host[(2 * i + it + 1) % npool]
 
-    def unit(i, feed=None):
+    def unit(i, feed=None, overlap=True):
         """feed: iterator of device batches copied from pinned host memory (e2e); None: batches resident in HBM"""
         losses = []
         for it in range(2):
             x, t = next(feed) if feed is not None else pool[(2 * i + it) % npool]
-            lw, _ = w_step(model, x, t, criterion, opt_w, 5.0, sync, bisample=True)
+            lw, _ = w_step(model, x, t, criterion, opt_w, 5.0, sync, bisample=True, overlap=overlap)
             losses.append(lw)
             if it % 2 == 0:
                 xa, ta = next(feed) if feed is not None else pool[(2 * i + it + 1) % npool]
@@ -365,14 +380,18 @@ def run_b200(args, rank, local, world, emit=print):
     sampler.stop()
     unit(0, iter(DevicePrefetcher(host_batches(1), dev)))     # warm the H2D path
     ms_e2e, _ = timed(True, args.steps)
-    # per-kernel attribution over the same K units (CUDA events on the launching stream)
+    # per-kernel attribution over the same K units (CUDA events on the launching stream).  The units run with their passes
+    # in sequence on ONE stream for this leg: with the two sampled passes and the weight-gradient side streams concurrent
+    # (as in the timed legs) an event pair brackets a kernel that shares the SMs with its neighbours' kernels.
+    prev_side = _lib.load().tfnas_config_side_stream(0)
     _lib.prof_enable(True)
     barrier()
     for i in range(args.steps):
-        unit(i)
+        unit(i, overlap=False)
     torch.cuda.synchronize()
     recs = _lib.prof_collect()
     _lib.prof_enable(False)
+    _lib.load().tfnas_config_side_stream(1 if prev_side != 0 else 0)
 
     imgs = 2 * BS * world * args.steps
     value = imgs / (ms / 1000.0)
@@ -392,6 +411,7 @@ def run_b200(args, rank, local, world, emit=print):
         p_.grad = None
     roofline = {'kernel': top['name'], 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'timed': 'CUDA events per launch, passes in sequence on one stream (no concurrent neighbour kernels)',
                 'bytes_model': 'materialised tensors this kernel reads + writes (DESIGN.md section 5), not SURVEY 8(d) compulsory bytes',
                 'algorithmic_frac': mop['hbm_frac_algorithmic'] if mop else None,
                 'share_of_step': top['ms'] / tot_ms, 'launches_per_step': top['launches'] / args.steps,

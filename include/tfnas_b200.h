@@ -322,6 +322,11 @@ int tfnas_adam_step(int n, const TfnasAdamTensor* t, int step, float lr, float b
  */
 int tfnas_softmax_ce(int N, int C, const float* logits, const int64_t* targets, float* loss, float* dlogits, void* stream);
 
+/* Weight-gradient GEMMs of the backward calls on a library-owned side stream (forked from / joined into the caller's stream
+ * inside the call): 1 = on (default; also TFNAS_SIDE_STREAM=0/1 at first use), 0 = everything on the caller's stream (e.g.
+ * for per-kernel timing without a concurrent neighbour).  Returns the previous setting (-1: was still undecided). */
+int tfnas_config_side_stream(int on);
+
 /* Number of kernel launches issued through this library since load (bench "gpu_launches"). */
 uint64_t tfnas_launch_count(void);
 

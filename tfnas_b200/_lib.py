@@ -85,7 +85,7 @@ EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_mixedop_saved_bytes', 'tfnas_mixedop_workspace_bytes',
            'tfnas_mixedop_fwd', 'tfnas_mixedop_bwd',
            'tfnas_stage_sink_fwd', 'tfnas_stage_sink_bwd', 'tfnas_debug_saved_layout', 'tfnas_debug_bwd_layout',
-           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_prof_timeline', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd',
+           'tfnas_prof_enable', 'tfnas_prof_collect', 'tfnas_prof_timeline', 'tfnas_config_side_stream', 'tfnas_umma_selftest', 'tfnas_bn_act_fwd', 'tfnas_bn_act_bwd',
            'tfnas_dwconv_fwd', 'tfnas_dwconv_bwd', 'tfnas_debug_ws_config',
            'tfnas_body_arena_bytes', 'tfnas_body_fwd', 'tfnas_body_bwd',
            'tfnas_stem_arena_bytes', 'tfnas_stem_fwd', 'tfnas_stem_bwd',
@@ -147,6 +147,8 @@ def load():
     lib.tfnas_prof_collect.argtypes = [ctypes.POINTER(ProfEntry), i32]
     lib.tfnas_prof_timeline.restype = i32
     lib.tfnas_prof_timeline.argtypes = [ctypes.POINTER(ProfLaunch), i32]
+    lib.tfnas_config_side_stream.restype = i32
+    lib.tfnas_config_side_stream.argtypes = [i32]
     lib.tfnas_umma_selftest.restype = i32
     lib.tfnas_umma_selftest.argtypes = [i32, i32, i32, vp, vp, vp, vp, sz, i32, vp]
     bp = ctypes.POINTER(BodyDesc)

@@ -908,9 +908,15 @@ static void launch_dxfin(const Plan& P, OcTile T, const float* x, const float* M
 #include <map>
 #include <mutex>
 struct SideStream { cudaStream_t s; cudaEvent_t fork1, fork2, join; };
+static int g_side_stream = -1;      // -1: not decided yet (TFNAS_SIDE_STREAM, default on); tfnas_config_side_stream overrides
+extern "C" int tfnas_config_side_stream(int on) {
+  const int prev = g_side_stream;
+  g_side_stream = on ? 1 : 0;
+  return prev;
+}
 static SideStream* side_stream_for(cudaStream_t main) {
-  static const bool on = !(getenv("TFNAS_SIDE_STREAM") && strcmp(getenv("TFNAS_SIDE_STREAM"), "0") == 0);
-  if (!on) return nullptr;
+  if (g_side_stream < 0) g_side_stream = !(getenv("TFNAS_SIDE_STREAM") && strcmp(getenv("TFNAS_SIDE_STREAM"), "0") == 0) ? 1 : 0;
+  if (!g_side_stream) return nullptr;
   static std::map<std::pair<int, cudaStream_t>, SideStream> streams;
   static std::mutex mu;
   int dev = 0;

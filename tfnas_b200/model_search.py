@@ -430,6 +430,8 @@ class Network(nn.Module):
                          sampled=lib.tfnas_body_arena_bytes(ctypes.byref(d), big, 1))
             if not sizes['alpha'] or not sizes['sampled']:
                 _lib.check(-1)
+            sizes['grad_numel'] = sum(max(sum(w.numel() for w in op.weight_list()) for op in m.m_ops)
+                                      for m in self._param_lists()[4])
             c[key] = [d, bi, out_shape, None, sizes, sizes_in]
         return c[key]
 
@@ -462,6 +464,7 @@ class Network(nn.Module):
             if any(m.m_ops[i].mid_channels > m.m_ops[-1].mid_channels for m, i in zip(mops, idx)):   # elastic widths
                 need = max(need, _lib.load().tfnas_body_arena_bytes(ctypes.byref(d), _lib.BodyMasks(*masks), 1))
             call = BodyCall(d, nb, len(betas), masks, False, T, None, None, [[i] for i in idx], n_per, pool, need, out_shape)
+            call.grad_numel = sizes['grad_numel']
             out, _ = BodyFn.apply(x, call, *(tensors + betas))
             return out, 0.0
         plan = _ACTIVE_PLAN[0]

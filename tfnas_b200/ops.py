@@ -294,6 +294,7 @@ class BodyCall(object):
         self.n_per = n_per            # per block: tensors per active candidate (3 or 7)
         self.nweights = sum(sum(n) for n in n_per)
         self.pool, self.arena_bytes, self.out_shape = pool, arena_bytes, out_shape
+        self.grad_numel = 0           # floats to allocate for the flat weight-gradient buffer (0: the exact sum)
 
     def cand_array(self, tensors):
         arr = _lib.BodyCandArray()
@@ -364,8 +365,12 @@ class BodyFn(torch.autograd.Function):
         dx = torch.empty_like(x) if need_dx else None
         grads, garr = (), None
         if need_dw:
-            flat = torch.empty(sum(t.numel() for t in tensors[:nw]), dtype=torch.float32, device=dev)
-            grads = tuple(g.view(t.shape) for g, t in zip(flat.split([t.numel() for t in tensors[:nw]]), tensors[:nw]))
+            # one flat buffer for all weight gradients of the pass (GradSync all-reduces it in place); sized for the largest
+            # candidate set so that every step asks the caching allocator for the same block
+            sizes = [t.numel() for t in tensors[:nw]]
+            tot = sum(sizes)
+            flat = torch.empty(max(tot, call.grad_numel), dtype=torch.float32, device=dev)
+            grads = tuple(g.view(t.shape) for g, t in zip(flat[:tot].split(sizes), tensors[:nw]))
             garr = call.cand_array(grads)
         dla = dla_rows = None
         if need_da:

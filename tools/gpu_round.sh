@@ -14,7 +14,7 @@ if [[ $stages == *t* ]]; then
   tail -5 $out/pytest_gpu.log
 fi
 if [[ $stages == *b* ]]; then
-  timeout 900 python bench.py --steps 8 --warmup 3 > $out/bench.json 2> $out/bench.err
+  timeout 900 python bench.py --steps 20 --warmup 5 > $out/bench.json 2> $out/bench.err
   echo "bench exit $?"; cat $out/bench.json | cut -c1-600
 fi
 if [[ $stages == *k* ]]; then
