@@ -282,6 +282,7 @@ def run_b200(args, rank, local, world, emit=print):
     from tfnas_b200 import _lib, config, model_search
     from tfnas_b200.model_search import Network
     from tfnas_b200.parallel import GradSync, SearchParallel
+    from tfnas_b200 import search_loop
     from tfnas_b200.search_loop import DevicePrefetcher, alpha_step, make_optimizers, w_step
 
     if not torch.cuda.is_available():
@@ -323,7 +324,9 @@ def run_b200(args, rank, local, world, emit=print):
             losses.append(lw)
             if it % 2 == 0:
                 xa, ta = next(feed) if feed is not None else pool[(2 * i + it + 1) % npool]
-                la, ll = alpha_step(model, xa, ta, criterion, opt_a, target_lat_for(world), 0.1, 5.0, sync)
+                # the attribution leg (overlap=False) runs the alpha step eagerly: a graph replay carries no profiler events
+                la, ll = alpha_step(model, xa, ta, criterion, opt_a, target_lat_for(world), 0.1, 5.0, sync,
+                                    graph=None if overlap else False)
                 losses += [la, ll]
         if feed is not None:
             return [float(v) for v in torch.stack([v.detach().float() for v in losses]).cpu()]
@@ -339,7 +342,7 @@ def run_b200(args, rank, local, world, emit=print):
     def timed(from_host, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = _lib.launch_count()
+        l0 = _lib.launch_count() + search_loop.GRAPH_LAUNCHES[0]
         e0.record()
         h0 = time.perf_counter()
         # e2e: every batch comes from pinned host memory inside the timed region (H2D on a copy stream, one batch ahead of
@@ -358,7 +361,7 @@ def run_b200(args, rank, local, world, emit=print):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
-        return ms, _lib.launch_count() - l0
+        return ms, _lib.launch_count() + search_loop.GRAPH_LAUNCHES[0] - l0
 
     for i in range(args.warmup):
         unit(i)
@@ -430,7 +433,8 @@ def run_b200(args, rank, local, world, emit=print):
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'launches_per_step': launches / args.steps,
             'host_enqueue_ms_per_step': host_enqueue, 'host_blocked_on_gpu_ms_per_step': host_blocked,
-            'host_busy_ms_per_step': host_enqueue - host_blocked, 'extra_untimed_warmup': EXTRA_WARMUP, 'clocks': sampler.summary(),
+            'host_busy_ms_per_step': host_enqueue - host_blocked,
+            'alpha_step_cuda_graph': '_alpha_graph' in net.__dict__, 'extra_untimed_warmup': EXTRA_WARMUP, 'clocks': sampler.summary(),
             'roofline': roofline}
     line['mixedop_roofline'] = mop
     if world == 1 and not args.no_cpu_baseline:

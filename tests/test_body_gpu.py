@@ -146,3 +146,32 @@ def test_softmax_ce_matches_torch():
     (loss * 1.7).backward()
     assert abs(float(loss) - float(F.cross_entropy(ref, tgt))) < 1e-5
     assert H.rel_l2(logits.grad, ref.grad) < 1e-5
+
+
+def test_graphed_alpha_step_equals_eager():
+    """search_loop.alpha_step replayed as a CUDA graph (forward + backward of the whole network captured once) gives the
+    same architecture-parameter trajectory as the eager step over three updates with fresh batches and fresh noise."""
+    from tfnas_b200.parallel import SearchParallel
+    from tfnas_b200.search_loop import alpha_step, make_optimizers
+    from tfnas_b200.step import FusedCrossEntropy
+    res = []
+    for graph in (False, True):
+        net, _x, _t = _net(True, N=4)
+        model = SearchParallel(net)
+        _ow, opt_a = make_optimizers(net)
+        crit = FusedCrossEntropy()
+        model_search.seed_noise(21)
+        g = torch.Generator().manual_seed(9)
+        losses = []
+        for step in range(3):
+            x = torch.randn(4, 3, 224, 224, generator=g).cuda()
+            t = torch.randint(0, 100, (4,), generator=g).cuda()
+            la, ll = alpha_step(model, x, t, crit, opt_a, 15.0, 0.1, 5.0, None, graph=graph)
+            losses.append((float(la), float(ll)))
+        res.append((losses, torch.cat([p.detach().reshape(-1) for p in net.arch_parameters()]).clone()))
+        assert ('_alpha_graph' in net.__dict__) == graph
+    model_search.seed_noise(None)
+    (l0, a0), (l1, a1) = res
+    print('graphed vs eager alpha steps: losses', l0, l1, 'arch params rel-l2 %.2e' % H.rel_l2(a1, a0))
+    assert all(abs(p[0] - q[0]) < 1e-4 and abs(p[1] - q[1]) < 1e-5 for p, q in zip(l0, l1))
+    assert H.rel_l2(a1, a0) < 1e-5

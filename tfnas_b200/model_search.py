@@ -105,9 +105,12 @@ class NoisePlan(object):
     sampling; ``indices``: list of candidate ids consumed by any sampling mode (overrides noise).
     """
 
-    def __init__(self, noise=None, indices=None):
+    def __init__(self, noise=None, indices=None, device_noise=None):
         self.noise = list(noise) if noise is not None else None
         self.indices = list(indices) if indices is not None else None
+        # [num_blocks, 8] device tensor the alpha-mode body reads in place (CUDA-graph replay: the caller refreshes its
+        # contents before every replay, search_loop.GraphedAlphaStep)
+        self.device_noise = device_noise
         self.pos = 0
 
     def next(self):
@@ -435,6 +438,15 @@ class Network(nn.Module):
             c[key] = [d, bi, out_shape, None, sizes, sizes_in]
         return c[key]
 
+    def draw_alpha_noise(self, plan=None):
+        """[num_blocks, 8] CPU tensor of the Gumbel draws of one alpha-mode forward, in forward order (one draw of num_ops
+        values per MixedOP: the same consumption of the CPU generator as 18 separate F.gumbel_softmax calls)."""
+        noise = []
+        for m in self._param_lists()[4]:
+            g = plan.next()[0] if plan is not None else None
+            noise.append(g if g is not None else draw_gumbel(m.num_ops))
+        return torch.stack([F.pad(g.float(), (0, _lib.MAX_OPS - g.numel())) for g in noise])
+
     def _body_lat_table(self, entry, device):
         """[num_blocks, 8] LUT latencies of every candidate at this input size (alpha mode only: the sampled passes never
         touch the LUT, models/model_search.py:84-85, so an image size the LUT does not cover is fine there)."""
@@ -468,11 +480,10 @@ class Network(nn.Module):
             out, _ = BodyFn.apply(x, call, *(tensors + betas))
             return out, 0.0
         plan = _ACTIVE_PLAN[0]
-        noise = []
-        for m in mops:
-            g = plan.next()[0] if plan is not None else None
-            noise.append(g if g is not None else draw_gumbel(m.num_ops))
-        gd = torch.stack([F.pad(g.float(), (0, _lib.MAX_OPS - g.numel())) for g in noise]).to(x.device, non_blocking=True)
+        if plan is not None and plan.device_noise is not None:
+            gd = plan.device_noise
+        else:
+            gd = self.draw_alpha_noise(plan).to(x.device, non_blocking=True)
         tensors, n_per, active = [], [], []
         for m in mops:
             per = []

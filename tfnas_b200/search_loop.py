@@ -178,10 +178,87 @@ def _apply_update(optimizer, params, grad_clip, sync):
     optimizer.step()
 
 
-def alpha_step(model, x_a, target_a, criterion, optimizer_a, target_lat, lambda_lat, grad_clip, sync=None):
-    """One architecture step (train_search.py:404-422) incl. the log_softmax renormalisation."""
+GRAPH_LAUNCHES = [0]      # library kernels launched through CUDA-graph replays (tfnas_launch_count only sees direct launches)
+
+
+class GraphedAlphaStep(object):
+    """The alpha step's forward + backward (stems -> 18 MixedOPs + 6 sinks -> head -> loss -> backward) captured ONCE as a
+    CUDA graph and replayed: its launch sequence is fixed (all candidates active, static shapes, every kernel in the library,
+    no host synchronisation), only the batch and the Gumbel noise change -- they are copied into static buffers before each
+    replay.  The optimiser update stays outside the graph (Adam's bias correction changes every step).  Re-captured when the
+    temperature, the batch shape or the loss constants change (once per epoch in train_search.py)."""
+
+    def __init__(self, model, criterion, x_a, target_a, target_lat, lambda_lat):
+        from .model_search import NoisePlan, injected
+        net = model.module
+        dev = x_a.device
+        self.key = (tuple(x_a.shape), float(getattr(net._param_lists()[4][0], 'T', 1.0)), float(target_lat), float(lambda_lat))
+        self.x = torch.empty_like(x_a)
+        self.t = torch.empty_like(target_a)
+        self.noise_host = torch.empty((len(net._param_lists()[4]), 8), dtype=torch.float32).pin_memory()
+        self.noise = torch.zeros_like(self.noise_host, device=dev)
+        self.x.copy_(x_a)
+        self.t.copy_(target_a)
+
+        def run():
+            with injected(NoisePlan(device_noise=self.noise)):
+                logits, lat = model(self.x, sampling=False)
+            loss_a = criterion(logits, self.t)
+            loss_l = torch.abs(lat / target_lat - 1.) * lambda_lat
+            (loss_a + loss_l).backward()
+            return loss_a, loss_l
+        # warm-up on a side stream (allocator, lazily initialised kernels), as torch.cuda.graphs asks, then capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                for p in net.arch_parameters():
+                    p.grad = None
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for p in net.arch_parameters():
+            p.grad = None
+        from . import _lib
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss_a, self.loss_l = run()
+        self.launches = _lib.launch_count() - l0          # kernel nodes of the library in the graph
+
+    def replay(self, net, x_a, target_a):
+        self.x.copy_(x_a, non_blocking=True)
+        self.t.copy_(target_a, non_blocking=True)
+        self.noise_host.copy_(net.draw_alpha_noise())
+        self.noise.copy_(self.noise_host, non_blocking=True)
+        self.graph.replay()
+        GRAPH_LAUNCHES[0] += self.launches
+        return self.loss_a, self.loss_l
+
+
+def alpha_step(model, x_a, target_a, criterion, optimizer_a, target_lat, lambda_lat, grad_clip, sync=None, graph=None):
+    """One architecture step (train_search.py:404-422) incl. the log_softmax renormalisation.  ``graph`` (default: on for
+    the library-only network with the fused Adam, TFNAS_GRAPH_ALPHA=0 turns it off) replays the step's forward + backward
+    as a CUDA graph (GraphedAlphaStep)."""
     net = model.module
     _set_requires_grad(net, False, True)
+    if graph is None:
+        import os
+        graph = (os.environ.get('TFNAS_GRAPH_ALPHA', '1') != '0' and isinstance(optimizer_a, FusedArchAdam)
+                 and getattr(net, 'use_body', False) and x_a.is_cuda)
+    if graph:
+        from . import model_search as _ms
+        if _ms._ACTIVE_PLAN[0] is not None:
+            graph = False            # injected noise / indices (tests): the eager path consumes the plan
+    if graph:
+        key = (tuple(x_a.shape), float(getattr(net._param_lists()[4][0], 'T', 1.0)), float(target_lat), float(lambda_lat))
+        g = net.__dict__.get('_alpha_graph')
+        if g is None or g.key != key or g.criterion is not criterion:
+            g = GraphedAlphaStep(model, criterion, x_a, target_a, target_lat, lambda_lat)
+            g.criterion = criterion
+            net.__dict__['_alpha_graph'] = g
+        loss_a, loss_l = g.replay(net, x_a, target_a)
+        _apply_update(optimizer_a, net.arch_parameters(), grad_clip, sync)
+        return loss_a, loss_l
     logits_a, lat = model(x_a, sampling=False)
     loss_a = criterion(logits_a, target_a)
     loss_l = torch.abs(lat / target_lat - 1.) * lambda_lat
