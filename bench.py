@@ -329,8 +329,22 @@ def run_b200(args, rank, local, world, emit=print):
                                     graph=None if overlap else False)
                 losses += [la, ll]
         if feed is not None:
-            return [float(v) for v in torch.stack([v.detach().float() for v in losses]).cpu()]
+            # D2H read of the unit's four losses: an async copy into pinned memory + an event; the VALUES of unit i are
+            # consumed while unit i+1 runs (and the last unit's before the timed region closes), so the read-back does not
+            # drain the stream between units -- how a training loop logs its meters
+            slot = readback[len(pending) % 2]
+            slot.copy_(torch.stack([v.detach().float() for v in losses]), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((slot, ev))
+            if len(pending) > 1:
+                pslot, pev = pending[-2]
+                pev.synchronize()
+                loss_log.append([float(v) for v in pslot])
         return losses
+
+    readback = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending, loss_log = [], []
 
     def barrier():
         if world > 1:
@@ -349,8 +363,12 @@ def run_b200(args, rank, local, world, emit=print):
         # the compute: search_loop.DevicePrefetcher, what train_search.py's loops use) and the losses are read back per unit
         feed = iter(DevicePrefetcher(host_batches(steps), dev)) if from_host else None
         b0 = net.__dict__.get('host_blocked_s', 0.0)
+        del pending[:]
         for i in range(steps):
             unit(i, feed)
+        if from_host and pending:          # the last unit's losses, still inside the timed region
+            pending[-1][1].synchronize()
+            loss_log.append([float(v) for v in pending[-1][0]])
         host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps     # host wall time to enqueue a unit ...
         host_ms[1] = (net.__dict__.get('host_blocked_s', 0.0) - b0) * 1e3 / steps   # ... of which blocked in the one D2H read
         # per unit (the new log_alphas the 'gumbel' sampling of the next w-step needs: it waits for the alpha update)

@@ -88,3 +88,35 @@ def test_persistent_gemm_configs_fit_the_sm():
             if nc <= 176:        # (project at 192 columns runs with a single weight slot: 4 stages + 48 KB slots + sums)
                 assert NB >= 2, (which, nc, list(out))
     assert lib.tfnas_debug_ws_config(7, 32, out) != 0 and lib.tfnas_debug_ws_config(1, 24, out) != 0
+
+
+def test_network_level_descriptors_validate_without_gpu():
+    """tfnas_{stem,body,head}_arena_bytes: sizes for valid descriptors, 0 (with a message) for invalid ones; host only."""
+    lib = _lib.load()
+    sd = _lib.StemDesc(4, 224, 224, 3, 32, 8, 16)
+    n0, n1 = lib.tfnas_stem_arena_bytes(ctypes.byref(sd), 0), lib.tfnas_stem_arena_bytes(ctypes.byref(sd), 1)
+    assert n1 >= n0 > 4 * 32 * 112 * 112 * 4 * 2            # at least UH + D
+    sd.c_mid = 48
+    assert lib.tfnas_stem_arena_bytes(ctypes.byref(sd), 0) == 0 and b'3 -> 32' in lib.tfnas_last_error()
+    hd = _lib.HeadDesc(4, 7, 7, 320, 1280, 100)
+    assert lib.tfnas_head_arena_bytes(ctypes.byref(hd)) > 4 * 1280 * 49 * 4 * 2
+    hd.num_classes = 0
+    assert lib.tfnas_head_arena_bytes(ctypes.byref(hd)) == 0
+    bd = _lib.BodyDesc()
+    bd.num_stages, bd.num_blocks = 2, 3
+    bd.stage_blocks[0], bd.stage_blocks[1] = 2, 1
+    shapes = [(16, 24, 2, 16), (24, 24, 1, 8), (24, 40, 2, 8)]
+    for i, (ic, oc, s, hw) in enumerate(shapes):
+        d = bd.op[i]
+        d.N, d.ic, d.oc, d.H, d.W, d.stride, d.act, d.num_ops = 2, ic, oc, hw, hw, s, 1, 8
+        for j in range(8):
+            d.mc[j], d.k[j], d.se[j] = 3 * ic, (3, 3, 5, 5)[j % 4], (ic if j >= 4 else 0)
+    full = _lib.BodyMasks(*([0xFF] * 3))
+    one = _lib.BodyMasks(*([0x04] * 3))
+    a, b = lib.tfnas_body_arena_bytes(ctypes.byref(bd), full, 0), lib.tfnas_body_arena_bytes(ctypes.byref(bd), one, 1)
+    assert a > b > 0
+    bd.op[1].ic = 32                                          # does not chain with op 0's 24 output channels
+    assert lib.tfnas_body_arena_bytes(ctypes.byref(bd), full, 0) == 0 and b'chain' in lib.tfnas_last_error()
+    bd.op[1].ic = 24
+    bd.num_blocks = 4
+    assert lib.tfnas_body_arena_bytes(ctypes.byref(bd), full, 0) == 0
