@@ -472,9 +472,9 @@ class Network(nn.Module):
                 tensors += wl
                 n_per.append([len(wl)])
             masks = [1 << i for i in idx]
-            need = sizes['sampled']
-            if any(m.m_ops[i].mid_channels > m.m_ops[-1].mid_channels for m, i in zip(mops, idx)):   # elastic widths
-                need = max(need, _lib.load().tfnas_body_arena_bytes(ctypes.byref(d), _lib.BodyMasks(*masks), 1))
+            # the pool hands out blocks of the "widest candidates" size so every step leases the same block; after elastic
+            # rescaling another candidate can need more (wider, or SE state): the exact size of this pass decides
+            need = max(sizes['sampled'], _lib.load().tfnas_body_arena_bytes(ctypes.byref(d), _lib.BodyMasks(*masks), 1))
             call = BodyCall(d, nb, len(betas), masks, False, T, None, None, [[i] for i in idx], n_per, pool, need, out_shape)
             call.grad_numel = sizes['grad_numel']
             out, _ = BodyFn.apply(x, call, *(tensors + betas))
