@@ -527,6 +527,8 @@ __global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ a
                                               float* __restrict__ cvec) {
   __shared__ __align__(16) float As[B4_KC][B4_T + 4];   // a2_c * W1[c][k0 + .]
   __shared__ __align__(16) float Bs[B4_KC][B4_T + 4];   // W1[c][kp0 + .]
+  __shared__ float a1s[B4_KC];                          // a1_c of the chunk (CTAs of the first tile row also form cvec)
+  float cv = 0.f;                                       // cvec[kp0 + tid] partial (tid < B4_T, blockIdx.x == 0)
   const int ic = P.ic, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int k0 = blockIdx.x * B4_T, kp0 = blockIdx.y * B4_T;
   const int c_lo = (int)((long long)P.MC * blockIdx.z / gridDim.z), c_hi = (int)((long long)P.MC * (blockIdx.z + 1) / gridDim.z);
@@ -551,7 +553,12 @@ __global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ a
       As[cc][kk] = wa;
       Bs[cc][kk] = wb;
     }
+    if (tid < B4_KC) a1s[tid] = cb + tid < c_hi ? a12[cb + tid] : 0.f;
     __syncthreads();
+    if (blockIdx.x == 0 && tid < B4_T) {          // cvec[k'] = sum_c W1[c][k'] a1_c (was a separate launch)
+#pragma unroll 8
+      for (int cc = 0; cc < B4_KC; ++cc) cv += Bs[cc][tid] * a1s[cc];
+    }
 #pragma unroll 8
     for (int cc = 0; cc < B4_KC; ++cc) {
       const float4 a = *(const float4*)&As[cc][ty * 4];
@@ -570,43 +577,31 @@ __global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ a
       const int k = k0 + ty * 4 + i, kp = kp0 + tx * 4 + j;
       if (k < ic && kp < ic) atomicAdd(&Mm[k * ic + kp], acc[i][j]);
     }
-  (void)cvec;
+  if (blockIdx.x == 0 && tid < B4_T && kp0 + tid < ic) atomicAdd(&cvec[kp0 + tid], cv);
 }
 
-// cvec[k] = sum_c W1[c][k] a1_c : grid (c-splits), thread = k, coalesced rows, float atomics
-__global__ void __launch_bounds__(NT) k_b4cvec(Plan P, const float* __restrict__ a12, float* __restrict__ cvec) {
-  const int ic = P.ic;
-  const int c_lo = (int)((long long)P.MC * blockIdx.x / gridDim.x), c_hi = (int)((long long)P.MC * (blockIdx.x + 1) / gridDim.x);
-  for (int k = threadIdx.x; k < ic; k += NT) {
-    float cv = 0.f;
-    for (int s = 0; s < P.na; ++s) {
-      const Cand& cd = P.c[s];
-      const int lo = max(c_lo, cd.coff), hi = min(c_hi, cd.coff + cd.mc);
-      for (int cst = lo; cst < hi; ++cst) cv += cd.w1[(size_t)(cst - cd.coff) * ic + k] * a12[cst];
-    }
-    atomicAdd(&cvec[k], cv);
-  }
-}
-
-// cvec2[k] = cvec[k] - sum_k' Mm[k][k'] mu_x[k']
-__global__ void k_b4fin(int ic, const float* __restrict__ Mm, const double* __restrict__ xmom, float* __restrict__ cvec) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= ic) return;
-  double t = 0.0;
-  for (int kp = 0; kp < ic; ++kp) t += (double)Mm[k * ic + kp] * xmom[kp];
-  cvec[k] = (float)((double)cvec[k] - t);
-}
-
-// dx = dx_main - Mm x - cvec2 (+ G)
+// dx = dx_main - Mm x - (cvec - Mm mu_x) (+ G); the per-channel constant is formed in the prologue
 template <int TK>
 __global__ void __launch_bounds__(NT) k_dxfin(Plan P, OcTile T, const float* __restrict__ x,
                                                const float* __restrict__ Mm, const float* __restrict__ cvec2,
+                                               const double* __restrict__ xmom,
                                                const float* __restrict__ G, float* __restrict__ dx) {
   __shared__ __align__(16) float ins[PW_KC * PW_LDP];
   __shared__ __align__(16) float ws[PW_KC * (8 * TK + 4)];
+  __shared__ float cvs[8 * TK];       // cvec[k] - sum_k' Mm[k][k'] mu_x[k'] for this CTA's channels (was k_b4fin)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ic = P.ic;
   const int o0 = blockIdx.y * T.occ;          // output-channel chunk of this CTA (small planes: several CTAs per pixel tile)
+  if (tid < 8 * TK) {
+    const int k = o0 + tid;
+    float c = 0.f;
+    if (k < ic && tid < T.occ) {
+      double t = 0.0;
+      for (int kp = 0; kp < ic; ++kp) t += (double)Mm[k * ic + kp] * xmom[kp];
+      c = (float)((double)cvec2[k] - t);
+    }
+    cvs[tid] = c;
+  }
   Px4 px;
   px_decomp(px, blockIdx.x * PW_TPX + lane * 4, P.P, P.HW);
   float acc[TK][4];
@@ -636,7 +631,7 @@ __global__ void __launch_bounds__(NT) k_dxfin(Plan P, OcTile T, const float* __r
         float m[4], o[4], g[4] = {0.f, 0.f, 0.f, 0.f};
         load4(m, dx, px, ic, k, P.HW);
         if (P.residual) load4(g, G, px, ic, k, P.HW);   // residual => oc == ic, HWo == HW
-        const float cv = cvec2[k];
+        const float cv = cvs[warp * TK + j];
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = m[e] - acc[j][e] - cv + g[e];
         store4(dx, o, px, ic, k, P.HW);
@@ -892,10 +887,10 @@ static void launch_dx(const Plan& P, OcTile T, int ksplit, const float* DA, cons
 }
 
 template <int TK>
-static void launch_dxfin(const Plan& P, OcTile T, const float* x, const float* Mm, const float* cvec2, const float* G,
-                         float* dx, cudaStream_t st) {
+static void launch_dxfin(const Plan& P, OcTile T, const float* x, const float* Mm, const float* cvec2, const double* xmom,
+                         const float* G, float* dx, cudaStream_t st) {
   ProfScope ps("dxfin", 4.0 * P.P * P.ic * (3.0 + (P.residual ? 1 : 0)), 2.0 * P.P * (double)P.ic * P.ic, st);
-  k_dxfin<TK><<<dim3(cdiv(P.P, PW_TPX), T.nchunk), NT, 0, st>>>(P, T, x, Mm, cvec2, G, dx);
+  k_dxfin<TK><<<dim3(cdiv(P.P, PW_TPX), T.nchunk), NT, 0, st>>>(P, T, x, Mm, cvec2, xmom, G, dx);
 }
 
 // ---- side stream for the weight-gradient GEMMs ---------------------------------------------------------------------
@@ -1120,11 +1115,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     { ProfScope ps("b4mm", 4.0 * P.MC * ic, 2.0 * P.MC * ic * ic, st);
       const int kt = cdiv(ic, B4_T);
       int nsplit = max(1, min(cdiv(P.MC, 2 * B4_KC), cdiv(2 * sm_count(), kt * kt)));
-      k_b4mm<<<dim3(kt, kt, nsplit), NT, 0, st>>>(P, S.a12, S.Mm, S.cvec2);
-      k_b4cvec<<<max(1, min(cdiv(P.MC, 64), 2 * sm_count())), NT, 0, st>>>(P, S.a12, S.cvec2);
-      count_launch(1); }
-    { ProfScope ps("b4fin", 4.0 * ic * ic, 2.0 * ic * ic, st);
-      k_b4fin<<<cdiv(ic, 64), 64, 0, st>>>(ic, S.Mm, xmom, S.cvec2); }
+      k_b4mm<<<dim3(kt, kt, nsplit), NT, 0, st>>>(P, S.a12, S.Mm, S.cvec2); }      // Mm and cvec (the k' tiles of row 0)
     // few pixel tiles (14x14 / 7x7 planes): split the output channels over several CTAs per tile so the grid covers the SMs
     OcTile Tf = Tx;
     {
@@ -1134,11 +1125,11 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
         if (tcs[t] < Tf.TC) Tf = oc_tile(ic, tcs[t]);
     }
     switch (Tf.TC) {
-      case 4: launch_dxfin<4>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
-      case 8: launch_dxfin<8>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
-      case 12: launch_dxfin<12>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
-      case 16: launch_dxfin<16>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
-      default: launch_dxfin<24>(P, Tf, x, S.Mm, S.cvec2, dout, dx, st); break;
+      case 4: launch_dxfin<4>(P, Tf, x, S.Mm, S.cvec2, xmom, dout, dx, st); break;
+      case 8: launch_dxfin<8>(P, Tf, x, S.Mm, S.cvec2, xmom, dout, dx, st); break;
+      case 12: launch_dxfin<12>(P, Tf, x, S.Mm, S.cvec2, xmom, dout, dx, st); break;
+      case 16: launch_dxfin<16>(P, Tf, x, S.Mm, S.cvec2, xmom, dout, dx, st); break;
+      default: launch_dxfin<24>(P, Tf, x, S.Mm, S.cvec2, xmom, dout, dx, st); break;
     }
   }
   if (alpha_mode && dlog_alphas) {

@@ -634,9 +634,11 @@ __global__ void __launch_bounds__(NT) k_project(Plan P, OcTile T, const float* _
 // ----------------------------------------------------------------------------------------------
 // one CTA: w = softmax((log_alpha + g)/T) over ALL num_ops (alpha mode) or 1.0 (sampled mode);
 // coef[slot][c] = w * r3 ; bias[c] = -sum w r3 mu3 ; out_lat = sum w lat
+// st3 != nullptr: the BN3 sums are finalised here first (mean, rstd -> bn3; one launch instead of k_bnfin + k_f4prep)
 __global__ void k_f4prep(Plan P, int alpha_mode, const float* __restrict__ log_alphas,
                          const float* __restrict__ gumbel, const float* __restrict__ lat8, float T,
-                         const float* __restrict__ bn3, float* __restrict__ mixw, float* __restrict__ latsave,
+                         const double* __restrict__ st3, double invQ,
+                         float* __restrict__ bn3, float* __restrict__ mixw, float* __restrict__ latsave,
                          float* __restrict__ coef, float* __restrict__ out_lat) {
   __shared__ float w[TFNAS_MAX_OPS];
   const int num_ops = P.num_ops;
@@ -664,6 +666,12 @@ __global__ void k_f4prep(Plan P, int alpha_mode, const float* __restrict__ log_a
     float b = 0.f;
     for (int s = 0; s < P.na; ++s) {
       float wi = w[P.c[s].id];
+      if (st3) {                       // same arithmetic as k_bnfin
+        const double m = st3[2 * (s * oc + c)] * invQ;
+        const double v = st3[2 * (s * oc + c) + 1] * invQ - m * m;
+        bn3[s * oc + c] = (float)m;
+        bn3[C3 + s * oc + c] = (float)(1.0 / sqrt(fmax(v, 0.0) + (double)BN_EPS));
+      }
       float r3 = bn3[C3 + s * oc + c], mu3 = bn3[s * oc + c];
       coef[s * oc + c] = wi * r3;
       b -= wi * r3 * mu3;
@@ -898,11 +906,10 @@ void launch_forward_tail(const Plan& P, const UmWAll* WPp, const float* x, const
       default: launch_project<16>(P, T3, D, bn2, seg, Zb, S.st3, st); break;
     }
   }
-  { ProfScope ps("bnfin", 24.0 * P.na * P.oc, 0, st);
-    k_bnfin<<<cdiv(P.na * P.oc, 256), 256, 0, st>>>(P.na * P.oc, 1.0 / (double)P.Q, S.st3, bn3); }
-  // F4
-  { ProfScope ps("f4prep", 12.0 * P.na * P.oc, 0, st);
-    k_f4prep<<<1, 256, 0, st>>>(P, alpha_mode, log_alphas, gumbel, lat8, T, bn3, mixw, latsave, S.coef, out_lat); }
+  // F4 (the BN3 sums are finalised inside k_f4prep)
+  { ProfScope ps("f4prep", 36.0 * P.na * P.oc, 0, st);
+    k_f4prep<<<1, 256, 0, st>>>(P, alpha_mode, log_alphas, gumbel, lat8, T, S.st3, 1.0 / (double)P.Q, bn3, mixw, latsave, S.coef,
+                                out_lat); }
   size_t total = (size_t)P.N * P.oc * P.HWo;
   int blocks = (int)min((size_t)(8 * sm_count()), (total / 4 + NT - 1) / NT);
   { ProfScope ps("combine", 4.0 * total * (P.na + 1 + (P.residual ? 1 : 0)), 2.0 * total * P.na, st);
