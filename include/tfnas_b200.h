@@ -321,6 +321,12 @@ int tfnas_adam_step(int n, const TfnasAdamTensor* t, int step, float lr, float b
  * logits_i[target_i]); dlogits = (softmax(logits) - onehot(target)) / N.  logits, dlogits: [N, C] fp32; targets: int64.
  */
 int tfnas_softmax_ce(int N, int C, const float* logits, const int64_t* targets, float* loss, float* dlogits, void* stream);
+/*
+ * The same with label smoothing — the derived-network criterion CrossEntropyLabelSmooth (train_eval.py:72-84): the target
+ * distribution is (1 - epsilon) onehot + epsilon / C.  epsilon in [0, 1); 0 is tfnas_softmax_ce.
+ */
+int tfnas_softmax_ce_smooth(int N, int C, const float* logits, const int64_t* targets, float epsilon, float* loss,
+                            float* dlogits, void* stream);
 
 /* Weight-gradient GEMMs of the backward calls on a library-owned side stream (forked from / joined into the caller's stream
  * inside the call): 1 = on (default; also TFNAS_SIDE_STREAM=0/1 at first use), 0 = everything on the caller's stream (e.g.

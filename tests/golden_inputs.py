@@ -64,3 +64,21 @@ def grad_projections(g, j):
     gen = torch.Generator().manual_seed(100003 + int(j))
     r = torch.randn(NPROJ, g.numel(), generator=gen, dtype=torch.float64)
     return (r @ g.detach().double().cpu().reshape(-1)).numpy()
+
+
+def derived_arch():
+    """A parsed architecture for the derived-network tests: stage2 and stage4 one block short, all eight candidates used."""
+    from collections import OrderedDict
+    depth = dict(stage1=2, stage2=2, stage3=4, stage4=3, stage5=4, stage6=1)
+    arch, i = OrderedDict(), 0
+    for s, k in depth.items():
+        arch[s] = OrderedDict()
+        for j in range(k):
+            arch[s]['block%d' % (j + 1)] = (5 * i + 3) % 8
+            i += 1
+    return arch
+
+
+def derived_inputs():
+    g = torch.Generator().manual_seed(11)
+    return torch.randn(4, 3, 64, 64, generator=g), torch.randn(3, 3, 64, 64, generator=g)

@@ -90,7 +90,7 @@ EXPORTS = ['tfnas_version', 'tfnas_last_error', 'tfnas_launch_count',
            'tfnas_body_arena_bytes', 'tfnas_body_fwd', 'tfnas_body_bwd',
            'tfnas_stem_arena_bytes', 'tfnas_stem_fwd', 'tfnas_stem_bwd',
            'tfnas_head_arena_bytes', 'tfnas_head_fwd', 'tfnas_head_bwd',
-           'tfnas_sgd_step', 'tfnas_adam_step', 'tfnas_softmax_ce']
+           'tfnas_sgd_step', 'tfnas_adam_step', 'tfnas_softmax_ce', 'tfnas_softmax_ce_smooth']
 
 _lib = None
 
@@ -180,6 +180,8 @@ def load():
     lib.tfnas_adam_step.argtypes = [i32, ctypes.POINTER(AdamTensor), i32, f32, f32, f32, f32, f32, f32, f32, vp]
     lib.tfnas_softmax_ce.restype = i32
     lib.tfnas_softmax_ce.argtypes = [i32, i32, vp, vp, vp, vp, vp]
+    lib.tfnas_softmax_ce_smooth.restype = i32
+    lib.tfnas_softmax_ce_smooth.argtypes = [i32, i32, vp, vp, ctypes.c_float, vp, vp, vp]
     if lib.tfnas_version() != 1:
         raise TfnasError('ABI version mismatch: %d' % lib.tfnas_version())
     _lib = lib

@@ -121,9 +121,10 @@ __global__ void __launch_bounds__(NT) k_adam(const __grid_constant__ AdamTab T, 
 }
 
 // one CTA of 1024 threads: warp w handles rows w, w+32, ...; deterministic final sum
+// eps = label smoothing: target distribution (1-eps) onehot + eps/C (train_eval.py:72-84); eps = 0 is nn.CrossEntropyLoss
 __global__ void __launch_bounds__(1024) k_softmax_ce(int N, int C, const float* __restrict__ logits,
-                                                      const long long* __restrict__ targets, float* __restrict__ loss,
-                                                      float* __restrict__ dlogits) {
+                                                      const long long* __restrict__ targets, float eps,
+                                                      float* __restrict__ loss, float* __restrict__ dlogits) {
   __shared__ float part[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float invN = 1.f / (float)N;
@@ -133,16 +134,18 @@ __global__ void __launch_bounds__(1024) k_softmax_ce(int N, int C, const float* 
     float mx = -INFINITY;
     for (int c = lane; c < C; c += 32) mx = fmaxf(mx, l[c]);
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float se = 0.f;
-    for (int c = lane; c < C; c += 32) se += expf(l[c] - mx);
+    float se = 0.f, sl = 0.f;
+    for (int c = lane; c < C; c += 32) { se += expf(l[c] - mx); sl += l[c]; }
     se = warp_sum(se);
+    sl = warp_sum(sl);
     const float lse = mx + logf(se);
     const int tg = (int)targets[r];
+    const float toff = eps / (float)C, ton = 1.f - eps + toff;
     if (dlogits) {
       float* d = dlogits + (size_t)r * C;
-      for (int c = lane; c < C; c += 32) d[c] = (expf(l[c] - lse) - (c == tg ? 1.f : 0.f)) * invN;
+      for (int c = lane; c < C; c += 32) d[c] = (expf(l[c] - lse) - (c == tg ? ton : toff)) * invN;
     }
-    if (lane == 0) acc += lse - l[tg];
+    if (lane == 0) acc += eps == 0.f ? lse - l[tg] : lse - (1.f - eps) * l[tg] - toff * sl;
   }
   if (lane == 0) part[warp] = acc;
   __syncthreads();
@@ -210,13 +213,19 @@ int tfnas_adam_step(int n, const TfnasAdamTensor* t, int step, float lr, float b
   return check_cuda("tfnas_adam_step");
 }
 
-int tfnas_softmax_ce(int N, int C, const float* logits, const int64_t* targets, float* loss, float* dlogits, void* stream) {
+int tfnas_softmax_ce_smooth(int N, int C, const float* logits, const int64_t* targets, float epsilon, float* loss,
+                            float* dlogits, void* stream) {
   if (N < 1 || C < 1 || !logits || !targets || !loss) return fail(TFNAS_E_INVALID, "softmax_ce: bad arguments");
+  if (!(epsilon >= 0.f && epsilon < 1.f)) return fail(TFNAS_E_INVALID, "softmax_ce: label smoothing %g not in [0, 1)", (double)epsilon);
   cudaStream_t st = (cudaStream_t)stream;
   cudaGetLastError();
   { ProfScope ps("softmax_ce", 8.0 * N * C, 4.0 * N * C, st);
-    k_softmax_ce<<<1, 1024, 0, st>>>(N, C, logits, (const long long*)targets, loss, dlogits); }
+    k_softmax_ce<<<1, 1024, 0, st>>>(N, C, logits, (const long long*)targets, epsilon, loss, dlogits); }
   return check_cuda("tfnas_softmax_ce");
+}
+
+int tfnas_softmax_ce(int N, int C, const float* logits, const int64_t* targets, float* loss, float* dlogits, void* stream) {
+  return tfnas_softmax_ce_smooth(N, C, logits, targets, 0.f, loss, dlogits, stream);
 }
 
 }  // extern "C"

@@ -41,6 +41,24 @@ class FusedSGD(object):
         for p in self.params:
             p.grad = None
 
+    def state_dict(self):
+        """Momentum buffers as ONE flat tensor in parameter order (None before the first step) plus the hyper-parameters."""
+        flat = None
+        if self._bufs is not None:
+            flat = torch.cat([self._bufs[id(p)].reshape(-1) for p in self.params]).clone()
+        return dict(momentum_flat=flat, lr=self.lr, momentum=self.momentum, weight_decay=self.weight_decay)
+
+    def load_state_dict(self, state):
+        self.lr, self.momentum, self.weight_decay = float(state['lr']), float(state['momentum']), float(state['weight_decay'])
+        self.param_groups[0]['lr'] = self.lr
+        if state.get('momentum_flat') is not None:
+            self._state(self.params[0].device)
+            torch.cat([self._bufs[id(p)].reshape(-1) for p in self.params])       # shape check
+            off = 0
+            for p in self.params:
+                self._bufs[id(p)].copy_(state['momentum_flat'][off:off + p.numel()].view(p.shape))
+                off += p.numel()
+
     def step(self, max_norm=0.0, grad_scale=1.0):
         live = [p for p in self.params if p.grad is not None]
         if not live:
@@ -101,31 +119,37 @@ def bump_versions(params):
 
 class _SoftmaxCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target):
+    def forward(ctx, logits, target, label_smooth=0.0):
         if not (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and target.dtype == torch.int64):
             raise _lib.TfnasError('softmax_ce: logits [N, C] float32 CUDA, target int64')
         logits = logits.contiguous()
         target = target.contiguous()
         loss = torch.empty((), dtype=torch.float32, device=logits.device)
         dl = torch.empty_like(logits)
-        _lib.check(_lib.load().tfnas_softmax_ce(logits.shape[0], logits.shape[1], _ptr(logits), _ptr(target), _ptr(loss),
-                                                _ptr(dl), _stream()))
+        _lib.check(_lib.load().tfnas_softmax_ce_smooth(logits.shape[0], logits.shape[1], _ptr(logits), _ptr(target),
+                                                       float(label_smooth), _ptr(loss), _ptr(dl), _stream()))
         ctx.save_for_backward(dl)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         (dl,) = ctx.saved_tensors
-        return dl * g, None
+        return dl * g, None, None
 
 
-def softmax_ce(logits, target):
-    """nn.CrossEntropyLoss()(logits, target) (mean reduction) with its gradient produced in the same launch."""
-    return _SoftmaxCE.apply(logits, target)
+def softmax_ce(logits, target, label_smooth=0.0):
+    """nn.CrossEntropyLoss()(logits, target) (mean reduction) with its gradient produced in the same launch;
+    ``label_smooth`` > 0 gives the derived-network criterion CrossEntropyLabelSmooth (train_eval.py:72-84)."""
+    return _SoftmaxCE.apply(logits, target, label_smooth)
 
 
 class FusedCrossEntropy(torch.nn.Module):
-    """Drop-in for ``nn.CrossEntropyLoss()`` (train_search.py:121) on the library kernel."""
+    """Drop-in for ``nn.CrossEntropyLoss()`` (train_search.py:121) and, with ``label_smooth``, for
+    ``CrossEntropyLabelSmooth(num_classes, epsilon)`` (train_eval.py:72-84), on the library kernel."""
+
+    def __init__(self, label_smooth=0.0):
+        super().__init__()
+        self.label_smooth = float(label_smooth)
 
     def forward(self, logits, target):
-        return softmax_ce(logits, target)
+        return softmax_ce(logits.float(), target, self.label_smooth)
