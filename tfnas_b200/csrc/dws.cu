@@ -11,7 +11,12 @@
 //
 //   forward  (F1b):  D  = DW (*) act(UH),  BN2 sums                       (models/layers.py:547-548)
 //   backward (B3a):  DA = DW^T (*) dd,  dd = r2 (dd-hat - m1 - d-hat m2) applied on load; optional dDW
+#include <stdlib.h>
 #include "kernels.h"
+
+#ifndef DWS_PF
+#define DWS_PF 4        // input rows in flight per lane in the fixed-plane instantiations
+#endif
 
 struct DwsWork {
   int n;             // channel segments (candidates with this kernel size)
@@ -82,12 +87,17 @@ __device__ __forceinline__ DwsPlane dws_plane(const Plan& P, const DwsWork& Wk, 
   return r;
 }
 
-template <int KS, int VW, int ACT>
-__global__ void __launch_bounds__(NT) k_dws_fwd(Plan P, DwsWork Wk, int lpl, const float* __restrict__ UH,
+// HH > 0: the plane is HH x HH, known at compile time (the 14x14 and 7x7 stages, 11 of the 14 stride-1 MixedOPs): the row
+// loop unrolls completely, every row / tap-row predicate and row offset folds to a constant -- the generic kernel spends
+// ~40 % of its instructions on them (ISETP / BRA / IMAD), and these kernels are issue-bound.
+template <int KS, int VW, int ACT, int HH>
+__global__ void __launch_bounds__(NT) k_dws_fwd(Plan P, DwsWork Wk, int lpl_rt, const float* __restrict__ UH,
                                                  float* __restrict__ D, double* __restrict__ st2) {
   constexpr int pad = KS / 2;
+  constexpr int LH = HH > 0 ? HH / VW : 0;
+  const int lpl = HH > 0 ? (LH <= 1 ? 0 : LH <= 2 ? 1 : LH <= 4 ? 2 : LH <= 8 ? 3 : LH <= 16 ? 4 : 5) : lpl_rt;
   const int lane = threadIdx.x & 31, li = lane & ((1 << lpl) - 1);
-  const int H = P.H, W = P.W, L = W / VW;
+  const int H = HH > 0 ? HH : P.H, W = HH > 0 ? HH : P.W, L = W / VW;
   const DwsPlane pl = dws_plane(P, Wk, lpl);
   const bool active = pl.ok && li < L;
   const Cand& cd = P.c[pl.e];
@@ -103,10 +113,17 @@ __global__ void __launch_bounds__(NT) k_dws_fwd(Plan P, DwsWork Wk, int lpl, con
 #pragma unroll
     for (int j = 0; j < VW; ++j) acc[a][j] = 0.f;
   float s1 = 0.f, s2 = 0.f;
-  float cur[VW];
+  // input rows in flight per lane: one ahead in the generic kernel; DWS_PF ahead when the rows are unrolled (the ring index
+  // is then static) -- on the small planes these kernels are bound by bytes in flight, not by issue slots
+  constexpr int PF = HH > 0 ? DWS_PF : 1;
+  float cur[PF][VW];
 #pragma unroll
-  for (int j = 0; j < VW; ++j) cur[j] = 0.f;
-  if (active) ldv<VW>(cur, src);
+  for (int a = 0; a < PF; ++a) {
+#pragma unroll
+    for (int j = 0; j < VW; ++j) cur[a][j] = 0.f;
+    if (active && a < H) ldv<VW>(cur[a], src + (size_t)a * W);
+  }
+#pragma unroll (HH > 0 ? 16 : 1)
   for (int r0 = 0; r0 < H + pad; r0 += KS) {
 #pragma unroll
     for (int u = 0; u < KS; ++u) {
@@ -114,8 +131,8 @@ __global__ void __launch_bounds__(NT) k_dws_fwd(Plan P, DwsWork Wk, int lpl, con
       if (r < H + pad) {
         float v[VW];
 #pragma unroll
-        for (int j = 0; j < VW; ++j) v[j] = (active && r < H) ? act_f<ACT>(cur[j]) : 0.f;
-        if (active && r + 1 < H) ldv<VW>(cur, src + (size_t)(r + 1) * W);     // next row in flight
+        for (int j = 0; j < VW; ++j) v[j] = (active && r < H) ? act_f<ACT>(cur[r % PF][j]) : 0.f;
+        if (active && r + PF < H) ldv<VW>(cur[r % PF], src + (size_t)(r + PF) * W);     // row r + PF in flight
         float win[VW + KS - 1];
         dws_window<KS, VW>(win, v, lane, li, L);
 #pragma unroll
@@ -152,14 +169,16 @@ __global__ void __launch_bounds__(NT) k_dws_fwd(Plan P, DwsWork Wk, int lpl, con
 
 // Transposed depthwise (stride 1 => a correlation with the flipped filter) over dd = ca*ddh + cb*d + cc.
 // WG: dDW[ky][kx] += sum dd[o][x] * a[o+ky-pad][x+kx-pad] with a = act(UH), accumulated per lane in registers.
-template <int KS, int VW, int ACT, bool WG>
-__global__ void __launch_bounds__(NT) k_dws_bwd(Plan P, DwsWork Wk, int lpl, const float* __restrict__ DC,
+template <int KS, int VW, int ACT, bool WG, int HH>
+__global__ void __launch_bounds__(NT) k_dws_bwd(Plan P, DwsWork Wk, int lpl_rt, const float* __restrict__ DC,
                                                  const float* __restrict__ D, const float* __restrict__ bn2,
                                                  const double* __restrict__ sD, const float* __restrict__ UH,
                                                  float* __restrict__ DA) {
   constexpr int pad = KS / 2;
+  constexpr int LH = HH > 0 ? HH / VW : 0;
+  const int lpl = HH > 0 ? (LH <= 1 ? 0 : LH <= 2 ? 1 : LH <= 4 ? 2 : LH <= 8 ? 3 : LH <= 16 ? 4 : 5) : lpl_rt;
   const int lane = threadIdx.x & 31, li = lane & ((1 << lpl) - 1);
-  const int H = P.H, W = P.W, L = W / VW;
+  const int H = HH > 0 ? HH : P.H, W = HH > 0 ? HH : P.W, L = W / VW;
   const DwsPlane pl = dws_plane(P, Wk, lpl);
   const bool active = pl.ok && li < L;
   const Cand& cd = P.c[pl.e];
@@ -203,11 +222,18 @@ __global__ void __launch_bounds__(NT) k_dws_bwd(Plan P, DwsWork Wk, int lpl, con
       }
     }
   }
-  float c0[VW], c1[VW], an[VW];
+  constexpr int PF = HH > 0 ? DWS_PF : 1;       // rows of DC and D in flight per lane (see k_dws_fwd)
+  float c0[PF][VW], c1[PF][VW], an[VW];
 #pragma unroll
-  for (int j = 0; j < VW; ++j) c0[j] = c1[j] = an[j] = 0.f;
-  if (active) { ldv<VW>(c0, s0); ldv<VW>(c1, s1p); }
+  for (int j = 0; j < VW; ++j) an[j] = 0.f;
+#pragma unroll
+  for (int a = 0; a < PF; ++a) {
+#pragma unroll
+    for (int j = 0; j < VW; ++j) c0[a][j] = c1[a][j] = 0.f;
+    if (active && a < H) { ldv<VW>(c0[a], s0 + (size_t)a * W); ldv<VW>(c1[a], s1p + (size_t)a * W); }
+  }
   if (WG && active && pad < H) ldv<VW>(an, ua + (size_t)pad * W);       // a row `pad`, committed at iteration 0
+#pragma unroll (HH > 0 ? 16 : 1)
   for (int r0 = 0; r0 < H + pad; r0 += KS) {
 #pragma unroll
     for (int u = 0; u < KS; ++u) {
@@ -215,8 +241,11 @@ __global__ void __launch_bounds__(NT) k_dws_bwd(Plan P, DwsWork Wk, int lpl, con
       if (r < H + pad) {
         float v[VW];
 #pragma unroll
-        for (int j = 0; j < VW; ++j) v[j] = (active && r < H) ? fmaf(ca, c0[j], fmaf(cb, c1[j], cc)) : 0.f;
-        if (active && r + 1 < H) { ldv<VW>(c0, s0 + (size_t)(r + 1) * W); ldv<VW>(c1, s1p + (size_t)(r + 1) * W); }
+        for (int j = 0; j < VW; ++j) v[j] = (active && r < H) ? fmaf(ca, c0[r % PF][j], fmaf(cb, c1[r % PF][j], cc)) : 0.f;
+        if (active && r + PF < H) {
+          ldv<VW>(c0[r % PF], s0 + (size_t)(r + PF) * W);
+          ldv<VW>(c1[r % PF], s1p + (size_t)(r + PF) * W);
+        }
         if (WG) {
           // commit a row r+pad (loaded one iteration ago) into its ring slot, prefetch row r+pad+1
           const int sl = (u + pad) % KS;
@@ -298,11 +327,22 @@ bool dws_supported(const Plan& P) {
   return P.W / VW <= 32 && n3 <= 4 && n5 <= 4 && (long long)P.N * P.MC < (1LL << 23);
 }
 
-template <int KS, int VW>
+template <int KS, int VW, int HH>
 static void dws_fwd_launch(const Plan& P, const DwsWork& w, int lpl, dim3 grid, const float* UH, float* D, double* st2,
                            cudaStream_t st) {
-  if (P.act == TFNAS_ACT_RELU) k_dws_fwd<KS, VW, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, w, lpl, UH, D, st2);
-  else k_dws_fwd<KS, VW, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, w, lpl, UH, D, st2);
+  if (P.act == TFNAS_ACT_RELU) k_dws_fwd<KS, VW, TFNAS_ACT_RELU, HH><<<grid, NT, 0, st>>>(P, w, lpl, UH, D, st2);
+  else k_dws_fwd<KS, VW, TFNAS_ACT_SWISH, HH><<<grid, NT, 0, st>>>(P, w, lpl, UH, D, st2);
+}
+
+// compile-time plane sizes (TFNAS_DWS_FIXED=0 keeps every shape on the generic kernels, for A/B timing)
+static int dws_fixed_plane(const Plan& P, int VW) {
+  static const bool on = [] { const char* e = getenv("TFNAS_DWS_FIXED"); return !(e && e[0] == '0'); }();
+  if (!on || P.H != P.W) return 0;
+  if (P.H == 14 && VW == 2) return 14;
+  if (P.H == 7 && VW == 1) return 7;
+  static const bool no28 = [] { const char* e = getenv("TFNAS_DWS_NO28"); return e && e[0] == '1'; }();
+  if (P.H == 28 && VW == 4 && !no28) return 28;
+  return 0;
 }
 
 template <int KS>
@@ -315,9 +355,13 @@ static void dws_fwd_ks(const Plan& P, const float* UH, float* D, double* st2, cu
   const long long warps = (planes + (32 >> lpl) - 1) / (32 >> lpl);
   dim3 grid((unsigned)((warps + NT / 32 - 1) / (NT / 32)));
   ProfScope ps(KS == 3 ? "dw_fwd_k3" : "dw_fwd_k5", 4.0 * mck * ((double)P.P + P.Q), 2.0 * KS * KS * mck * P.Q, st);
-  if (VW == 4) dws_fwd_launch<KS, 4>(P, w, lpl, grid, UH, D, st2, st);
-  else if (VW == 2) dws_fwd_launch<KS, 2>(P, w, lpl, grid, UH, D, st2, st);
-  else dws_fwd_launch<KS, 1>(P, w, lpl, grid, UH, D, st2, st);
+  const int hh = dws_fixed_plane(P, VW);
+  if (hh == 28) dws_fwd_launch<KS, 4, 28>(P, w, lpl, grid, UH, D, st2, st);
+  else if (hh == 14) dws_fwd_launch<KS, 2, 14>(P, w, lpl, grid, UH, D, st2, st);
+  else if (hh == 7) dws_fwd_launch<KS, 1, 7>(P, w, lpl, grid, UH, D, st2, st);
+  else if (VW == 4) dws_fwd_launch<KS, 4, 0>(P, w, lpl, grid, UH, D, st2, st);
+  else if (VW == 2) dws_fwd_launch<KS, 2, 0>(P, w, lpl, grid, UH, D, st2, st);
+  else dws_fwd_launch<KS, 1, 0>(P, w, lpl, grid, UH, D, st2, st);
 }
 
 void launch_dws_fwd(const Plan& P, const float* UH, float* D, double* st2, cudaStream_t st) {
@@ -325,11 +369,11 @@ void launch_dws_fwd(const Plan& P, const float* UH, float* D, double* st2, cudaS
   dws_fwd_ks<5>(P, UH, D, st2, st);
 }
 
-template <int KS, int VW, bool WG>
+template <int KS, int VW, bool WG, int HH>
 static void dws_bwd_launch(const Plan& P, const DwsWork& w, int lpl, dim3 grid, const float* DC, const float* D,
                            const float* bn2, const double* sD, const float* UH, float* DA, cudaStream_t st) {
-  if (P.act == TFNAS_ACT_RELU) k_dws_bwd<KS, VW, TFNAS_ACT_RELU, WG><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, UH, DA);
-  else k_dws_bwd<KS, VW, TFNAS_ACT_SWISH, WG><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, UH, DA);
+  if (P.act == TFNAS_ACT_RELU) k_dws_bwd<KS, VW, TFNAS_ACT_RELU, WG, HH><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, UH, DA);
+  else k_dws_bwd<KS, VW, TFNAS_ACT_SWISH, WG, HH><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, UH, DA);
 }
 
 template <int KS>
@@ -344,12 +388,16 @@ static void dws_bwd_ks(const Plan& P, const float* DC, const float* D, const flo
   dim3 grid((unsigned)((warps + NT / 32 - 1) / (NT / 32)));
   ProfScope ps(KS == 3 ? "dw_bwd_k3" : "dw_bwd_k5", 4.0 * mck * (2.0 * P.Q + (dweights ? 2.0 : 1.0) * P.P),
                2.0 * KS * KS * mck * P.Q * (dweights ? 2 : 1), st);
-#define DWS_B(VW_) do { \
-    if (dweights) dws_bwd_launch<KS, VW_, true>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st); \
-    else dws_bwd_launch<KS, VW_, false>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st); } while (0)
-  if (VW == 4) DWS_B(4);
-  else if (VW == 2) DWS_B(2);
-  else DWS_B(1);
+#define DWS_B(VW_, HH_) do { \
+    if (dweights) dws_bwd_launch<KS, VW_, true, HH_>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st); \
+    else dws_bwd_launch<KS, VW_, false, HH_>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st); } while (0)
+  const int hh = dws_fixed_plane(P, VW);
+  if (hh == 28) DWS_B(4, 28);
+  else if (hh == 14) DWS_B(2, 14);
+  else if (hh == 7) DWS_B(1, 7);
+  else if (VW == 4) DWS_B(4, 0);
+  else if (VW == 2) DWS_B(2, 0);
+  else DWS_B(1, 0);
 #undef DWS_B
 }
 

@@ -108,8 +108,19 @@ def main(argv=None):
     np.random.seed(args.seed)
     torch.manual_seed(args.seed)
     torch.cuda.manual_seed(args.seed)
-    torch.backends.cudnn.benchmark = True
     logging.info('args = %s', args)
+    bench_flag = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True                    # train_eval.py:99; restored for in-process callers (tests)
+    try:
+        _run(args, rank, world)
+    finally:
+        torch.backends.cudnn.benchmark = bench_flag
+        if rank == 0:
+            logging.getLogger().removeHandler(fh)
+            fh.close()
+
+
+def _run(args, rank, world):
 
     logging.info('parsing the architecture')
     lat_lookup = load_lut(args.lookup_path) if args.lookup_path else None
