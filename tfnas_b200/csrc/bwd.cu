@@ -1042,7 +1042,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     for (int s = 0; s < P.na; ++s)
       cudaMemsetAsync(dweights[P.c[s].id].dw, 0, (size_t)P.c[s].mc * P.c[s].k * P.c[s].k * sizeof(float), st);
   static const bool dw_tile = getenv("TFNAS_DW") && strcmp(getenv("TFNAS_DW"), "tile") == 0;
-  if (!dw_tile && dws_supported(P)) {
+  if (!dw_tile && dws_supported(P, dweights != nullptr)) {
     launch_dws_bwd(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
   } else if (P.stride == 1) {
     launch_dw_bwd<3, 1>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);

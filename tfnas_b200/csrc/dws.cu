@@ -1,4 +1,4 @@
-// Register sliding-window depthwise kernels for the stride-1 MixedOPs (14 of the 18 blocks).
+// Register sliding-window depthwise kernels: stride 1 (14 of the 18 MixedOPs) and, further down, stride 2 (even planes).
 //
 // A lane owns VW consecutive columns of one (image, channel) plane and walks the plane's rows top to bottom:
 //   * every input element is loaded from global memory exactly once (coalesced VW-wide loads, next row prefetched),
@@ -297,6 +297,171 @@ __global__ void __launch_bounds__(NT) k_dws_bwd(Plan P, DwsWork Wk, int lpl_rt, 
   }
 }
 
+
+// ---- stride 2 ------------------------------------------------------------------------------------------------------
+// Same idea on the stride-2 MixedOPs (even H, W): a lane owns VW consecutive INPUT columns (VO = VW/2 output columns)
+// of one plane.  Forward walks the input rows: row r feeds output row o through tap row ky = r + pad - 2o, so at most
+// RS = (KS+1)/2 output rows are live; rows are processed in unrolled groups of 2*RS so that every ring slot and the
+// parity tests are compile-time.  Backward walks the dd (output-plane) rows: row oy feeds the KS input-plane rows
+// 2oy - pad .. 2oy + pad and completes two of them; ring of KS+1 accumulator rows, groups of KS+1 dd rows.
+// Input rows are prefetched a whole group ahead (static ring index).
+template <int KS, int VW, int ACT>
+__global__ void __launch_bounds__(NT) k_dws2_fwd(Plan P, DwsWork Wk, int lpl, const float* __restrict__ UH,
+                                                  float* __restrict__ D, double* __restrict__ st2) {
+  constexpr int pad = KS / 2, VO = VW / 2, RS = (KS + 1) / 2, G = 2 * RS;
+  const int lane = threadIdx.x & 31, li = lane & ((1 << lpl) - 1);
+  const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, L = W / VW;
+  const DwsPlane pl = dws_plane(P, Wk, lpl);
+  const bool active = pl.ok && li < L;
+  const Cand& cd = P.c[pl.e];
+  float wr[KS * KS];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) wr[i] = active ? cd.dw[(size_t)pl.cl * KS * KS + i] : 0.f;
+  const size_t plane = (size_t)pl.n * P.MC + pl.cst;
+  const float* src = UH + plane * H * W + (size_t)li * VW;
+  float* dst = D + plane * Ho * Wo + (size_t)li * VO;
+  float acc[RS][VO];
+#pragma unroll
+  for (int a = 0; a < RS; ++a)
+#pragma unroll
+    for (int j = 0; j < VO; ++j) acc[a][j] = 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  float cur[G][VW];
+#pragma unroll
+  for (int a = 0; a < G; ++a) {
+#pragma unroll
+    for (int j = 0; j < VW; ++j) cur[a][j] = 0.f;
+    if (active && a < H) ldv<VW>(cur[a], src + (size_t)a * W);
+  }
+  for (int r0 = 0; r0 < H + pad; r0 += G) {
+    const int ob = r0 >> 1;                            // multiple of RS: ring slots below are compile-time
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int r = r0 + u;
+      if (r < H + pad) {
+        float v[VW];
+#pragma unroll
+        for (int j = 0; j < VW; ++j) v[j] = (active && r < H) ? act_f<ACT>(cur[u][j]) : 0.f;
+        if (active && r + G < H) ldv<VW>(cur[u], src + (size_t)(r + G) * W);
+        float win[VW + KS - 1];
+        dws_window<KS, VW>(win, v, lane, li, L);
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+          constexpr int dummy = 0; (void)dummy;
+          const int t = u + pad - ky;                  // 2 * (o - ob)
+          if ((t & 1) == 0) {
+            const int o = ob + t / 2;
+            if (o >= 0 && o < Ho) {
+              const int sl = ((t / 2) % RS + RS) % RS;
+#pragma unroll
+              for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+                for (int j = 0; j < VO; ++j) acc[sl][j] += wr[ky * KS + kx] * win[2 * j + kx];
+            }
+          }
+        }
+        if (((u - pad) & 1) == 0) {                    // output row (r - pad) / 2 is complete after input row r
+          const int o = ob + (u - pad) / 2;
+          if (o >= 0 && o < Ho) {
+            const int sl = (((u - pad) / 2) % RS + RS) % RS;
+            if (active) stv<VO>(dst + (size_t)o * Wo, acc[sl]);
+#pragma unroll
+            for (int j = 0; j < VO; ++j) { s1 += acc[sl][j]; s2 += acc[sl][j] * acc[sl][j]; acc[sl][j] = 0.f; }
+          }
+        }
+      }
+    }
+  }
+  for (int o = (1 << lpl) >> 1; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (pl.ok && li == 0) {
+    atomicAdd(&st2[2 * pl.cst], (double)s1);
+    atomicAdd(&st2[2 * pl.cst + 1], (double)s2);
+  }
+}
+
+// DA[iy][ix] = sum w[ky][kx] dd[oy][ox] over 2oy + ky - pad = iy, 2ox + kx - pad = ix;  dd = ca*ddh + cb*d + cc on load
+template <int KS, int VW, int ACT>
+__global__ void __launch_bounds__(NT) k_dws2_bwd(Plan P, DwsWork Wk, int lpl, const float* __restrict__ DC,
+                                                  const float* __restrict__ D, const float* __restrict__ bn2,
+                                                  const double* __restrict__ sD, float* __restrict__ DA) {
+  constexpr int pad = KS / 2, VO = VW / 2, RB = KS + 1;
+  const int lane = threadIdx.x & 31, li = lane & ((1 << lpl) - 1);
+  const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, L = W / VW;
+  const DwsPlane pl = dws_plane(P, Wk, lpl);
+  const bool active = pl.ok && li < L;
+  const Cand& cd = P.c[pl.e];
+  float wr[KS * KS];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) wr[i] = active ? cd.dw[(size_t)pl.cl * KS * KS + i] : 0.f;
+  float ca = 0.f, cb = 0.f, cc = 0.f;
+  if (active) {
+    const double invQ = 1.0 / (double)P.Q;
+    const float mu = bn2[pl.cst], r = bn2[P.MC + pl.cst];
+    const float m1 = (float)(sD[2 * pl.cst] * invQ), m2 = (float)(sD[2 * pl.cst + 1] * invQ);
+    ca = r; cb = -r * r * m2; cc = r * (mu * r * m2 - m1);
+  }
+  const size_t plane = (size_t)pl.n * P.MC + pl.cst;
+  const float* s0 = DC + plane * Ho * Wo + (size_t)li * VO;
+  const float* s1p = D + plane * Ho * Wo + (size_t)li * VO;
+  float* dst = DA + plane * H * W + (size_t)li * VW;
+  float acc[RB][VW];
+#pragma unroll
+  for (int a = 0; a < RB; ++a)
+#pragma unroll
+    for (int j = 0; j < VW; ++j) acc[a][j] = 0.f;
+  float c0[RB][VO], c1[RB][VO];
+#pragma unroll
+  for (int a = 0; a < RB; ++a) {
+#pragma unroll
+    for (int j = 0; j < VO; ++j) c0[a][j] = c1[a][j] = 0.f;
+    if (active && a < Ho) { ldv<VO>(c0[a], s0 + (size_t)a * Wo); ldv<VO>(c1[a], s1p + (size_t)a * Wo); }
+  }
+  for (int g0 = 0; g0 < Ho + 1; g0 += RB) {            // 2 * g0 is a multiple of RB: ring slots are compile-time
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int oy = g0 + u;
+      if (oy < Ho + 1) {                                // oy == Ho: a zero row that flushes the last `pad` input rows
+        float v[VO];
+#pragma unroll
+        for (int j = 0; j < VO; ++j) v[j] = (active && oy < Ho) ? fmaf(ca, c0[u][j], fmaf(cb, c1[u][j], cc)) : 0.f;
+        if (active && oy + RB < Ho) {
+          ldv<VO>(c0[u], s0 + (size_t)(oy + RB) * Wo);
+          ldv<VO>(c1[u], s1p + (size_t)(oy + RB) * Wo);
+        }
+        float win[VO + 2];                              // win[i] = dd column (first own column) + i - 1
+        dws_window<3, VO>(win, v, lane, li, L);
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+          const int iy = 2 * oy + ky - pad;
+          if (iy >= 0 && iy < H) {
+            const int sl = ((2 * u + ky - pad) % RB + RB) % RB;
+#pragma unroll
+            for (int j = 0; j < VW; ++j)
+#pragma unroll
+              for (int kx = 0; kx < KS; ++kx) {
+                const int t = j + pad - kx;             // 2 * (ox - first own dd column)
+                if ((t & 1) == 0) acc[sl][j] += wr[ky * KS + kx] * win[t / 2 + 1];
+              }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {                   // input rows 2oy - pad, 2oy - pad + 1 are complete
+          const int iy = 2 * oy - pad + e;
+          if (iy >= 0 && iy < H) {
+            const int sl = ((2 * u - pad + e) % RB + RB) % RB;
+            if (active) stv<VW>(dst + (size_t)iy * W, acc[sl]);
+#pragma unroll
+            for (int j = 0; j < VW; ++j) acc[sl][j] = 0.f;
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 static bool dws_setup(const Plan& P, int KS, const TfnasCandPtrs* dweights, DwsWork& w, int& VW, int& lpl, double& mck) {
   w.n = 0;
@@ -319,8 +484,15 @@ static bool dws_setup(const Plan& P, int KS, const TfnasCandPtrs* dweights, DwsW
   return L <= 32;
 }
 
-bool dws_supported(const Plan& P) {
-  if (P.stride != 1) return false;
+// wgrad: the caller wants the depthwise weight gradient from the backward kernel (stride 2: not in the sliding-window
+// kernels yet -- the shared-memory tile kernel of bwd.cu serves the sampled passes there)
+bool dws_supported(const Plan& P, bool wgrad) {
+  if (P.stride == 2) {
+    static const bool on = [] { const char* e = getenv("TFNAS_DWS_S2"); return !(e && e[0] == '0'); }();
+    if (!on || wgrad || (P.H & 1) || (P.W & 1)) return false;
+  } else if (P.stride != 1) {
+    return false;
+  }
   const int VW = (P.W & 3) == 0 ? 4 : (P.W & 1) == 0 ? 2 : 1;
   int n3 = 0, n5 = 0;
   for (int s = 0; s < P.na; ++s) (P.c[s].k == 3 ? n3 : n5)++;
@@ -355,6 +527,17 @@ static void dws_fwd_ks(const Plan& P, const float* UH, float* D, double* st2, cu
   const long long warps = (planes + (32 >> lpl) - 1) / (32 >> lpl);
   dim3 grid((unsigned)((warps + NT / 32 - 1) / (NT / 32)));
   ProfScope ps(KS == 3 ? "dw_fwd_k3" : "dw_fwd_k5", 4.0 * mck * ((double)P.P + P.Q), 2.0 * KS * KS * mck * P.Q, st);
+  if (P.stride == 2) {
+    const bool relu = P.act == TFNAS_ACT_RELU;
+    if (VW == 4) {
+      if (relu) k_dws2_fwd<KS, 4, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, w, lpl, UH, D, st2);
+      else k_dws2_fwd<KS, 4, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, w, lpl, UH, D, st2);
+    } else {
+      if (relu) k_dws2_fwd<KS, 2, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, w, lpl, UH, D, st2);
+      else k_dws2_fwd<KS, 2, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, w, lpl, UH, D, st2);
+    }
+    return;
+  }
   const int hh = dws_fixed_plane(P, VW);
   if (hh == 28) dws_fwd_launch<KS, 4, 28>(P, w, lpl, grid, UH, D, st2, st);
   else if (hh == 14) dws_fwd_launch<KS, 2, 14>(P, w, lpl, grid, UH, D, st2, st);
@@ -388,6 +571,17 @@ static void dws_bwd_ks(const Plan& P, const float* DC, const float* D, const flo
   dim3 grid((unsigned)((warps + NT / 32 - 1) / (NT / 32)));
   ProfScope ps(KS == 3 ? "dw_bwd_k3" : "dw_bwd_k5", 4.0 * mck * (2.0 * P.Q + (dweights ? 2.0 : 1.0) * P.P),
                2.0 * KS * KS * mck * P.Q * (dweights ? 2 : 1), st);
+  if (P.stride == 2) {                                 // (dws_supported refused the weight-gradient mode)
+    const bool relu = P.act == TFNAS_ACT_RELU;
+    if (VW == 4) {
+      if (relu) k_dws2_bwd<KS, 4, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, DA);
+      else k_dws2_bwd<KS, 4, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, DA);
+    } else {
+      if (relu) k_dws2_bwd<KS, 2, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, DA);
+      else k_dws2_bwd<KS, 2, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, DA);
+    }
+    return;
+  }
 #define DWS_B(VW_, HH_) do { \
     if (dweights) dws_bwd_launch<KS, VW_, true, HH_>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st); \
     else dws_bwd_launch<KS, VW_, false, HH_>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st); } while (0)
