@@ -82,8 +82,8 @@ def test_fused_trajectory_matches_torch_optim():
         assert abs(float(lf) - float(lt)) <= 1e-4 * abs(float(lt))
     assert worst() < 2e-2, worst()
     for (k, u), v in zip(a.state_dict().items(), b.state_dict().values()):
-        if 'running' in k:
-            assert torch.allclose(u, v, rtol=1e-4, atol=1e-6), k
+        if 'running' in k:              # same bound as the parameters: the two arms' statistics drift with their weights
+            assert float((u - v).abs().max()) <= 2e-2 * float(v.abs().max()) + 1e-5, k
     # optimiser state round trip (checkpoint 'optimizer' entry)
     st = opt_f.state_dict()
     c = copy.deepcopy(a)
