@@ -1042,8 +1042,14 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     for (int s = 0; s < P.na; ++s)
       cudaMemsetAsync(dweights[P.c[s].id].dw, 0, (size_t)P.c[s].mc * P.c[s].k * P.c[s].k * sizeof(float), st);
   static const bool dw_tile = getenv("TFNAS_DW") && strcmp(getenv("TFNAS_DW"), "tile") == 0;
-  if (!dw_tile && dws_supported(P, dweights != nullptr)) {
-    launch_dws_bwd(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
+  if (!dw_tile && dws_supported(P)) {
+    cudaStream_t dwst = st;
+    if (side && P.stride == 2) {     // stride 2: dDW is a kernel of its own beside the transposed depthwise (DC, sD are final)
+      cudaEventRecord(side->fork2, st);
+      cudaStreamWaitEvent(wst, side->fork2, 0);
+      dwst = wst;
+    }
+    launch_dws_bwd(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st, dwst);
   } else if (P.stride == 1) {
     launch_dw_bwd<3, 1>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);
     launch_dw_bwd<5, 1>(P, S.DC, D, bn2, S.sD, UH, S.DA, dweights, st);

@@ -462,6 +462,105 @@ __global__ void __launch_bounds__(NT) k_dws2_bwd(Plan P, DwsWork Wk, int lpl, co
   }
 }
 
+
+// Depthwise weight gradient for stride 2 (sampled passes): dDW[ky][kx] += sum dd[oy][ox] * a[2oy+ky-pad][2ox+kx-pad],
+// a = act(UH).  Walks the INPUT rows like the forward kernel (activation and horizontal window once per row); the dd
+// rows an input row meets (oy = (r + pad - ky) / 2) sit in a ring of RS rows of the lane's own VO columns, each
+// committed when first needed from loads issued two input rows earlier.  Runs beside k_dws2_bwd (weight-gradient
+// side stream): it only reads DC / D / UH.
+template <int KS, int VW, int ACT>
+__global__ void __launch_bounds__(NT) k_dws2_wg(Plan P, DwsWork Wk, int lpl, const float* __restrict__ DC,
+                                                 const float* __restrict__ D, const float* __restrict__ bn2,
+                                                 const double* __restrict__ sD, const float* __restrict__ UH) {
+  constexpr int pad = KS / 2, VO = VW / 2, RS = (KS + 1) / 2, G = 2 * RS;
+  const int lane = threadIdx.x & 31, li = lane & ((1 << lpl) - 1);
+  const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, L = W / VW;
+  const DwsPlane pl = dws_plane(P, Wk, lpl);
+  const bool active = pl.ok && li < L;
+  float ca = 0.f, cb = 0.f, cc = 0.f;
+  if (active) {
+    const double invQ = 1.0 / (double)P.Q;
+    const float mu = bn2[pl.cst], r = bn2[P.MC + pl.cst];
+    const float m1 = (float)(sD[2 * pl.cst] * invQ), m2 = (float)(sD[2 * pl.cst + 1] * invQ);
+    ca = r; cb = -r * r * m2; cc = r * (mu * r * m2 - m1);
+  }
+  const size_t plane = (size_t)pl.n * P.MC + pl.cst;
+  const float* src = UH + plane * H * W + (size_t)li * VW;
+  const float* s0 = DC + plane * Ho * Wo + (size_t)li * VO;
+  const float* s1p = D + plane * Ho * Wo + (size_t)li * VO;
+  float gacc[KS * KS];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) gacc[i] = 0.f;
+  float ddr[RS][VO], n0[VO], n1[VO];
+#pragma unroll
+  for (int a = 0; a < RS; ++a)
+#pragma unroll
+    for (int j = 0; j < VO; ++j) ddr[a][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < VO; ++j) n0[j] = n1[j] = 0.f;
+  if (active) {                                        // dd row 0 is needed from input row 0 on; stage row 1
+    ldv<VO>(n0, s0); ldv<VO>(n1, s1p);
+#pragma unroll
+    for (int j = 0; j < VO; ++j) ddr[0][j] = fmaf(ca, n0[j], fmaf(cb, n1[j], cc));
+    if (1 < Ho) { ldv<VO>(n0, s0 + Wo); ldv<VO>(n1, s1p + Wo); }
+  }
+  float cur[G][VW];
+#pragma unroll
+  for (int a = 0; a < G; ++a) {
+#pragma unroll
+    for (int j = 0; j < VW; ++j) cur[a][j] = 0.f;
+    if (active && a < H) ldv<VW>(cur[a], src + (size_t)a * W);
+  }
+  for (int r0 = 0; r0 < H; r0 += G) {
+    const int ob = r0 >> 1;                            // multiple of RS
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int r = r0 + u;
+      if (r < H) {
+        if (((u + pad) & 1) == 0) {                    // dd row (r + pad) / 2 >= 1 enters the ring at input row r
+          const int on = ob + (u + pad) / 2;
+          const int sl = (((u + pad) / 2) % RS + RS) % RS;
+          if (on >= 1) {
+#pragma unroll
+            for (int j = 0; j < VO; ++j) ddr[sl][j] = (active && on < Ho) ? fmaf(ca, n0[j], fmaf(cb, n1[j], cc)) : 0.f;
+            if (active && on + 1 < Ho) { ldv<VO>(n0, s0 + (size_t)(on + 1) * Wo); ldv<VO>(n1, s1p + (size_t)(on + 1) * Wo); }
+          }
+        }
+        float v[VW];
+#pragma unroll
+        for (int j = 0; j < VW; ++j) v[j] = active ? act_f<ACT>(cur[u][j]) : 0.f;
+        if (active && r + G < H) ldv<VW>(cur[u], src + (size_t)(r + G) * W);
+        float win[VW + KS - 1];
+        dws_window<KS, VW>(win, v, lane, li, L);
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+          const int t = u + pad - ky;
+          if ((t & 1) == 0) {
+            const int o = ob + t / 2;
+            if (o >= 0 && o < Ho) {
+              const int sl = ((t / 2) % RS + RS) % RS;
+#pragma unroll
+              for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+                for (int j = 0; j < VO; ++j) gacc[ky * KS + kx] += ddr[sl][j] * win[2 * j + kx];
+            }
+          }
+        }
+      }
+    }
+  }
+  float* gp = nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < Wk.n && Wk.slot[i] == pl.e) gp = Wk.gw[i];
+#pragma unroll
+  for (int i = 0; i < KS * KS; ++i) {
+    float t = gacc[i];
+    for (int o = (1 << lpl) >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (pl.ok && li == 0 && gp) atomicAdd(&gp[(size_t)pl.cl * KS * KS + i], t);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 static bool dws_setup(const Plan& P, int KS, const TfnasCandPtrs* dweights, DwsWork& w, int& VW, int& lpl, double& mck) {
   w.n = 0;
@@ -484,12 +583,11 @@ static bool dws_setup(const Plan& P, int KS, const TfnasCandPtrs* dweights, DwsW
   return L <= 32;
 }
 
-// wgrad: the caller wants the depthwise weight gradient from the backward kernel (stride 2: not in the sliding-window
-// kernels yet -- the shared-memory tile kernel of bwd.cu serves the sampled passes there)
-bool dws_supported(const Plan& P, bool wgrad) {
+// TFNAS_DWS_S2=0 sends the stride-2 MixedOPs back to the shared-memory tile kernels of fwd.cu / bwd.cu (A/B timing)
+bool dws_supported(const Plan& P) {
   if (P.stride == 2) {
     static const bool on = [] { const char* e = getenv("TFNAS_DWS_S2"); return !(e && e[0] == '0'); }();
-    if (!on || wgrad || (P.H & 1) || (P.W & 1)) return false;
+    if (!on || (P.H & 1) || (P.W & 1)) return false;
   } else if (P.stride != 1) {
     return false;
   }
@@ -561,7 +659,7 @@ static void dws_bwd_launch(const Plan& P, const DwsWork& w, int lpl, dim3 grid, 
 
 template <int KS>
 static void dws_bwd_ks(const Plan& P, const float* DC, const float* D, const float* bn2, const double* sD,
-                       const float* UH, float* DA, const TfnasCandPtrs* dweights, cudaStream_t st) {
+                       const float* UH, float* DA, const TfnasCandPtrs* dweights, cudaStream_t st, cudaStream_t wg_st) {
   DwsWork w;
   int VW, lpl;
   double mck;
@@ -571,7 +669,7 @@ static void dws_bwd_ks(const Plan& P, const float* DC, const float* D, const flo
   dim3 grid((unsigned)((warps + NT / 32 - 1) / (NT / 32)));
   ProfScope ps(KS == 3 ? "dw_bwd_k3" : "dw_bwd_k5", 4.0 * mck * (2.0 * P.Q + (dweights ? 2.0 : 1.0) * P.P),
                2.0 * KS * KS * mck * P.Q * (dweights ? 2 : 1), st);
-  if (P.stride == 2) {                                 // (dws_supported refused the weight-gradient mode)
+  if (P.stride == 2) {                                 // DA on the caller's stream, dDW beside it on wg_st
     const bool relu = P.act == TFNAS_ACT_RELU;
     if (VW == 4) {
       if (relu) k_dws2_bwd<KS, 4, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, DA);
@@ -579,6 +677,16 @@ static void dws_bwd_ks(const Plan& P, const float* DC, const float* D, const flo
     } else {
       if (relu) k_dws2_bwd<KS, 2, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, DA);
       else k_dws2_bwd<KS, 2, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, w, lpl, DC, D, bn2, sD, DA);
+    }
+    if (dweights) {
+      count_launch(1);
+      if (VW == 4) {
+        if (relu) k_dws2_wg<KS, 4, TFNAS_ACT_RELU><<<grid, NT, 0, wg_st>>>(P, w, lpl, DC, D, bn2, sD, UH);
+        else k_dws2_wg<KS, 4, TFNAS_ACT_SWISH><<<grid, NT, 0, wg_st>>>(P, w, lpl, DC, D, bn2, sD, UH);
+      } else {
+        if (relu) k_dws2_wg<KS, 2, TFNAS_ACT_RELU><<<grid, NT, 0, wg_st>>>(P, w, lpl, DC, D, bn2, sD, UH);
+        else k_dws2_wg<KS, 2, TFNAS_ACT_SWISH><<<grid, NT, 0, wg_st>>>(P, w, lpl, DC, D, bn2, sD, UH);
+      }
     }
     return;
   }
@@ -596,8 +704,9 @@ static void dws_bwd_ks(const Plan& P, const float* DC, const float* D, const flo
 }
 
 // dweights != nullptr: the dDW buffers must have been zeroed by the caller (atomic accumulation)
+// wg_st: stream of the stride-2 depthwise weight-gradient kernel (ordered after DC / sD are final; may equal st)
 void launch_dws_bwd(const Plan& P, const float* DC, const float* D, const float* bn2, const double* sD, const float* UH,
-                    float* DA, const TfnasCandPtrs* dweights, cudaStream_t st) {
-  dws_bwd_ks<3>(P, DC, D, bn2, sD, UH, DA, dweights, st);
-  dws_bwd_ks<5>(P, DC, D, bn2, sD, UH, DA, dweights, st);
+                    float* DA, const TfnasCandPtrs* dweights, cudaStream_t st, cudaStream_t wg_st) {
+  dws_bwd_ks<3>(P, DC, D, bn2, sD, UH, DA, dweights, st, wg_st);
+  dws_bwd_ks<5>(P, DC, D, bn2, sD, UH, DA, dweights, st, wg_st);
 }

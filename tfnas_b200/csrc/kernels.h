@@ -104,10 +104,10 @@ bool ws_dx(const Plan& P, const UmW& W, const DxChunks& CH, const float* DA, con
            cudaStream_t st);
 
 // register sliding-window depthwise kernels (dws.cu): stride-1 MixedOPs; TFNAS_DW=tile forces the smem-tile kernels
-bool dws_supported(const Plan& P, bool wgrad = false);
+bool dws_supported(const Plan& P);
 void launch_dws_fwd(const Plan& P, const float* UH, float* D, double* st2, cudaStream_t st);
 void launch_dws_bwd(const Plan& P, const float* DC, const float* D, const float* bn2, const double* sD, const float* UH,
-                    float* DA, const TfnasCandPtrs* dweights, cudaStream_t st);
+                    float* DA, const TfnasCandPtrs* dweights, cudaStream_t st, cudaStream_t wg_st);
 
 void launch_forward(const Plan& P, const float* x, const float* log_alphas, const float* gumbel,
                     const float* lat8, float T, int alpha_mode, float* out, float* out_lat,
