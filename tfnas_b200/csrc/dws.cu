@@ -309,6 +309,7 @@ template <int KS, int VW, int ACT>
 __global__ void __launch_bounds__(NT) k_dws2_fwd(Plan P, DwsWork Wk, int lpl, const float* __restrict__ UH,
                                                   float* __restrict__ D, double* __restrict__ st2) {
   constexpr int pad = KS / 2, VO = VW / 2, RS = (KS + 1) / 2, G = 2 * RS;
+  constexpr int PF = KS == 5 ? G / 2 : G;              // input rows in flight per lane (5x5: 97 registers with a full group)
   const int lane = threadIdx.x & 31, li = lane & ((1 << lpl) - 1);
   const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, L = W / VW;
   const DwsPlane pl = dws_plane(P, Wk, lpl);
@@ -326,9 +327,9 @@ __global__ void __launch_bounds__(NT) k_dws2_fwd(Plan P, DwsWork Wk, int lpl, co
 #pragma unroll
     for (int j = 0; j < VO; ++j) acc[a][j] = 0.f;
   float s1 = 0.f, s2 = 0.f;
-  float cur[G][VW];
+  float cur[PF][VW];
 #pragma unroll
-  for (int a = 0; a < G; ++a) {
+  for (int a = 0; a < PF; ++a) {
 #pragma unroll
     for (int j = 0; j < VW; ++j) cur[a][j] = 0.f;
     if (active && a < H) ldv<VW>(cur[a], src + (size_t)a * W);
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(NT) k_dws2_fwd(Plan P, DwsWork Wk, int lpl, co
       if (r < H + pad) {
         float v[VW];
 #pragma unroll
-        for (int j = 0; j < VW; ++j) v[j] = (active && r < H) ? act_f<ACT>(cur[u][j]) : 0.f;
-        if (active && r + G < H) ldv<VW>(cur[u], src + (size_t)(r + G) * W);
+        for (int j = 0; j < VW; ++j) v[j] = (active && r < H) ? act_f<ACT>(cur[u % PF][j]) : 0.f;
+        if (active && r + PF < H) ldv<VW>(cur[u % PF], src + (size_t)(r + PF) * W);
         float win[VW + KS - 1];
         dws_window<KS, VW>(win, v, lane, li, L);
 #pragma unroll
@@ -384,10 +385,11 @@ __global__ void __launch_bounds__(NT) k_dws2_fwd(Plan P, DwsWork Wk, int lpl, co
 
 // DA[iy][ix] = sum w[ky][kx] dd[oy][ox] over 2oy + ky - pad = iy, 2ox + kx - pad = ix;  dd = ca*ddh + cb*d + cc on load
 template <int KS, int VW, int ACT>
-__global__ void __launch_bounds__(NT) k_dws2_bwd(Plan P, DwsWork Wk, int lpl, const float* __restrict__ DC,
+__global__ void __launch_bounds__(NT, 3) k_dws2_bwd(Plan P, DwsWork Wk, int lpl, const float* __restrict__ DC,
                                                   const float* __restrict__ D, const float* __restrict__ bn2,
                                                   const double* __restrict__ sD, float* __restrict__ DA) {
   constexpr int pad = KS / 2, VO = VW / 2, RB = KS + 1;
+  constexpr int PF = KS == 5 ? RB / 2 : RB;            // dd rows in flight per lane
   const int lane = threadIdx.x & 31, li = lane & ((1 << lpl) - 1);
   const int H = P.H, W = P.W, Ho = P.Ho, Wo = P.Wo, L = W / VW;
   const DwsPlane pl = dws_plane(P, Wk, lpl);
@@ -412,9 +414,9 @@ __global__ void __launch_bounds__(NT) k_dws2_bwd(Plan P, DwsWork Wk, int lpl, co
   for (int a = 0; a < RB; ++a)
 #pragma unroll
     for (int j = 0; j < VW; ++j) acc[a][j] = 0.f;
-  float c0[RB][VO], c1[RB][VO];
+  float c0[PF][VO], c1[PF][VO];
 #pragma unroll
-  for (int a = 0; a < RB; ++a) {
+  for (int a = 0; a < PF; ++a) {
 #pragma unroll
     for (int j = 0; j < VO; ++j) c0[a][j] = c1[a][j] = 0.f;
     if (active && a < Ho) { ldv<VO>(c0[a], s0 + (size_t)a * Wo); ldv<VO>(c1[a], s1p + (size_t)a * Wo); }
@@ -426,10 +428,10 @@ __global__ void __launch_bounds__(NT) k_dws2_bwd(Plan P, DwsWork Wk, int lpl, co
       if (oy < Ho + 1) {                                // oy == Ho: a zero row that flushes the last `pad` input rows
         float v[VO];
 #pragma unroll
-        for (int j = 0; j < VO; ++j) v[j] = (active && oy < Ho) ? fmaf(ca, c0[u][j], fmaf(cb, c1[u][j], cc)) : 0.f;
-        if (active && oy + RB < Ho) {
-          ldv<VO>(c0[u], s0 + (size_t)(oy + RB) * Wo);
-          ldv<VO>(c1[u], s1p + (size_t)(oy + RB) * Wo);
+        for (int j = 0; j < VO; ++j) v[j] = (active && oy < Ho) ? fmaf(ca, c0[u % PF][j], fmaf(cb, c1[u % PF][j], cc)) : 0.f;
+        if (active && oy + PF < Ho) {
+          ldv<VO>(c0[u % PF], s0 + (size_t)(oy + PF) * Wo);
+          ldv<VO>(c1[u % PF], s1p + (size_t)(oy + PF) * Wo);
         }
         float win[VO + 2];                              // win[i] = dd column (first own column) + i - 1
         dws_window<3, VO>(win, v, lane, li, L);
@@ -693,9 +695,12 @@ static void dws_bwd_ks(const Plan& P, const float* DC, const float* D, const flo
 #define DWS_B(VW_, HH_) do { \
     if (dweights) dws_bwd_launch<KS, VW_, true, HH_>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st); \
     else dws_bwd_launch<KS, VW_, false, HH_>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st); } while (0)
-  const int hh = dws_fixed_plane(P, VW);
-  if (hh == 28) DWS_B(4, 28);
-  else if (hh == 14) DWS_B(2, 14);
+  // with the weight gradient in the kernel (sampled passes) the unrolled 28 / 14 planes need 125-255 registers and measured
+  // slower than the generic kernel (28x28: 0.178 vs 0.129 ms); only the 7x7 plane keeps its fixed instantiation there
+  int hh = dws_fixed_plane(P, VW);
+  if (dweights && hh != 7) hh = 0;
+  if (hh == 28) dws_bwd_launch<KS, 4, false, 28>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st);
+  else if (hh == 14) dws_bwd_launch<KS, 2, false, 14>(P, w, lpl, grid, DC, D, bn2, sD, UH, DA, st);
   else if (hh == 7) DWS_B(1, 7);
   else if (VW == 4) DWS_B(4, 0);
   else if (VW == 2) DWS_B(2, 0);
