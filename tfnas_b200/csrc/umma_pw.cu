@@ -1175,7 +1175,10 @@ struct WgArgs {
 // NBR = B rows per thread (Nc <= 32 * NBR).  Software pipeline per 32-pixel K chunk: the raw rows of chunk c+1 are
 // loaded into registers right after chunk c's operands are stored, so they fly during the barrier, the MMA issue and
 // the tensor core's round trip; per-row constants (BN2 mean / rstd, BN3-backward coefficients) are hoisted.
-template <int MODE, int ACT, int NBR>
+// VEC (HW % 4 == 0): a thread's 4 pixels are one aligned 16-byte group of one image; every row is then ONE vector load at
+// (per-row element offset, fixed) + (per-chunk pixel offset, shared by all rows) -- the general path recomputes
+// ((n * C + ch) * HW + hw) per row and pixel, which made integer address arithmetic the bulk of the instruction stream.
+template <int MODE, int ACT, int NBR, bool VEC>
 __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
   extern __shared__ __align__(1024) unsigned char um_raw[];
   unsigned char* sm = um_raw + ((1024u - (smem_u32(um_raw) & 1023u)) & 1023u);
@@ -1227,8 +1230,25 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
     if (MODE == 0) b_cf[j] = b_row[j] >= 0 ? g.dzc[slot * P.oc + b] : make_float4(0.f, 0.f, 0.f, 0.f);
     if (MODE == 2) b_cf[j] = make_float4(b_row[j] >= 0 ? (float)(((const double*)g.out)[b] / (double)P.P) : 0.f, 0.f, 0.f, 0.f);
   }
-  const bool vecshape = (HWp & 3) == 0;
+  const bool vecshape = VEC || (HWp & 3) == 0;
   const bool gated = MODE == 0 && cd.se > 0;
+  // VEC: element offsets of the rows inside their tensors (all tensors of this path hold < 2^32 elements)
+  uint32_t a_off[VEC ? 4 : 1], a1_off[(VEC && MODE == 1) ? 4 : 1], g_off[VEC ? 4 : 1], b_off[VEC ? NBR : 1], b1_off[(VEC && MODE == 0) ? NBR : 1];
+  if (VEC) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cst = a_cst[i] >= 0 ? a_cst[i] : 0;
+      a_off[i] = (uint32_t)cst * (uint32_t)HWp;
+      if (MODE == 1) a1_off[i] = (uint32_t)cst * (uint32_t)HWp;
+      g_off[i] = (uint32_t)(cd.soff + (cst - cd.coff));
+    }
+#pragma unroll
+    for (int j = 0; j < NBR; ++j) {
+      const int ch = b_row[j] >= 0 ? b_row[j] : 0;
+      b_off[j] = (uint32_t)ch * (uint32_t)HWp;
+      if (MODE == 0) b1_off[j] = (uint32_t)(slot * P.oc + ch) * (uint32_t)HWp;
+    }
+  }
   // ---- raw registers of one chunk ----
   float4 ra0[4], ra1[MODE == 1 ? 4 : 1], rb0[NBR], rb1[MODE == 0 ? NBR : 1];
   float rgt[4];                        // MODE 0: SE gate per A row (vector path: one image per 4 pixels)
@@ -1236,6 +1256,30 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
   int p = p_lo + q * 4, n = 0, hw = 0;
   if (p < p_hi) { n = fast_div(p, HWp, __frcp_rn((float)HWp)); hw = p - n * HWp; }
   auto load_chunk = [&]() {
+    if (VEC) {
+      const bool ok = p < p_hi;        // p, p_hi are multiples of 4: all four pixels or none
+      px.vec = ok;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { px.v[e] = ok; px.n[e] = ok ? n : 0; px.hw[e] = ok ? hw + e : 0; }
+      const uint32_t nhw = ok ? (uint32_t)n * (uint32_t)HWp : 0u, hw0 = ok ? (uint32_t)hw : 0u;
+      const uint32_t pa = nhw * (uint32_t)CA + hw0, pa1 = nhw * (uint32_t)P.MC + hw0;
+      const uint32_t pb = nhw * (uint32_t)(MODE == 0 ? P.oc : P.ic) + hw0, pb1 = nhw * (uint32_t)(P.na * P.oc) + hw0;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool rok = ok && a_cst[i] >= 0;
+        ra0[i] = rok ? *(const float4*)(g.A0 + (size_t)(a_off[i] + pa)) : z4;
+        if (MODE == 1) ra1[i] = rok ? *(const float4*)(g.A1 + (size_t)(a1_off[i] + pa1)) : z4;
+        rgt[i] = (gated && rok) ? g.seg[(size_t)((uint32_t)n * (uint32_t)P.MCse + g_off[i])] : 1.f;
+      }
+#pragma unroll
+      for (int j = 0; j < NBR; ++j) {
+        const bool rok = ok && b_row[j] >= 0;
+        rb0[j] = rok ? *(const float4*)(g.B0 + (size_t)(b_off[j] + pb)) : z4;
+        if (MODE == 0) rb1[j] = rok ? *(const float4*)(g.B1 + (size_t)(b1_off[j] + pb1)) : z4;
+      }
+      return;
+    }
     if (vecshape) {                    // 4 valid pixels of one image (p, p_hi are multiples of 4)
       px.vec = p < p_hi;
 #pragma unroll
@@ -1291,7 +1335,7 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float b = act_f<ACT>((d[e] - a_mu[i]) * a_r[i]);
-            if (gated) b *= px.vec ? rgt[i] : g.seg[(size_t)px.n[e] * P.MCse + cd.soff + (a_cst[i] - cd.coff)];
+            if (gated) b *= (VEC || px.vec) ? rgt[i] : g.seg[(size_t)px.n[e] * P.MCse + cd.soff + (a_cst[i] - cd.coff)];
             v[e] = px.v[e] ? b : 0.f;
           }
         } else if (MODE == 1) {
@@ -1393,9 +1437,15 @@ __global__ void __launch_bounds__(NT) k_um_wgrad(Plan P, int slot, WgArgs g) {
 
 template <int MODE, int ACT>
 static void launch_um_wgrad(int nbr, dim3 grid, size_t smem, const Plan& P, int slot, const WgArgs& g, cudaStream_t st) {
+  const int HWp = MODE == 0 ? P.HWo : P.HW;
+  // vector rows: whole 16-byte groups per image, 32-bit element offsets (largest tensor: UH / DA with N * MC * HW elements)
+  const bool vec = MODE != 2 && (HWp & 3) == 0 && (unsigned long long)P.N * P.MC * P.HW < (1ULL << 32) &&
+                   (unsigned long long)P.N * P.na * P.oc * P.HWo < (1ULL << 32);
 #define UM_WG(NBR_) do { \
-    ensure_smem(k_um_wgrad<MODE, ACT, NBR_>, (size_t)(smem)); \
-    k_um_wgrad<MODE, ACT, NBR_><<<grid, NT, smem, st>>>(P, slot, g); } while (0)
+    if (vec) { ensure_smem(k_um_wgrad<MODE, ACT, NBR_, true>, (size_t)(smem)); \
+               k_um_wgrad<MODE, ACT, NBR_, true><<<grid, NT, smem, st>>>(P, slot, g); } \
+    else { ensure_smem(k_um_wgrad<MODE, ACT, NBR_, false>, (size_t)(smem)); \
+           k_um_wgrad<MODE, ACT, NBR_, false><<<grid, NT, smem, st>>>(P, slot, g); } } while (0)
   if (nbr <= 2) UM_WG(2);
   else if (nbr <= 4) UM_WG(4);
   else UM_WG(8);
