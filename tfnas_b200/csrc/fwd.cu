@@ -170,12 +170,16 @@ __global__ void __launch_bounds__(NT) k_xmom(Plan P, const float* __restrict__ x
   const int nsplit = nut >= NT ? 1 : NT / nut;
   const int sp = nut >= NT ? 0 : tid / nut;
   const bool active = nut >= NT ? true : tid < nut * nsplit;
+  // gridDim.y > 1 (few pixel tiles, many blocks: the 7x7 stages): the CTAs of one tile slot share the upper triangle,
+  // blocks [q_lo, q_hi) each, and write disjoint parts of the same xpart slice
+  const int nper = (nut + gridDim.y - 1) / gridDim.y;
+  const int q_lo = blockIdx.y * nper, q_hi = min(nut, q_lo + nper);
   int bi[XM_MAXB], bj[XM_MAXB];
 #pragma unroll
   for (int l = 0; l < XM_MAXB; ++l) {
-    int q = (nut >= NT ? tid : tid % nut) + l * NT;
+    int q = q_lo + (nut >= NT ? tid : tid % nut) + l * NT;
     bi[l] = -1; bj[l] = 0;
-    if (active && q < nut && (l == 0 || nut > NT)) {
+    if (active && q < q_hi && (l == 0 || nut > NT)) {
       int r = 0, rowlen = nb;
       while (q >= rowlen) { q -= rowlen; ++r; --rowlen; }
       bi[l] = r; bj[l] = r + q;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(NT) k_xmom(Plan P, const float* __restrict__ x
 #pragma unroll
     for (int l = 0; l < XM_MAXB; ++l) {
       if (bi[l] < 0) continue;
-      const int q = tid + l * NT;
+      const int q = q_lo + tid + l * NT;
 #pragma unroll
       for (int e4 = 0; e4 < 4; ++e4)
         *(float4*)(mine + (size_t)q * 16 + e4 * 4) = make_float4(acc[l][e4 * 4], acc[l][e4 * 4 + 1], acc[l][e4 * 4 + 2], acc[l][e4 * 4 + 3]);
@@ -790,9 +794,15 @@ void launch_forward(const Plan& P, const float* x, const float* log_alphas, cons
     const int nb4 = icp >> 2, nut = nb4 * (nb4 + 1) / 2, maxb = cdiv(nut, NT);
     { ProfScope ps("xmom", xbytes, 1.0 * P.P * ic * ic, st);
       const int grid = max(1, min(tiles, min(2 * sm_count(), XM_MAXCTA)));
-      if (maxb <= 1) { ensure_smem(k_xmom<1>, smem); k_xmom<1><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
-      else if (maxb <= 2) { ensure_smem(k_xmom<2>, smem); k_xmom<2><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
-      else { ensure_smem(k_xmom<5>, smem); k_xmom<5><<<grid, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
+      // fewer pixel tiles than SMs and several blocks per thread (ic = 192 on 7x7 planes: 98 tiles, 5 blocks per thread):
+      // split the blocks of the triangle over gridDim.y CTAs per tile
+      int nsb = 1;
+      if (grid < sm_count() && maxb > 1) nsb = min(maxb, cdiv(2 * sm_count(), grid));
+      const int mb = cdiv(cdiv(nut, nsb), NT);
+      const dim3 g2(grid, nsb);
+      if (mb <= 1) { ensure_smem(k_xmom<1>, smem); k_xmom<1><<<g2, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
+      else if (mb <= 2) { ensure_smem(k_xmom<2>, smem); k_xmom<2><<<g2, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
+      else { ensure_smem(k_xmom<5>, smem); k_xmom<5><<<g2, NT, smem, st>>>(P, x, TP, tp_shift, S.xpart); }
       count_launch(1);
       k_xred<<<cdiv(nut * 16 * 8, NT), NT, 0, st>>>(ic, grid, S.xpart, S.xsum, S.xcov); }
     { ProfScope ps("xfin", 16.0 * ic * ic, 0, st);
