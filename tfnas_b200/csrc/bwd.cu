@@ -1026,14 +1026,16 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
       if (relu) k_b2b<TFNAS_ACT_RELU><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD);
       else k_b2b<TFNAS_ACT_SWISH><<<gpl, NT, 0, st>>>(P, D, bn2, seg, S.dg, S.DC, S.sD); }
     if (dweights) {
+      // the SE weight gradients only read what se_bwd left (sede, sedt) and saved state: beside b2b, on the side stream
+      if (side) { cudaEventRecord(side->fork2, st); cudaStreamWaitEvent(wst, side->fork2, 0); }
       for (int s = 0; s < P.na; ++s) {
         const Cand& cd = P.c[s];
         if (!cd.se) continue;
         const int big = max(cd.mc, cd.se);
         dim3 gwg(cdiv(big, FC_TN), cdiv(big, FC_TO), 2);
-        ProfScope ps("se_wgrad", 8.0 * cd.mc * cd.se, 4.0 * P.N * cd.mc * cd.se, st);
-        if (relu) k_se_wgrad<TFNAS_ACT_RELU><<<gwg, NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
-        else k_se_wgrad<TFNAS_ACT_SWISH><<<gwg, NT, 0, st>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
+        ProfScope ps("se_wgrad", 8.0 * cd.mc * cd.se, 4.0 * P.N * cd.mc * cd.se, wst);
+        if (relu) k_se_wgrad<TFNAS_ACT_RELU><<<gwg, NT, 0, wst>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
+        else k_se_wgrad<TFNAS_ACT_SWISH><<<gwg, NT, 0, wst>>>(P, s, S.sede, S.sedt, sep, set, dweights[cd.id]);
       }
     }
   }
@@ -1088,9 +1090,9 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     }
   }
   if (dweights) {   // dW1 via Smat
-    if (side) {       // Smat was accumulated on the side stream (forked before the dx GEMM); join before the finishing kernels
-      cudaEventRecord(side->join, wst);
-      cudaStreamWaitEvent(st, side->join, 0);
+    if (side) {       // Smat was accumulated on the side stream (forked before the dx GEMM); the finishing kernel needs the
+      cudaEventRecord(side->fork2, st);           // BN1-backward sums of the dx GEMM too and then stays on the side stream:
+      cudaStreamWaitEvent(wst, side->fork2, 0);   // nothing on the caller's stream reads dW1 (joined at the end of the call)
     }
     for (int s = 0; s < P.na; ++s) {
       const Cand& cd = P.c[s];
@@ -1108,8 +1110,8 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
         if (relu) k_wgrad<1, TFNAS_ACT_RELU><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
         else k_wgrad<1, TFNAS_ACT_SWISH><<<grid, NT, 0, st>>>(P, s, S.DA, UH, x, nullptr, nullptr, nullptr, nullptr, Sm);
       }
-      { ProfScope ps("w1fin", 12.0 * cd.mc * ic, 2.0 * cd.mc * ic * ic, st);
-        k_w1fin<<<cdiv(cd.mc, W1F_CH), NT, (size_t)W1F_CH * ic * 4, st>>>(P, s, Sm, smat_t, bn1, S.sU, xmom, dweights[cd.id].w1); }
+      { ProfScope ps("w1fin", 12.0 * cd.mc * ic, 2.0 * cd.mc * ic * ic, wst);
+        k_w1fin<<<cdiv(cd.mc, W1F_CH), NT, (size_t)W1F_CH * ic * 4, wst>>>(P, s, Sm, smat_t, bn1, S.sU, xmom, dweights[cd.id].w1); }
     }
   }
   // B4
@@ -1141,5 +1143,9 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   if (alpha_mode && dlog_alphas) {
     ProfScope ps("alpha_grad", 128, 0, st);
     k_alpha_grad<<<1, 32, 0, st>>>(P.num_ops, mixw, latsave, S.dmix, dlat, T, dlog_alphas);
+  }
+  if (side) {         // every weight gradient is written and the workspace may be reused once the side stream has joined
+    cudaEventRecord(side->join, wst);
+    cudaStreamWaitEvent(st, side->join, 0);
   }
 }
