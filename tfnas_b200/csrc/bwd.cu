@@ -922,7 +922,11 @@ static SideStream* side_stream_for(cudaStream_t main) {
   if (it == streams.end()) {
     if (streams.size() >= 64) return nullptr;
     SideStream sd;
-    if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // lowest priority: when SM slots free up, the pending CTAs of the caller's stream (the dx critical path: dozens of
+    // small dependent kernels) go first; the weight-gradient kernels fill what is left
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&sd.s, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     cudaEventCreateWithFlags(&sd.fork1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sd.fork2, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming);
