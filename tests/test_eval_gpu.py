@@ -44,8 +44,8 @@ def test_label_smoothing_ce_kernel(eps):
 
 
 def test_fused_trajectory_matches_torch_optim():
-    """Four fp32 steps at lr 0.1: FusedCrossEntropy(0.1) + FusedSGD(clip 5) vs nn.CrossEntropyLoss(label_smoothing) +
-    clip_grad_norm_ + torch.optim.SGD from the same start on the same batches."""
+    """FusedCrossEntropy(0.1) + FusedSGD(clip 5) vs nn.CrossEntropyLoss(label_smoothing) + clip_grad_norm_ +
+    torch.optim.SGD: the update rule on identical gradients, then one whole step from identical weights."""
     a = _net().cuda()
     b = copy.deepcopy(a)
     xa, _ = gi.derived_inputs()
@@ -74,16 +74,18 @@ def test_fused_trajectory_matches_torch_optim():
         opt_f.zero_grad(), opt_t.zero_grad()
         b.load_state_dict({k: v for k, v in a.state_dict().items() if 'running' in k or 'tracked' in k}, strict=False)
         assert worst() < 2e-6, worst()
-    # whole steps, each arm with its own criterion and gradients: fp32 round-off (the early layers' gradients of this net
-    # differ by ~1e-3 between two valid fp32 evaluations) grows through 17 BN blocks over four steps at lr 0.1
-    for x, t in batches:
-        lf, _ = eval_loop.train_step(a, x, t, smooth_f, opt_f, 5.0)
-        lt, _ = eval_loop.train_step(b, x, t, smooth_t, opt_t, 5.0)
-        assert abs(float(lf) - float(lt)) <= 5e-3 * abs(float(lt))      # the arms' weights drift apart at round-off level
-    assert worst() < 2e-2, worst()
+    # one whole step from identical weights, each arm with its own criterion and gradients.  (Further steps are not
+    # compared: the early layers' fp32 gradients of this net differ by ~1e-3 between two valid evaluations, and the two
+    # trajectories drift apart chaotically -- 0.4 % to 3 % after four steps at lr 0.1 from run to run.)
+    b.load_state_dict(a.state_dict())
+    x, t = batches[2]
+    lf, _ = eval_loop.train_step(a, x, t, smooth_f, opt_f, 5.0)
+    lt, _ = eval_loop.train_step(b, x, t, smooth_t, opt_t, 5.0)
+    assert abs(float(lf) - float(lt)) <= 1e-5 * abs(float(lt))
+    assert worst() < 2e-3, worst()
     for (k, u), v in zip(a.state_dict().items(), b.state_dict().values()):
-        if 'running' in k:              # same bound as the parameters: the two arms' statistics drift with their weights
-            assert float((u - v).abs().max()) <= 2e-2 * float(v.abs().max()) + 1e-5, k
+        if 'running' in k:
+            assert float((u - v).abs().max()) <= 1e-4 * float(v.abs().max()) + 1e-6, k
     # optimiser state round trip (checkpoint 'optimizer' entry)
     st = opt_f.state_dict()
     c = copy.deepcopy(a)
