@@ -401,6 +401,21 @@ def run_b200(args, rank, local, world, emit=print):
     sampler.stop()
     unit(0, iter(DevicePrefetcher(host_batches(1), dev)))     # warm the H2D path
     ms_e2e, _ = timed(True, args.steps)
+    # pinned host -> device bandwidth of THIS box, idle GPU: the e2e leg needs 3 batches (231 MB) per unit, i.e. 2.5 GB/s at
+    # 92 ms per unit -- boxes were seen where pinned copies ran at exactly that rate and e2e sat at 94.0 ms whatever the
+    # kernels did, so the number is reported next to e2e
+    xh = host[0][0]
+    xd = torch.empty_like(pool[0][0])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xd.copy_(xh, non_blocking=True)
+    e0.record()
+    for _ in range(3):
+        xd.copy_(xh, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * xh.numel() * 4 / (e0.elapsed_time(e1) / 1e3) / 1e9
+    del xd
     # per-kernel attribution over the same K units (CUDA events on the launching stream).  The units run with their passes
     # in sequence on ONE stream for this leg: with the two sampled passes and the weight-gradient side streams concurrent
     # (as in the timed legs) an event pair brackets a kernel that shares the SMs with its neighbours' kernels.
@@ -448,7 +463,7 @@ def run_b200(args, rank, local, world, emit=print):
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': base_config(world),
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * 4,
-                    'ms_per_step': ms_e2e / args.steps},
+                    'ms_per_step': ms_e2e / args.steps, 'h2d_pinned_GBps_idle': h2d_gbps},
             'gpu_launches': launches, 'launches_per_step': launches / args.steps,
             'host_enqueue_ms_per_step': host_enqueue, 'host_blocked_on_gpu_ms_per_step': host_blocked,
             'host_busy_ms_per_step': host_enqueue - host_blocked,
