@@ -153,18 +153,20 @@ size_t fwd_scratch(const Plan& P, char* base, FwdScratch& S) {
 size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch& S) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-  // [sG | sGY | sD | sU] contiguous doubles (one memset)
+  // everything the backward accumulates into with atomics sits in ONE zeroed region: [sG | sGY | sD | sU] doubles, then
+  // cvec2, Mm, sedt, dg -- a single memset at the start of the call (S.zero_bytes) instead of four along the way
   size_t nd = (size_t)P.oc + (size_t)P.na * P.oc + 4 * (size_t)P.MC;
   size_t acc = take(nd * sizeof(double));
-  size_t dzc = take((size_t)P.na * P.oc * sizeof(float4));
-  size_t dzc2 = take((size_t)P.na * P.oc * sizeof(float4));
   size_t cvec2 = take((size_t)P.ic * 4);
   size_t Mm = take((size_t)P.ic * P.ic * 4);
+  size_t sedt = take((size_t)P.N * P.SEH * 4 + 16);
+  size_t dg = take((size_t)P.N * P.MCse * 4);
+  const size_t zero_end = o;
+  size_t dzc = take((size_t)P.na * P.oc * sizeof(float4));
+  size_t dzc2 = take((size_t)P.na * P.oc * sizeof(float4));
   size_t a12 = take((size_t)2 * P.MC * 4);
   size_t dmix = take(TFNAS_MAX_OPS * 4);
-  size_t dg = take((size_t)P.N * P.MCse * 4);
   size_t sede = want_wgrad ? take((size_t)P.N * P.MCse * 4) : 0;
-  size_t sedt = take((size_t)P.N * P.SEH * 4 + 16);
   size_t Smat = want_wgrad ? take((size_t)P.MC * P.ic * 4) : 0;
   size_t DC = take((size_t)P.N * P.MC * P.HWo * 4);
   size_t DA = take((size_t)P.N * P.MC * P.HW * 4);
@@ -172,6 +174,7 @@ size_t bwd_scratch(const Plan& P, int want_wgrad, char* base, BwdScratch& S) {
   if (base) {
     S.umprep = (float*)(base + umprep);
     S.sG = (double*)(base + acc);
+    S.zero_bytes = zero_end - acc;
     S.sGY = S.sG + P.oc;
     S.sD = S.sGY + (size_t)P.na * P.oc;
     S.sU = S.sD + 2 * (size_t)P.MC;

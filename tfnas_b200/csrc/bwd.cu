@@ -509,25 +509,17 @@ __global__ void __launch_bounds__(NT) k_dx(Plan P, OcTile T, int ksplit, const f
 // ----------------------------------------------------------------------------------------------
 // B4: fold the BN1 backward into an ic x ic correction
 // ----------------------------------------------------------------------------------------------
-// per stacked channel: a1 = r1*m1, a2 = r1^2*m2  (m = BN1-backward means)
-__global__ void k_b4coef(int MC, double invP, const float* __restrict__ bn1, const double* __restrict__ sU,
-                         float* __restrict__ a12) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= MC) return;
-  double r1 = (double)bn1[MC + c];
-  a12[c] = (float)(r1 * sU[2 * c] * invP);
-  a12[MC + c] = (float)(r1 * r1 * sU[2 * c + 1] * invP);
-}
-
 // Mm[k][k'] = sum_c W1[c][k] a2_c W1[c][k'] as a tiled CUDA-core GEMM over the stacked channels:
 // grid (ic/64, ic/64, c-splits); 64x64 tile, 4x4 per thread, 32 channels per smem chunk; float atomics into Mm.
 #define B4_T 64
 #define B4_KC 32
-__global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ a12, float* __restrict__ Mm,
-                                              float* __restrict__ cvec) {
+// The per-channel coefficients a1 = r1 m1, a2 = r1^2 m2 (m = BN1-backward means, from the sums of the dx GEMM) are formed
+// here per chunk (they were a launch of their own, k_b4coef).
+__global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ bn1, const double* __restrict__ sU, double invP,
+                                              float* __restrict__ Mm, float* __restrict__ cvec) {
   __shared__ __align__(16) float As[B4_KC][B4_T + 4];   // a2_c * W1[c][k0 + .]
   __shared__ __align__(16) float Bs[B4_KC][B4_T + 4];   // W1[c][kp0 + .]
-  __shared__ float a1s[B4_KC];                          // a1_c of the chunk (CTAs of the first tile row also form cvec)
+  __shared__ float a1s[B4_KC], a2s[B4_KC];              // a1_c, a2_c of the chunk (CTAs of the first tile row also form cvec)
   float cv = 0.f;                                       // cvec[kp0 + tid] partial (tid < B4_T, blockIdx.x == 0)
   const int ic = P.ic, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int k0 = blockIdx.x * B4_T, kp0 = blockIdx.y * B4_T;
@@ -539,6 +531,18 @@ __global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ a
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int cb = c_lo; cb < c_hi; cb += B4_KC) {
     __syncthreads();
+    if (tid < B4_KC) {
+      const int c = cb + tid;
+      float a1 = 0.f, a2 = 0.f;
+      if (c < c_hi) {
+        const double r1 = (double)bn1[P.MC + c];
+        a1 = (float)(r1 * sU[2 * c] * invP);
+        a2 = (float)(r1 * r1 * sU[2 * c + 1] * invP);
+      }
+      a1s[tid] = a1;
+      a2s[tid] = a2;
+    }
+    __syncthreads();
     for (int i = tid; i < B4_KC * B4_T; i += NT) {
       const int cc = i / B4_T, kk = i - cc * B4_T;
       const int cst = cb + cc;
@@ -547,13 +551,12 @@ __global__ void __launch_bounds__(NT) k_b4mm(Plan P, const float* __restrict__ a
         int s = 0;
         while (s + 1 < P.na && cst >= P.c[s + 1].coff) ++s;
         const float* w = P.c[s].w1 + (size_t)(cst - P.c[s].coff) * ic;
-        if (k0 + kk < ic) wa = w[k0 + kk] * a12[P.MC + cst];
+        if (k0 + kk < ic) wa = w[k0 + kk] * a2s[cc];
         if (kp0 + kk < ic) wb = w[kp0 + kk];
       }
       As[cc][kk] = wa;
       Bs[cc][kk] = wb;
     }
-    if (tid < B4_KC) a1s[tid] = cb + tid < c_hi ? a12[cb + tid] : 0.f;
     __syncthreads();
     if (blockIdx.x == 0 && tid < B4_T) {          // cvec[k'] = sum_c W1[c][k'] a1_c (was a separate launch)
 #pragma unroll 8
@@ -954,8 +957,7 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   const bool relu = P.act == TFNAS_ACT_RELU;
   const int ic = P.ic, oc = P.oc;
   // zero the accumulators: [sG | sGY | sD | sU] doubles are contiguous, then dg floats
-  cudaMemsetAsync(S.sG, 0, (size_t)(oc + P.na * oc + 4 * P.MC) * sizeof(double), st);
-  if (P.MCse > 0) cudaMemsetAsync(S.dg, 0, (size_t)P.N * P.MCse * sizeof(float), st);
+  cudaMemsetAsync(S.sG, 0, S.zero_bytes, st);       // sums, cvec2, Mm, sedt, dg (api.cu::bwd_scratch)
   // B1
   {
     int nsplit = max(1, min(cdiv(P.Q, 1024), cdiv(4 * sm_count(), oc)));
@@ -1018,7 +1020,6 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
     dim3 gpl(cdiv(P.MCse * 32, NT), P.N);
     { ProfScope ps("se_bwd", 4.0 * fcw + 12.0 * P.N * P.MCse, 2.0 * P.N * fcw, st);
       const int ksplit = max(1, min(8, cdiv(maxmc, 2 * FC_KC)));
-      cudaMemsetAsync(S.sedt, 0, (size_t)P.N * P.SEH * sizeof(float), st);
       dim3 g1(cdiv(P.N, FC_TN), cdiv(maxse, FC_TO), P.na * ksplit);
       if (relu) k_se_bwd1<TFNAS_ACT_RELU><<<g1, NT, 0, st>>>(P, ksplit, seg, S.dg, sede, S.sedt);
       else k_se_bwd1<TFNAS_ACT_SWISH><<<g1, NT, 0, st>>>(P, ksplit, seg, S.dg, sede, S.sedt);
@@ -1120,14 +1121,10 @@ void launch_backward(const Plan& P, const float* x, const float* dout, const flo
   }
   // B4
   {
-    // cvec2 and Mm are adjacent in the workspace: one memset
-    cudaMemsetAsync(S.cvec2, 0, (size_t)((char*)(S.Mm + ic * ic) - (char*)S.cvec2), st);
-    { ProfScope ps("b4coef", 24.0 * P.MC, 0, st);
-      k_b4coef<<<cdiv(P.MC, 256), 256, 0, st>>>(P.MC, 1.0 / (double)P.P, bn1, S.sU, S.a12); }
     { ProfScope ps("b4mm", 4.0 * P.MC * ic, 2.0 * P.MC * ic * ic, st);
       const int kt = cdiv(ic, B4_T);
       int nsplit = max(1, min(cdiv(P.MC, 2 * B4_KC), cdiv(2 * sm_count(), kt * kt)));
-      k_b4mm<<<dim3(kt, kt, nsplit), NT, 0, st>>>(P, S.a12, S.Mm, S.cvec2); }      // Mm and cvec (the k' tiles of row 0)
+      k_b4mm<<<dim3(kt, kt, nsplit), NT, 0, st>>>(P, bn1, S.sU, 1.0 / (double)P.P, S.Mm, S.cvec2); }   // Mm and cvec (k' tiles of row 0)
     // few pixel tiles (14x14 / 7x7 planes): split the output channels over several CTAs per tile so the grid covers the SMs
     OcTile Tf = Tx;
     {

@@ -42,7 +42,8 @@ struct BwdScratch {
   float4* dzc2;   // [na*oc]  the same folded into dz = a*g + b*z + c (tcgen05 dc prologue: two FMAs per element)
   float* cvec2;   // [ic]        (cvec2 and Mm adjacent: zeroed by one memset)
   float* Mm;      // [ic*ic]
-  float* a12;     // [2*MC]  BN1-backward per-channel coefficients
+  float* a12;     // [2*MC]  (unused since b4mm forms the BN1-backward coefficients itself)
+  size_t zero_bytes;   // bytes from sG to the end of dg: the atomically accumulated region, zeroed once per call
   float* dmix;    // [8]  dL/dw_i (data term)
   float* sede;    // [N*MCse]  SE: dL/de (pre-sigmoid)     (weight-grad mode)
   float* sedt;    // [N*SEH]   SE: dL/dt (pre-act hidden)  (weight-grad mode)
