@@ -1523,8 +1523,11 @@ void umma_wgrad(const Plan& P, int slot, int mode, const float* A0, const float*
   // only 25k / 6k pixels: with 1024-pixel splits a 1152-wide candidate ran on 54 CTAs)
   int nsplit = max(1, min(cdiv(total, 256), cdiv(3 * sm_count(), mt * g.nN)));
   // every split adds its partial tile with float atomics: keep (output elements x splits) bounded -- the head's
-  // 1280 x 320 feature-mix gradient at 25 splits spent its time in 10 M atomics
-  nsplit = max(1, min(nsplit, (int)(3000000LL / ((long long)cd.mc * nb))));
+  // 1280 x 320 feature-mix gradient at 25 splits spent its time in 10 M atomics (cap: 6 M)
+  // (cap swept on B200 with the vector-row kernels: dW1 2.56 / 2.31 / 2.09 / 2.06 ms per sampled pass at 1.5 / 3 / 6 / 12 M,
+  //  dW3 flat from 3 M on; TFNAS_WG_ATOM overrides for A/B runs)
+  static const long long atom_cap = [] { const char* e = getenv("TFNAS_WG_ATOM"); return e ? atoll(e) : 6000000LL; }();
+  nsplit = max(1, min(nsplit, (int)(atom_cap / ((long long)cd.mc * nb))));
   size_t smem = 1024 + 32768 + (size_t)2 * g.Nc * 128 + 64;
   dim3 grid(mt, g.nN, nsplit);
   const bool relu = P.act == TFNAS_ACT_RELU;
