@@ -925,8 +925,9 @@ static SideStream* side_stream_for(cudaStream_t main) {
   if (it == streams.end()) {
     if (streams.size() >= 64) return nullptr;
     SideStream sd;
-    // lowest priority: when SM slots free up, the pending CTAs of the caller's stream (the dx critical path: dozens of
-    // small dependent kernels) go first; the weight-gradient kernels fill what is left
+    // lowest priority (on current drivers that IS the default, 0): a caller that wants its dx critical path (dozens of small
+    // dependent kernels) scheduled ahead of the weight-gradient tiles runs the pass on a higher-priority stream, as
+    // search_loop.w_step does (torch.cuda.Stream(priority=-1))
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&sd.s, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { cudaGetLastError(); return nullptr; }

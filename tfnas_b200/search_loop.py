@@ -107,10 +107,12 @@ if hasattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch'):
 
 
 def _side_streams(device):
-    """Two side streams per device for the bi-sampled w-step (created once)."""
+    """Two pass streams per device for the bi-sampled w-step (created once).  They are HIGH-priority streams: the library's
+    weight-gradient side streams (csrc/bwd.cu) sit at the default, lowest priority, so when SM slots free up the pending
+    CTAs of a pass's dx critical path are scheduled before weight-gradient tiles."""
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=key), torch.cuda.Stream(device=key))
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=key, priority=-1), torch.cuda.Stream(device=key, priority=-1))
     return _SIDE_STREAMS[key]
 
 
