@@ -238,3 +238,21 @@ def test_two_rank_gloo_training_step_equals_mean_of_shard_gradients():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(err < 1e-5 for _, err in res), res
+
+
+def test_fused_sgd_state_dict_round_trip_on_host():
+    """The checkpoint 'optimizer' entry of train_eval.py: hyper-parameters plus the momentum buffers as one flat tensor in
+    parameter order (no kernel call involved, so this runs without a GPU)."""
+    from tfnas_b200.step import FusedSGD
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
+    a = FusedSGD(params, 0.2, momentum=0.9, weight_decay=1e-5)
+    assert a.state_dict()['momentum_flat'] is None                 # nothing stepped yet
+    a._state(params[0].device)
+    flat = torch.arange(17, dtype=torch.float32)
+    a.load_state_dict(dict(momentum_flat=flat, lr=0.05, momentum=0.8, weight_decay=1e-4))
+    assert (a.lr, a.momentum, a.weight_decay, a.param_groups[0]['lr']) == (0.05, 0.8, 1e-4, 0.05)
+    assert torch.equal(a._bufs[id(params[0])], flat[:12].view(3, 4)) and torch.equal(a._bufs[id(params[1])], flat[12:])
+    b = FusedSGD(params, 0.2)
+    b.load_state_dict(a.state_dict())
+    assert torch.equal(b.state_dict()['momentum_flat'], flat) and b.lr == 0.05
