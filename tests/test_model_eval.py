@@ -256,3 +256,22 @@ def test_fused_sgd_state_dict_round_trip_on_host():
     b = FusedSGD(params, 0.2)
     b.load_state_dict(a.state_dict())
     assert torch.equal(b.state_dict()['momentum_flat'], flat) and b.lr == 0.05
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference not mounted')
+def test_label_smoothing_against_the_reference_class():
+    """CrossEntropyLabelSmooth lifted out of the reference's train_eval.py (:72-84; the script itself cannot be imported:
+    argparse with required arguments and mkdir at import) against the unfused criterion of eval_loop and, on the same
+    numbers, the closed form the kernel implements: lse - (1 - eps) l[target] - eps / C * sum(l)."""
+    src = open(os.path.join(ref_shim.REF_ROOT, 'train_eval.py')).read()
+    start, end = src.index('class CrossEntropyLabelSmooth'), src.index('def set_seed')
+    ns = {'nn': torch.nn, 'torch': torch}
+    exec(compile(src[start:end], 'ref_train_eval_criterion', 'exec'), ns)
+    torch.manual_seed(4)
+    logits, target = 3 * torch.randn(16, 100, dtype=torch.float64), torch.randint(0, 100, (16,))
+    for eps in (0.0, 0.1, 0.3):
+        ref = ns['CrossEntropyLabelSmooth'](100, eps)(logits, target)
+        ours = torch.nn.CrossEntropyLoss(label_smoothing=eps)(logits, target)
+        lse = torch.logsumexp(logits, 1)
+        closed = (lse - (1 - eps) * logits.gather(1, target[:, None])[:, 0] - eps / 100 * logits.sum(1)).mean()
+        assert abs(float(ref) - float(ours)) < 1e-12 and abs(float(ref) - float(closed)) < 1e-12
